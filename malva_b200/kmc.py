@@ -1,0 +1,224 @@
+"""Host-side k-mer utilities: 2-bit packing, a KMC-database reader/writer and a
+small k-mer counter that emulates the KMC defaults the MALVA pipeline relies on.
+
+Reference call sites served: the KMC listing loop ``main.cpp:482-490`` (reader)
+and the wrapper's ``kmc -m4 -k43 -t1 -fm`` invocation ``MALVA:107`` (counter:
+canonical k-mers, ``-ci2`` minimum count, ``-cs255`` counter cap).
+
+The KMC API itself is third party (KMC >= 2.3, not vendored by the reference);
+the on-disk layout implemented here is restated from the published format
+description (KMC1 "version 0" / KMC2 "0x200") and is UNPINNED by any reference
+test -- see DESIGN.md.
+
+Packed k-mer word (the device format of ``mg_scan_sample_kmers``): A=0 C=1 G=2
+T=3, first base in the most significant position, right-aligned in 128 bits and
+stored as two little-endian u64 ``(lo, hi)``.  Integer order == lexicographic
+order, so the canonical form is ``min(x, revcomp(x))``.
+"""
+from __future__ import annotations
+
+import os
+import struct
+from collections import Counter
+from typing import Iterable, Tuple
+
+import numpy as np
+
+_CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+_SYM = "ACGT"
+_M64 = (1 << 64) - 1
+
+KMER_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8")])
+
+
+def pack_kmer(s: str) -> int:
+    """ASCII ACGT string -> integer code (first base most significant)."""
+    x = 0
+    for ch in s:
+        x = (x << 2) | _CODE[ch]
+    return x
+
+
+def unpack_kmer(x: int, k: int) -> str:
+    return "".join(_SYM[(x >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def revcomp_int(x: int, k: int) -> int:
+    r = 0
+    for _ in range(k):
+        r = (r << 2) | (3 - (x & 3))
+        x >>= 2
+    return r
+
+
+def canonical_int(x: int, k: int) -> int:
+    return min(x, revcomp_int(x, k))
+
+
+def ints_to_packed(vals: Iterable[int]) -> np.ndarray:
+    vals = list(vals)
+    out = np.zeros(len(vals), dtype=KMER_DTYPE)
+    out["lo"] = np.array([v & _M64 for v in vals], dtype=np.uint64)
+    out["hi"] = np.array([(v >> 64) & _M64 for v in vals], dtype=np.uint64)
+    return out
+
+
+def packed_to_ints(arr: np.ndarray) -> list:
+    lo = arr["lo"].tolist()
+    hi = arr["hi"].tolist()
+    return [(h << 64) | l for l, h in zip(lo, hi)]
+
+
+def packed_to_strings(arr: np.ndarray, k: int) -> list:
+    return [unpack_kmer(v, k) for v in packed_to_ints(arr)]
+
+
+def count_kmers(reads: Iterable[str], k: int, min_count: int = 2, counter_max: int = 255,
+                canonical: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Emulate ``kmc -k<k> -ci<min_count> -cs<counter_max>`` on an iterable of reads.
+
+    k-mers containing a non-ACGT symbol are skipped, as KMC does.  Returns the
+    sorted packed k-mers and their (capped) u32 counts.
+    """
+    cnt: Counter = Counter()
+    mask = (1 << (2 * k)) - 1
+    for r in reads:
+        r = r.strip().upper()
+        x = 0
+        valid = 0
+        for ch in r:
+            c = _CODE.get(ch)
+            if c is None:
+                valid = 0
+                x = 0
+                continue
+            x = ((x << 2) | c) & mask
+            valid += 1
+            if valid >= k:
+                cnt[canonical_int(x, k) if canonical else x] += 1
+    keys = sorted(v for v, c in cnt.items() if c >= min_count)
+    counts = np.array([min(cnt[v], counter_max) for v in keys], dtype=np.uint32)
+    return ints_to_packed(keys), counts
+
+
+def read_fastx(path: str) -> list:
+    """Minimal FASTA/FASTQ sequence reader (plain or gz)."""
+    import gzip
+
+    op = gzip.open if path.endswith(".gz") else open
+    seqs = []
+    with op(path, "rt") as fh:
+        lines = [l.rstrip("\n") for l in fh]
+    i = 0
+    while i < len(lines):
+        l = lines[i]
+        if l.startswith("@"):
+            seqs.append(lines[i + 1])
+            i += 4
+        elif l.startswith(">"):
+            j = i + 1
+            s = []
+            while j < len(lines) and not lines[j].startswith(">"):
+                s.append(lines[j])
+                j += 1
+            seqs.append("".join(s))
+            i = j
+        else:
+            i += 1
+    return seqs
+
+
+def _choose_lut_prefix_len(k: int, n: int) -> int:
+    best = None
+    for p in range(1, min(k, 15) + 1):
+        if (k - p) % 4:
+            continue
+        if best is None or (4 ** p) <= max(64, n):
+            best = p
+    if best is None:
+        raise ValueError(f"no LUT prefix length with (k-p)%4==0 for k={k}")
+    return best
+
+
+def write_kmc_db(prefix: str, kmers: np.ndarray, counts: np.ndarray, k: int, *,
+                 lut_prefix_len: int | None = None, version: int = 0x200, counter_size: int = 1,
+                 min_count: int = 2, max_count: int = 255, signature_len: int = 5,
+                 both_strands: bool = True) -> None:
+    """Write ``<prefix>.kmc_pre`` / ``.kmc_suf`` holding the given sorted records."""
+    vals = packed_to_ints(kmers)
+    order = sorted(range(len(vals)), key=vals.__getitem__)
+    vals = [vals[i] for i in order]
+    cts = [int(counts[i]) for i in order]
+    n = len(vals)
+    p = lut_prefix_len if lut_prefix_len is not None else _choose_lut_prefix_len(k, n)
+    if (k - p) % 4:
+        raise ValueError("(k - lut_prefix_len) must be a multiple of 4")
+    suf_syms = k - p
+    suf_bytes = suf_syms // 4
+    lut = [0] * (4 ** p + 1)
+    suf = bytearray(b"KMCS")
+    smask = (1 << (2 * suf_syms)) - 1
+    for v, c in zip(vals, cts):
+        lut[(v >> (2 * suf_syms)) + 1] += 1
+        suf += (v & smask).to_bytes(suf_bytes, "big")
+        suf += int(c).to_bytes(counter_size, "little")
+    suf += b"KMCS"
+    for i in range(1, len(lut)):
+        lut[i] += lut[i - 1]
+    # lut[i] = number of records whose prefix is < i ; lut[4^p] = n (guard)
+    pre = bytearray(b"KMCP")
+    pre += struct.pack(f"<{len(lut)}Q", *lut)
+    if version == 0x200:
+        pre += struct.pack(f"<{4 ** signature_len + 1}I", *([0] * (4 ** signature_len + 1)))
+        hdr = struct.pack("<7IQB", k, 0, counter_size, p, signature_len, min_count,
+                          max_count & 0xFFFFFFFF, n, 0 if both_strands else 1)
+    elif version == 0:
+        hdr = struct.pack("<6IQB", k, 0, counter_size, p, min_count, max_count & 0xFFFFFFFF, n,
+                          0 if both_strands else 1)
+    else:
+        raise ValueError("version must be 0 or 0x200")
+    hdr += b"\0" * (60 - len(hdr)) + struct.pack("<I", version)
+    pre += hdr + struct.pack("<I", len(hdr)) + b"KMCP"
+    os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+    with open(prefix + ".kmc_pre", "wb") as fh:
+        fh.write(pre)
+    with open(prefix + ".kmc_suf", "wb") as fh:
+        fh.write(suf)
+
+
+def read_kmc_db(prefix: str) -> Tuple[np.ndarray, np.ndarray, int]:
+    """List a KMC database: (packed k-mers, u32 counts, k); count filter applied."""
+    pre = open(prefix + ".kmc_pre", "rb").read()
+    if pre[:4] != b"KMCP" or pre[-4:] != b"KMCP":
+        raise ValueError("bad .kmc_pre markers")
+    version, hoff = struct.unpack("<II", pre[-12:-4])
+    if version not in (0, 0x200):
+        raise ValueError(f"unsupported KMC version {version:#x}")
+    h = pre[len(pre) - 8 - hoff:]
+    if version == 0x200:
+        k, _mode, csz, p, sig, minc, maxc, total = struct.unpack("<7IQ", h[:36])
+        sigmap = (4 ** sig + 1) * 4
+    else:
+        k, _mode, csz, p, minc, maxc, total = struct.unpack("<6IQ", h[:32])
+        sigmap = 0
+    lut_bytes = len(pre) - 4 - 8 - hoff - sigmap
+    lut = np.frombuffer(pre, dtype="<u8", count=lut_bytes // 8, offset=4)
+    single = 4 ** p
+    n_lut = (len(lut) // single) * single
+    suf = open(prefix + ".kmc_suf", "rb").read()
+    if suf[:4] != b"KMCS":
+        raise ValueError("bad .kmc_suf marker")
+    sb = (k - p) // 4
+    rec = sb + csz
+    vals, cts = [], []
+    pi = 0
+    for i in range(total):
+        while pi + 1 < n_lut and lut[pi + 1] <= i:
+            pi += 1
+        o = 4 + i * rec
+        c = int.from_bytes(suf[o + sb:o + rec], "little") if csz else 1
+        if c < minc or c > maxc:
+            continue
+        vals.append(((pi % single) << (2 * (k - p))) | int.from_bytes(suf[o:o + sb], "big"))
+        cts.append(c)
+    return ints_to_packed(vals), np.array(cts, dtype=np.uint32), k
