@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: takes more than a few seconds on CPU")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import pyoracle
+
+    pyoracle.build()
+    return pyoracle.oracle()
+
+
+@pytest.fixture(scope="session")
+def ref_lib():
+    from oracle import pyoracle
+
+    pyoracle.build()
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return pyoracle.ref()
