@@ -1,0 +1,132 @@
+/* malva_gpu.h -- C ABI of the B200-native MALVA genotyping hot path.
+ *
+ * The reference (AlgoLab/malva) has no FFI layer: its hot path is the public
+ * surface of the header-only classes BF (bloom_filter.hpp:76-146) and KMAP
+ * (kmap.hpp:46-131), the four loops of main.cpp that drive them, and
+ * VB::genotype / VB::output_variants (var_block.hpp:224-396).  This header is
+ * the boundary cut at exactly those call sites, turned into batch calls: the
+ * caller owns host buffers, the library owns device memory, every call returns
+ * 0 or a negative error code (text via mg_last_error()).  Calls on one context
+ * are not thread-safe.  No torch types, no C++ types.
+ *
+ * k-mer word format of the sample stream: A=0 C=1 G=2 T=3, first base in the
+ * most significant position, right-aligned in 128 bits, stored as two
+ * little-endian u64 {lo, hi}.  ref_k <= 64.
+ *
+ * Signature k-mers (index side and genotyping side) are passed as the
+ * reference passes them -- ASCII strings -- batched as a byte pool plus n+1
+ * offsets; they may be shorter than k or contain non-ACGT symbols and are then
+ * hashed exactly as BF::_get_hash would hash them.
+ */
+#ifndef MALVA_GPU_H
+#define MALVA_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_OK 0
+#define MG_ERR_ARG (-1)     /* bad argument / unsupported parameter        */
+#define MG_ERR_CUDA (-2)    /* CUDA runtime failure (no CPU fallback)      */
+#define MG_ERR_STATE (-3)   /* call out of order (e.g. scan before finalize) */
+#define MG_ERR_NOMEM (-4)
+#define MG_ERR_IO (-5)
+
+typedef struct mg_ctx mg_ctx;
+
+const char *mg_last_error(void);
+int mg_version(void);
+/* number of CUDA devices visible; <0 on failure (used to fail loudly) */
+int mg_device_count(void);
+
+/* BF bf(size); KMAP ref_bf; BF context_bf(size)      main.cpp:300-302, 451-453 */
+int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf_bits);
+void mg_destroy(mg_ctx *ctx);
+
+/* ------------------------------ index side ------------------------------ */
+/* add_kmers_to_bf                                        main.cpp:122-144
+ * is_ref[i] != 0 -> ref_bf.add_key(kmer i) ; else bf.add_key(kmer i)        */
+int mg_add_signatures(mg_ctx *ctx, const char *pool, const uint64_t *kmer_off, const uint8_t *is_ref,
+                      uint64_t n);
+/* bf.switch_mode()                                       main.cpp:378      */
+int mg_finalize_alt(mg_ctx *ctx);
+/* reference rolling pass over one (upper-cased) contig   main.cpp:385-400  */
+int mg_scan_reference(mg_ctx *ctx, const char *seq, uint64_t len);
+/* context_bf.switch_mode()                               main.cpp:404      */
+int mg_finalize_context(mg_ctx *ctx);
+
+/* ------------------------------- call side ------------------------------ */
+/* sample k-mer scan                                      main.cpp:487-500
+ * lohi = n x {lo,hi} u64 pairs, counts = n x u32, HOST memory (pinned memory
+ * from mg_host_alloc makes the copies asynchronous and double-buffered).
+ * Returns after the work is enqueued; mg_sync() completes it.               */
+int mg_scan_sample_kmers(mg_ctx *ctx, const uint64_t *lohi, const uint32_t *counts, uint64_t n);
+/* same with DEVICE-resident inputs (GPU-side producers, kernel-only timing)  */
+int mg_scan_sample_kmers_device(mg_ctx *ctx, const void *d_lohi, const void *d_counts, uint64_t n);
+int mg_sync(mg_ctx *ctx);
+
+/* set_coverages + VB::genotype + arg-max/GQ of VB::output_variants
+ *                         main.cpp:151-184, var_block.hpp:224-330, 367-394  */
+typedef struct {
+  uint64_t n_variants;
+  const uint64_t *var_allele_off; /* [n_variants+1]; allele slot j of a variant is allele index j (0 = REF) */
+  const uint64_t *allele_sig_off; /* [n_alleles+1]  signatures of each allele slot          */
+  const uint64_t *sig_kmer_off;   /* [n_sigs+1]     k-mers of each signature, enumeration order */
+  const uint64_t *kmer_off;       /* [n_kmers+1]    byte range of each k-mer in pool        */
+  const char *pool;
+  const float *freq;              /* [n_alleles]    a-priori allele frequencies (Variant::frequencies) */
+} mg_variant_batch;
+
+typedef struct {
+  uint32_t *cov;           /* [n_alleles]   Variant::coverages                               */
+  int32_t *n_gts;          /* [n_variants]  number of computed_gts entries                   */
+  int32_t *status;         /* [n_variants]  0 normal, 1 max-coverage veto, 2 no coverage     */
+  int32_t *best_gt;        /* [n_variants]  index (emission order) of the printed GT; 0 if status != 0 */
+  int32_t *gq;             /* [n_variants]  printed GQ                                        */
+  const uint64_t *lik_off; /* [n_variants+1] slots reserved per variant (>= n or n(n+1)/2)     */
+  double *lik;             /* un-normalised probabilities, emission order (may be NULL)      */
+} mg_genotype_out;
+
+int mg_genotype(mg_ctx *ctx, const mg_variant_batch *in, const mg_genotype_out *out, float error_rate,
+                int max_coverage, int haploid);
+
+/* ------------------------- batch queries (BF / KMAP) --------------------- */
+/* which: 0 = bf, 1 = context_bf, 2 = ref_bf (KMAP).  BF::test_key / KMAP::test_key */
+int mg_test_keys(mg_ctx *ctx, int which, const char *pool, const uint64_t *kmer_off, uint64_t n, uint8_t *out);
+/* BF::get_count (is_ref==0, u16 semantics) / KMAP::get_count (is_ref!=0, int semantics) */
+int mg_get_counts(mg_ctx *ctx, const char *pool, const uint64_t *kmer_off, const uint8_t *is_ref, uint64_t n,
+                  int32_t *out);
+
+/* ------------------------------ state access ----------------------------- */
+int mg_bf_popcount(mg_ctx *ctx, int which, uint64_t *ones);
+/* bit i = (words[i>>6] >> (i&63)) & 1 ; n_words = ceil(bf_bits/64)          */
+int mg_bf_download_bits(mg_ctx *ctx, int which, uint64_t *words, uint64_t n_words);
+/* rank-indexed u16 counters of bf (valid after mg_finalize_alt)             */
+int mg_bf_download_counts(mg_ctx *ctx, uint16_t *counts, uint64_t n);
+/* number of ref_bf keys (packed + irregular)                                */
+int mg_kmap_size(mg_ctx *ctx, uint64_t *n);
+
+/* device pointers of the two counter arrays, for an external (NCCL) sum-reduce
+ * across replicas: u32 per set bit of bf, u32 per table slot of ref_bf.      */
+int mg_counter_buffers(mg_ctx *ctx, void **d_bf_counts, uint64_t *n_bf, void **d_ref_counts, uint64_t *n_ref);
+
+/* pinned host memory for the sample stream */
+int mg_host_alloc(void **p, size_t bytes);
+int mg_host_free(void *p);
+
+/* ----------------------- host-side self tests (no GPU) ------------------- */
+/* The device helpers are __host__ __device__; these run them on the CPU so the
+ * CPU-only test-suite can pin the exact code the kernels execute.            */
+uint64_t mg_selftest_hash_packed(uint64_t lo, uint64_t hi, int k, uint64_t *canon_lo, uint64_t *canon_hi);
+uint64_t mg_selftest_hash_packed_k35(uint64_t lo, uint64_t hi);
+uint64_t mg_selftest_hash_packed_k43(uint64_t lo, uint64_t hi);
+uint64_t mg_selftest_hash_ascii(const char *s, int len);
+float mg_selftest_logf(float x);
+int mg_selftest_genotype(const uint32_t *cov, const float *freq, int n_alleles, float error_rate, int max_cov,
+                         int haploid, double *lik, int *status, int *best_gt, int *gq);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MALVA_GPU_H */

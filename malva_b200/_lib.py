@@ -1,0 +1,109 @@
+"""ctypes binding of libmalva_gpu.so (the C ABI declared in include/malva_gpu.h).
+
+There is no CPU fallback: if the shared library is missing this raises, and if
+no CUDA device is usable every compute entry point returns MG_ERR_CUDA, which
+``check`` turns into a ``MalvaGpuError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmalva_gpu.so")
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+u16p = C.POINTER(C.c_uint16)
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+
+
+class MalvaGpuError(RuntimeError):
+    pass
+
+
+class VariantBatch(C.Structure):
+    _fields_ = [
+        ("n_variants", C.c_uint64),
+        ("var_allele_off", u64p),
+        ("allele_sig_off", u64p),
+        ("sig_kmer_off", u64p),
+        ("kmer_off", u64p),
+        ("pool", C.c_char_p),
+        ("freq", f32p),
+    ]
+
+
+class GenotypeOut(C.Structure):
+    _fields_ = [
+        ("cov", u32p),
+        ("n_gts", i32p),
+        ("status", i32p),
+        ("best_gt", i32p),
+        ("gq", i32p),
+        ("lik_off", u64p),
+        ("lik", f64p),
+    ]
+
+
+# every symbol include/malva_gpu.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mg_last_error": (C.c_char_p, []),
+    "mg_version": (C.c_int, []),
+    "mg_device_count": (C.c_int, []),
+    "mg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "mg_destroy": (None, [C.c_void_p]),
+    "mg_add_signatures": (C.c_int, [C.c_void_p, C.c_char_p, u64p, u8p, C.c_uint64]),
+    "mg_finalize_alt": (C.c_int, [C.c_void_p]),
+    "mg_scan_reference": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
+    "mg_finalize_context": (C.c_int, [C.c_void_p]),
+    "mg_scan_sample_kmers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "mg_scan_sample_kmers_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "mg_sync": (C.c_int, [C.c_void_p]),
+    "mg_genotype": (C.c_int, [C.c_void_p, C.POINTER(VariantBatch), C.POINTER(GenotypeOut), C.c_float, C.c_int,
+                              C.c_int]),
+    "mg_test_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, u64p, C.c_uint64, u8p]),
+    "mg_get_counts": (C.c_int, [C.c_void_p, C.c_char_p, u64p, u8p, C.c_uint64, i32p]),
+    "mg_bf_popcount": (C.c_int, [C.c_void_p, C.c_int, u64p]),
+    "mg_bf_download_bits": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64]),
+    "mg_bf_download_counts": (C.c_int, [C.c_void_p, u16p, C.c_uint64]),
+    "mg_kmap_size": (C.c_int, [C.c_void_p, u64p]),
+    "mg_counter_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_void_p), u64p]),
+    "mg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "mg_host_free": (C.c_int, [C.c_void_p]),
+    "mg_selftest_hash_packed": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_int, u64p, u64p]),
+    "mg_selftest_hash_packed_k35": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "mg_selftest_hash_packed_k43": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "mg_selftest_hash_ascii": (C.c_uint64, [C.c_char_p, C.c_int]),
+    "mg_selftest_logf": (C.c_float, [C.c_float]),
+    "mg_selftest_genotype": (C.c_int, [u32p, f32p, C.c_int, C.c_float, C.c_int, C.c_int, f64p, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MalvaGpuError(
+            f"{LIB_PATH} is missing: build it with `python -m malva_b200.build` "
+            "(there is no CPU fallback for the MALVA hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().mg_last_error()
+        raise MalvaGpuError(f"libmalva_gpu error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's hot-path interface, over the C ABI.
+
+The reference drives three objects -- ``BF bf``, ``BF context_bf``, ``KMAP ref_bf``
+(main.cpp:300-302) -- through per-k-mer methods.  ``MalvaGpu`` owns the device
+copies of all three and exposes the same operations as batch calls, with the
+reference's names where a 1:1 method exists:
+
+    reference                                      here
+    ---------------------------------------------  -----------------------------------
+    add_kmers_to_bf(bf, ref_bf, kmers)  main:122   MalvaGpu.add_signatures(kmers, is_ref)
+    bf.switch_mode()                    main:378   MalvaGpu.finalize_alt()
+    reference rolling loop              main:385   MalvaGpu.scan_reference(seq)
+    context_bf.switch_mode()            main:404   MalvaGpu.finalize_context()
+    KMC loop: increment / test_key      main:487   MalvaGpu.scan_sample_kmers(packed, counts)
+    set_coverages + VB::genotype        main:151   MalvaGpu.genotype(batch, ...)
+    BF::test_key / KMAP::test_key                  MalvaGpu.bf.test_key(...) etc. (views)
+    BF::get_count / KMAP::get_count                MalvaGpu.bf.get_count(...)
+
+All arithmetic runs in the CUDA kernels of malva_b200/csrc; nothing here
+computes a hash, a count or a likelihood on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MalvaGpuError, check  # noqa: F401
+from .kmc import KMER_DTYPE
+
+BF_ALT, BF_CONTEXT, KMAP_REF = 0, 1, 2
+
+
+def _as_bytes(k) -> bytes:
+    return k if isinstance(k, (bytes, bytearray)) else str(k).encode()
+
+
+def make_pool(kmers: Iterable) -> tuple:
+    """list of ASCII k-mers -> (pool bytes, u64 offsets[n+1])."""
+    ks = [_as_bytes(k) for k in kmers]
+    off = np.zeros(len(ks) + 1, dtype=np.uint64)
+    if ks:
+        off[1:] = np.cumsum([len(k) for k in ks], dtype=np.uint64)
+    return b"".join(ks), off
+
+
+def _p(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+@dataclass
+class SignatureBatch:
+    """CSR image of a list of VK_GROUPs (var_block.hpp:33): variant -> allele -> signature -> k-mers."""
+    var_allele_off: np.ndarray
+    allele_sig_off: np.ndarray
+    sig_kmer_off: np.ndarray
+    kmer_off: np.ndarray
+    pool: bytes
+    freq: np.ndarray
+
+    @property
+    def n_variants(self) -> int:
+        return len(self.var_allele_off) - 1
+
+    @staticmethod
+    def from_nested(variants: Sequence[Sequence[Sequence[Sequence]]], freqs: Sequence[Sequence[float]]) -> "SignatureBatch":
+        """variants[v][allele][signature] = list of k-mer strings; freqs[v][allele] = a-priori frequency."""
+        vao, aso, sko, kmers, fr = [0], [0], [0], [], []
+        for v, alleles in enumerate(variants):
+            assert len(freqs[v]) == len(alleles)
+            for a, sigs in enumerate(alleles):
+                for ks in sigs:
+                    kmers.extend(ks)
+                    sko.append(len(kmers))
+                aso.append(len(sko) - 1)
+                fr.append(freqs[v][a])
+            vao.append(len(aso) - 1)
+        pool, koff = make_pool(kmers)
+        return SignatureBatch(np.array(vao, dtype=np.uint64), np.array(aso, dtype=np.uint64),
+                              np.array(sko, dtype=np.uint64), koff, pool, np.array(fr, dtype=np.float32))
+
+
+@dataclass
+class GenotypeResult:
+    cov: np.ndarray       # u32 per allele slot
+    n_gts: np.ndarray     # entries of computed_gts per variant
+    status: np.ndarray    # 0 normal / 1 max-coverage veto / 2 no coverage
+    best_gt: np.ndarray   # emission-order index of the printed GT
+    gq: np.ndarray
+    lik_off: np.ndarray
+    lik: np.ndarray       # un-normalised probabilities
+
+
+def genotype_names(n_alleles: int, haploid: bool) -> List[str]:
+    """Emission order of VB::genotype (var_block.hpp:270, 290-292)."""
+    if haploid:
+        return [str(g) for g in range(n_alleles)]
+    return [f"{a}/{b}" for a in range(n_alleles) for b in range(a, n_alleles)]
+
+
+class _View:
+    """A BF or KMAP seen through its reference method names (batch of any size)."""
+
+    def __init__(self, owner: "MalvaGpu", which: int):
+        self._o, self._w = owner, which
+
+    def add_key(self, kmers) -> None:
+        if self._w == BF_CONTEXT:
+            raise MalvaGpuError("context_bf is only filled by scan_reference (main.cpp:385-400)")
+        ks = [kmers] if isinstance(kmers, (bytes, str)) else list(kmers)
+        self._o.add_signatures(ks, [1 if self._w == KMAP_REF else 0] * len(ks))
+
+    def test_key(self, kmers):
+        single = isinstance(kmers, (bytes, str))
+        ks = [kmers] if single else list(kmers)
+        r = self._o.test_keys(self._w, ks)
+        return bool(r[0]) if single else r
+
+    def get_count(self, kmers):
+        if self._w == BF_CONTEXT:
+            raise MalvaGpuError("context_bf carries no counters on the device")
+        single = isinstance(kmers, (bytes, str))
+        ks = [kmers] if single else list(kmers)
+        r = self._o.get_counts(ks, [1 if self._w == KMAP_REF else 0] * len(ks))
+        return int(r[0]) if single else r
+
+
+class MalvaGpu:
+    """Device-resident bf / context_bf / ref_bf of one malva-geno run (main.cpp:300-302)."""
+
+    def __init__(self, k: int = 35, ref_k: int = 43, bf_bits: int = 1 << 35, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.k, self.ref_k, self.bf_bits, self.device = k, ref_k, bf_bits, device
+        check(self._L.mg_create(C.byref(self._h), device, k, ref_k, bf_bits))
+        self.bf = _View(self, BF_ALT)
+        self.context_bf = _View(self, BF_CONTEXT)
+        self.ref_bf = _View(self, KMAP_REF)
+
+    def close(self) -> None:
+        if self._h:
+            self._L.mg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- index side -------------------------------------------------------
+    def add_signatures(self, kmers, is_ref) -> None:
+        pool, off = make_pool(kmers)
+        flags = np.asarray(is_ref, dtype=np.uint8)
+        assert len(flags) == len(off) - 1
+        check(self._L.mg_add_signatures(self._h, pool, _p(off, _lib.u64p), _p(flags, _lib.u8p), len(flags)))
+
+    def finalize_alt(self) -> None:
+        check(self._L.mg_finalize_alt(self._h))
+
+    def scan_reference(self, seq) -> None:
+        s = _as_bytes(seq)
+        check(self._L.mg_scan_reference(self._h, s, len(s)))
+
+    def finalize_context(self) -> None:
+        check(self._L.mg_finalize_context(self._h))
+
+    # ---- call side --------------------------------------------------------
+    def scan_sample_kmers(self, packed: np.ndarray, counts: np.ndarray, sync: bool = True) -> None:
+        assert packed.dtype == KMER_DTYPE and packed.flags.c_contiguous
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        assert len(counts) == len(packed)
+        check(self._L.mg_scan_sample_kmers(self._h, packed.ctypes.data, counts.ctypes.data, len(packed)))
+        if sync:
+            self.sync()
+
+    def scan_sample_kmers_ptr(self, lohi_ptr: int, counts_ptr: int, n: int, device: bool) -> None:
+        """Raw-pointer variant: host (pinned) pointers or device pointers."""
+        fn = self._L.mg_scan_sample_kmers_device if device else self._L.mg_scan_sample_kmers
+        check(fn(self._h, lohi_ptr, counts_ptr, n))
+
+    def sync(self) -> None:
+        check(self._L.mg_sync(self._h))
+
+    def genotype(self, batch: SignatureBatch, error_rate: float = 0.001, max_coverage: int = 200,
+                 haploid: bool = False, want_lik: bool = True) -> GenotypeResult:
+        nv = batch.n_variants
+        na = int(batch.var_allele_off[-1]) if nv else 0
+        nall = np.diff(batch.var_allele_off).astype(np.int64)
+        slots = nall if haploid else nall * (nall + 1) // 2
+        slots = np.maximum(slots, nall)  # the veto path emits up to n entries
+        lik_off = np.zeros(nv + 1, dtype=np.uint64)
+        lik_off[1:] = np.cumsum(slots, dtype=np.uint64)
+        res = GenotypeResult(np.zeros(max(na, 1), np.uint32)[:na], np.zeros(nv, np.int32), np.zeros(nv, np.int32),
+                             np.zeros(nv, np.int32), np.zeros(nv, np.int32), lik_off,
+                             np.zeros(int(lik_off[-1]), np.float64))
+        if nv == 0:
+            return res
+        vb = _lib.VariantBatch(nv, _p(batch.var_allele_off, _lib.u64p), _p(batch.allele_sig_off, _lib.u64p),
+                               _p(batch.sig_kmer_off, _lib.u64p), _p(batch.kmer_off, _lib.u64p), batch.pool,
+                               _p(batch.freq, _lib.f32p))
+        cov = np.zeros(max(na, 1), np.uint32)
+        out = _lib.GenotypeOut(_p(cov, _lib.u32p), _p(res.n_gts, _lib.i32p), _p(res.status, _lib.i32p),
+                               _p(res.best_gt, _lib.i32p), _p(res.gq, _lib.i32p), _p(lik_off, _lib.u64p),
+                               _p(res.lik, _lib.f64p) if want_lik and len(res.lik) else None)
+        check(self._L.mg_genotype(self._h, C.byref(vb), C.byref(out), C.c_float(error_rate), int(max_coverage),
+                                  int(bool(haploid))))
+        res.cov = cov[:na]
+        return res
+
+    # ---- queries ----------------------------------------------------------
+    def test_keys(self, which: int, kmers) -> np.ndarray:
+        pool, off = make_pool(kmers)
+        out = np.zeros(max(len(off) - 1, 1), dtype=np.uint8)
+        check(self._L.mg_test_keys(self._h, which, pool, _p(off, _lib.u64p), len(off) - 1, _p(out, _lib.u8p)))
+        return out[:len(off) - 1]
+
+    def get_counts(self, kmers, is_ref) -> np.ndarray:
+        pool, off = make_pool(kmers)
+        flags = np.asarray(is_ref, dtype=np.uint8)
+        out = np.zeros(max(len(flags), 1), dtype=np.int32)
+        check(self._L.mg_get_counts(self._h, pool, _p(off, _lib.u64p), _p(flags, _lib.u8p), len(flags),
+                                    _p(out, _lib.i32p)))
+        return out[:len(flags)]
+
+    def popcount(self, which: int) -> int:
+        v = C.c_uint64(0)
+        check(self._L.mg_bf_popcount(self._h, which, C.byref(v)))
+        return v.value
+
+    def bits(self, which: int) -> np.ndarray:
+        n = (self.bf_bits + 63) // 64
+        w = np.zeros(n, dtype=np.uint64)
+        check(self._L.mg_bf_download_bits(self._h, which, _p(w, _lib.u64p), n))
+        return w
+
+    def bf_counts(self) -> np.ndarray:
+        n = self.popcount(BF_ALT)
+        out = np.zeros(max(n, 1), dtype=np.uint16)
+        check(self._L.mg_bf_download_counts(self._h, _p(out, _lib.u16p), n))
+        return out[:n]
+
+    def kmap_size(self) -> int:
+        v = C.c_uint64(0)
+        check(self._L.mg_kmap_size(self._h, C.byref(v)))
+        return v.value
+
+    def counter_buffers(self):
+        """(bf_counts device ptr, n, ref counts device ptr, n) for an external NCCL sum-reduce."""
+        p1, p2, n1, n2 = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        check(self._L.mg_counter_buffers(self._h, C.byref(p1), C.byref(n1), C.byref(p2), C.byref(n2)))
+        return p1.value, n1.value, p2.value, n2.value
