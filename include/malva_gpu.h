@@ -49,6 +49,9 @@ void mg_destroy(mg_ctx *ctx);
  * is_ref[i] != 0 -> ref_bf.add_key(kmer i) ; else bf.add_key(kmer i)        */
 int mg_add_signatures(mg_ctx *ctx, const char *pool, const uint64_t *kmer_off, const uint8_t *is_ref,
                       uint64_t n);
+/* same inserts for signature k-mers the host already packed (exactly k symbols of ACGT each;
+ * {lo,hi} words as in the sample stream): 16 B instead of k bytes over PCIe  */
+int mg_add_signatures_packed(mg_ctx *ctx, const uint64_t *lohi, const uint8_t *is_ref, uint64_t n);
 /* bf.switch_mode()                                       main.cpp:378      */
 int mg_finalize_alt(mg_ctx *ctx);
 /* reference rolling pass over one (upper-cased) contig   main.cpp:385-400  */
@@ -90,6 +93,12 @@ typedef struct {
 
 int mg_genotype(mg_ctx *ctx, const mg_variant_batch *in, const mg_genotype_out *out, float error_rate,
                 int max_coverage, int haploid);
+/* same with every array of in/out DEVICE-resident (enqueued on the context's stream; mg_sync completes it) */
+typedef struct {
+  uint64_t n_variants, n_alleles, n_sigs, n_kmers;
+} mg_batch_dims;
+int mg_genotype_device(mg_ctx *ctx, const mg_variant_batch *in, const mg_genotype_out *out, const mg_batch_dims *dims,
+                       float error_rate, int max_coverage, int haploid);
 
 /* ------------------------- batch queries (BF / KMAP) --------------------- */
 /* which: 0 = bf, 1 = context_bf, 2 = ref_bf (KMAP).  BF::test_key / KMAP::test_key */
@@ -110,6 +119,20 @@ int mg_kmap_size(mg_ctx *ctx, uint64_t *n);
 /* device pointers of the two counter arrays, for an external (NCCL) sum-reduce
  * across replicas: u32 per set bit of bf, u32 per table slot of ref_bf.      */
 int mg_counter_buffers(mg_ctx *ctx, void **d_bf_counts, uint64_t *n_bf, void **d_ref_counts, uint64_t *n_ref);
+
+/* ------------------------------ measurement ------------------------------ */
+/* CUDA-event timing on the library's own streams (64 event slots): record marks a point that follows
+ * all work enqueued so far; elapsed waits for event b.  The device-side counterpart of the reference's
+ * pelapsed() phase timers (main.cpp:93-115). */
+int mg_event_record(mg_ctx *ctx, int idx);
+int mg_event_elapsed_ms(mg_ctx *ctx, int a, int b, float *ms);
+/* device time of the last mg_genotype call: {signature look-ups, coverage, likelihood} kernels, ms */
+int mg_genotype_kernel_ms(mg_ctx *ctx, float *ms3);
+/* kernels launched by this context so far */
+int mg_launch_count(mg_ctx *ctx, uint64_t *n);
+/* measured ceilings: mode 0 = independent random 32-byte sector reads over `bytes` of HBM,
+ * mode 1 = streaming reads; GB/s of useful bytes, best of reps */
+int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps, double *gbs);
 
 /* pinned host memory for the sample stream */
 int mg_host_alloc(void **p, size_t bytes);

@@ -32,7 +32,7 @@ class VariantBatch(C.Structure):
         ("allele_sig_off", u64p),
         ("sig_kmer_off", u64p),
         ("kmer_off", u64p),
-        ("pool", C.c_char_p),
+        ("pool", C.c_void_p),
         ("freq", f32p),
     ]
 
@@ -49,6 +49,11 @@ class GenotypeOut(C.Structure):
     ]
 
 
+class BatchDims(C.Structure):
+    _fields_ = [("n_variants", C.c_uint64), ("n_alleles", C.c_uint64), ("n_sigs", C.c_uint64),
+                ("n_kmers", C.c_uint64)]
+
+
 # every symbol include/malva_gpu.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mg_last_error": (C.c_char_p, []),
@@ -57,6 +62,7 @@ SYMBOLS = {
     "mg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "mg_destroy": (None, [C.c_void_p]),
     "mg_add_signatures": (C.c_int, [C.c_void_p, C.c_char_p, u64p, u8p, C.c_uint64]),
+    "mg_add_signatures_packed": (C.c_int, [C.c_void_p, C.c_void_p, u8p, C.c_uint64]),
     "mg_finalize_alt": (C.c_int, [C.c_void_p]),
     "mg_scan_reference": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "mg_finalize_context": (C.c_int, [C.c_void_p]),
@@ -65,6 +71,8 @@ SYMBOLS = {
     "mg_sync": (C.c_int, [C.c_void_p]),
     "mg_genotype": (C.c_int, [C.c_void_p, C.POINTER(VariantBatch), C.POINTER(GenotypeOut), C.c_float, C.c_int,
                               C.c_int]),
+    "mg_genotype_device": (C.c_int, [C.c_void_p, C.POINTER(VariantBatch), C.POINTER(GenotypeOut),
+                                     C.POINTER(BatchDims), C.c_float, C.c_int, C.c_int]),
     "mg_test_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, u64p, C.c_uint64, u8p]),
     "mg_get_counts": (C.c_int, [C.c_void_p, C.c_char_p, u64p, u8p, C.c_uint64, i32p]),
     "mg_bf_popcount": (C.c_int, [C.c_void_p, C.c_int, u64p]),
@@ -72,6 +80,11 @@ SYMBOLS = {
     "mg_bf_download_counts": (C.c_int, [C.c_void_p, u16p, C.c_uint64]),
     "mg_kmap_size": (C.c_int, [C.c_void_p, u64p]),
     "mg_counter_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_void_p), u64p]),
+    "mg_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "mg_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, f32p]),
+    "mg_genotype_kernel_ms": (C.c_int, [C.c_void_p, f32p]),
+    "mg_launch_count": (C.c_int, [C.c_void_p, u64p]),
+    "mg_diag_bandwidth": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, f64p]),
     "mg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "mg_host_free": (C.c_int, [C.c_void_p]),
     "mg_selftest_hash_packed": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_int, u64p, u64p]),

@@ -164,6 +164,12 @@ class MalvaGpu:
         assert len(flags) == len(off) - 1
         check(self._L.mg_add_signatures(self._h, pool, _p(off, _lib.u64p), _p(flags, _lib.u8p), len(flags)))
 
+    def add_signatures_packed(self, packed: np.ndarray, is_ref) -> None:
+        assert packed.dtype == KMER_DTYPE and packed.flags.c_contiguous
+        flags = np.ascontiguousarray(is_ref, dtype=np.uint8)
+        assert len(flags) == len(packed)
+        check(self._L.mg_add_signatures_packed(self._h, packed.ctypes.data, _p(flags, _lib.u8p), len(packed)))
+
     def finalize_alt(self) -> None:
         check(self._L.mg_finalize_alt(self._h))
 
@@ -206,7 +212,8 @@ class MalvaGpu:
         if nv == 0:
             return res
         vb = _lib.VariantBatch(nv, _p(batch.var_allele_off, _lib.u64p), _p(batch.allele_sig_off, _lib.u64p),
-                               _p(batch.sig_kmer_off, _lib.u64p), _p(batch.kmer_off, _lib.u64p), batch.pool,
+                               _p(batch.sig_kmer_off, _lib.u64p), _p(batch.kmer_off, _lib.u64p),
+                               C.cast(C.c_char_p(batch.pool), C.c_void_p),
                                _p(batch.freq, _lib.f32p))
         cov = np.zeros(max(na, 1), np.uint32)
         out = _lib.GenotypeOut(_p(cov, _lib.u32p), _p(res.n_gts, _lib.i32p), _p(res.status, _lib.i32p),
@@ -254,8 +261,47 @@ class MalvaGpu:
         check(self._L.mg_kmap_size(self._h, C.byref(v)))
         return v.value
 
+    # ---- measurement ------------------------------------------------------
+    def event_record(self, idx: int) -> None:
+        check(self._L.mg_event_record(self._h, idx))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        check(self._L.mg_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def genotype_device(self, ptrs: dict, dims: tuple, error_rate: float, max_coverage: int, haploid: bool) -> None:
+        """ptrs: device addresses keyed like mg_variant_batch / mg_genotype_out fields; dims = (nv, na, ns, nk)."""
+        c = lambda name, typ: C.cast(C.c_void_p(ptrs[name]), typ)
+        vb = _lib.VariantBatch(dims[0], c("var_allele_off", _lib.u64p), c("allele_sig_off", _lib.u64p),
+                               c("sig_kmer_off", _lib.u64p), c("kmer_off", _lib.u64p), C.c_void_p(ptrs["pool"]),
+                               c("freq", _lib.f32p))
+        out = _lib.GenotypeOut(c("cov", _lib.u32p), c("n_gts", _lib.i32p), c("status", _lib.i32p),
+                               c("best_gt", _lib.i32p), c("gq", _lib.i32p), c("lik_off", _lib.u64p),
+                               c("lik", _lib.f64p))
+        dm = _lib.BatchDims(*dims)
+        check(self._L.mg_genotype_device(self._h, C.byref(vb), C.byref(out), C.byref(dm), C.c_float(error_rate),
+                                         int(max_coverage), int(bool(haploid))))
+
+    def genotype_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        check(self._L.mg_genotype_kernel_ms(self._h, ms))
+        return list(ms)
+
+    def launch_count(self) -> int:
+        v = C.c_uint64(0)
+        check(self._L.mg_launch_count(self._h, C.byref(v)))
+        return v.value
+
     def counter_buffers(self):
         """(bf_counts device ptr, n, ref counts device ptr, n) for an external NCCL sum-reduce."""
         p1, p2, n1, n2 = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
         check(self._L.mg_counter_buffers(self._h, C.byref(p1), C.byref(n1), C.byref(p2), C.byref(n2)))
         return p1.value, n1.value, p2.value, n2.value
+
+
+def diag_bandwidth(device: int, mode: int, nbytes: int, reps: int = 3) -> float:
+    """Measured ceiling in GB/s: mode 0 = random 32-byte sector reads, mode 1 = streaming reads."""
+    g = C.c_double(0)
+    check(_lib.load().mg_diag_bandwidth(device, mode, nbytes, reps, C.byref(g)))
+    return g.value

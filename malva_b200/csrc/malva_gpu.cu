@@ -100,6 +100,12 @@ struct mg_ctx {
   void *d_stage_k[2] = {nullptr, nullptr};
   uint32_t *d_stage_c[2] = {nullptr, nullptr};
   int next_stage = 0;
+  uint64_t launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
+  cudaEvent_t tj = nullptr;
+  cudaEvent_t ge[4] = {nullptr, nullptr, nullptr, nullptr};
+  void *geno_scratch = nullptr;  // per-k-mer weights + ref flags of mg_genotype
+  uint64_t geno_scratch_bytes = 0;
+  cudaEvent_t evs[64] = {};
 
   DevView view() const {
     DevView v;
@@ -228,6 +234,37 @@ __global__ void __launch_bounds__(128) k_add_signatures(const uint8_t *__restric
     v.tab_counts[slot] = 0;
   } else {  // bf.add_key
     uint64_t h = regular ? mg::canon_hash_rt(x, v.k, &canon) : mg::hash_ascii(s, len);
+    uint64_t idx = bf_index(v, h);
+    atomicOr(bf_words_rw + (idx >> 5), 1u << (idx & 31));
+  }
+}
+
+// same inserts for signature k-mers that arrive already packed (exactly k symbols of ACGT)
+__global__ void __launch_bounds__(256) k_add_packed(const uint4 *__restrict__ kmers, const uint8_t *__restrict__ is_ref,
+                                                   uint64_t n, DevView v, uint32_t *bf_words_rw, u128 *tab_keys_rw,
+                                                   unsigned long long *scalars) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint4 q = kmers[i];
+  u128 x, canon;
+  x.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+  x.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+  x = mg::mask128(x, 2 * v.k);
+  uint64_t h = mg::canon_hash_rt(x, v.k, &canon);
+  if (is_ref[i]) {
+    uint64_t slot = tab_slot0(v, h);
+    const u128 empty = {~0ull, ~0ull};
+    while (true) {
+      u128 old = cas128(tab_keys_rw + slot, empty, canon);
+      if (key_empty(old)) {
+        atomicAdd(&scalars[0], 1ull);
+        break;
+      }
+      if (key_eq(old, canon)) break;
+      slot = (slot + 1) & v.tab_mask;
+    }
+    v.tab_counts[slot] = 0;
+  } else {
     uint64_t idx = bf_index(v, h);
     atomicOr(bf_words_rw + (idx >> 5), 1u << (idx & 31));
   }
@@ -608,6 +645,37 @@ __global__ void __launch_bounds__(128) k_genotype(const uint32_t *__restrict__ c
 }
 
 // ---------------------------------------------------------------------------
+// roofline diagnostics: measured ceilings for independent random sector reads
+// and for a streaming read on this device (bench.py records them next to the
+// driver's MEASURED_PEAKS.json)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_diag_random(const uint32_t *__restrict__ buf, uint64_t n_sectors,
+                                                    uint64_t per_thread, uint32_t *sink) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s = (t + 1) * GOLD;
+  uint32_t acc = 0;
+#pragma unroll 4
+  for (uint64_t i = 0; i < per_thread; ++i) {
+    s ^= s >> 29;
+    s *= 0xBF58476D1CE4E5B9ULL;
+    s ^= s >> 32;
+    uint64_t sec = mg::mulhi64(s, n_sectors);  // uniform in [0, n_sectors)
+    acc += __ldg(buf + sec * 8);               // one 4-byte load per 32-byte sector
+    s += GOLD;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+__global__ void __launch_bounds__(256) k_diag_stream(const uint4 *__restrict__ buf, uint64_t n16, uint32_t *sink) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    uint4 q = __ldg(buf + i);
+    acc += q.x ^ q.y ^ q.z ^ q.w;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
+// ---------------------------------------------------------------------------
 // host side of the C ABI
 // ---------------------------------------------------------------------------
 static int grid_for(uint64_t n, int threads) { return (int)((n + (uint64_t)threads - 1) / (uint64_t)threads); }
@@ -616,6 +684,7 @@ static int tab_alloc(mg_ctx *c, int log2cap, u128 **keys, uint32_t **counts) {
   uint64_t cap = 1ull << log2cap;
   CU(cudaMalloc(keys, cap * sizeof(u128)));
   CU(cudaMalloc(counts, cap * sizeof(uint32_t)));
+  c->launches++;
   k_fill_keys<<<grid_for(cap, 256), 256, 0, c->stream[0]>>>(*keys, cap);
   CU(cudaGetLastError());
   CU(cudaMemsetAsync(*counts, 0, cap * sizeof(uint32_t), c->stream[0]));
@@ -639,6 +708,7 @@ static int tab_reserve(mg_ctx *c, uint64_t extra) {
   c->tab_counts = nc;
   c->tab_log2 = nl;
   if (c->tab_n) {
+    c->launches++;
     k_rehash<<<grid_for(ocap, 256), 256, 0, c->stream[0]>>>(ok, oc, ocap, c->view(), nk);
     CU(cudaGetLastError());
   }
@@ -703,6 +773,12 @@ extern "C" void mg_destroy(mg_ctx *c) {
     if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   }
+  if (c->tj) cudaEventDestroy(c->tj);
+  for (int i = 0; i < 64; ++i)
+    if (c->evs[i]) cudaEventDestroy(c->evs[i]);
+  cudaFree(c->geno_scratch);
+  for (int i = 0; i < 4; ++i)
+    if (c->ge[i]) cudaEventDestroy(c->ge[i]);
   delete c;
 }
 
@@ -758,6 +834,7 @@ extern "C" int mg_add_signatures(mg_ctx *c, const char *pool, const uint64_t *of
   uint32_t *d_irr = nullptr;
   CU(cudaMalloc(&d_irr, (n_ref ? n_ref : 1) * 4));
   CU(cudaMemsetAsync(c->d_scalars, 0, 2 * sizeof(unsigned long long), c->stream[0]));
+  c->launches++;
   k_add_signatures<<<grid_for(n, 128), 128, 0, c->stream[0]>>>(b.pool, b.off, b.flags, n, c->view(), c->bf_words,
                                                               c->tab_keys, c->d_scalars, d_irr);
   CU(cudaGetLastError());
@@ -788,6 +865,7 @@ extern "C" int mg_finalize_alt(mg_ctx *c) {
   CU(cudaMalloc(&c->bf_rank, (c->n_blocks + 1) * 4));
   CU(cudaMemsetAsync(blk + c->n_blocks, 0, 4, c->stream[0]));
   CU(cudaMemsetAsync(c->d_scalars + 2, 0, 8, c->stream[0]));
+  c->launches++;
   k_block_popc<<<grid_for(c->n_blocks, 256), 256, 0, c->stream[0]>>>(c->bf_words, c->n_blocks, c->n_words32, blk,
                                                                     c->d_scalars + 2);
   CU(cudaGetLastError());
@@ -814,6 +892,7 @@ static cudaError_t launch_refpass(mg_ctx *c, const uint8_t *d_seq, uint64_t len)
   uint64_t n_pos = len - (uint64_t)(c->ref_k - 1);
   int grid = (int)((n_pos + RP_TILE - 1) / RP_TILE);
   size_t smem = RP_TILE + 64;
+  c->launches++;
   k_refpass<K, REFK><<<grid, RP_THREADS, smem, c->stream[0]>>>(d_seq, len, c->view(), c->ctx_words);
   return cudaGetLastError();
 }
@@ -830,6 +909,7 @@ extern "C" int mg_scan_reference(mg_ctx *c, const char *seq, uint64_t len) {
     uint8_t *d_seq = nullptr;
     CU(cudaMalloc(&d_seq, len ? len : 1));
     CU(cudaMemcpyAsync(d_seq, seq, len, cudaMemcpyHostToDevice, c->stream[0]));
+    c->launches++;
     k_refpass_short<<<1, 32, 0, c->stream[0]>>>(d_seq, len, c->view(), c->ctx_words);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream[0]));
@@ -866,6 +946,7 @@ static cudaError_t launch_scan(mg_ctx *c, const void *d_lohi, const void *d_coun
   uint64_t cap = (uint64_t)c->sms * 8;
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
+  c->launches++;
   k_scan<K, REFK, ILP><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_lohi),
                                              reinterpret_cast<const uint32_t *>(d_counts), n, c->view());
   return cudaGetLastError();
@@ -931,6 +1012,7 @@ static int lookup_common(mg_ctx *c, const char *pool, const uint64_t *off, const
   if (rc) return rc;
   int32_t *d_out = nullptr;
   CU(cudaMalloc(&d_out, (n ? n : 1) * 4));
+  c->launches++;
   k_lookup<<<grid_for(n, 128), 128, 0, c->stream[0]>>>(b.pool, b.off, b.flags, n, c->view(), mode, which, d_out,
                                                       c->d_scalars);
   CU(cudaGetLastError());
@@ -966,6 +1048,73 @@ extern "C" int mg_get_counts(mg_ctx *c, const char *pool, const uint64_t *off, c
   return lookup_common(c, pool, off, is_ref, n, 0, 0, out);
 }
 
+// flags the k-mers of allele slot 0 of every variant (they are looked up in ref_bf, main.cpp:167-170)
+__global__ void __launch_bounds__(256) k_mark_ref(const uint64_t *__restrict__ var_allele_off,
+                                                 const uint64_t *__restrict__ allele_sig_off,
+                                                 const uint64_t *__restrict__ sig_kmer_off, uint64_t n_variants,
+                                                 uint8_t *__restrict__ flags) {
+  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_variants) return;
+  uint64_t a0 = var_allele_off[v];
+  if (var_allele_off[v + 1] == a0) return;
+  for (uint64_t s = allele_sig_off[a0]; s < allele_sig_off[a0 + 1]; ++s)
+    for (uint64_t q = sig_kmer_off[s]; q < sig_kmer_off[s + 1]; ++q) flags[q] = 1;
+}
+
+// all pointers of in/out are DEVICE pointers here; scratch (k-mer flags + weights) is library-owned
+static int genotype_on_device(mg_ctx *c, const mg_variant_batch *in, const mg_genotype_out *out,
+                              const mg_batch_dims *dm, float error_rate, int max_coverage, int haploid) {
+  cudaStream_t st = c->stream[0];
+  uint64_t nv = dm->n_variants, na = dm->n_alleles, nk = dm->n_kmers;
+  uint64_t need = (nk ? nk : 1) * 5;
+  if (c->geno_scratch_bytes < need) {
+    cudaFree(c->geno_scratch);
+    c->geno_scratch = nullptr;
+    c->geno_scratch_bytes = 0;
+    CU(cudaMalloc(&c->geno_scratch, need));
+    c->geno_scratch_bytes = need;
+  }
+  int32_t *d_w = reinterpret_cast<int32_t *>(c->geno_scratch);
+  uint8_t *d_flags = reinterpret_cast<uint8_t *>(c->geno_scratch) + (nk ? nk : 1) * 4;
+  for (int i = 0; i < 4; ++i)
+    if (!c->ge[i]) CU(cudaEventCreate(&c->ge[i]));
+  CU(cudaEventRecord(c->ge[0], st));
+  if (nk) {
+    CU(cudaMemsetAsync(d_flags, 0, nk, st));
+    c->launches++;
+    k_mark_ref<<<grid_for(nv, 256), 256, 0, st>>>(in->var_allele_off, in->allele_sig_off, in->sig_kmer_off, nv, d_flags);
+    CU(cudaGetLastError());
+    c->launches++;
+    k_lookup<<<grid_for(nk, 128), 128, 0, st>>>(reinterpret_cast<const uint8_t *>(in->pool), in->kmer_off, d_flags, nk,
+                                                c->view(), 0, 0, d_w, c->d_scalars);
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(c->ge[1], st));
+  c->launches++;
+  k_coverage<<<grid_for(na, 128), 128, 0, st>>>(d_w, in->sig_kmer_off, in->allele_sig_off, na, out->cov);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ge[2], st));
+  c->launches++;
+  k_genotype<<<grid_for(nv, 128), 128, 0, st>>>(out->cov, in->freq, in->var_allele_off, out->lik_off, nv, error_rate,
+                                               max_coverage, haploid, out->lik, out->n_gts, out->status, out->best_gt,
+                                               out->gq);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ge[3], st));
+  return MG_OK;
+}
+
+extern "C" int mg_genotype_device(mg_ctx *c, const mg_variant_batch *in, const mg_genotype_out *out,
+                                  const mg_batch_dims *dims, float error_rate, int max_coverage, int haploid) {
+  if (!c || !in || !out || !dims) return set_err(MG_ERR_ARG, "NULL argument");
+  if (!c->alt_final) return set_err(MG_ERR_STATE, "mg_genotype_device before mg_finalize_alt");
+  if (dims->n_variants == 0) return MG_OK;
+  if (!in->var_allele_off || !in->allele_sig_off || !in->sig_kmer_off || !in->kmer_off || !in->freq || !out->cov ||
+      !out->n_gts || !out->status || !out->best_gt || !out->gq || !out->lik_off || !out->lik)
+    return set_err(MG_ERR_ARG, "NULL array in batch");
+  CU(cudaSetDevice(c->device));
+  return genotype_on_device(c, in, out, dims, error_rate, max_coverage, haploid);
+}
+
 extern "C" int mg_genotype(mg_ctx *c, const mg_variant_batch *in, const mg_genotype_out *out, float error_rate,
                            int max_coverage, int haploid) {
   if (!c || !in || !out) return set_err(MG_ERR_ARG, "NULL argument");
@@ -978,64 +1127,59 @@ extern "C" int mg_genotype(mg_ctx *c, const mg_variant_batch *in, const mg_genot
   CU(cudaSetDevice(c->device));
   int rc = mg_sync(c);
   if (rc) return rc;
-  uint64_t na = in->var_allele_off[nv], ns = in->allele_sig_off[na], nk = in->sig_kmer_off[ns];
-  uint64_t nl = out->lik_off[nv];
+  mg_batch_dims dm;
+  dm.n_variants = nv;
+  dm.n_alleles = in->var_allele_off[nv];
+  dm.n_sigs = in->allele_sig_off[dm.n_alleles];
+  dm.n_kmers = in->sig_kmer_off[dm.n_sigs];
+  uint64_t na = dm.n_alleles, ns = dm.n_sigs, nk = dm.n_kmers, nl = out->lik_off[nv];
+  uint64_t pool_bytes = in->kmer_off[nk];
   cudaStream_t st = c->stream[0];
-  // is_ref flag per k-mer is derived on the host from the CSR (allele slot 0 of each variant)
-  std::vector<uint8_t> kflag(nk ? nk : 1, 0);
-  for (uint64_t v = 0; v < nv; ++v) {
-    uint64_t a0 = in->var_allele_off[v];
-    if (in->var_allele_off[v + 1] == a0) continue;
-    for (uint64_t s = in->allele_sig_off[a0]; s < in->allele_sig_off[a0 + 1]; ++s)
-      for (uint64_t q = in->sig_kmer_off[s]; q < in->sig_kmer_off[s + 1]; ++q) kflag[q] = 1;
-  }
-  DevBatch b;
-  rc = upload_batch(c, b, in->pool, in->kmer_off, kflag.data(), nk);
+  // one device arena for the whole batch
+  auto al = [](uint64_t x) { return (x + 255) & ~255ull; };
+  uint64_t o_vao = 0, o_aso = o_vao + al((nv + 1) * 8), o_sko = o_aso + al((na + 1) * 8),
+           o_ko = o_sko + al((ns + 1) * 8), o_lo = o_ko + al((nk + 1) * 8), o_freq = o_lo + al((nv + 1) * 8),
+           o_pool = o_freq + al(na * 4), o_cov = o_pool + al(pool_bytes), o_i32 = o_cov + al(na * 4),
+           o_lik = o_i32 + al(nv * 16), total = o_lik + al(nl * 8) + 256;
+  uint8_t *d = nullptr;
+  CU(cudaMalloc(&d, total));
+  struct Guard {
+    uint8_t *p;
+    ~Guard() { cudaFree(p); }
+  } guard{d};
+  CU(cudaMemcpyAsync(d + o_vao, in->var_allele_off, (nv + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_aso, in->allele_sig_off, (na + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_sko, in->sig_kmer_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_ko, in->kmer_off, (nk + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_lo, out->lik_off, (nv + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_freq, in->freq, na * 4, cudaMemcpyHostToDevice, st));
+  if (pool_bytes) CU(cudaMemcpyAsync(d + o_pool, in->pool, pool_bytes, cudaMemcpyHostToDevice, st));
+  mg_variant_batch din;
+  din.n_variants = nv;
+  din.var_allele_off = reinterpret_cast<uint64_t *>(d + o_vao);
+  din.allele_sig_off = reinterpret_cast<uint64_t *>(d + o_aso);
+  din.sig_kmer_off = reinterpret_cast<uint64_t *>(d + o_sko);
+  din.kmer_off = reinterpret_cast<uint64_t *>(d + o_ko);
+  din.pool = reinterpret_cast<const char *>(d + o_pool);
+  din.freq = reinterpret_cast<float *>(d + o_freq);
+  mg_genotype_out dout;
+  int32_t *i32 = reinterpret_cast<int32_t *>(d + o_i32);
+  dout.cov = reinterpret_cast<uint32_t *>(d + o_cov);
+  dout.n_gts = i32;
+  dout.status = i32 + nv;
+  dout.best_gt = i32 + 2 * nv;
+  dout.gq = i32 + 3 * nv;
+  dout.lik_off = reinterpret_cast<uint64_t *>(d + o_lo);
+  dout.lik = reinterpret_cast<double *>(d + o_lik);
+  rc = genotype_on_device(c, &din, &dout, &dm, error_rate, max_coverage, haploid);
   if (rc) return rc;
-  uint64_t *d_vao = nullptr, *d_aso = nullptr, *d_sko = nullptr, *d_lo = nullptr;
-  float *d_freq = nullptr;
-  int32_t *d_w = nullptr, *d_i32 = nullptr;
-  uint32_t *d_cov = nullptr;
-  double *d_lik = nullptr;
-  CU(cudaMalloc(&d_vao, (nv + 1) * 8));
-  CU(cudaMalloc(&d_aso, (na + 1) * 8));
-  CU(cudaMalloc(&d_sko, (ns + 1) * 8));
-  CU(cudaMalloc(&d_lo, (nv + 1) * 8));
-  CU(cudaMalloc(&d_freq, (na ? na : 1) * 4));
-  CU(cudaMalloc(&d_w, (nk ? nk : 1) * 4));
-  CU(cudaMalloc(&d_cov, (na ? na : 1) * 4));
-  CU(cudaMalloc(&d_i32, nv * 4 * 4));
-  CU(cudaMalloc(&d_lik, (nl ? nl : 1) * 8));
-  CU(cudaMemcpyAsync(d_vao, in->var_allele_off, (nv + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_aso, in->allele_sig_off, (na + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_sko, in->sig_kmer_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_lo, out->lik_off, (nv + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_freq, in->freq, na * 4, cudaMemcpyHostToDevice, st));
-  if (nk) {
-    k_lookup<<<grid_for(nk, 128), 128, 0, st>>>(b.pool, b.off, b.flags, nk, c->view(), 0, 0, d_w, c->d_scalars);
-    CU(cudaGetLastError());
-  }
-  k_coverage<<<grid_for(na, 128), 128, 0, st>>>(d_w, d_sko, d_aso, na, d_cov);
-  CU(cudaGetLastError());
-  k_genotype<<<grid_for(nv, 128), 128, 0, st>>>(d_cov, d_freq, d_vao, d_lo, nv, error_rate, max_coverage, haploid,
-                                               d_lik, d_i32, d_i32 + nv, d_i32 + 2 * nv, d_i32 + 3 * nv);
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out->cov, d_cov, na * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out->n_gts, d_i32, nv * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out->status, d_i32 + nv, nv * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out->best_gt, d_i32 + 2 * nv, nv * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out->gq, d_i32 + 3 * nv, nv * 4, cudaMemcpyDeviceToHost, st));
-  if (out->lik) CU(cudaMemcpyAsync(out->lik, d_lik, nl * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->cov, dout.cov, na * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->n_gts, dout.n_gts, nv * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->status, dout.status, nv * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->best_gt, dout.best_gt, nv * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->gq, dout.gq, nv * 4, cudaMemcpyDeviceToHost, st));
+  if (out->lik && nl) CU(cudaMemcpyAsync(out->lik, dout.lik, nl * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  cudaFree(d_vao);
-  cudaFree(d_aso);
-  cudaFree(d_sko);
-  cudaFree(d_lo);
-  cudaFree(d_freq);
-  cudaFree(d_w);
-  cudaFree(d_cov);
-  cudaFree(d_i32);
-  cudaFree(d_lik);
   return check_too_long(c);
 }
 
@@ -1047,6 +1191,7 @@ extern "C" int mg_bf_popcount(mg_ctx *c, int which, uint64_t *ones) {
   uint32_t *blk = nullptr;
   CU(cudaMalloc(&blk, c->n_blocks * 4));
   CU(cudaMemset(c->d_scalars + 2, 0, 8));
+  c->launches++;
   k_block_popc<<<grid_for(c->n_blocks, 256), 256, 0, c->stream[0]>>>(which ? c->ctx_words : c->bf_words, c->n_blocks,
                                                                     c->n_words32, blk, c->d_scalars + 2);
   CU(cudaGetLastError());
@@ -1095,6 +1240,109 @@ extern "C" int mg_counter_buffers(mg_ctx *c, void **d_bf_counts, uint64_t *n_bf,
   if (n_bf) *n_bf = c->bf_ones;
   if (d_ref_counts) *d_ref_counts = c->tab_counts;
   if (n_ref) *n_ref = 1ull << c->tab_log2;
+  return MG_OK;
+}
+
+extern "C" int mg_add_signatures_packed(mg_ctx *c, const uint64_t *lohi, const uint8_t *is_ref, uint64_t n) {
+  if (!c || ((!lohi || !is_ref) && n)) return set_err(MG_ERR_ARG, "NULL argument");
+  if (c->alt_final) return set_err(MG_ERR_STATE, "mg_add_signatures_packed after mg_finalize_alt");
+  if (n == 0) return MG_OK;
+  CU(cudaSetDevice(c->device));
+  uint64_t n_ref = 0;
+  for (uint64_t i = 0; i < n; ++i) n_ref += is_ref[i] != 0;
+  int rc = tab_reserve(c, n_ref);
+  if (rc) return rc;
+  void *d_k = nullptr;
+  uint8_t *d_f = nullptr;
+  CU(cudaMalloc(&d_k, n * 16));
+  CU(cudaMalloc(&d_f, n));
+  CU(cudaMemcpyAsync(d_k, lohi, n * 16, cudaMemcpyHostToDevice, c->stream[0]));
+  CU(cudaMemcpyAsync(d_f, is_ref, n, cudaMemcpyHostToDevice, c->stream[0]));
+  CU(cudaMemsetAsync(c->d_scalars, 0, 2 * sizeof(unsigned long long), c->stream[0]));
+  c->launches++;
+  k_add_packed<<<grid_for(n, 256), 256, 0, c->stream[0]>>>(reinterpret_cast<const uint4 *>(d_k), d_f, n, c->view(),
+                                                          c->bf_words, c->tab_keys, c->d_scalars);
+  CU(cudaGetLastError());
+  unsigned long long added = 0;
+  CU(cudaMemcpyAsync(&added, c->d_scalars, 8, cudaMemcpyDeviceToHost, c->stream[0]));
+  CU(cudaStreamSynchronize(c->stream[0]));
+  c->tab_n += added;
+  cudaFree(d_k);
+  cudaFree(d_f);
+  return MG_OK;
+}
+
+// ---- timing on the library's own streams (torch.cuda.Event cannot see them) ----
+extern "C" int mg_event_record(mg_ctx *c, int idx) {
+  if (!c || idx < 0 || idx >= 64) return set_err(MG_ERR_ARG, "bad event index");
+  CU(cudaSetDevice(c->device));
+  if (!c->tj) CU(cudaEventCreateWithFlags(&c->tj, cudaEventDisableTiming));
+  if (!c->evs[idx]) CU(cudaEventCreate(&c->evs[idx]));
+  // the event follows everything enqueued so far on both streams, and precedes what comes next
+  CU(cudaEventRecord(c->tj, c->stream[1]));
+  CU(cudaStreamWaitEvent(c->stream[0], c->tj, 0));
+  CU(cudaEventRecord(c->evs[idx], c->stream[0]));
+  CU(cudaStreamWaitEvent(c->stream[1], c->evs[idx], 0));
+  return MG_OK;
+}
+extern "C" int mg_event_elapsed_ms(mg_ctx *c, int a, int b, float *ms) {
+  if (!c || !ms || a < 0 || b < 0 || a >= 64 || b >= 64 || !c->evs[a] || !c->evs[b])
+    return set_err(MG_ERR_ARG, "bad event index");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->evs[b]));
+  CU(cudaEventElapsedTime(ms, c->evs[a], c->evs[b]));
+  return MG_OK;
+}
+extern "C" int mg_genotype_kernel_ms(mg_ctx *c, float *ms3) {
+  if (!c || !ms3 || !c->ge[3]) return set_err(MG_ERR_ARG, "no mg_genotype call to report");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ge[3]));
+  for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms3[i], c->ge[i], c->ge[i + 1]));
+  return MG_OK;
+}
+extern "C" int mg_launch_count(mg_ctx *c, uint64_t *n) {
+  if (!c || !n) return set_err(MG_ERR_ARG, "bad argument");
+  *n = c->launches;
+  return MG_OK;
+}
+
+// measured ceilings on `device`: mode 0 = independent uniformly random 32-byte sector reads over
+// `bytes` of HBM, mode 1 = streaming 16-byte reads.  Best of `reps`, in GB/s of useful bytes.
+extern "C" int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps, double *gbs) {
+  if (!gbs || bytes < (1ull << 20) || reps < 1) return set_err(MG_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  uint32_t *buf = nullptr, *sink = nullptr;
+  CU(cudaMalloc(&buf, bytes));
+  CU(cudaMalloc(&sink, 4));
+  CU(cudaMemset(buf, 0, bytes));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  const int grid = prop.multiProcessorCount * 8;
+  const uint64_t per_thread = 256;
+  double best = 0.0;
+  for (int r = 0; r < reps + 1; ++r) {
+    CU(cudaEventRecord(a));
+    if (mode == 0)
+      k_diag_random<<<grid * 4, 256>>>(buf, bytes / 32, per_thread, sink);
+    else
+      k_diag_stream<<<grid, 256>>>(reinterpret_cast<const uint4 *>(buf), bytes / 16, sink);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b));
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    double useful = mode == 0 ? (double)grid * 4 * 256 * (double)per_thread * 32.0 : (double)bytes;
+    double g = useful / (ms * 1e-3) / 1e9;
+    if (r > 0 && g > best) best = g;  // first repetition is the warm-up
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(buf);
+  cudaFree(sink);
+  *gbs = best;
   return MG_OK;
 }
 

@@ -116,6 +116,8 @@ def ref() -> C.CDLL:
     L.ref_kmap_size.restype = C.c_uint64
     L.ref_kmap_size.argtypes = [C.c_void_p]
     L.ref_scan_kmer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int]
+    L.ref_add_packed.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u8p, C.c_uint64, C.c_int]
+    L.ref_scan_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u32p, C.c_uint64, C.c_int, C.c_int]
     L.ref_reference_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int]
     L.ref_genotype.argtypes = [_u32p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, _f64p, C.c_int,
                                C.c_char_p, C.c_int]

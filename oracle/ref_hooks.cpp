@@ -64,6 +64,36 @@ void ref_scan_kmer(void *bf, void *context_bf, void *ref_bf, const char *context
   }
 }
 
+// ---- batch variants over packed k-mers (A=0 C=1 G=2 T=3, first base most significant), used by
+// bench.py's CPU baseline: the same reference classes, fed like the KMC listing loop feeds them ----
+static void unpack_kmer(uint64_t lo, uint64_t hi, int k, char *out) {
+  static const char SYM[4] = {'A', 'C', 'G', 'T'};
+  for (int j = 0; j < k; ++j) {
+    int sh = 2 * (k - 1 - j);
+    uint64_t code = sh >= 64 ? (hi >> (sh - 64)) : (lo >> sh);
+    out[j] = SYM[code & 3];
+  }
+  out[k] = '\0';
+}
+void ref_add_packed(void *bf, void *ref_bf, const uint64_t *lohi, const uint8_t *is_ref, uint64_t n, int k) {
+  char kmer[130];
+  for (uint64_t i = 0; i < n; ++i) {  // add_kmers_to_bf, main.cpp:133-140
+    unpack_kmer(lohi[2 * i], lohi[2 * i + 1], k, kmer);
+    if (is_ref[i])
+      ((KMAP *)ref_bf)->add_key(kmer);
+    else
+      ((BF *)bf)->add_key(kmer);
+  }
+}
+void ref_scan_packed(void *bf, void *context_bf, void *ref_bf, const uint64_t *lohi, const uint32_t *counts,
+                     uint64_t n, int k, int ref_k) {
+  char context[130];
+  for (uint64_t i = 0; i < n; ++i) {
+    unpack_kmer(lohi[2 * i], lohi[2 * i + 1], ref_k, context);  // kmer_obj.to_string(context), main.cpp:490
+    ref_scan_kmer(bf, context_bf, ref_bf, context, counts[i], k, ref_k);
+  }
+}
+
 // ---- reference rolling pass over one contig (main.cpp:385-400) ---------------
 void ref_reference_pass(void *bf_, void *context_bf_, const char *seq, int k_, int ref_k_) {
   BF &bf = *(BF *)bf_;

@@ -1,0 +1,192 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Bar: bit-exact bits, counters, coverages,
+GT and GQ; likelihoods within 1e-9 relative (north_star)."""
+import random
+
+import numpy as np
+import pytest
+
+from malva_b200 import MalvaGpu, SignatureBatch, kmc
+import parity_util as util
+
+pytestmark = pytest.mark.gpu
+
+LIK_RTOL = 1e-9
+
+
+def _run_pair(oracle_lib, k, ref_k, bf_bits, seed, n_var=300, glen=20000, n_sample=6000, big_counts=False):
+    rng = random.Random(seed)
+    genome = util.make_genome(rng, glen)
+    nested, freqs = util.synth_signatures(rng, genome, k, n_var)
+    ks, fl = util.flatten(nested)
+    g = MalvaGpu(k=k, ref_k=ref_k, bf_bits=bf_bits)
+    o = util.OracleRun(oracle_lib, k, ref_k, bf_bits)
+    # index side, in three batches (exercises table growth + rehash)
+    cuts = [0, len(ks) // 3, 2 * len(ks) // 3, len(ks)]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g.add_signatures(ks[a:b], fl[a:b])
+        o.add_signatures(ks[a:b], fl[a:b])
+    g.finalize_alt()
+    o.finalize_alt()
+    g.scan_reference(genome)
+    o.scan_reference(genome)
+    g.finalize_context()
+    o.finalize_context()
+    words, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, n_sample, big_counts)
+    g.scan_sample_kmers(packed, counts)
+    o.scan_sample_kmers(packed, counts)
+    return g, o, genome, nested, freqs, ks, fl, words
+
+
+@pytest.mark.parametrize("k,ref_k,bf_bits", [
+    (35, 43, 1 << 22),          # default k / ref_k, power-of-two filter (mask path)
+    (35, 43, 3 * (1 << 20) + 7),  # non power of two (modulo path), dense -> many bit collisions
+    (31, 39, 1 << 22),          # runtime-k kernels, 17..32-byte XXH3 branch
+    (36, 43, 1 << 21),          # odd ref_k - k: the reference's non-contiguous window quirk
+    (15, 21, 1 << 20),          # <=16-byte XXH3 branch
+    (43, 43, 1 << 21),          # k == ref_k
+    (63, 64, 1 << 21),          # widest supported words
+])
+def test_index_scan_state_bit_exact(oracle_lib, k, ref_k, bf_bits):
+    g, o, genome, nested, freqs, ks, fl, words = _run_pair(oracle_lib, k, ref_k, bf_bits, seed=100 + k)
+    try:
+        assert np.array_equal(g.bits(0), o.bits(0)), "bf bits"
+        assert np.array_equal(g.bits(1), o.bits(1)), "context_bf bits"
+        assert g.popcount(0) == int(np.unpackbits(o.bits(0).view(np.uint8)).sum())
+        assert g.popcount(1) > 0, "reference pass never hit: test input too weak"
+        assert g.kmap_size() == o.kmap_size()
+        gc, oc = g.bf_counts(), o.bf_counts()
+        assert np.array_equal(gc, oc), "rank-indexed bf counters"
+        assert oc.sum() > 0
+        # every signature k-mer, plus unrelated keys, through get_count / test_key
+        rng = random.Random(7)
+        extra = [util.rand_seq(rng, k) for _ in range(200)] + [util.rand_seq(rng, k - 2, "ACGTN") for _ in range(50)]
+        q = ks + extra
+        for flag in (0, 1):
+            fl_q = [flag] * len(q)
+            assert np.array_equal(g.get_counts(q, fl_q), o.get_counts(q, fl_q)), f"get_count is_ref={flag}"
+        for which in (0, 1, 2):
+            assert np.array_equal(g.test_keys(which, q), o.test_keys(which, q)), f"test_key which={which}"
+        ctx_q = [genome[p:p + ref_k] for p in range(0, len(genome) - ref_k, 37)]
+        assert np.array_equal(g.test_keys(1, ctx_q), o.test_keys(1, ctx_q))
+        ref_counts = o.get_counts(ks, [1] * len(ks))
+        assert (ref_counts > 0).sum() > 20
+    finally:
+        g.close()
+        o.close()
+
+
+def test_u16_wraparound_and_int_counts(oracle_lib):
+    # counts up to 70000 per record: bf counters wrap mod 2^16, ref_bf counts do not
+    g, o, genome, nested, freqs, ks, fl, words = _run_pair(oracle_lib, 35, 43, 1 << 18, seed=5, n_sample=20000,
+                                                          big_counts=True)
+    try:
+        assert np.array_equal(g.bf_counts(), o.bf_counts())
+        a, b = g.get_counts(ks, [1] * len(ks)), o.get_counts(ks, [1] * len(ks))
+        assert np.array_equal(a, b)
+        assert b.max() > 65535
+    finally:
+        g.close()
+        o.close()
+
+
+@pytest.mark.parametrize("glen", [10, 20, 42, 43, 44, 4095 + 43, 4096 + 43, 4097 + 43, 9000])
+def test_reference_pass_edges(oracle_lib, glen):
+    # contigs shorter than ref_k, exactly ref_k, around the CTA tile size
+    k, ref_k, bits = 35, 43, 1 << 16
+    rng = random.Random(glen)
+    genome = util.rand_seq(rng, glen)
+    g, o = MalvaGpu(k=k, ref_k=ref_k, bf_bits=bits), util.OracleRun(oracle_lib, k, ref_k, bits)
+    try:
+        d = (ref_k - k) // 2
+        alts = [genome[p:p + k] for p in range(d, max(d + 1, glen - k), 5)] if glen >= k + d else [genome[d:]]
+        alts += [util.rand_seq(rng, k) for _ in range(20)]
+        for x in (g, o):
+            x.add_signatures(alts, [0] * len(alts))
+            x.finalize_alt()
+            x.scan_reference(genome)
+            x.finalize_context()
+        assert np.array_equal(g.bits(1), o.bits(1))
+        if glen >= ref_k:
+            assert g.popcount(1) > 0
+    finally:
+        g.close()
+        o.close()
+
+
+def test_empty_and_ragged_inputs(oracle_lib):
+    g = MalvaGpu(k=35, ref_k=43, bf_bits=1 << 16)
+    try:
+        g.add_signatures([], [])
+        g.finalize_alt()
+        g.scan_reference("")  # len 0 < ref_k: nothing to do
+        g.finalize_context()
+        g.scan_sample_kmers(np.zeros(0, dtype=kmc.KMER_DTYPE), np.zeros(0, dtype=np.uint32))
+        assert g.popcount(0) == 0 and g.popcount(1) == 0 and g.kmap_size() == 0
+        assert len(g.bf_counts()) == 0
+        b = SignatureBatch.from_nested([[[], []]], [[0.9, 0.1]])  # a variant whose alleles have no signatures
+        r = g.genotype(b, 0.001, 200, False)
+        assert r.cov.tolist() == [0, 0] and r.status.tolist() == [2] and r.gq.tolist() == [0]
+        assert g.get_counts(["A" * 35, ""], [0, 1]).tolist() == [0, 0]
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("haploid", [False, True])
+@pytest.mark.parametrize("err", [0.001, 0.05])
+def test_coverage_and_genotype(oracle_lib, haploid, err):
+    g, o, genome, nested, freqs, ks, fl, words = _run_pair(oracle_lib, 35, 43, 1 << 22, seed=42, n_var=600,
+                                                          n_sample=20000)
+    try:
+        batch = SignatureBatch.from_nested(nested, freqs)
+        max_cov = 120  # low enough that some alleles trip the veto
+        r = g.genotype(batch, err, max_cov, haploid)
+        cov, exp = o.genotype(batch, err, max_cov, haploid)
+        assert np.array_equal(r.cov, cov), "COVS"
+        assert (cov > 0).sum() > 100
+        seen = set()
+        for v, e in enumerate(exp):
+            assert r.status[v] == e["status"], v
+            assert r.n_gts[v] == len(e["probs"]), v
+            assert r.best_gt[v] == e["best"], (v, r.lik[int(r.lik_off[v]):int(r.lik_off[v]) + r.n_gts[v]], e)
+            assert r.gq[v] == e["gq"], v
+            got = r.lik[int(r.lik_off[v]):int(r.lik_off[v]) + r.n_gts[v]]
+            assert np.allclose(got, e["probs"], rtol=LIK_RTOL, atol=0.0), (v, got, e["probs"])
+            assert np.array_equal(got == 0, e["probs"] == 0)
+            seen.add(e["status"])
+        assert seen == {0, 1, 2}, seen
+    finally:
+        g.close()
+        o.close()
+
+
+def test_scan_large_batch_properties(oracle_lib):
+    """Full-size style properties that need no oracle: linearity (scanning a batch twice doubles every
+    counter mod 2^16 / 2^32) and order independence (a permuted batch gives identical state)."""
+    k, ref_k, bits = 35, 43, 1 << 26
+    rng = random.Random(9)
+    genome = util.make_genome(rng, 50000)
+    nested, freqs = util.synth_signatures(rng, genome, k, 1500)
+    ks, fl = util.flatten(nested)
+    words, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, 200000)
+    states = []
+    for variant in ("once", "twice", "permuted"):
+        g = MalvaGpu(k=k, ref_k=ref_k, bf_bits=bits)
+        g.add_signatures(ks, fl)
+        g.finalize_alt()
+        g.scan_reference(genome)
+        g.finalize_context()
+        if variant == "permuted":
+            perm = np.random.default_rng(1).permutation(len(packed))
+            g.scan_sample_kmers(packed[perm].copy(), counts[perm].copy())
+        else:
+            g.scan_sample_kmers(packed, counts)
+            if variant == "twice":
+                g.scan_sample_kmers(packed, counts)
+        states.append((g.bf_counts().astype(np.uint32), g.get_counts(ks, [1] * len(ks)).astype(np.int64)))
+        g.close()
+    once, twice, perm = states
+    assert np.array_equal(once[0], perm[0]) and np.array_equal(once[1], perm[1])
+    assert np.array_equal((once[0] * 2) & 0xFFFF, twice[0])
+    assert np.array_equal(once[1] * 2, twice[1])
+    assert once[0].sum() > 0 and once[1].sum() > 0
