@@ -159,7 +159,11 @@ class ClockSampler:
 
     def _read(self):
         for l in self.proc.stdout:
-            self.lines.append(l.strip())
+            self.lines.append((time.time(), l.strip()))
+
+    def mark(self):
+        """start of the timed region: earlier samples are dropped"""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -171,7 +175,10 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, l in self.lines:
+            if ts < t_mark:
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -405,12 +412,13 @@ def run_ours(args, wl, rank, local_rank, world):
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     barrier()
     launches0 = g.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     g.event_record(2)
     for i in range(args.steps):
         g.event_record(10 + 2 * (i % 8))
@@ -438,9 +446,10 @@ def run_ours(args, wl, rank, local_rank, world):
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI, H2D and D2H inside the timed region ----
-    e2e_steps = max(2, min(args.steps, 4))
-    g.scan_sample_kmers_ptr(hk.data_ptr(), hc.data_ptr(), B, device=False)
-    g.sync()
+    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 4))
+    if e2e_steps:
+        g.scan_sample_kmers_ptr(hk.data_ptr(), hc.data_ptr(), B, device=False)
+        g.sync()
     barrier()
     t0 = time.perf_counter()
     g.event_record(4)
@@ -448,8 +457,8 @@ def run_ours(args, wl, rank, local_rank, world):
         g.scan_sample_kmers_ptr(hk.data_ptr(), hc.data_ptr(), B, device=False)
         res = g.genotype(host_batch, 0.001, 200, False)   # syncs: results are on the host when it returns
     g.event_record(5)
-    e2e_ms = g.event_elapsed_ms(4, 5) / e2e_steps
-    wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms = g.event_elapsed_ms(4, 5) / max(e2e_steps, 1)
+    wall_ms = (time.perf_counter() - t0) * 1e3 / max(e2e_steps, 1)
     e2e_ms = max(e2e_ms, wall_ms)  # host-side packing/alloc time of the call counts too
     te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -467,12 +476,13 @@ def run_ours(args, wl, rank, local_rank, world):
     peak, peak_src = measured_peaks()
     k1_ms = float(np.mean(scan_ms))
     achieved = B * ALGO_BYTES_PER_KMER / (k1_ms * 1e-3) / 1e9
-    try:
-        rand_gbs = diag_bandwidth(local_rank, 0, 8 << 30, 3)
-        stream_gbs = diag_bandwidth(local_rank, 1, 8 << 30, 3)
-    except Exception as e:  # noqa: BLE001
-        rand_gbs = stream_gbs = None
-        log("diag_bandwidth failed:", e)
+    rand_gbs = stream_gbs = None
+    if not args.no_diag:
+        try:
+            rand_gbs = diag_bandwidth(local_rank, 0, 8 << 30, 3)
+            stream_gbs = diag_bandwidth(local_rank, 1, 8 << 30, 3)
+        except Exception as e:  # noqa: BLE001
+            log("diag_bandwidth failed:", e)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tp):
@@ -526,11 +536,13 @@ def run_ours(args, wl, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="wg", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-diag", action="store_true", help="skip the bandwidth microbenchmarks (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -130,8 +130,8 @@ int mg_event_elapsed_ms(mg_ctx *ctx, int a, int b, float *ms);
 int mg_genotype_kernel_ms(mg_ctx *ctx, float *ms3);
 /* kernels launched by this context so far */
 int mg_launch_count(mg_ctx *ctx, uint64_t *n);
-/* measured ceilings: mode 0 = independent random 32-byte sector reads over `bytes` of HBM,
- * mode 1 = streaming reads; GB/s of useful bytes, best of reps */
+/* measured ceilings: mode 0 / 2 / 3 = independent random reads of aligned 32 / 64 / 128-byte units over
+ * `bytes` of HBM, mode 1 = streaming reads; GB/s of useful bytes, best of reps */
 int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps, double *gbs);
 
 /* pinned host memory for the sample stream */

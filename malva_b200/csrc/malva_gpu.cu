@@ -649,8 +649,9 @@ __global__ void __launch_bounds__(128) k_genotype(const uint32_t *__restrict__ c
 // and for a streaming read on this device (bench.py records them next to the
 // driver's MEASURED_PEAKS.json)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_diag_random(const uint32_t *__restrict__ buf, uint64_t n_sectors,
+__global__ void __launch_bounds__(256) k_diag_random(const uint32_t *__restrict__ buf, uint64_t n_units, int gran,
                                                     uint64_t per_thread, uint32_t *sink) {
+  // every access touches `gran` consecutive 32-byte sectors of one aligned gran*32-byte unit
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t s = (t + 1) * GOLD;
   uint32_t acc = 0;
@@ -659,8 +660,11 @@ __global__ void __launch_bounds__(256) k_diag_random(const uint32_t *__restrict_
     s ^= s >> 29;
     s *= 0xBF58476D1CE4E5B9ULL;
     s ^= s >> 32;
-    uint64_t sec = mg::mulhi64(s, n_sectors);  // uniform in [0, n_sectors)
-    acc += __ldg(buf + sec * 8);               // one 4-byte load per 32-byte sector
+    uint64_t unit = mg::mulhi64(s, n_units);  // uniform in [0, n_units)
+    const uint32_t *p = buf + unit * 8 * (uint64_t)gran;
+    acc += __ldg(p);
+    if (gran >= 2) acc += __ldg(p + 8);
+    if (gran >= 4) acc += __ldg(p + 16) + __ldg(p + 24);
     s += GOLD;
   }
   if (acc == 0x12345678u) *sink = acc;
@@ -1306,8 +1310,8 @@ extern "C" int mg_launch_count(mg_ctx *c, uint64_t *n) {
   return MG_OK;
 }
 
-// measured ceilings on `device`: mode 0 = independent uniformly random 32-byte sector reads over
-// `bytes` of HBM, mode 1 = streaming 16-byte reads.  Best of `reps`, in GB/s of useful bytes.
+// measured ceilings on `device`: mode 0 / 2 / 3 = independent uniformly random reads of aligned 32 / 64 /
+// 128-byte units over `bytes` of HBM, mode 1 = streaming 16-byte reads.  Best of `reps`, in GB/s of useful bytes.
 extern "C" int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps, double *gbs) {
   if (!gbs || bytes < (1ull << 20) || reps < 1) return set_err(MG_ERR_ARG, "bad argument");
   CU(cudaSetDevice(device));
@@ -1325,8 +1329,9 @@ extern "C" int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps,
   double best = 0.0;
   for (int r = 0; r < reps + 1; ++r) {
     CU(cudaEventRecord(a));
-    if (mode == 0)
-      k_diag_random<<<grid * 4, 256>>>(buf, bytes / 32, per_thread, sink);
+    const int gran = mode == 0 ? 1 : mode == 2 ? 2 : 4;
+    if (mode != 1)
+      k_diag_random<<<grid * 4, 256>>>(buf, bytes / (32 * (uint64_t)gran), gran, per_thread, sink);
     else
       k_diag_stream<<<grid, 256>>>(reinterpret_cast<const uint4 *>(buf), bytes / 16, sink);
     CU(cudaGetLastError());
@@ -1334,7 +1339,7 @@ extern "C" int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps,
     CU(cudaEventSynchronize(b));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, a, b));
-    double useful = mode == 0 ? (double)grid * 4 * 256 * (double)per_thread * 32.0 : (double)bytes;
+    double useful = mode != 1 ? (double)grid * 4 * 256 * (double)per_thread * 32.0 * gran : (double)bytes;
     double g = useful / (ms * 1e-3) / 1e9;
     if (r > 0 && g > best) best = g;  // first repetition is the warm-up
   }

@@ -382,13 +382,24 @@ void mo_reference_pass(const mo_bf *bf, mo_bf *context_bf, const char *seq, uint
    * k-mer window of the first step starts at d=(ref_k-k)/2, and every slide
    * appends seq[p-d], i.e. it ends at p-d. */
   char context[512], ksub[512];
-  uint64_t d = (uint64_t)(ref_k - k) / 2, p;
-  if (len < (uint64_t)ref_k) return; /* reference behaviour there is undefined (substr past end) */
-  for (p = (uint64_t)ref_k - 1; p < len; ++p) {
-    memcpy(context, seq + p - (uint64_t)ref_k + 1, (size_t)ref_k);
-    context[ref_k] = 0;
-    memcpy(ksub, seq + p - d - (uint64_t)k + 1, (size_t)k);
-    ksub[k] = 0;
+  uint64_t d = (uint64_t)(ref_k - k) / 2, p, cl, kl;
+  /* string ref_ksub(reference, d, k); string context(reference, 0, ref_k);  -- substr() clamps to the
+   * end of the string, and throws when d > size() (callers never pass that) */
+  if (d > len) return;
+  kl = len - d < (uint64_t)k ? len - d : (uint64_t)k;
+  cl = len < (uint64_t)ref_k ? len : (uint64_t)ref_k;
+  memcpy(ksub, seq + d, kl);
+  ksub[kl] = 0;
+  memcpy(context, seq, cl);
+  context[cl] = 0;
+  if (mo_bf_test_key(bf, ksub)) mo_bf_add_key(context_bf, context);
+  for (p = (uint64_t)ref_k; p < len; ++p) {
+    /* erase(0,1) then append: the windows slide literally as in the reference, so for an odd
+     * (ref_k - k) the k-mer window is non-contiguous during its first k-1 slides */
+    memmove(context, context + 1, cl - 1);
+    context[cl - 1] = seq[p];
+    memmove(ksub, ksub + 1, kl - 1);
+    ksub[kl - 1] = seq[p - d];
     if (mo_bf_test_key(bf, ksub)) mo_bf_add_key(context_bf, context);
   }
 }

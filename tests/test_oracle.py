@@ -242,3 +242,54 @@ def test_genotype_bit_exact_against_reference(oracle_lib, ref_lib):
         assert gtgq == f"{exp_gt}:{gq}", (line, status, bi, gq)
         checked += 1
     assert checked == 4000
+
+
+@pytest.mark.parametrize("k,ref_k", [(35, 43), (36, 43), (31, 40), (20, 21), (43, 43), (15, 21)])
+@pytest.mark.parametrize("glen", [12, 30, 43, 44, 100, 1500])
+def test_reference_pass_matches_reference_loop_all_shapes(oracle_lib, ref_lib, k, ref_k, glen):
+    """Odd (ref_k - k) makes the reference's k-mer window non-contiguous for its first k-1 slides
+    (main.cpp:395-397); contigs shorter than ref_k hash truncated substr() results."""
+    rng = random.Random(1000 * k + ref_k + glen)
+    d = (ref_k - k) // 2
+    if glen < d:
+        pytest.skip("the reference throws std::out_of_range here")
+    genome = "".join(rng.choice("ACGT") for _ in range(glen))
+    if glen > 200:
+        genome = genome[:100] + "NNWN" + genome[104:]
+    size = 1 << 12
+    ob, oc = oracle_lib.mo_bf_new(size), oracle_lib.mo_bf_new(size)
+    rb, rc = ref_lib.ref_bf_new(size), ref_lib.ref_bf_new(size)
+    # dense alt filter: about a third of all probes hit, so the context filter gets many bits
+    for _ in range(1500):
+        s = "".join(rng.choice("ACGT") for _ in range(k)).encode()
+        oracle_lib.mo_bf_add_key(ob, s)
+        ref_lib.ref_bf_add_key(rb, s)
+    oracle_lib.mo_reference_pass(ob, oc, genome.encode(), len(genome), k, ref_k)
+    ref_lib.ref_reference_pass(rb, rc, genome.encode(), k, ref_k)
+    n = size // 64
+    a = np.ctypeslib.as_array(oracle_lib.mo_bf_words(oc), shape=(n,)).copy()
+    # compare through test_key on every window the reference could have inserted, plus popcount
+    ref_lib.ref_bf_switch_mode(rc)
+    oracle_lib.mo_bf_switch_mode(oc)
+    probes = set()
+    for p in range(0, max(1, glen - ref_k + 1)):
+        probes.add(genome[p:p + ref_k])
+    probes.add(genome[:ref_k])
+    for w in probes:
+        assert oracle_lib.mo_bf_test_key(oc, w.encode()) == ref_lib.ref_bf_test_key(rc, w.encode()), w
+    hits = sum(ref_lib.ref_bf_test_key(rc, w.encode()) for w in probes)
+    assert int(np.unpackbits(a.view(np.uint8)).sum()) == len(_distinct_bits(ref_lib, rc, probes, size, oracle_lib))
+    if glen >= 100:
+        assert hits > 5
+
+
+def _distinct_bits(ref_lib, rc, probes, size, oracle_lib):
+    """bit indices of the probes the reference reports as present."""
+    import ctypes as C
+    out = set()
+    for w in probes:
+        if ref_lib.ref_bf_test_key(rc, w.encode()):
+            buf = C.create_string_buffer(len(w) + 1)
+            oracle_lib.mo_canonical(w.encode(), len(w), buf)
+            out.add(oracle_lib.mo_xxh3_64(buf.raw[:len(w)], len(w)) % size)
+    return out
