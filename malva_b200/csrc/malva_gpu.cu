@@ -100,6 +100,7 @@ struct mg_ctx {
   void *d_stage_k[2] = {nullptr, nullptr};
   uint32_t *d_stage_c[2] = {nullptr, nullptr};
   int next_stage = 0;
+  int scan_ilp = 2, scan_ctas_per_sm = 8;
   uint64_t launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
   cudaEvent_t tj = nullptr;
   cudaEvent_t ge[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -466,7 +467,8 @@ __global__ void __launch_bounds__(256) k_scan(const uint4 *__restrict__ kmers, c
     }
 #pragma unroll
     for (int u = 0; u < ILP; ++u) {
-      u128 x35 = mg::mask128(mg::shr128(x43[u], 2 * d), 2 * k);
+      // kmer = context + (ref_k-k)/2 (main.cpp:493): the k-mer starts d bases in, so ref_k-k-d bases follow it
+      u128 x35 = mg::mask128(mg::shr128(x43[u], 2 * (ref_k - k - d)), 2 * k);
       h[u] = canon_hash_k<K>(x35, k, &canon[u]);
       idx[u] = bf_index(v, h[u]);
       slot[u] = tab_slot0(v, h[u]);
@@ -742,6 +744,17 @@ extern "C" int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sms = prop.multiProcessorCount;
+  // tuning knobs (read once per context; defaults are the measured best)
+  if (const char *e = getenv("MG_SCAN_ILP")) c->scan_ilp = atoi(e);
+  if (const char *e = getenv("MG_SCAN_CTAS_PER_SM")) c->scan_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 8;
+  {
+    // The probes of this workload are independent random 4..16-byte reads: ask the L2 to fetch single
+    // 32-byte sectors from HBM instead of promoting every miss to a wider fetch.
+    size_t gran = 32;
+    if (const char *e = getenv("MG_L2_FETCH_GRANULARITY")) gran = (size_t)atoi(e);
+    if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();
+  }
   for (int i = 0; i < 2; ++i) {
     CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
@@ -943,17 +956,24 @@ extern "C" int mg_finalize_context(mg_ctx *c) {
   return MG_OK;
 }
 
-template <int K, int REFK>
-static cudaError_t launch_scan(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
-  constexpr int ILP = 2;
+template <int K, int REFK, int ILP>
+static cudaError_t launch_scan_ilp(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
   uint64_t want = (n + 256ull * ILP - 1) / (256ull * ILP);
-  uint64_t cap = (uint64_t)c->sms * 8;
+  uint64_t cap = (uint64_t)c->sms * (uint64_t)c->scan_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
   c->launches++;
   k_scan<K, REFK, ILP><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_lohi),
                                              reinterpret_cast<const uint32_t *>(d_counts), n, c->view());
   return cudaGetLastError();
+}
+template <int K, int REFK>
+static cudaError_t launch_scan(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
+  switch (c->scan_ilp) {
+    case 1: return launch_scan_ilp<K, REFK, 1>(c, d_lohi, d_counts, n, st);
+    case 4: return launch_scan_ilp<K, REFK, 4>(c, d_lohi, d_counts, n, st);
+    default: return launch_scan_ilp<K, REFK, 2>(c, d_lohi, d_counts, n, st);
+  }
 }
 
 static int scan_device(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
@@ -1317,6 +1337,12 @@ extern "C" int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps,
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
+  {
+    size_t gran = 32;  // same L2 fetch policy as the contexts use (see mg_create)
+    if (const char *e = getenv("MG_L2_FETCH_GRANULARITY")) gran = (size_t)atoi(e);
+    if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();
+  }
   uint32_t *buf = nullptr, *sink = nullptr;
   CU(cudaMalloc(&buf, bytes));
   CU(cudaMalloc(&sink, 4));

@@ -6,7 +6,7 @@ import random
 import numpy as np
 import pytest
 
-from malva_b200 import MalvaGpu, SignatureBatch, kmc
+from malva_b200 import MalvaGpu, MalvaGpuError, SignatureBatch, kmc
 import parity_util as util
 
 pytestmark = pytest.mark.gpu
@@ -119,7 +119,9 @@ def test_empty_and_ragged_inputs(oracle_lib):
     try:
         g.add_signatures([], [])
         g.finalize_alt()
-        g.scan_reference("")  # len 0 < ref_k: nothing to do
+        with pytest.raises(MalvaGpuError):  # the reference's substr(d, k) throws on a contig shorter than d
+            g.scan_reference("")
+        g.scan_reference("ACGT")  # shorter than ref_k: one truncated probe, no hit
         g.finalize_context()
         g.scan_sample_kmers(np.zeros(0, dtype=kmc.KMER_DTYPE), np.zeros(0, dtype=np.uint32))
         assert g.popcount(0) == 0 and g.popcount(1) == 0 and g.kmap_size() == 0
