@@ -397,9 +397,7 @@ def run_ours(args, wl, rank, local_rank, world):
     from malva_b200.api import SignatureBatch
     host_batch = SignatureBatch(vb["vao"], vb["aso"], vb["sko"], vb["koff"], host_pool, vb["freq"])
 
-    p_bf, n_bf, p_tab, n_tab = g.counter_buffers()
-    t_bf = torch.as_tensor(DevArray(p_bf, n_bf), device=dev) if world > 1 else None
-    t_tab = torch.as_tensor(DevArray(p_tab, n_tab), device=dev) if world > 1 else None
+    counters = [torch.as_tensor(DevArray(p, n), device=dev) for p, n in g.counter_buffers() if n] if world > 1 else []
 
     def step(i):
         kk, cc = batches[i & 1]
@@ -428,8 +426,8 @@ def run_ours(args, wl, rank, local_rank, world):
         g.genotype_device(ptrs, vb["dims"], 0.001, 200, False)
     if world > 1:
         g.sync()  # the library's streams -> torch's stream, then the NCCL sum-reduce of both counter arrays
-        dist.reduce(t_bf, dst=0)
-        dist.reduce(t_tab, dst=0)
+        for t in counters:
+            dist.reduce(t, dst=0)
         torch.cuda.synchronize()
     g.event_record(3)
     region_ms = g.event_elapsed_ms(2, 3)

@@ -11,7 +11,7 @@
  *
  * k-mer word format of the sample stream: A=0 C=1 G=2 T=3, first base in the
  * most significant position, right-aligned in 128 bits, stored as two
- * little-endian u64 {lo, hi}.  ref_k <= 64.
+ * little-endian u64 {lo, hi}.  k <= 63, ref_k <= 64.
  *
  * Signature k-mers (index side and genotyping side) are passed as the
  * reference passes them -- ASCII strings -- batched as a byte pool plus n+1
@@ -116,9 +116,13 @@ int mg_bf_download_counts(mg_ctx *ctx, uint16_t *counts, uint64_t n);
 /* number of ref_bf keys (packed + irregular)                                */
 int mg_kmap_size(mg_ctx *ctx, uint64_t *n);
 
-/* device pointers of the two counter arrays, for an external (NCCL) sum-reduce
- * across replicas: u32 per set bit of bf, u32 per table slot of ref_bf.      */
-int mg_counter_buffers(mg_ctx *ctx, void **d_bf_counts, uint64_t *n_bf, void **d_ref_counts, uint64_t *n_ref);
+/* {probe lines, set bits of bf, packed ref keys, keys in the overflow table, overflow capacity,
+ * irregular (non-ACGT / short) ref keys}; n >= 6 */
+int mg_index_stats(mg_ctx *ctx, uint64_t *stats, int n);
+
+/* device pointers + lengths of the three u32 counter arrays, for an external (NCCL) sum-reduce across
+ * replicas: [0] one per set bit of bf, [1] one per key slot of the probe lines, [2] overflow table */
+int mg_counter_buffers(mg_ctx *ctx, void **d_ptr /*[3]*/, uint64_t *n /*[3]*/);
 
 /* ------------------------------ measurement ------------------------------ */
 /* CUDA-event timing on the library's own streams (64 event slots): record marks a point that follows
@@ -130,8 +134,9 @@ int mg_event_elapsed_ms(mg_ctx *ctx, int a, int b, float *ms);
 int mg_genotype_kernel_ms(mg_ctx *ctx, float *ms3);
 /* kernels launched by this context so far */
 int mg_launch_count(mg_ctx *ctx, uint64_t *n);
-/* measured ceilings: mode 0 / 2 / 3 = independent random reads of aligned 32 / 64 / 128-byte units over
- * `bytes` of HBM, mode 1 = streaming reads; GB/s of useful bytes, best of reps */
+/* measured ceilings over `bytes` of HBM, GB/s of useful bytes, best of reps: mode 0 / 2 / 3 = independent
+ * random reads of 1 / 2 / 4 separate sectors of an aligned 32 / 64 / 128-byte unit; mode 4 = random 128-byte
+ * lines fetched by 8 lanes in one coalesced request (the sample scan's pattern); mode 1 = streaming reads */
 int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps, double *gbs);
 
 /* pinned host memory for the sample stream */

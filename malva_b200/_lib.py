@@ -79,7 +79,8 @@ SYMBOLS = {
     "mg_bf_download_bits": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64]),
     "mg_bf_download_counts": (C.c_int, [C.c_void_p, u16p, C.c_uint64]),
     "mg_kmap_size": (C.c_int, [C.c_void_p, u64p]),
-    "mg_counter_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_void_p), u64p]),
+    "mg_index_stats": (C.c_int, [C.c_void_p, u64p, C.c_int]),
+    "mg_counter_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
     "mg_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, f32p]),
     "mg_genotype_kernel_ms": (C.c_int, [C.c_void_p, f32p]),

@@ -294,14 +294,22 @@ class MalvaGpu:
         return v.value
 
     def counter_buffers(self):
-        """(bf_counts device ptr, n, ref counts device ptr, n) for an external NCCL sum-reduce."""
-        p1, p2, n1, n2 = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
-        check(self._L.mg_counter_buffers(self._h, C.byref(p1), C.byref(n1), C.byref(p2), C.byref(n2)))
-        return p1.value, n1.value, p2.value, n2.value
+        """[(device ptr, n_u32)] x 3 -- bf counters, probe-line key counts, overflow counts -- for an
+        external NCCL sum-reduce across replicas."""
+        p = (C.c_void_p * 3)()
+        n = (C.c_uint64 * 3)()
+        check(self._L.mg_counter_buffers(self._h, p, n))
+        return [(p[i] or 0, int(n[i])) for i in range(3)]
+
+    def index_stats(self) -> dict:
+        s = (C.c_uint64 * 6)()
+        check(self._L.mg_index_stats(self._h, s, 6))
+        return dict(zip(("probe_lines", "bf_ones", "ref_keys", "overflow_keys", "overflow_capacity",
+                         "irregular_ref_keys"), [int(x) for x in s]))
 
 
 def diag_bandwidth(device: int, mode: int, nbytes: int, reps: int = 3) -> float:
-    """Measured ceiling in GB/s: mode 0 = random 32-byte sector reads, mode 1 = streaming reads."""
+    """Measured ceiling in GB/s (see mg_diag_bandwidth): 0/2/3 random 32/64/128 B, 4 coalesced random lines, 1 stream."""
     g = C.c_double(0)
     check(_lib.load().mg_diag_bandwidth(device, mode, nbytes, reps, C.byref(g)))
     return g.value

@@ -1,0 +1,597 @@
+// Hand-written sm_100a kernels of the MALVA hot path (see index.cuh for the data layout).
+//   K3  k_add_signatures / k_add_packed / k_add_spill / k_line_popc    index-time inserts + switch_mode
+//   K2  k_refpass / k_refpass_short                                    reference rolling pass
+//   K1  k_scan                                                         sample k-mer scan
+//   K4  k_mark_ref / k_lookup / k_coverage                             coverage read-back
+//   K5  k_genotype                                                     likelihoods + posterior arg-max
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "geno.cuh"
+#include "index.cuh"
+#include "xxh3.cuh"
+
+namespace mg {
+
+template <int K>
+__device__ __forceinline__ uint64_t canon_hash_k(u128 x, int k, u128 *canon) {
+  if constexpr (K > 0) {
+    return canon_hash<K>(x, canon);
+  } else {
+    return canon_hash_rt(x, k, canon);
+  }
+}
+
+// scalars: [0] new keys, [1] irregular ref keys, [2] popcount, [3] error flag, [4] spilled keys
+// ---------------------------------------------------------------------------
+// K3a: index-time inserts (add_kmers_to_bf, main.cpp:122-144)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void insert_ref_key(const DevView &v, uint4 *lines_rw, uint64_t h, u128 canon, uint64_t i,
+                                               unsigned long long *scalars, uint32_t *spill_idx) {
+  uint64_t line = bf_index(v, h) >> 8;
+  int r = line_insert(lines_rw, line, canon);
+  if (r == 1) {
+    atomicAdd(&scalars[0], 1ull);
+  } else if (r < 0) {  // line full: flag it and leave the key for the overflow pass
+    line_set_overflow(lines_rw, line);
+    unsigned long long p = atomicAdd(&scalars[4], 1ull);
+    spill_idx[p] = (uint32_t)i;
+  }
+}
+__device__ __forceinline__ void set_bf_bit(const DevView &v, uint4 *lines_rw, uint64_t h) {
+  uint64_t idx = bf_index(v, h);
+  uint32_t *w = reinterpret_cast<uint32_t *>(lines_rw) + (idx >> 8) * 32 + ((idx & 255) >> 5);
+  atomicOr(w, 1u << (idx & 31));
+}
+
+__global__ void __launch_bounds__(128) k_add_signatures(const uint8_t *__restrict__ pool,
+                                                       const uint64_t *__restrict__ off,
+                                                       const uint8_t *__restrict__ is_ref, uint64_t n, DevView v,
+                                                       uint4 *lines_rw, unsigned long long *scalars,
+                                                       uint32_t *irregular_idx, uint32_t *spill_idx) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t b = off[i], e = off[i + 1];
+  int len = (int)(e - b);
+  if (len > 128) {
+    atomicExch(&scalars[3], 1ull);
+    return;
+  }
+  uint8_t s[128];
+  for (int j = 0; j < len; ++j) s[j] = pool[b + j];
+  u128 x, canon;
+  bool regular = pack_ascii(s, len, v.k, &x);
+  if (is_ref[i]) {  // ref_bf.add_key
+    if (!regular) {  // not k symbols of ACGT: can never match a sample k-mer; kept on the host
+      unsigned long long p = atomicAdd(&scalars[1], 1ull);
+      irregular_idx[p] = (uint32_t)i;
+      return;
+    }
+    uint64_t h = canon_hash_rt(x, v.k, &canon);
+    insert_ref_key(v, lines_rw, h, canon, i, scalars, spill_idx);
+  } else {  // bf.add_key
+    uint64_t h = regular ? canon_hash_rt(x, v.k, &canon) : hash_ascii(s, len);
+    set_bf_bit(v, lines_rw, h);
+  }
+}
+
+// same inserts for signature k-mers that arrive already packed (exactly k symbols of ACGT)
+__global__ void __launch_bounds__(256) k_add_packed(const uint4 *__restrict__ kmers, const uint8_t *__restrict__ is_ref,
+                                                   uint64_t n, DevView v, uint4 *lines_rw, unsigned long long *scalars,
+                                                   uint32_t *spill_idx) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint4 q = kmers[i];
+  u128 x, canon;
+  x.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+  x.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+  x = mask128(x, 2 * v.k);
+  uint64_t h = canon_hash_rt(x, v.k, &canon);
+  if (is_ref[i])
+    insert_ref_key(v, lines_rw, h, canon, i, scalars, spill_idx);
+  else
+    set_bf_bit(v, lines_rw, h);
+}
+
+// second pass over the keys whose line was full: insert into the overflow table.
+// Keys come either from an ASCII pool (off != nullptr) or from a packed array.
+__global__ void __launch_bounds__(128) k_add_spill(const uint32_t *__restrict__ spill_idx, uint64_t n_spill,
+                                                  const uint8_t *__restrict__ pool, const uint64_t *__restrict__ off,
+                                                  const uint4 *__restrict__ packed, DevView v, u128 *ovf_keys_rw,
+                                                  unsigned long long *scalars) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_spill) return;
+  uint64_t i = spill_idx[j];
+  u128 x, canon;
+  if (off) {
+    uint64_t b = off[i];
+    int len = (int)(off[i + 1] - b);
+    uint8_t s[64];
+    for (int t = 0; t < len && t < 64; ++t) s[t] = pool[b + t];
+    pack_ascii(s, len, v.k, &x);
+  } else {
+    uint4 q = packed[i];
+    x.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+    x.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+    x = mask128(x, 2 * v.k);
+  }
+  uint64_t h = canon_hash_rt(x, v.k, &canon);
+  if (ovf_insert(v, ovf_keys_rw, h, canon) == 1) atomicAdd(&scalars[0], 1ull);
+}
+
+__global__ void k_fill_keys(u128 *keys, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i].lo = ~0ull;
+    keys[i].hi = KEY_HI_MASK;
+  }
+}
+// a fresh probe-line array: filter bits 0, key slots empty
+__global__ void k_init_lines(uint4 *lines, uint64_t n_lines) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one uint4 per thread
+  if (i >= n_lines * LINE_U4) return;
+  uint32_t hi = (uint32_t)(KEY_HI_MASK >> 32);
+  lines[i] = (i & 7) < 2 ? make_uint4(0, 0, 0, 0) : make_uint4(~0u, ~0u, ~0u, hi);
+}
+
+// re-insert every key of an old overflow table into a larger one (counts carried over)
+__global__ void k_rehash(const u128 *old_keys, const uint32_t *old_counts, uint64_t old_cap, DevView v,
+                         u128 *ovf_keys_rw) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= old_cap) return;
+  u128 key = old_keys[i];
+  key.hi &= KEY_HI_MASK;
+  if (key_empty(key)) return;
+  u128 canon;
+  uint64_t h = canon_hash_rt(key, v.k, &canon);  // keys are canonical: canon == key
+  const u128 empty = {~0ull, KEY_HI_MASK};
+  uint64_t slot = ovf_slot0(v, h);
+  while (true) {
+    u128 old = cas128(ovf_keys_rw + slot, empty, key);
+    old.hi &= KEY_HI_MASK;
+    if (key_empty(old)) break;
+    slot = (slot + 1) & v.ovf_mask;
+  }
+  v.ovf_counts[slot] = old_counts[i];
+}
+
+// ---------------------------------------------------------------------------
+// K3b: switch_mode (bloom_filter.hpp:93-98): ones per probe line (then an exclusive scan -> rank)
+// also used on a plain bit array (stride_u32 = 8) for context_bf statistics
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_line_popc(const uint32_t *__restrict__ words, uint64_t n_units, int stride_u32,
+                                                  uint32_t *__restrict__ unit_count, unsigned long long *total) {
+  uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t c = 0;
+  if (b < n_units) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(words + b * (uint64_t)stride_u32);
+    uint4 q0 = p[0], q1 = p[1];
+    c = __popc(q0.x) + __popc(q0.y) + __popc(q0.z) + __popc(q0.w) + __popc(q1.x) + __popc(q1.y) + __popc(q1.z) +
+        __popc(q1.w);
+    if (unit_count) unit_count[b] = c;
+  }
+  __shared__ uint32_t red[8];
+  uint32_t s = c;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    s = red[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_down_sync(0xffu, s, o);
+    if (threadIdx.x == 0 && s) atomicAdd(total, (unsigned long long)s);
+  }
+}
+// the 256 filter bits of every probe line, gathered into a plain bit array (state download)
+__global__ void k_extract_bits(const uint4 *__restrict__ lines, uint64_t n_lines, uint4 *__restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one uint4 (128 bits) per thread
+  if (i >= n_lines * 2) return;
+  out[i] = lines[(i >> 1) * LINE_U4 + (i & 1)];
+}
+
+// ---------------------------------------------------------------------------
+// K2: reference rolling pass (main.cpp:385-400)
+// Each CTA stages a tile of the contig in shared memory (with a ref_k-1 halo); each thread rolls RP_RUN
+// consecutive windows through 2-bit registers.  Windows that contain a non-ACGT symbol take the
+// byte-exact ASCII path (the RCN table maps IUPAC symbols to NUL, bloom_filter.hpp:36-50).
+// ---------------------------------------------------------------------------
+constexpr int RP_THREADS = 256;
+constexpr int RP_RUN = 16;
+constexpr int RP_TILE = RP_THREADS * RP_RUN;
+
+__device__ __forceinline__ uint32_t base_code(uint8_t c) {  // 0..3, or 4 for anything else
+  return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+}
+
+template <int K, int REFK>
+__global__ void __launch_bounds__(RP_THREADS) k_refpass(const uint8_t *__restrict__ seq, uint64_t len, DevView v,
+                                                        uint32_t *ctx_words_rw) {
+  extern __shared__ uint8_t sm[];
+  const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
+  const int d = (ref_k - k) / 2;
+  const bool odd = ((ref_k - k) & 1) != 0;
+  // window end positions handled by this CTA: [p0, p1)
+  uint64_t p0 = (uint64_t)(ref_k - 1) + (uint64_t)blockIdx.x * RP_TILE;
+  uint64_t p1 = p0 + RP_TILE < len ? p0 + RP_TILE : len;
+  uint64_t base = p0 - (uint64_t)(ref_k - 1);  // first byte staged
+  int nbytes = (int)(p1 - base);
+  for (int i = threadIdx.x; i < nbytes; i += RP_THREADS) sm[i] = seq[base + i];
+  __syncthreads();
+  uint64_t q0 = p0 + (uint64_t)threadIdx.x * RP_RUN;
+  if (q0 >= p1) return;
+  uint64_t q1 = q0 + RP_RUN < p1 ? q0 + RP_RUN : p1;
+  // prime the rolling state with the ref_k-1 bases before q0
+  u128 x = {0, 0};
+  uint64_t bad = 0;  // bit j set <=> base (p - j) is not ACGT
+  const u128 m = mask128(u128{~0ull, ~0ull}, 2 * ref_k);
+  int o = (int)(q0 - base) - (ref_k - 1);
+  for (int j = 0; j < ref_k - 1; ++j) {
+    uint32_t c = base_code(sm[o + j]);
+    x.hi = (x.hi << 2) | (x.lo >> 62);
+    x.lo = (x.lo << 2) | (c & 3u);
+    bad = (bad << 1) | (c >> 2);
+  }
+  const uint64_t m43 = ref_k >= 64 ? ~0ull : ((1ull << ref_k) - 1);
+  const uint64_t mk = k >= 64 ? ~0ull : ((1ull << k) - 1);
+  for (uint64_t p = q0; p < q1; ++p) {
+    int sp = (int)(p - base);
+    uint32_t c = base_code(sm[sp]);
+    x.hi = (x.hi << 2) | (x.lo >> 62);
+    x.lo = (x.lo << 2) | (c & 3u);
+    x.hi &= m.hi;
+    x.lo &= m.lo;
+    bad = (bad << 1) | (c >> 2);
+    // k-mer window of the reference at this step.  With t = p-(ref_k-1) slides done:
+    //   (ref_k-k) even        : ref[p-d-k+1 .. p-d]
+    //   odd, t == 0 (primed)  : ref[d .. d+k-1]                 (ends at p-d-1)
+    //   odd, 1 <= t < k       : ref[d+t .. d+k-1] ++ ref[k+d+1 .. k+d+t]   (main.cpp:395-397 skips ref[d+k])
+    //   odd, t >= k           : ref[p-d-k+1 .. p-d]
+    uint64_t t = p - (uint64_t)(ref_k - 1);
+    bool quirk = odd && t >= 1 && t < (uint64_t)k;
+    int shift = d + ((odd && t == 0) ? 1 : 0);
+    uint64_t h35;
+    if (!quirk && ((bad >> shift) & mk) == 0) {
+      u128 x35 = mask128(shr128(x, 2 * shift), 2 * k), canon;
+      h35 = canon_hash_k<K>(x35, k, &canon);
+    } else {
+      uint8_t s[64];
+      if (!quirk) {
+        for (int j = 0; j < k; ++j) s[j] = sm[sp - shift - k + 1 + j];
+      } else {
+        int n_old = k - (int)t;
+        for (int j = 0; j < n_old; ++j) s[j] = seq[(uint64_t)d + t + (uint64_t)j];
+        for (int j = 0; j < (int)t; ++j) s[n_old + j] = seq[(uint64_t)(k + d + 1) + (uint64_t)j];
+      }
+      h35 = hash_ascii(s, k);
+    }
+    if (!bf_test(v, bf_index(v, h35))) continue;
+    uint64_t h43;
+    if ((bad & m43) == 0) {
+      u128 canon;
+      h43 = canon_hash_k<REFK>(x, ref_k, &canon);
+    } else {
+      uint8_t s[64];
+      for (int j = 0; j < ref_k; ++j) s[j] = sm[sp - ref_k + 1 + j];
+      h43 = hash_ascii(s, ref_k);
+    }
+    uint64_t cidx = bf_index(v, h43);
+    atomicOr(ctx_words_rw + (cidx >> 5), 1u << (cidx & 31));
+  }
+}
+
+// contig shorter than ref_k: the reference hashes the (shorter) substr() results once
+__global__ void k_refpass_short(const uint8_t *seq, uint64_t len, DevView v, uint32_t *ctx_words_rw) {
+  if (threadIdx.x || blockIdx.x) return;
+  int d = (v.ref_k - v.k) / 2;
+  int kl = (int)len - d < v.k ? (int)len - d : v.k;
+  uint64_t h = hash_ascii(seq + d, kl);
+  if (!bf_test(v, bf_index(v, h))) return;
+  uint64_t hc = hash_ascii(seq, (int)len);
+  uint64_t cidx = bf_index(v, hc);
+  atomicOr(ctx_words_rw + (cidx >> 5), 1u << (cidx & 31));
+}
+
+// ---------------------------------------------------------------------------
+// K1: sample k-mer scan (main.cpp:487-500)
+//   ref_bf.increment(kmer, c);  if (!context_bf.test_key(context)) bf.increment(kmer, c);
+// A warp owns 32 k-mers (lane i hashes k-mer i: one coalesced 16-byte load, canonical form, XXH3).
+// The probe line of each k-mer is then fetched COOPERATIVELY: in round r the four 8-lane groups of the
+// warp fetch the lines of k-mers 4r..4r+3, lane j of a group loading uint4 j of the line, so that one
+// k-mer costs exactly one fully coalesced 128-byte request.  All eight rounds are issued before the
+// first is consumed (8 x 128 B in flight per lane group).  Filter-bit test and the six key compares are
+// evaluated by the lanes that hold the data and returned to the owner lane with warp ballots.
+// The context filter, the rank directory and the counters are touched only on the ~1-4 % hit paths.
+// ---------------------------------------------------------------------------
+template <int K, int REFK>
+__global__ void __launch_bounds__(256) k_scan(const uint4 *__restrict__ kmers, const uint32_t *__restrict__ counts,
+                                              uint64_t n, DevView v) {
+  const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
+  const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t base = warp * 32; base < n; base += n_warps * 32) {
+    const uint64_t i = base + lane;
+    const bool live = i < n;
+    uint4 q = live ? __ldg(kmers + i) : make_uint4(0, 0, 0, 0);
+    uint32_t cnt = live ? __ldg(counts + i) : 0u;
+    u128 x43, canon;
+    x43.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+    x43.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+    u128 x35 = mask128(shr128(x43, 2 * tail), 2 * k);
+    uint64_t h = canon_hash_k<K>(x35, k, &canon);
+    uint64_t idx = bf_index(v, h);
+    uint32_t line = (uint32_t)(idx >> 8);  // n_lines < 2^32 (bf_bits < 2^40)
+    uint32_t bit = (uint32_t)(idx & 255);
+    // ---- cooperative fetch: 8 rounds x (4 lines x 8 lanes x 16 B) ----
+    uint4 part[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      uint32_t l = __shfl_sync(0xffffffffu, line, 4 * r + grp);
+      part[r] = __ldg(v.lines + (uint64_t)l * LINE_U4 + sub);
+    }
+    uint32_t res = 0;  // owner's result: bit 0 filter hit, bits 1..6 key slot match, bit 7 overflow flag
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int src = 4 * r + grp;
+      uint32_t b = __shfl_sync(0xffffffffu, bit, src);
+      uint32_t c0 = __shfl_sync(0xffffffffu, (uint32_t)canon.lo, src);
+      uint32_t c1 = __shfl_sync(0xffffffffu, (uint32_t)(canon.lo >> 32), src);
+      uint32_t c2 = __shfl_sync(0xffffffffu, (uint32_t)canon.hi, src);
+      uint32_t c3 = K > 0 && K <= 48 ? 0u : __shfl_sync(0xffffffffu, (uint32_t)(canon.hi >> 32), src);
+      uint4 p = part[r];
+      bool hit;
+      if (sub < 2) {  // the two uint4 that hold the 256 filter bits
+        uint32_t wsel = (b >> 5) & 3u;
+        uint32_t w = wsel == 0 ? p.x : wsel == 1 ? p.y : wsel == 2 ? p.z : p.w;
+        hit = ((b >> 7) == (uint32_t)sub) && ((w >> (b & 31u)) & 1u);
+      } else {  // a key slot
+        hit = p.x == c0 && p.y == c1 && p.z == c2 && (p.w & (uint32_t)(KEY_HI_MASK >> 32)) == c3;
+      }
+      uint32_t mh = __ballot_sync(0xffffffffu, hit);
+      uint32_t mo = __ballot_sync(0xffffffffu, sub == 7 && (p.w & OVF_FLAG_W));
+      if ((lane >> 2) == r) {  // lanes 4r..4r+3 own this round's k-mers; group g = lane & 3
+        uint32_t g8 = (mh >> (8 * (lane & 3))) & 0xFFu;
+        uint32_t o8 = (mo >> (8 * (lane & 3) + 7)) & 1u;
+        res = ((g8 & 3u) ? 1u : 0u) | ((g8 >> 2) << 1) | (o8 << 7);
+      }
+    }
+    if (!live) continue;
+    // ---- ref_bf.increment ----
+    uint32_t km = (res >> 1) & 0x3Fu;
+    if (km) {
+      atomicAdd(v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)(__ffs(km) - 1), cnt);
+    } else if (res & 0x80u) {  // line overflowed at index time: the key may live in the overflow table
+      uint64_t slot = ovf_slot0(v, h);
+      while (true) {
+        u128 key = key_of(__ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + slot)));
+        if (key_eq(key, canon)) {
+          atomicAdd(v.ovf_counts + slot, cnt);
+          break;
+        }
+        if (key_empty(key)) break;
+        slot = (slot + 1) & v.ovf_mask;
+      }
+    }
+    // ---- bf.increment unless the context filter vetoes it ----
+    if (res & 1u) {
+      u128 c43;
+      uint64_t h43 = canon_hash_k<REFK>(x43, ref_k, &c43);
+      if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + bf_rank_of(v, idx), cnt);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: signature look-ups (BF::get_count / KMAP::get_count) + coverage
+// ---------------------------------------------------------------------------
+// flags the k-mers of allele slot 0 of every variant (they are looked up in ref_bf, main.cpp:167-170)
+__global__ void __launch_bounds__(256) k_mark_ref(const uint64_t *__restrict__ var_allele_off,
+                                                 const uint64_t *__restrict__ allele_sig_off,
+                                                 const uint64_t *__restrict__ sig_kmer_off, uint64_t n_variants,
+                                                 uint8_t *__restrict__ flags) {
+  uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vi >= n_variants) return;
+  uint64_t a0 = var_allele_off[vi];
+  if (var_allele_off[vi + 1] == a0) return;
+  for (uint64_t s = allele_sig_off[a0]; s < allele_sig_off[a0 + 1]; ++s)
+    for (uint64_t q = sig_kmer_off[s]; q < sig_kmer_off[s + 1]; ++q) flags[q] = 1;
+}
+
+// mode 0: get_count  (is_ref selects KMAP/BF, out = int32 count)
+// mode 1: test_key on filter/table `which` (0 bf, 1 context_bf, 2 ref_bf; out = 0/1, -1 = irregular KMAP key)
+__global__ void __launch_bounds__(128) k_lookup(const uint8_t *__restrict__ pool, const uint64_t *__restrict__ off,
+                                               const uint8_t *__restrict__ is_ref, uint64_t n, DevView v, int mode,
+                                               int which, int32_t *__restrict__ out, unsigned long long *scalars) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t b = off[i], e = off[i + 1];
+  int len = (int)(e - b);
+  if (len > 128) {
+    atomicExch(&scalars[3], 1ull);
+    out[i] = 0;
+    return;
+  }
+  uint8_t s[128];
+  for (int j = 0; j < len; ++j) s[j] = pool[b + j];
+  bool use_table = mode == 0 ? (is_ref[i] != 0) : (which == 2);
+  u128 x, canon;
+  if (use_table) {
+    if (!pack_ascii(s, len, v.k, &x)) {
+      out[i] = (mode == 1) ? -1 : 0;  // irregular keys are resolved on the host (always count 0)
+      return;
+    }
+    uint64_t h = canon_hash_rt(x, v.k, &canon);
+    int64_t loc = key_locate(v, h, bf_index(v, h), canon);
+    if (mode == 1)
+      out[i] = loc != -1;
+    else
+      out[i] = loc != -1 ? (int32_t)*count_ptr(v, loc) : 0;
+    return;
+  }
+  // a Bloom filter: hash the canonical ASCII bytes of whatever length was given
+  bool regular = len >= 1 && len <= 64 && pack_ascii(s, len, len, &x);
+  uint64_t h = regular ? canon_hash_rt(x, len, &canon) : hash_ascii(s, len);
+  uint64_t idx = bf_index(v, h);
+  bool set = (mode == 1 && which == 1) ? ctx_test(v, idx) : bf_test(v, idx);
+  if (mode == 1) {
+    out[i] = set;
+  } else {
+    out[i] = (set && v.rank) ? (int32_t)(v.bf_counts[bf_rank_of(v, idx)] & 0xFFFFu) : 0;
+  }
+}
+
+// set_coverages (main.cpp:157-182): per allele slot, max over signatures of the order-dependent integer
+// running mean of the non-zero k-mer weights
+__global__ void __launch_bounds__(128) k_coverage(const int32_t *__restrict__ w, const uint64_t *__restrict__ sig_kmer_off,
+                                                 const uint64_t *__restrict__ allele_sig_off, uint64_t n_alleles,
+                                                 uint32_t *__restrict__ cov) {
+  uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_alleles) return;
+  uint32_t allele_cov = 0;
+  for (uint64_t s = allele_sig_off[a]; s < allele_sig_off[a + 1]; ++s) {
+    uint32_t curr = 0;
+    int n = 0;
+    for (uint64_t q = sig_kmer_off[s]; q < sig_kmer_off[s + 1]; ++q) {
+      int32_t wi = w[q];
+      if (wi > 0) {
+        curr = (curr * (uint32_t)n + (uint32_t)wi) / (uint32_t)(n + 1);
+        ++n;
+      }
+    }
+    if (curr > allele_cov) allele_cov = curr;
+  }
+  cov[a] = allele_cov;
+}
+
+// ---------------------------------------------------------------------------
+// K5: genotype likelihoods + posterior arg-max (var_block.hpp:224-330, 367-394)
+// ---------------------------------------------------------------------------
+MG_HD int genotype_one(const uint32_t *cov, const float *freq, int n, float err, int max_cov, bool haploid,
+                       double *lik, int *status, int *best_gt, int *gq) {
+  int ng = 0;
+  for (int i = 0; i < n; ++i)
+    if ((int)cov[i] > max_cov) lik[ng++] = 0.0;  // one {best,0} per offending allele
+  if (ng) {
+    *status = 1;
+    *best_gt = 0;
+    *gq = 0;
+    return ng;
+  }
+  if (n == 1) {
+    lik[0] = 1.0;
+    *status = 0;
+    *best_gt = 0;
+    *gq = 100;
+    return 1;
+  }
+  uint32_t tot = 0;
+  for (int i = 0; i < n; ++i) tot += cov[i];
+  if (tot == 0) {
+    lik[0] = 0.0;
+    *status = 2;
+    *best_gt = 0;
+    *gq = 0;
+    return 1;
+  }
+  GenoConsts c = geno_consts(err, n);
+  double total = 0.0;
+  for (int g1 = 0; g1 < n; ++g1) {
+    for (int g2 = g1; g2 < n; ++g2) {
+      if (haploid && g2 != g1) break;
+      double p = (g1 == g2) ? geno_hom(cov[g1], tot, freq[g1], c)
+                            : geno_het(cov[g1], cov[g2], tot, freq[g1], freq[g2], n, c);
+      lik[ng++] = p;
+      total = f64_add(total, p);
+    }
+  }
+  double best = 0.0;
+  int bi = 0;
+  for (int i = 0; i < ng; ++i) {
+    double q = lik[i] / total;
+    if (q > best) {
+      best = q;
+      bi = i;
+    }
+  }
+  *status = 0;
+  *best_gt = bi;
+  *gq = (int)round(f64_mul(best, 100.0));
+  return ng;
+}
+
+__global__ void __launch_bounds__(128) k_genotype(const uint32_t *__restrict__ cov, const float *__restrict__ freq,
+                                                 const uint64_t *__restrict__ var_allele_off,
+                                                 const uint64_t *__restrict__ lik_off, uint64_t n_variants, float err,
+                                                 int max_cov, int haploid, double *__restrict__ lik,
+                                                 int32_t *__restrict__ n_gts, int32_t *__restrict__ status,
+                                                 int32_t *__restrict__ best_gt, int32_t *__restrict__ gq) {
+  uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vi >= n_variants) return;
+  uint64_t a0 = var_allele_off[vi];
+  int n = (int)(var_allele_off[vi + 1] - a0);
+  int st, bg, q;
+  int ng = genotype_one(cov + a0, freq + a0, n, err, max_cov, haploid != 0, lik + lik_off[vi], &st, &bg, &q);
+  n_gts[vi] = ng;
+  status[vi] = st;
+  best_gt[vi] = bg;
+  gq[vi] = q;
+}
+
+// ---------------------------------------------------------------------------
+// roofline diagnostics: measured ceilings on this device (bench.py records them)
+//   k_diag_random  : independent random reads, `gran` separate 4-byte loads inside one aligned
+//                    gran*32-byte unit (1, 2 or 4 sectors)
+//   k_diag_lines   : random 128-byte lines, each fetched by 8 lanes x 16 B in ONE coalesced request
+//                    (the access pattern of k_scan)
+//   k_diag_stream  : streaming 16-byte reads
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_diag_random(const uint32_t *__restrict__ buf, uint64_t n_units, int gran,
+                                                    uint64_t per_thread, uint32_t *sink) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s = (t + 1) * GOLD;
+  uint32_t acc = 0;
+#pragma unroll 4
+  for (uint64_t i = 0; i < per_thread; ++i) {
+    s ^= s >> 29;
+    s *= 0xBF58476D1CE4E5B9ULL;
+    s ^= s >> 32;
+    uint64_t unit = mulhi64(s, n_units);  // uniform in [0, n_units)
+    const uint32_t *p = buf + unit * 8 * (uint64_t)gran;
+    acc += __ldg(p);
+    if (gran >= 2) acc += __ldg(p + 8);
+    if (gran >= 4) acc += __ldg(p + 16) + __ldg(p + 24);
+    s += GOLD;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+__global__ void __launch_bounds__(256) k_diag_lines(const uint4 *__restrict__ buf, uint64_t n_lines, uint64_t per_group,
+                                                   uint32_t *sink) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s = ((t >> 3) + 1) * GOLD;  // one random stream per 8-lane group
+  const int sub = threadIdx.x & 7;
+  uint32_t acc = 0;
+#pragma unroll 8
+  for (uint64_t i = 0; i < per_group; ++i) {
+    s ^= s >> 29;
+    s *= 0xBF58476D1CE4E5B9ULL;
+    s ^= s >> 32;
+    uint64_t line = mulhi64(s, n_lines);
+    uint4 q = __ldg(buf + line * 8 + sub);
+    acc += q.x ^ q.y ^ q.z ^ q.w;
+    s += GOLD;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+__global__ void __launch_bounds__(256) k_diag_stream(const uint4 *__restrict__ buf, uint64_t n16, uint32_t *sink) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    uint4 q = __ldg(buf + i);
+    acc += q.x ^ q.y ^ q.z ^ q.w;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
+}  // namespace mg
