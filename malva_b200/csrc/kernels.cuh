@@ -296,19 +296,33 @@ __global__ void k_refpass_short(const uint8_t *seq, uint64_t len, DevView v, uin
 // K1: sample k-mer scan (main.cpp:487-500)
 //   ref_bf.increment(kmer, c);  if (!context_bf.test_key(context)) bf.increment(kmer, c);
 // A warp owns 32 k-mers (lane i hashes k-mer i: one coalesced 16-byte load, canonical form, XXH3).
-// The probe line of each k-mer is then fetched COOPERATIVELY: in round r the four 8-lane groups of the
-// warp fetch the lines of k-mers 4r..4r+3, lane j of a group loading uint4 j of the line, so that one
-// k-mer costs exactly one fully coalesced 128-byte request.  All eight rounds are issued before the
-// first is consumed (8 x 128 B in flight per lane group).  Filter-bit test and the six key compares are
-// evaluated by the lanes that hold the data and returned to the owner lane with warp ballots.
+// The probe lines of the 32 k-mers are then copied into the warp's 4 KB shared-memory tile with
+// cp.async (LDGSTS, no register staging): in round r the four 8-lane groups of the warp copy the lines
+// of k-mers 4r..4r+3, lane j of a group moving uint4 j, so that one k-mer costs exactly one fully
+// coalesced 128-byte request, and all 32 lines are in flight together.  The tile is XOR-swizzled
+// (uint4 j of line L sits at column j ^ (L & 7)) so that every lane can then read ITS OWN line with
+// conflict-free 16-byte shared loads and do the filter-bit test and the six key compares locally.
 // The context filter, the rank directory and the counters are touched only on the ~1-4 % hit paths.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_SMEM = (SCAN_THREADS / 32) * 32 * 128;  // one 4 KB tile per warp
+
 template <int K, int REFK>
-__global__ void __launch_bounds__(256) k_scan(const uint4 *__restrict__ kmers, const uint32_t *__restrict__ counts,
-                                              uint64_t n, DevView v) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const uint4 *__restrict__ kmers,
+                                                       const uint32_t *__restrict__ counts, uint64_t n, DevView v) {
+  extern __shared__ uint4 scan_sm[];
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
   const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  uint4 *tile = scan_sm + (threadIdx.x >> 5) * 256;  // 32 lines x 8 uint4
+  const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t base = warp * 32; base < n; base += n_warps * 32) {
@@ -324,58 +338,50 @@ __global__ void __launch_bounds__(256) k_scan(const uint4 *__restrict__ kmers, c
     uint64_t idx = bf_index(v, h);
     uint32_t line = (uint32_t)(idx >> 8);  // n_lines < 2^32 (bf_bits < 2^40)
     uint32_t bit = (uint32_t)(idx & 255);
-    // ---- cooperative fetch: 8 rounds x (4 lines x 8 lanes x 16 B) ----
-    uint4 part[8];
+    __syncwarp();  // the previous iteration's reads of the tile are done
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      uint32_t l = __shfl_sync(0xffffffffu, line, 4 * r + grp);
-      part[r] = __ldg(v.lines + (uint64_t)l * LINE_U4 + sub);
+      const int L = 4 * r + grp;
+      uint32_t l = __shfl_sync(0xffffffffu, line, L);
+      cp_async16(tile_addr + (uint32_t)((L * 8 + (sub ^ (L & 7))) * 16), v.lines + (uint64_t)l * LINE_U4 + sub);
     }
-    uint32_t res = 0;  // owner's result: bit 0 filter hit, bits 1..6 key slot match, bit 7 overflow flag
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- every lane now owns line `lane` of the tile ----
+    const uint4 *mine = tile + lane * 8;
+    const int sw = lane & 7;
+    uint32_t wsel = bit >> 5;  // which of the 8 filter words
+    uint32_t fw = reinterpret_cast<const uint32_t *>(mine + ((wsel >> 2) ^ sw))[wsel & 3];
+    bool bf_hit = (fw >> (bit & 31u)) & 1u;
+    const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
+                   c3 = (uint32_t)(canon.hi >> 32);
+    int slot = -1;
+    uint32_t last_w = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int src = 4 * r + grp;
-      uint32_t b = __shfl_sync(0xffffffffu, bit, src);
-      uint32_t c0 = __shfl_sync(0xffffffffu, (uint32_t)canon.lo, src);
-      uint32_t c1 = __shfl_sync(0xffffffffu, (uint32_t)(canon.lo >> 32), src);
-      uint32_t c2 = __shfl_sync(0xffffffffu, (uint32_t)canon.hi, src);
-      uint32_t c3 = K > 0 && K <= 48 ? 0u : __shfl_sync(0xffffffffu, (uint32_t)(canon.hi >> 32), src);
-      uint4 p = part[r];
-      bool hit;
-      if (sub < 2) {  // the two uint4 that hold the 256 filter bits
-        uint32_t wsel = (b >> 5) & 3u;
-        uint32_t w = wsel == 0 ? p.x : wsel == 1 ? p.y : wsel == 2 ? p.z : p.w;
-        hit = ((b >> 7) == (uint32_t)sub) && ((w >> (b & 31u)) & 1u);
-      } else {  // a key slot
-        hit = p.x == c0 && p.y == c1 && p.z == c2 && (p.w & (uint32_t)(KEY_HI_MASK >> 32)) == c3;
-      }
-      uint32_t mh = __ballot_sync(0xffffffffu, hit);
-      uint32_t mo = __ballot_sync(0xffffffffu, sub == 7 && (p.w & OVF_FLAG_W));
-      if ((lane >> 2) == r) {  // lanes 4r..4r+3 own this round's k-mers; group g = lane & 3
-        uint32_t g8 = (mh >> (8 * (lane & 3))) & 0xFFu;
-        uint32_t o8 = (mo >> (8 * (lane & 3) + 7)) & 1u;
-        res = ((g8 & 3u) ? 1u : 0u) | ((g8 >> 2) << 1) | (o8 << 7);
-      }
+    for (int s = 0; s < LINE_KEYS; ++s) {
+      uint4 p = mine[(2 + s) ^ sw];
+      uint32_t diff = (p.x ^ c0) | (p.y ^ c1) | (p.z ^ c2) | ((p.w & (uint32_t)(KEY_HI_MASK >> 32)) ^ c3);
+      if (diff == 0) slot = s;
+      if (s == LINE_KEYS - 1) last_w = p.w;
     }
     if (!live) continue;
     // ---- ref_bf.increment ----
-    uint32_t km = (res >> 1) & 0x3Fu;
-    if (km) {
-      atomicAdd(v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)(__ffs(km) - 1), cnt);
-    } else if (res & 0x80u) {  // line overflowed at index time: the key may live in the overflow table
-      uint64_t slot = ovf_slot0(v, h);
+    if (slot >= 0) {
+      atomicAdd(v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot, cnt);
+    } else if (last_w & OVF_FLAG_W) {  // line overflowed at index time: the key may live in the overflow table
+      uint64_t os = ovf_slot0(v, h);
       while (true) {
-        u128 key = key_of(__ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + slot)));
+        u128 key = key_of(__ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + os)));
         if (key_eq(key, canon)) {
-          atomicAdd(v.ovf_counts + slot, cnt);
+          atomicAdd(v.ovf_counts + os, cnt);
           break;
         }
         if (key_empty(key)) break;
-        slot = (slot + 1) & v.ovf_mask;
+        os = (os + 1) & v.ovf_mask;
       }
     }
     // ---- bf.increment unless the context filter vetoes it ----
-    if (res & 1u) {
+    if (bf_hit) {
       u128 c43;
       uint64_t h43 = canon_hash_k<REFK>(x43, ref_k, &c43);
       if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + bf_rank_of(v, idx), cnt);

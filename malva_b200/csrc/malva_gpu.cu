@@ -428,7 +428,7 @@ static cudaError_t launch_scan(mg_ctx *c, const void *d_lohi, const void *d_coun
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
   c->launches++;
-  mg::k_scan<K, REFK><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(d_lohi),
+  mg::k_scan<K, REFK><<<grid, mg::SCAN_THREADS, mg::SCAN_SMEM, st>>>(reinterpret_cast<const uint4 *>(d_lohi),
                                             reinterpret_cast<const uint32_t *>(d_counts), n, c->view());
   return cudaGetLastError();
 }
