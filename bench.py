@@ -89,6 +89,25 @@ def make_sample_batch(torch, n, alt, ref, gen, dev):
     return x.contiguous(), counts
 
 
+def make_kmc_records(torch, x, counts, p=7):
+    """A batch of 43-mer words -> (sorted raw .kmc_suf records uint8 [n*10], prefix LUT int64 [4^p]) as KMC lays them out."""
+    lo, hi = x[:, 0], x[:, 1]
+    o1 = torch.argsort(lo ^ (-(1 << 63)), stable=True)          # unsigned order of the low word
+    o2 = torch.argsort(hi[o1], stable=True)
+    order = o1[o2]
+    lo, hi, c = lo[order], hi[order], counts[order]
+    suf_syms = REF_K - p                                         # 36 symbols = 72 bits = 9 bytes
+    prefix = hi >> (2 * suf_syms - 64)
+    lut = torch.zeros(4 ** p, dtype=torch.int64, device=x.device)
+    lut[1:] = torch.cumsum(torch.bincount(prefix, minlength=4 ** p), 0)[:-1]
+    rec = torch.empty((x.shape[0], 10), dtype=torch.uint8, device=x.device)
+    rec[:, 0] = (hi & 0xFF).to(torch.uint8)
+    for j in range(8):
+        rec[:, 1 + j] = ((lo >> (56 - 8 * j)) & 0xFF).to(torch.uint8)
+    rec[:, 9] = (c & 0xFF).to(torch.uint8)
+    return rec.reshape(-1), lut
+
+
 def kmers_to_ascii(torch, sig, k):
     """[n,2] int64 words -> uint8 [n,k] ASCII."""
     lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=sig.device)
@@ -388,14 +407,26 @@ def run_ours(args, wl, rank, local_rank, world):
     log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s: bf ones {pop_alt}, context ones {pop_ctx}, ref keys {n_keys}, "
         f"K2 reference pass {wl['ref_bases'] / refpass_ms / 1e6:.1f} Gbases/s incl. H2D")
 
-    # ---- host-side copies for the e2e leg (pinned) ----
-    hk = torch.empty((B, 2), dtype=torch.int64).pin_memory()
-    hc = torch.empty((B,), dtype=torch.int32).pin_memory()
-    hk.copy_(batches[0][0])
-    hc.copy_(batches[0][1])
-    host_pool = vb["pool"].cpu().numpy().tobytes()
-    from malva_b200.api import SignatureBatch
-    host_batch = SignatureBatch(vb["vao"], vb["aso"], vb["sko"], vb["koff"], host_pool, vb["freq"])
+    # ---- host-side inputs of the e2e leg, all in pinned memory ----
+    #  (a) the batch as raw KMC suffix records (+ prefix LUT): what malva-geno call reads from <db>.kmc_suf
+    #  (b) the same batch as packed {lo,hi} words + u32 counts (the host-decoded form)
+    #  (c) the variant CSR; outputs land in pinned buffers too
+    pin = lambda t: t.cpu().pin_memory()
+    kmc_rec, kmc_lut = make_kmc_records(torch, batches[0][0], batches[0][1])
+    h_rec = pin(kmc_rec)
+    kmc_db = dict(lut=kmc_lut.cpu().numpy().astype(np.uint64), lut_prefix_len=7, k=REF_K, counter_size=1, min_count=2,
+                  max_count=255)
+    del kmc_rec
+    hk, hc = pin(batches[0][0]), pin(batches[0][1])
+    h_in = {k2: pin(torch.from_numpy(vb[k1])) for k1, k2 in (("vao", "var_allele_off"), ("aso", "allele_sig_off"),
+                                                             ("sko", "sig_kmer_off"), ("koff", "kmer_off"),
+                                                             ("lik_off", "lik_off"), ("freq", "freq"))}
+    h_in["pool"] = pin(vb["pool"])
+    h_out = {"cov": torch.zeros(na, dtype=torch.int32).pin_memory(), "lik": torch.zeros(nl, dtype=torch.float64).pin_memory()}
+    for nme in ("n_gts", "status", "best_gt", "gq"):
+        h_out[nme] = torch.zeros(nv, dtype=torch.int32).pin_memory()
+    h_ptrs = {k2: t.data_ptr() for k2, t in {**h_in, **h_out}.items()}
+    csr_bytes = sum(t.numel() * t.element_size() for t in h_in.values())
 
     counters = [torch.as_tensor(DevArray(p, n), device=dev) for p, n in g.counter_buffers() if n] if world > 1 else []
 
@@ -444,27 +475,31 @@ def run_ours(args, wl, rank, local_rank, world):
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI, H2D and D2H inside the timed region ----
-    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 4))
-    if e2e_steps:
-        g.scan_sample_kmers_ptr(hk.data_ptr(), hc.data_ptr(), B, device=False)
-        g.sync()
-    barrier()
-    t0 = time.perf_counter()
-    g.event_record(4)
-    for i in range(e2e_steps):
-        g.scan_sample_kmers_ptr(hk.data_ptr(), hc.data_ptr(), B, device=False)
-        res = g.genotype(host_batch, 0.001, 200, False)   # syncs: results are on the host when it returns
-    g.event_record(5)
-    e2e_ms = g.event_elapsed_ms(4, 5) / max(e2e_steps, 1)
-    wall_ms = (time.perf_counter() - t0) * 1e3 / max(e2e_steps, 1)
-    e2e_ms = max(e2e_ms, wall_ms)  # host-side packing/alloc time of the call counts too
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
-    h2d = B * 20 + len(host_pool) + 8 * (len(vb["vao"]) + len(vb["aso"]) + len(vb["sko"]) + len(vb["koff"]) +
-                                         len(vb["lik_off"])) + 4 * na
+    def e2e_leg(scan):
+        steps = 0 if args.no_e2e else max(3, min(args.steps, 6))
+        if not steps:
+            return None
+        scan()
+        g.genotype_host(h_ptrs, nv, 0.001, 200, False)
+        barrier()
+        t0 = time.perf_counter()
+        g.event_record(4)
+        for _ in range(steps):
+            scan()                                            # asynchronous, chunked, double-buffered H2D + K1
+            g.genotype_host(h_ptrs, nv, 0.001, 200, False)    # H2D CSR, K4+K5, D2H results; returns when they landed
+        g.event_record(5)
+        ms = max(g.event_elapsed_ms(4, 5), (time.perf_counter() - t0) * 1e3) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    g.kmc_open(kmc_db)
+    e2e_ms = e2e_leg(lambda: g.scan_kmc_records(h_rec.data_ptr(), 0, B, sync=False))
+    e2e_packed_ms = e2e_leg(lambda: g.scan_sample_kmers_ptr(hk.data_ptr(), hc.data_ptr(), B, device=False))
     d2h = 4 * na + 16 * nv + 8 * nl
+    h2d = B * 10 + csr_bytes
+    h2d_packed = B * 20 + csr_bytes
 
     if rank != 0:
         if world > 1:
@@ -474,11 +509,12 @@ def run_ours(args, wl, rank, local_rank, world):
     peak, peak_src = measured_peaks()
     k1_ms = float(np.mean(scan_ms))
     achieved = B * ALGO_BYTES_PER_KMER / (k1_ms * 1e-3) / 1e9
-    rand_gbs = stream_gbs = None
+    rand_gbs = stream_gbs = line_gbs = None
     if not args.no_diag:
         try:
-            rand_gbs = diag_bandwidth(local_rank, 0, 8 << 30, 3)
-            stream_gbs = diag_bandwidth(local_rank, 1, 8 << 30, 3)
+            rand_gbs = diag_bandwidth(local_rank, 0, 16 << 30, 3)
+            line_gbs = diag_bandwidth(local_rank, 4, 16 << 30, 3)
+            stream_gbs = diag_bandwidth(local_rank, 1, 16 << 30, 3)
         except Exception as e:  # noqa: BLE001
             log("diag_bandwidth failed:", e)
     traffic = None
@@ -513,16 +549,25 @@ def run_ours(args, wl, rank, local_rank, world):
                       "k2_reference_pass_incl_h2d": refpass_ms},
         "ref_bases_per_sec_incl_h2d": wl["ref_bases"] / (refpass_ms * 1e-3),
         "index": {"bf_ones": pop_alt, "context_ones": pop_ctx, "ref_keys": n_keys},
-        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "variants_per_sec": world * nv / (e2e_ms * 1e-3),
-                "note": "per step: mg_scan_sample_kmers(pinned host batch) + mg_genotype(host CSR) -> host results"},
+        "e2e": None if e2e_ms is None else {
+            "value": world * B / (e2e_ms * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "variants_per_sec": world * nv / (e2e_ms * 1e-3),
+            "h2d_GBps": h2d / (e2e_ms * 1e-3) / 1e9,
+            "note": "per step: mg_scan_kmc_records(pinned raw .kmc_suf records, 10 B per 43-mer, decoded on the device) + "
+                    "mg_genotype(pinned host CSR) -> pinned host results",
+            "packed128": {"value": world * B / (e2e_packed_ms * 1e-3), "ms_per_step": e2e_packed_ms,
+                          "h2d_bytes_per_step": h2d_packed,
+                          "note": "same step with host-decoded {lo,hi} words + u32 counts (20 B per 43-mer) through "
+                                  "mg_scan_sample_kmers"}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_scan<35,43>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
-                     "measured_random_32B_sector_GBps": rand_gbs, "measured_stream_read_GBps": stream_gbs,
-                     "frac_of_random_sector_ceiling": (achieved / rand_gbs) if rand_gbs else None},
+                     "measured_random_32B_sector_GBps": rand_gbs, "measured_random_128B_line_GBps": line_gbs,
+                     "measured_stream_read_GBps": stream_gbs,
+                     "frac_of_random_sector_ceiling": (achieved / rand_gbs) if rand_gbs else None,
+                     "lines_per_sec_vs_ceiling": (B / (k1_ms * 1e-3)) / (line_gbs * 1e9 / 128) if line_gbs else None},
     }
     if cpu:
         line["cpu_baseline"] = cpu

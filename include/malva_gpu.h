@@ -67,6 +67,15 @@ int mg_finalize_context(mg_ctx *ctx);
 int mg_scan_sample_kmers(mg_ctx *ctx, const uint64_t *lohi, const uint32_t *counts, uint64_t n);
 /* same with DEVICE-resident inputs (GPU-side producers, kernel-only timing)  */
 int mg_scan_sample_kmers_device(mg_ctx *ctx, const void *d_lohi, const void *d_counts, uint64_t n);
+/* KMC database ingestion without a host-side decode (replaces CKMCFile::ReadNextKmer + CKmerAPI::to_string,
+ * main.cpp:482-490).  mg_kmc_open takes the parameters and the prefix LUT of <db>.kmc_pre (lut[j] = number of
+ * records before prefix index j; n_lut a multiple of 4^lut_prefix_len); mg_scan_kmc_records takes raw records of
+ * <db>.kmc_suf (HOST memory, the bytes after the 4-byte "KMCS" marker): n whole records starting at global
+ * record index first_record.  Records whose count is outside [min_count, max_count] are skipped like the KMC API
+ * does.  10 bytes per 43-mer over PCIe instead of 20.                                                        */
+int mg_kmc_open(mg_ctx *ctx, const uint64_t *lut, uint64_t n_lut, uint32_t lut_prefix_len, uint32_t kmer_len,
+                uint32_t counter_size, uint32_t min_count, uint64_t max_count);
+int mg_scan_kmc_records(mg_ctx *ctx, const uint8_t *records, uint64_t first_record, uint64_t n);
 int mg_sync(mg_ctx *ctx);
 
 /* set_coverages + VB::genotype + arg-max/GQ of VB::output_variants
@@ -135,8 +144,9 @@ int mg_genotype_kernel_ms(mg_ctx *ctx, float *ms3);
 /* kernels launched by this context so far */
 int mg_launch_count(mg_ctx *ctx, uint64_t *n);
 /* measured ceilings over `bytes` of HBM, GB/s of useful bytes, best of reps: mode 0 / 2 / 3 = independent
- * random reads of 1 / 2 / 4 separate sectors of an aligned 32 / 64 / 128-byte unit; mode 4 = random 128-byte
- * lines fetched by 8 lanes in one coalesced request (the sample scan's pattern); mode 1 = streaming reads */
+ * random reads of 1 / 2 / 4 separate sectors of an aligned 32 / 64 / 128-byte unit; mode 4 / 5 / 6 = random
+ * aligned 128 / 64 / 32-byte units fetched by 8 / 4 / 2 lanes in one coalesced request (mode 4 is the sample
+ * scan's pattern); mode 1 = streaming reads */
 int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps, double *gbs);
 
 /* pinned host memory for the sample stream */

@@ -68,6 +68,9 @@ SYMBOLS = {
     "mg_finalize_context": (C.c_int, [C.c_void_p]),
     "mg_scan_sample_kmers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "mg_scan_sample_kmers_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "mg_kmc_open": (C.c_int, [C.c_void_p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                              C.c_uint64]),
+    "mg_scan_kmc_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "mg_sync": (C.c_int, [C.c_void_p]),
     "mg_genotype": (C.c_int, [C.c_void_p, C.POINTER(VariantBatch), C.POINTER(GenotypeOut), C.c_float, C.c_int,
                               C.c_int]),

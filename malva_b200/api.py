@@ -194,6 +194,23 @@ class MalvaGpu:
         fn = self._L.mg_scan_sample_kmers_device if device else self._L.mg_scan_sample_kmers
         check(fn(self._h, lohi_ptr, counts_ptr, n))
 
+    def kmc_open(self, db: dict) -> None:
+        """db = malva_b200.kmc.open_kmc_db(prefix): hand the prefix LUT + header of a KMC database to the device."""
+        lut = np.ascontiguousarray(db["lut"], dtype=np.uint64)
+        check(self._L.mg_kmc_open(self._h, _p(lut, _lib.u64p), len(lut), db["lut_prefix_len"], db["k"],
+                                  db["counter_size"], db["min_count"], db["max_count"]))
+
+    def scan_kmc_records(self, records, first_record: int = 0, n: int | None = None, sync: bool = True) -> None:
+        """records: uint8 array (or host address) of whole .kmc_suf records, decoded on the device."""
+        if isinstance(records, np.ndarray):
+            records = np.ascontiguousarray(records, dtype=np.uint8)
+            ptr = records.ctypes.data
+        else:
+            ptr = int(records)
+        check(self._L.mg_scan_kmc_records(self._h, ptr, first_record, n))
+        if sync:
+            self.sync()
+
     def sync(self) -> None:
         check(self._L.mg_sync(self._h))
 
@@ -269,6 +286,19 @@ class MalvaGpu:
         ms = C.c_float(0)
         check(self._L.mg_event_elapsed_ms(self._h, a, b, C.byref(ms)))
         return ms.value
+
+    def genotype_host(self, ptrs: dict, n_variants: int, error_rate: float, max_coverage: int, haploid: bool) -> None:
+        """mg_genotype on caller-owned HOST buffers given by address (e.g. pinned memory), keyed like the fields of
+        mg_variant_batch / mg_genotype_out.  Results are in the output buffers when this returns."""
+        c = lambda name, typ: C.cast(C.c_void_p(ptrs[name]), typ)
+        vb = _lib.VariantBatch(n_variants, c("var_allele_off", _lib.u64p), c("allele_sig_off", _lib.u64p),
+                               c("sig_kmer_off", _lib.u64p), c("kmer_off", _lib.u64p), C.c_void_p(ptrs["pool"]),
+                               c("freq", _lib.f32p))
+        out = _lib.GenotypeOut(c("cov", _lib.u32p), c("n_gts", _lib.i32p), c("status", _lib.i32p),
+                               c("best_gt", _lib.i32p), c("gq", _lib.i32p), c("lik_off", _lib.u64p),
+                               c("lik", _lib.f64p))
+        check(self._L.mg_genotype(self._h, C.byref(vb), C.byref(out), C.c_float(error_rate), int(max_coverage),
+                                  int(bool(haploid))))
 
     def genotype_device(self, ptrs: dict, dims: tuple, error_rate: float, max_coverage: int, haploid: bool) -> None:
         """ptrs: device addresses keyed like mg_variant_batch / mg_genotype_out fields; dims = (nv, na, ns, nk)."""

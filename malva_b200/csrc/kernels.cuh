@@ -314,9 +314,37 @@ __device__ __forceinline__ void cp_async_wait_all() {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_SMEM = (SCAN_THREADS / 32) * 32 * 128;  // one 4 KB tile per warp
 
-template <int K, int REFK>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const uint4 *__restrict__ kmers,
-                                                       const uint32_t *__restrict__ counts, uint64_t n, DevView v) {
+// Where the sample k-mers come from.  MODE 0: packed {lo,hi} words + u32 counts.  MODE 1: raw records of a
+// KMC database suffix file (.kmc_suf): (ref_k - p)/4 suffix bytes (2-bit codes, first base most significant)
+// + counter_size little-endian count bytes; the p-symbol prefix of record g is the LUT bucket that contains g
+// (lut[j] = records before prefix j; listing order = record order).  Decoding them here halves the PCIe
+// bytes per k-mer (10 B instead of 20 B for k = 43) and removes the host-side CKmerAPI::to_string pass.
+struct ScanSrc {
+  const uint4 *kmers;
+  const uint32_t *counts;
+  const uint8_t *recs;  // 16-byte aligned, padded by 16 bytes
+  const uint64_t *lut;  // n_lut entries + a guard of ~0
+  uint64_t first_rec;   // global index of recs[0]
+  uint32_t n_lut, prefix_mask;
+  int prefix_len, suf_bytes, counter_size;
+  uint32_t min_count;
+  uint64_t max_count;
+};
+
+__device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_lut, uint64_t g) {
+  uint32_t lo = 0, hi = n_lut;  // largest j with lut[j] <= g (lut[0] == 0, lut[n_lut] == ~0)
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(lut + mid) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+template <int K, int REFK, int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, DevView v) {
   extern __shared__ uint4 scan_sm[];
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
@@ -327,12 +355,53 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const uint4 *__restrict__
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t base = warp * 32; base < n; base += n_warps * 32) {
     const uint64_t i = base + lane;
-    const bool live = i < n;
-    uint4 q = live ? __ldg(kmers + i) : make_uint4(0, 0, 0, 0);
-    uint32_t cnt = live ? __ldg(counts + i) : 0u;
+    bool live = i < n;
+    uint32_t cnt;
     u128 x43, canon;
-    x43.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
-    x43.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+    if constexpr (MODE == 0) {
+      uint4 q = live ? __ldg(src.kmers + i) : make_uint4(0, 0, 0, 0);
+      cnt = live ? __ldg(src.counts + i) : 0u;
+      x43.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+      x43.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+    } else {
+      // stage the warp's 32 records (contiguous bytes) in its shared-memory tile, then decode one per lane
+      const int rec = src.suf_bytes + src.counter_size;
+      const uint64_t byte0 = base * (uint64_t)rec, start = byte0 & ~3ull;
+      const int n_words = (int)((byte0 - start) + 32u * (uint32_t)rec + 3u) >> 2;
+      __syncwarp();
+      uint32_t *stage = reinterpret_cast<uint32_t *>(tile);
+      for (int w = lane; w < n_words; w += 32) stage[w] = __ldg(reinterpret_cast<const uint32_t *>(src.recs + start) + w);
+      __syncwarp();
+      const uint8_t *rb = reinterpret_cast<const uint8_t *>(stage) + (byte0 - start) + (uint32_t)lane * (uint32_t)rec;
+      u128 suf = {0, 0};
+      for (int j = 0; j < src.suf_bytes; ++j) {
+        suf.hi = (suf.hi << 8) | (suf.lo >> 56);
+        suf.lo = (suf.lo << 8) | rb[j];
+      }
+      uint64_t c64 = src.counter_size ? 0 : 1;
+      for (int j = 0; j < src.counter_size; ++j) c64 |= (uint64_t)rb[src.suf_bytes + j] << (8 * j);
+      __syncwarp();  // the tile is reused for the probe lines below
+      // prefix of each record: one LUT search per warp in the common case (a prefix bucket spans many records)
+      const uint64_t g = src.first_rec + i;
+      const uint64_t g_first = src.first_rec + base;
+      const uint64_t g_last = src.first_rec + (base + 31 < n ? base + 31 : n - 1);
+      uint32_t pj = lut_bucket(src.lut, src.n_lut, g_first);
+      if (__ldg(src.lut + pj + 1) <= g_last) pj = lut_bucket(src.lut, src.n_lut, live ? g : g_first);
+      u128 pre = {(uint64_t)(pj & src.prefix_mask), 0};
+      const int sh = 8 * src.suf_bytes;  // the suffix holds 4 * suf_bytes symbols
+      if (sh >= 64) {
+        pre.hi = pre.lo << (sh - 64);
+        pre.lo = 0;
+      } else {
+        pre.hi = sh ? (pre.lo >> (64 - sh)) : 0;
+        pre.lo <<= sh;
+      }
+      x43.lo = pre.lo | suf.lo;
+      x43.hi = pre.hi | suf.hi;
+      // CKMCFile::ReadNextKmer skips records whose count is outside [min_count, max_count]
+      if (c64 < src.min_count || c64 > src.max_count) live = false;
+      cnt = (uint32_t)c64;
+    }
     u128 x35 = mask128(shr128(x43, 2 * tail), 2 * k);
     uint64_t h = canon_hash_k<K>(x35, k, &canon);
     uint64_t idx = bf_index(v, h);
@@ -572,19 +641,20 @@ __global__ void __launch_bounds__(256) k_diag_random(const uint32_t *__restrict_
   }
   if (acc == 0x12345678u) *sink = acc;
 }
-__global__ void __launch_bounds__(256) k_diag_lines(const uint4 *__restrict__ buf, uint64_t n_lines, uint64_t per_group,
-                                                   uint32_t *sink) {
+__global__ void __launch_bounds__(256) k_diag_lines(const uint4 *__restrict__ buf, uint64_t n_units, int lanes_log2,
+                                                   uint64_t per_group, uint32_t *sink) {
+  // groups of 2^lanes_log2 lanes (8 / 4 / 2) read one random aligned unit of 128 / 64 / 32 bytes per instruction
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t s = ((t >> 3) + 1) * GOLD;  // one random stream per 8-lane group
-  const int sub = threadIdx.x & 7;
+  uint64_t s = ((t >> lanes_log2) + 1) * GOLD;  // one random stream per lane group
+  const int sub = threadIdx.x & ((1 << lanes_log2) - 1);
   uint32_t acc = 0;
 #pragma unroll 8
   for (uint64_t i = 0; i < per_group; ++i) {
     s ^= s >> 29;
     s *= 0xBF58476D1CE4E5B9ULL;
     s ^= s >> 32;
-    uint64_t line = mulhi64(s, n_lines);
-    uint4 q = __ldg(buf + line * 8 + sub);
+    uint64_t unit = mulhi64(s, n_units);
+    uint4 q = __ldg(buf + (unit << lanes_log2) + sub);
     acc += q.x ^ q.y ^ q.z ^ q.w;
     s += GOLD;
   }

@@ -79,11 +79,17 @@ struct mg_ctx {
   uint32_t *d_stage_c[2] = {nullptr, nullptr};
   int next_stage = 0;
   int scan_ctas_per_sm = 8;
+  uint64_t *kmc_lut = nullptr;  // device copy of the KMC prefix LUT (+ guard)
+  uint32_t kmc_n_lut = 0, kmc_min = 0;
+  uint64_t kmc_max = 0;
+  int kmc_prefix_len = 0, kmc_suf_bytes = 0, kmc_counter_size = 0;
   uint64_t launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
   cudaEvent_t tj = nullptr;
   cudaEvent_t ge[4] = {nullptr, nullptr, nullptr, nullptr};
   void *geno_scratch = nullptr;  // per-k-mer weights + ref flags of mg_genotype
   uint64_t geno_scratch_bytes = 0;
+  void *geno_arena = nullptr;  // device image of the last mg_genotype batch (grow-only)
+  uint64_t geno_arena_bytes = 0;
   cudaEvent_t evs[64] = {};
 
   DevView view() const {
@@ -200,6 +206,8 @@ extern "C" void mg_destroy(mg_ctx *c) {
   cudaFree(c->ovf_counts);
   cudaFree(c->d_scalars);
   cudaFree(c->geno_scratch);
+  cudaFree(c->geno_arena);
+  cudaFree(c->kmc_lut);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->d_stage_k[i]);
     cudaFree(c->d_stage_c[i]);
@@ -421,26 +429,33 @@ extern "C" int mg_finalize_context(mg_ctx *c) {
   return MG_OK;
 }
 
-template <int K, int REFK>
-static cudaError_t launch_scan(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
+template <int K, int REFK, int MODE>
+static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t st) {
   uint64_t want = (n + 255) / 256;  // one warp per 32 k-mers, 8 warps per CTA
   uint64_t cap = (uint64_t)c->sms * (uint64_t)c->scan_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
   c->launches++;
-  mg::k_scan<K, REFK><<<grid, mg::SCAN_THREADS, mg::SCAN_SMEM, st>>>(reinterpret_cast<const uint4 *>(d_lohi),
-                                            reinterpret_cast<const uint32_t *>(d_counts), n, c->view());
+  mg::k_scan<K, REFK, MODE><<<grid, mg::SCAN_THREADS, mg::SCAN_SMEM, st>>>(src, n, c->view());
   return cudaGetLastError();
 }
 
-static int scan_device(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
+template <int MODE>
+static int scan_src(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t st) {
   cudaError_t e;
   if (c->k == 35 && c->ref_k == 43)
-    e = launch_scan<35, 43>(c, d_lohi, d_counts, n, st);
+    e = launch_scan<35, 43, MODE>(c, src, n, st);
   else
-    e = launch_scan<0, 0>(c, d_lohi, d_counts, n, st);
+    e = launch_scan<0, 0, MODE>(c, src, n, st);
   if (e != cudaSuccess) return set_err(MG_ERR_CUDA, "k_scan launch -> %s", cudaGetErrorString(e));
   return MG_OK;
+}
+
+static int scan_device(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
+  mg::ScanSrc src = {};
+  src.kmers = reinterpret_cast<const uint4 *>(d_lohi);
+  src.counts = reinterpret_cast<const uint32_t *>(d_counts);
+  return scan_src<0>(c, src, n, st);
 }
 
 extern "C" int mg_scan_sample_kmers_device(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n) {
@@ -457,7 +472,7 @@ extern "C" int mg_scan_sample_kmers(mg_ctx *c, const uint64_t *lohi, const uint3
   CU(cudaSetDevice(c->device));
   for (int i = 0; i < 2; ++i) {
     if (!c->d_stage_k[i]) {
-      CU(cudaMalloc(&c->d_stage_k[i], STAGE_KMERS * 16));
+      CU(cudaMalloc(&c->d_stage_k[i], STAGE_KMERS * 16 + 64));
       CU(cudaMalloc(&c->d_stage_c[i], STAGE_KMERS * 4));
     }
   }
@@ -470,6 +485,69 @@ extern "C" int mg_scan_sample_kmers(mg_ctx *c, const uint64_t *lohi, const uint3
     CU(cudaMemcpyAsync(c->d_stage_k[s], lohi + 2 * o, m * 16, cudaMemcpyHostToDevice, c->stream[s]));
     CU(cudaMemcpyAsync(c->d_stage_c[s], counts + o, m * 4, cudaMemcpyHostToDevice, c->stream[s]));
     int rc = scan_device(c, c->d_stage_k[s], c->d_stage_c[s], m, c->stream[s]);
+    if (rc) return rc;
+  }
+  return MG_OK;
+}
+
+// ---- KMC database ingestion without a host-side decode (call sites main.cpp:482-490) ----
+extern "C" int mg_kmc_open(mg_ctx *c, const uint64_t *lut, uint64_t n_lut, uint32_t lut_prefix_len, uint32_t kmer_len,
+                           uint32_t counter_size, uint32_t min_count, uint64_t max_count) {
+  if (!c || !lut || n_lut == 0) return set_err(MG_ERR_ARG, "NULL argument");
+  if ((int)kmer_len != c->ref_k)
+    return set_err(MG_ERR_ARG, "KMC database holds %u-mers but ref_k is %d (the reference would overrun its buffer)",
+                   kmer_len, c->ref_k);
+  if (lut_prefix_len > 15 || lut_prefix_len >= kmer_len || (kmer_len - lut_prefix_len) % 4 != 0 || counter_size > 8)
+    return set_err(MG_ERR_ARG, "unsupported KMC layout (prefix %u, counter %u bytes)", lut_prefix_len, counter_size);
+  if (n_lut % (1ull << (2 * lut_prefix_len)) != 0 || n_lut > 0x7FFFFFFFull)
+    return set_err(MG_ERR_ARG, "LUT size %llu is not a multiple of 4^%u", (unsigned long long)n_lut, lut_prefix_len);
+  CU(cudaSetDevice(c->device));
+  int rc = mg_sync(c);
+  if (rc) return rc;
+  cudaFree(c->kmc_lut);
+  c->kmc_lut = nullptr;
+  CU(cudaMalloc(&c->kmc_lut, (n_lut + 1) * 8));
+  CU(cudaMemcpy(c->kmc_lut, lut, n_lut * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemset(c->kmc_lut + n_lut, 0xFF, 8));
+  c->kmc_n_lut = (uint32_t)n_lut;
+  c->kmc_prefix_len = (int)lut_prefix_len;
+  c->kmc_suf_bytes = (int)((kmer_len - lut_prefix_len) / 4);
+  c->kmc_counter_size = (int)counter_size;
+  c->kmc_min = min_count;
+  c->kmc_max = max_count;
+  return MG_OK;
+}
+
+extern "C" int mg_scan_kmc_records(mg_ctx *c, const uint8_t *records, uint64_t first_record, uint64_t n) {
+  if (!c || (!records && n)) return set_err(MG_ERR_ARG, "NULL argument");
+  if (!c->kmc_lut) return set_err(MG_ERR_STATE, "mg_scan_kmc_records before mg_kmc_open");
+  if (!c->alt_final) return set_err(MG_ERR_STATE, "scan before mg_finalize_alt (BF::increment is a no-op in write mode)");
+  CU(cudaSetDevice(c->device));
+  const uint64_t rec = (uint64_t)(c->kmc_suf_bytes + c->kmc_counter_size);
+  if (rec > 16) return set_err(MG_ERR_ARG, "KMC record of %llu bytes does not fit the staging buffers", (unsigned long long)rec);
+  for (int i = 0; i < 2; ++i) {
+    if (!c->d_stage_k[i]) {
+      CU(cudaMalloc(&c->d_stage_k[i], STAGE_KMERS * 16 + 64));
+      CU(cudaMalloc(&c->d_stage_c[i], STAGE_KMERS * 4));
+    }
+  }
+  for (uint64_t o = 0; o < n; o += STAGE_KMERS) {
+    uint64_t m = n - o < STAGE_KMERS ? n - o : STAGE_KMERS;
+    int s = c->next_stage;
+    c->next_stage ^= 1;
+    CU(cudaMemcpyAsync(c->d_stage_k[s], records + o * rec, m * rec, cudaMemcpyHostToDevice, c->stream[s]));
+    mg::ScanSrc src = {};
+    src.recs = reinterpret_cast<const uint8_t *>(c->d_stage_k[s]);
+    src.lut = c->kmc_lut;
+    src.first_rec = first_record + o;
+    src.n_lut = c->kmc_n_lut;
+    src.prefix_mask = (uint32_t)((1ull << (2 * c->kmc_prefix_len)) - 1);
+    src.prefix_len = c->kmc_prefix_len;
+    src.suf_bytes = c->kmc_suf_bytes;
+    src.counter_size = c->kmc_counter_size;
+    src.min_count = c->kmc_min;
+    src.max_count = c->kmc_max;
+    int rc = scan_src<1>(c, src, m, c->stream[s]);
     if (rc) return rc;
   }
   return MG_OK;
@@ -609,9 +687,15 @@ extern "C" int mg_genotype(mg_ctx *c, const mg_variant_batch *in, const mg_genot
            o_ko = o_sko + al((ns + 1) * 8), o_lo = o_ko + al((nk + 1) * 8), o_freq = o_lo + al((nv + 1) * 8),
            o_pool = o_freq + al(na * 4), o_cov = o_pool + al(pool_bytes), o_i32 = o_cov + al(na * 4),
            o_lik = o_i32 + al(nv * 16), total = o_lik + al(nl * 8) + 256;
-  DevFree arena;
-  CU(cudaMalloc(&arena.p, total));
-  uint8_t *d = (uint8_t *)arena.p;
+  if (c->geno_arena_bytes < total) {  // grow-only device arena, reused across calls
+    cudaFree(c->geno_arena);
+  cudaFree(c->kmc_lut);
+    c->geno_arena = nullptr;
+    c->geno_arena_bytes = 0;
+    CU(cudaMalloc(&c->geno_arena, total + total / 4));
+    c->geno_arena_bytes = total + total / 4;
+  }
+  uint8_t *d = (uint8_t *)c->geno_arena;
   CU(cudaMemcpyAsync(d + o_vao, in->var_allele_off, (nv + 1) * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d + o_aso, in->allele_sig_off, (na + 1) * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d + o_sko, in->sig_kmer_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -761,10 +845,11 @@ extern "C" int mg_launch_count(mg_ctx *c, uint64_t *n) {
 
 // measured ceilings on `device`, GB/s of useful bytes, best of `reps`:
 //   mode 0 / 2 / 3 : independent random reads of 1 / 2 / 4 separate sectors of an aligned 32 / 64 / 128-byte unit
-//   mode 4         : random 128-byte lines, each fetched by 8 lanes in one coalesced request (k_scan's pattern)
+//   mode 4 / 5 / 6 : random aligned 128 / 64 / 32-byte units, each fetched by 8 / 4 / 2 lanes in one coalesced
+//                    request (mode 4 is k_scan's pattern)
 //   mode 1         : streaming 16-byte reads
 extern "C" int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps, double *gbs) {
-  if (!gbs || bytes < (1ull << 20) || reps < 1 || mode < 0 || mode > 4) return set_err(MG_ERR_ARG, "bad argument");
+  if (!gbs || bytes < (1ull << 20) || reps < 1 || mode < 0 || mode > 6) return set_err(MG_ERR_ARG, "bad argument");
   CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -785,9 +870,11 @@ extern "C" int mg_diag_bandwidth(int device, int mode, uint64_t bytes, int reps,
     if (mode == 1) {
       mg::k_diag_stream<<<grid, 256>>>((const uint4 *)buf.p, bytes / 16, (uint32_t *)sink.p);
       useful = (double)bytes;
-    } else if (mode == 4) {
-      mg::k_diag_lines<<<grid * 4, 256>>>((const uint4 *)buf.p, bytes / 128, per_thread, (uint32_t *)sink.p);
-      useful = (double)grid * 4 * 256 / 8 * (double)per_thread * 128.0;
+    } else if (mode >= 4) {  // 4: 128 B by 8 lanes, 5: 64 B by 4 lanes, 6: 32 B by 2 lanes
+      const int ll = mode == 4 ? 3 : mode == 5 ? 2 : 1;
+      mg::k_diag_lines<<<grid * 4, 256>>>((const uint4 *)buf.p, bytes / (16ull << ll), ll, per_thread,
+                                          (uint32_t *)sink.p);
+      useful = (double)grid * 4 * 256 * (double)per_thread * 16.0;
     } else {
       mg::k_diag_random<<<grid * 4, 256>>>((const uint32_t *)buf.p, bytes / (32 * (uint64_t)gran), gran, per_thread,
                                            (uint32_t *)sink.p);

@@ -222,3 +222,32 @@ def read_kmc_db(prefix: str) -> Tuple[np.ndarray, np.ndarray, int]:
         vals.append(((pi % single) << (2 * (k - p))) | int.from_bytes(suf[o:o + sb], "big"))
         cts.append(c)
     return ints_to_packed(vals), np.array(cts, dtype=np.uint32), k
+
+
+def open_kmc_db(prefix: str) -> dict:
+    """Raw view of a KMC database for device-side decoding (``mg_kmc_open`` / ``mg_scan_kmc_records``):
+    the prefix LUT, the header fields and the suffix records as a flat uint8 array (no per-record work)."""
+    pre = open(prefix + ".kmc_pre", "rb").read()
+    if pre[:4] != b"KMCP" or pre[-4:] != b"KMCP":
+        raise ValueError("bad .kmc_pre markers")
+    version, hoff = struct.unpack("<II", pre[-12:-4])
+    if version not in (0, 0x200):
+        raise ValueError(f"unsupported KMC version {version:#x}")
+    h = pre[len(pre) - 8 - hoff:]
+    if version == 0x200:
+        k, _mode, csz, p, sig, minc, maxc, total = struct.unpack("<7IQ", h[:36])
+        sigmap = (4 ** sig + 1) * 4
+    else:
+        k, _mode, csz, p, minc, maxc, total = struct.unpack("<6IQ", h[:32])
+        sigmap = 0
+    lut_bytes = len(pre) - 4 - 8 - hoff - sigmap
+    lut = np.frombuffer(pre, dtype="<u8", count=lut_bytes // 8, offset=4)
+    single = 4 ** p
+    n_lut = (len(lut) // single) * single
+    rec = (k - p) // 4 + csz
+    suf = np.memmap(prefix + ".kmc_suf", dtype=np.uint8, mode="r")
+    if bytes(suf[:4]) != b"KMCS":
+        raise ValueError("bad .kmc_suf marker")
+    records = suf[4:4 + total * rec]
+    return dict(k=k, lut=np.ascontiguousarray(lut[:n_lut]), lut_prefix_len=p, counter_size=csz, min_count=minc,
+                max_count=maxc, total=total, record_bytes=rec, records=records)

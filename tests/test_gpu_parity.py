@@ -192,3 +192,47 @@ def test_scan_large_batch_properties(oracle_lib):
     assert np.array_equal((once[0] * 2) & 0xFFFF, twice[0])
     assert np.array_equal(once[1] * 2, twice[1])
     assert once[0].sum() > 0 and once[1].sum() > 0
+
+
+@pytest.mark.parametrize("version,p,k,ref_k", [(0x200, 7, 35, 43), (0, 3, 35, 43), (0x200, 3, 31, 39), (0, 5, 36, 41)])
+def test_kmc_records_decoded_on_device(oracle_lib, tmp_path, version, p, k, ref_k):
+    """mg_scan_kmc_records (raw .kmc_suf records + prefix LUT, decoded by the scan kernel) must leave the same
+    state as the oracle scanning the KMC listing -- including the [min_count, max_count] record filter."""
+    rng = random.Random(4000 + p + k)
+    bits = 1 << 20
+    genome = util.make_genome(rng, 20000)
+    nested, freqs = util.synth_signatures(rng, genome, k, 300)
+    ks, fl = util.flatten(nested)
+    words, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, 5000)
+    counts = np.minimum(counts, 255).astype(np.uint32)
+    counts[::7] = 2          # below min_count=3: skipped by ReadNextKmer
+    counts[::11] = 250       # above max_count=200: skipped too
+    prefix = str(tmp_path / "db")
+    kmc.write_kmc_db(prefix, packed, counts, ref_k, lut_prefix_len=p, version=version, min_count=3, max_count=200)
+    listed, lcounts, kk = kmc.read_kmc_db(prefix)
+    assert kk == ref_k and 0 < len(listed) < len(packed)
+    db = kmc.open_kmc_db(prefix)
+    assert db["total"] == len(packed)
+    g, o = MalvaGpu(k=k, ref_k=ref_k, bf_bits=bits), util.OracleRun(oracle_lib, k, ref_k, bits)
+    try:
+        for x in (g, o):
+            x.add_signatures(ks, fl)
+            x.finalize_alt()
+            x.scan_reference(genome)
+            x.finalize_context()
+        o.scan_sample_kmers(listed, lcounts)
+        g.kmc_open(db)
+        rec = db["record_bytes"]
+        half = (db["total"] // 2 // 32) * 32 + 5   # two calls, the second starting inside a warp tile
+        g.scan_kmc_records(db["records"][:half * rec], 0, half)
+        g.scan_kmc_records(db["records"][half * rec:], half, db["total"] - half)
+        assert np.array_equal(g.bf_counts(), o.bf_counts())
+        assert np.array_equal(g.get_counts(ks, [1] * len(ks)), o.get_counts(ks, [1] * len(ks)))
+        assert o.bf_counts().sum() > 0
+        with pytest.raises(MalvaGpuError):      # a database of the wrong k-mer length is refused
+            bad = dict(db)
+            bad["k"] = ref_k + 4
+            g.kmc_open(bad)
+    finally:
+        g.close()
+        o.close()
