@@ -375,7 +375,11 @@ def run_ours(args, wl, rank, local_rank, world):
     del rb
     n_plant = min(200_000, wl["ref_bases"] // 1000)
     plant = kmers_to_ascii(torch, alt[:n_plant], K)
-    ppos = torch.randint(100, wl["ref_bases"] - 100, (n_plant,), generator=gen, device=dev)
+    # one plant per stride, jittered: the planted windows never overlap, so the scatter below is deterministic
+    # and every rank builds the same context filter
+    stride = (wl["ref_bases"] - 200) // n_plant
+    ppos = 100 + torch.arange(n_plant, device=dev) * stride + \
+        torch.randint(0, max(1, stride - K), (n_plant,), generator=gen, device=dev)
     ref_seq[(ppos[:, None] + torch.arange(K, device=dev)[None, :]).reshape(-1)] = plant.reshape(-1)
     ref_host = ref_seq.cpu().numpy().tobytes()
     del ref_seq

@@ -133,12 +133,23 @@ int mg_index_stats(mg_ctx *ctx, uint64_t *stats, int n);
  * replicas: [0] one per set bit of bf, [1] one per key slot of the probe lines, [2] overflow table */
 int mg_counter_buffers(mg_ctx *ctx, void **d_ptr /*[3]*/, uint64_t *n /*[3]*/);
 
+/* index image for the index file (BF::operator>> / KMAP::operator>>, main.cpp:406-412; loading :455-461).
+ * Filters travel as sorted lists of set-bit indices (the reference writes the raw 2 x bf_bits/8 bytes), ref_bf
+ * as its packed canonical keys.  Call with out == NULL to get the count first.  Import the bits of bf (which=0)
+ * and the keys (mg_add_signatures_packed, is_ref=1) BEFORE mg_finalize_alt, the bits of context_bf after it. */
+int mg_export_set_bits(mg_ctx *ctx, int which, uint64_t *out, uint64_t cap, uint64_t *n);
+int mg_import_set_bits(mg_ctx *ctx, int which, const uint64_t *idx, uint64_t n);
+int mg_export_ref_keys(mg_ctx *ctx, uint64_t *lohi, uint64_t cap, uint64_t *n);
+
 /* ------------------------------ measurement ------------------------------ */
 /* CUDA-event timing on the library's own streams (64 event slots): record marks a point that follows
  * all work enqueued so far; elapsed waits for event b.  The device-side counterpart of the reference's
  * pelapsed() phase timers (main.cpp:93-115). */
 int mg_event_record(mg_ctx *ctx, int idx);
 int mg_event_elapsed_ms(mg_ctx *ctx, int a, int b, float *ms);
+/* blocks until everything enqueued before mg_event_record(ctx, idx) has completed (e.g. before a pinned
+ * buffer handed to mg_scan_kmc_records / mg_scan_sample_kmers is refilled) */
+int mg_event_sync(mg_ctx *ctx, int idx);
 /* device time of the last mg_genotype call: {signature look-ups, coverage, likelihood} kernels, ms */
 int mg_genotype_kernel_ms(mg_ctx *ctx, float *ms3);
 /* kernels launched by this context so far */

@@ -84,8 +84,12 @@ SYMBOLS = {
     "mg_kmap_size": (C.c_int, [C.c_void_p, u64p]),
     "mg_index_stats": (C.c_int, [C.c_void_p, u64p, C.c_int]),
     "mg_counter_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
+    "mg_export_set_bits": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64, u64p]),
+    "mg_import_set_bits": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64]),
+    "mg_export_ref_keys": (C.c_int, [C.c_void_p, u64p, C.c_uint64, u64p]),
     "mg_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, f32p]),
+    "mg_event_sync": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_genotype_kernel_ms": (C.c_int, [C.c_void_p, f32p]),
     "mg_launch_count": (C.c_int, [C.c_void_p, u64p]),
     "mg_diag_bandwidth": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, f64p]),

@@ -1,4 +1,5 @@
-"""In-tree build of libmalva_gpu.so (hand-written sm_100a kernels + C ABI).
+"""In-tree build of libmalva_gpu.so (hand-written sm_100a kernels + C ABI) and of the C++ host
+program malva-geno (csrc/host/, the drop-in `malva-geno index|call` CLI over that C ABI).
 
     python -m malva_b200.build [--force] [-v]
 
@@ -14,8 +15,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmalva_gpu.so")
+CLI = os.path.join(HERE, "malva-geno")
 SOURCES = ["malva_gpu.cu"]
-HEADERS = ["xxh3.cuh", "geno.cuh", os.path.join("..", "..", "include", "malva_gpu.h")]
+HEADERS = ["xxh3.cuh", "geno.cuh", "index.cuh", "kernels.cuh", os.path.join("..", "..", "include", "malva_gpu.h")]
+HOST_DIR = os.path.join(CSRC, "host")
+HOST_SOURCES = ["malva_geno.cpp"]
+HOST_HEADERS = ["signatures.hpp", "vcf_io.hpp", "kmc_db.hpp", "index_file.hpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,7 +37,47 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _find(*cands):
+    return next((p for p in cands if os.path.exists(p)), None)
+
+
+def _cli_stale() -> bool:
+    if not os.path.exists(CLI):
+        return True
+    t = os.path.getmtime(CLI)
+    deps = [os.path.join(HOST_DIR, s) for s in HOST_SOURCES + HOST_HEADERS] + \
+        [os.path.join(HERE, "..", "include", "malva_gpu.h"), LIB, os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_cli(force: bool = False) -> str:
+    """g++ build of malva-geno against libmalva_gpu.so (found at run time next to the binary, rpath $ORIGIN)."""
+    if not force and not _cli_stale():
+        return CLI
+    stdcxx = _find("/usr/lib/x86_64-linux-gnu/libstdc++.so.6", "/lib/x86_64-linux-gnu/libstdc++.so.6")
+    zstd = _find("/usr/lib/x86_64-linux-gnu/libzstd.so.1", "/lib/x86_64-linux-gnu/libzstd.so.1")
+    if zstd is None:
+        raise RuntimeError("libzstd.so.1 not found (needed for the index file)")
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", CLI] + \
+        [os.path.join(HOST_DIR, s) for s in HOST_SOURCES] + [LIB, zstd, "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN"]
+    if stdcxx:
+        cmd += ["-nostdlib++", stdcxx, "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building malva-geno")
+    if r.stderr.strip():
+        sys.stderr.write(r.stderr)
+    return CLI
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    lib = _build_lib(force, verbose)
+    build_cli(force)
+    return lib
+
+
+def _build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1,0 +1,604 @@
+// malva-geno -- the MALVA genotyping CLI over the B200 hot path.
+//
+//   malva-geno index [flags] <reference.fa> <variants.vcf> <kmc_output_prefix>
+//   malva-geno call  [flags] <reference.fa> <variants.vcf> <kmc_output_prefix>   > out.vcf
+//
+// Same sub-commands, flags (-k -r -e -s -f -c -b -p -u -v -1), index file name, stderr phase lines and VCF
+// output as the reference (main.cpp:226-594, argument_parser.hpp:51-159).  The host keeps VCF/FASTA reading and
+// var_block signature enumeration (signatures.hpp, vcf_io.hpp); everything the reference does through BF / KMAP /
+// VB::genotype goes through the C ABI of include/malva_gpu.h into the sm_100a kernels.  There is no CPU path:
+// without a usable CUDA device both sub-commands fail.
+//
+// What is organised differently from the reference's two loops:
+//   * VCF lines are decoded and var_blocks enumerated in parallel (blocks are independent), in batches, and a
+//     batch goes to the device in one call (mg_add_signatures / mg_genotype) instead of one k-mer at a time;
+//   * the KMC database is not decoded on the host: raw suffix records stream through pinned buffers into
+//     mg_scan_kmc_records;
+//   * the index file holds sparse lists (index_file.hpp).
+//
+// Extra (non-reference) flags: --threads N, --device N.  Extra sub-command for the CPU-only tests:
+//   malva-geno signatures [--index-blocks] [flags] <reference.fa> <variants.vcf>     (no GPU involved)
+#include <getopt.h>
+#include <sys/resource.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/malva_gpu.h"
+#include "index_file.hpp"
+#include "kmc_db.hpp"
+#include "signatures.hpp"
+#include "vcf_io.hpp"
+
+namespace {
+
+const char *USAGE =
+    "Usage: malva-geno <index|call> [-k KMER-SIZE] [-r REF-KMER-SIZE] [-c MAX-COV] "
+    "<reference.fa> <variants.vcf> <kmc_output_prefix>\n"
+    "\n"
+    "      -h, --help                        display this help and exit\n"
+    "      -k, --kmer-size                   size of the kmers to index (default:35)\n"
+    "      -r, --ref-kmer-size               size of the reference kmers to index (default:43)\n"
+    "      -e, --error-rate                  expected sample error rate (default:0.001)\n"
+    "      -s, --samples                     file containing the list of (VCF) samples to consider (default:-, i.e. all samples)\n"
+    "      -f, --freq-key                    a priori frequency key in the INFO column of the input VCF (default:AF)\n"
+    "      -c, --max-coverage                maximum coverage for variant alleles (default:200)\n"
+    "      -b, --bf-size                     bloom filter size in GB (default:4)\n"
+    "      -p, --strip-chr                   strip \"chr\" from sequence names (default:false)\n"
+    "      -u, --uniform                     use uniform a priori probabilities (default:false)\n"
+    "      -v, --verbose                     output COVS and GTS in INFO column (default: false)\n"
+    "      -1, --haploid                     run MALVA in haploid mode (default: false)\n"
+    "          --threads N                   host threads for VCF decoding / signature enumeration (default: all)\n"
+    "          --device N                    CUDA device (default: 0)\n"
+    "\n";
+
+struct Options {
+  unsigned k = 35, ref_k = 43;
+  float error_rate = 0.001f;
+  std::string samples = "-", freq_key = "AF";
+  unsigned max_coverage = 200;
+  uint64_t bf_size = 1ull << 35;
+  bool strip_chr = false, uniform = false, verbose = false, haploid = false, index_blocks = false;
+  int threads = 0, device = 0;
+  std::string fasta_path, vcf_path, kmc_path;
+};
+
+// argument_parser.hpp:86-159; values are read like `istringstream >> x` reads them
+bool parse_arguments(int argc, char **argv, Options &o, int n_positional) {
+  static const option longopts[] = {{"kmer-size", required_argument, nullptr, 'k'},
+                                    {"ref-kmer-size", required_argument, nullptr, 'r'},
+                                    {"error-rate", required_argument, nullptr, 'e'},
+                                    {"freq-key", required_argument, nullptr, 'f'},
+                                    {"samples", required_argument, nullptr, 's'},
+                                    {"max-coverage", required_argument, nullptr, 'c'},
+                                    {"bf-size", required_argument, nullptr, 'b'},
+                                    // the reference declares these two with required_argument (argument_parser.hpp:79-80)
+                                    {"strip-chr", required_argument, nullptr, 'p'},
+                                    {"uniform", required_argument, nullptr, 'u'},
+                                    {"verbose", no_argument, nullptr, 'v'},
+                                    {"haplod", no_argument, nullptr, '1'},  // sic (argument_parser.hpp:82)
+                                    {"haploid", no_argument, nullptr, '1'},
+                                    {"help", no_argument, nullptr, 'h'},
+                                    {"threads", required_argument, nullptr, 1000},
+                                    {"device", required_argument, nullptr, 1001},
+                                    {"index-blocks", no_argument, nullptr, 1002},
+                                    {nullptr, 0, nullptr, 0}};
+  bool die = false;
+  optind = 1;
+  for (int c; (c = getopt_long(argc, argv, "k:r:e:s:f:c:b:hpuv1", longopts, nullptr)) != -1;) {
+    std::istringstream arg(optarg ? optarg : "");
+    switch (c) {
+      case 'p': o.strip_chr = true; break;
+      case 'u': o.uniform = true; break;
+      case 'k': arg >> o.k; break;
+      case 'r': arg >> o.ref_k; break;
+      case 'e': arg >> o.error_rate; break;
+      case 's': arg >> o.samples; break;
+      case 'f': arg >> o.freq_key; break;
+      case 'c': arg >> o.max_coverage; break;
+      case 'b':
+        arg >> o.bf_size;
+        o.bf_size *= 1ull << 33;  // GB -> bits (argument_parser.hpp:119-123)
+        break;
+      case 'v': o.verbose = true; break;
+      case '1': o.haploid = true; break;
+      case 1000: arg >> o.threads; break;
+      case 1001: arg >> o.device; break;
+      case 1002: o.index_blocks = true; break;
+      case '?': die = true; break;
+      case 'h':
+        std::cout << USAGE;
+        exit(EXIT_SUCCESS);
+    }
+  }
+  if (argc - optind < n_positional) {
+    std::cerr << "malva : missing arguments\n";
+    die = true;
+  } else if (argc - optind > n_positional) {
+    std::cerr << "malva : too many arguments\n";
+    die = true;
+  }
+  if (die) {
+    std::cerr << "\n" << USAGE;
+    return false;
+  }
+  o.fasta_path = argv[optind++];
+  o.vcf_path = argv[optind++];
+  if (n_positional > 2) o.kmc_path = argv[optind++];
+  if (o.threads <= 0) o.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  return true;
+}
+
+// ---- phase timers: the reference's pelapsed() lines (main.cpp:93-115), same labels, same layout ----
+using Clock = std::chrono::high_resolution_clock;
+Clock::time_point g_start = Clock::now(), g_last = g_start;
+double cpu_seconds() {
+  rusage u;
+  getrusage(RUSAGE_SELF, &u);
+  return (double)u.ru_utime.tv_sec + (double)u.ru_utime.tv_usec * 1e-6;
+}
+double g_cpu_start = cpu_seconds();
+void pelapsed(const std::string &s, bool rollback = false) {
+  auto now = Clock::now();
+  char buf[512];
+  rusage u;
+  getrusage(RUSAGE_SELF, &u);
+  snprintf(buf, sizeof(buf),
+           "[malva-geno/%s] Execution Time %.4gs\n[malva-geno/%s] Time elapsed %.4gs\n"
+           "[malva-geno/%s] Used CPU-time elapsed %.4gs\n[malva-geno/%s] Maximum memory used %ldMb\n%s",
+           s.c_str(), std::chrono::duration<double>(now - g_last).count(), s.c_str(),
+           std::chrono::duration<double>(now - g_start).count(), s.c_str(), cpu_seconds() - g_cpu_start, s.c_str(),
+           u.ru_maxrss / 1024, rollback ? "\r" : "\n");
+  std::cerr << buf;
+  g_last = Clock::now();
+}
+
+void parallel_for(size_t n, int threads, const std::function<void(size_t)> &fn) {
+  if (n == 0) return;
+  int t = (int)std::min<size_t>((size_t)threads, n);
+  if (t <= 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::exception_ptr> errs((size_t)t);
+  std::vector<std::thread> pool;
+  for (int w = 0; w < t; ++w)
+    pool.emplace_back([&, w] {
+      try {
+        for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+      } catch (...) {
+        errs[(size_t)w] = std::current_exception();
+        next.store(n);
+      }
+    });
+  for (auto &th : pool) th.join();
+  for (auto &e : errs)
+    if (e) std::rethrow_exception(e);
+}
+
+struct GpuError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+void gpu(int rc, const char *what) {
+  if (rc != MG_OK) throw GpuError(std::string(what) + ": " + mg_last_error());
+}
+
+// ---- the VCF loop of index_main / call_main (main.cpp:309-370, 522-579) as a stream of batches of blocks ----
+class BlockStream {
+ public:
+  BlockStream(const Options &o, bool index_mode) : o_(o), index_mode_(index_mode), reader_(o.vcf_path), vb_((int)o.k) {
+    is_file_ = o.samples != "-";
+    samples_code = reader_.header.set_samples(o.samples);
+    freq_declared_ = reader_.header.has_info(o.freq_key);
+  }
+  int samples_code = 0;
+  std::vector<std::string> used_seq_names;  // main.cpp:304-306, 323-328, 352-356
+  uint64_t n_records = 0;
+  const mh::VcfHeader &header() const { return reader_.header; }
+
+  // up to `max_lines` more records; blocks flushed by them are appended to `out`.  false when nothing is left.
+  bool next_batch(std::vector<mh::VarBlock> &out, size_t max_lines) {
+    out.clear();
+    if (done_) return false;
+    lines_.clear();
+    std::string line;
+    size_t bytes = 0;
+    while (lines_.size() < max_lines && bytes < (256u << 20) && reader_.next_line(line)) {
+      bytes += line.size();
+      lines_.push_back(std::move(line));
+    }
+    std::vector<mh::Variant> vars(lines_.size());
+    parallel_for(lines_.size(), o_.threads, [&](size_t i) {
+      vars[i] = mh::parse_record(lines_[i], reader_.header, o_.freq_key, o_.uniform, freq_declared_);
+    });
+    for (auto &v : vars) {
+      ++n_records;
+      if (n_records % 5000 == 0) pelapsed("Processed " + std::to_string(n_records) + " variants", true);
+      if (last_seq_name_.empty()) {
+        last_seq_name_ = v.seq_name;
+        used_seq_names.push_back(last_seq_name_);
+      }
+      // index: variants with only symbolic ALTs or carried by no sample are skipped; call: the latter are kept
+      // (they are genotyped 0/0, main.cpp:332 vs :538)
+      if (!v.has_alts || (index_mode_ && !v.is_present)) continue;
+      if (vb_.empty()) {
+        vb_.add(std::move(v));
+        continue;
+      }
+      if (!vb_.is_near_to_last(v) || last_seq_name_ != v.seq_name) {
+        flush(out);
+        if (last_seq_name_ != v.seq_name) {
+          last_seq_name_ = v.seq_name;
+          used_seq_names.push_back(last_seq_name_);
+        }
+      }
+      vb_.add(std::move(v));
+    }
+    if (lines_.size() < max_lines && bytes < (256u << 20)) {  // end of file
+      done_ = true;
+      if (!vb_.empty()) flush(out);
+    }
+    return !out.empty() || !done_;
+  }
+
+ private:
+  void flush(std::vector<mh::VarBlock> &out) {
+    vb_.contig = last_seq_name_;
+    out.push_back(std::move(vb_));
+    vb_ = mh::VarBlock((int)o_.k);
+  }
+  const Options &o_;
+  bool index_mode_, is_file_ = false, freq_declared_ = false, done_ = false;
+  mh::VcfReader reader_;
+  mh::VarBlock vb_;
+  std::string last_seq_name_;
+  std::vector<std::string> lines_;
+};
+
+// signatures of a batch of blocks, enumerated in parallel, concatenated in block order
+void enumerate_batch(const std::vector<mh::VarBlock> &blocks, std::map<std::string, std::string> &refs, const Options &o,
+                     mh::SignatureCsr &out) {
+  for (const auto &b : blocks) refs[b.contig];  // (the reference's refs[name] creates missing contigs as empty)
+  // chunks of blocks per task keep the per-task CSR allocations coarse
+  const size_t chunk = 64, n_chunks = (blocks.size() + chunk - 1) / chunk;
+  std::vector<mh::SignatureCsr> parts(n_chunks);
+  parallel_for(n_chunks, o.threads, [&](size_t c) {
+    for (size_t b = c * chunk; b < std::min(blocks.size(), (c + 1) * chunk); ++b)
+      blocks[b].enumerate(refs.find(blocks[b].contig)->second, o.haploid, parts[c]);
+  });
+  out.clear();
+  for (const auto &p : parts) out.append(p);
+}
+
+constexpr size_t LINES_PER_BATCH = 1 << 16;
+
+struct Ctx {
+  mg_ctx *c = nullptr;
+  ~Ctx() { mg_destroy(c); }
+};
+
+// ------------------------------------------------------------------------------------------------
+int index_main(int argc, char **argv) {
+  Options o;
+  if (!parse_arguments(argc, argv, o, 3)) return EXIT_FAILURE;
+  BlockStream stream(o, true);
+  if (stream.samples_code != 0) {
+    std::cerr << "ERROR: VCF samples subset (code: " << stream.samples_code << ")" << std::endl;
+    return 1;
+  }
+  {
+    mh::KmcDb db;  // opened and unused, like the reference (main.cpp:273-279)
+    std::string why;
+    if (!db.open(o.kmc_path, why)) {
+      std::cerr << "ERROR: cannot open " << o.kmc_path << std::endl;
+      return 1;
+    }
+  }
+  pelapsed("Reference parsing");
+  std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
+  pelapsed("Reference processed");
+
+  pelapsed("VCF parsing (Bloom Filter construction)");
+  Ctx g;
+  gpu(mg_create(&g.c, o.device, (int)o.k, (int)o.ref_k, o.bf_size), "mg_create");
+  std::vector<mh::VarBlock> blocks;
+  mh::SignatureCsr sigs;
+  while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+    enumerate_batch(blocks, refs, o, sigs);
+    // add_kmers_to_bf (main.cpp:122-144): allele 0 -> ref_bf, others -> bf
+    gpu(mg_add_signatures(g.c, sigs.pool.data(), sigs.kmer_off.data(), sigs.kmer_is_ref.data(), sigs.n_kmers()),
+        "mg_add_signatures");
+  }
+  pelapsed("Processed " + std::to_string(stream.n_records) + " variants");
+  gpu(mg_finalize_alt(g.c), "mg_finalize_alt");  // bf.switch_mode()
+  pelapsed("BF creation complete");
+
+  pelapsed("Reference BF construction");
+  for (const std::string &name : stream.used_seq_names) {
+    const std::string &seq = refs[name];
+    gpu(mg_scan_reference(g.c, seq.data(), seq.size()), "mg_scan_reference");
+  }
+  pelapsed("Reference BF creation complete");
+  gpu(mg_finalize_context(g.c), "mg_finalize_context");  // context_bf.switch_mode()
+
+  {
+    mh::IndexWriter w(o.vcf_path + ".c" + std::to_string(o.ref_k) + ".k" + std::to_string(o.k) + ".malvax.zst", o.k,
+                      o.ref_k, o.bf_size);
+    for (int which : {1, 0}) {  // context_bf, then bf, then ref_bf (main.cpp:409-411)
+      uint64_t n = 0;
+      gpu(mg_export_set_bits(g.c, which, nullptr, 0, &n), "mg_export_set_bits");
+      std::vector<uint64_t> idx(n);
+      if (n) gpu(mg_export_set_bits(g.c, which, idx.data(), n, &n), "mg_export_set_bits");
+      w.write_bits(idx);
+    }
+    uint64_t n = 0;
+    gpu(mg_export_ref_keys(g.c, nullptr, 0, &n), "mg_export_ref_keys");
+    std::vector<uint64_t> keys(2 * n);
+    if (n) gpu(mg_export_ref_keys(g.c, keys.data(), n, &n), "mg_export_ref_keys");
+    w.write_keys(keys);
+    w.close();
+  }
+  std::cout.flush();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one VCF line per variant of the batch, VB::output_variants (var_block.hpp:337-396)
+void format_variant(const mh::Variant &v, const uint32_t *cov, int n_gts, int status, int best, int gq, const double *lik,
+                    const Options &o, std::string &out) {
+  char num[64];
+  out += v.seq_name;
+  out += '\t';
+  out += std::to_string(v.ref_pos + 1);
+  out += '\t';
+  out += v.idx;
+  out += '\t';
+  out += v.ref_sub;
+  out += '\t';
+  for (size_t i = 0; i < v.alts.size(); ++i) {
+    if (i) out += ',';
+    out += v.alts[i];
+  }
+  out += '\t';
+  if (std::isnan(v.quality)) {
+    out += '.';
+  } else {
+    snprintf(num, sizeof(num), "%g", (double)v.quality);  // ostream << float
+    out += num;
+  }
+  const int n = v.n_alleles();
+  // name of the i-th computed genotype: "g" / "g1/g2" in emission order, or the default for vetoed variants
+  auto gt_name = [&](int i) -> std::string {
+    if (status != 0) return o.haploid ? "0" : "0/0";
+    if (o.haploid) return std::to_string(i);
+    int g1 = 0, left = i;
+    while (left >= n - g1) {
+      left -= n - g1;
+      ++g1;
+    }
+    return std::to_string(g1) + "/" + std::to_string(g1 + left);
+  };
+  std::string info = ".";
+  if (o.verbose) {
+    info = "COVS=";
+    for (int a = 0; a < n; ++a) {
+      if (a) info += ',';
+      info += std::to_string((int)cov[a]);
+    }
+    info += ";GTS=";
+    double total = 0.0;
+    for (int i = 0; i < n_gts; ++i) total += lik[i];
+    for (int i = 0; i < n_gts; ++i) {
+      if (i) info += ',';
+      info += gt_name(i);
+      info += ':';
+      volatile double q = lik[i] / total;  // 0/0 -> the machine's default NaN, printed "-nan" like the reference
+      info += std::to_string((double)q);
+    }
+  }
+  out += "\tPASS\t";
+  out += info;
+  out += "\tGT:GQ\t";
+  out += gt_name(best);
+  out += ':';
+  out += std::to_string(gq);
+  out += '\n';
+}
+
+int call_main(int argc, char **argv) {
+  Options o;
+  if (!parse_arguments(argc, argv, o, 3)) return EXIT_FAILURE;
+  BlockStream stream(o, false);
+  if (stream.samples_code != 0) {
+    std::cerr << "ERROR: VCF samples subset (code: " << stream.samples_code << ")" << std::endl;
+    return 1;
+  }
+  mh::KmcDb db;
+  {
+    std::string why;
+    if (!db.open(o.kmc_path, why)) {
+      std::cerr << "ERROR: cannot open " << o.kmc_path << std::endl;
+      return 1;
+    }
+  }
+  Ctx g;
+  {  // load the index: context_bf, bf, ref_bf (main.cpp:455-461)
+    mh::IndexReader r(o.vcf_path + ".c" + std::to_string(o.ref_k) + ".k" + std::to_string(o.k) + ".malvax.zst");
+    if (r.k != o.k || r.ref_k != o.ref_k)
+      throw std::runtime_error("the index was built with -k " + std::to_string(r.k) + " -r " + std::to_string(r.ref_k));
+    // the filter size travels with the index, like the reference's serialised bit vectors (-b matters at index time)
+    gpu(mg_create(&g.c, o.device, (int)o.k, (int)o.ref_k, r.bf_bits), "mg_create");
+    std::vector<uint64_t> ctx_bits = r.read_bits();
+    {
+      std::vector<uint64_t> bf_bits = r.read_bits();
+      gpu(mg_import_set_bits(g.c, 0, bf_bits.data(), bf_bits.size()), "mg_import_set_bits");
+    }
+    {
+      std::vector<uint64_t> keys = r.read_keys();
+      std::vector<uint8_t> flags(keys.size() / 2, 1);
+      gpu(mg_add_signatures_packed(g.c, keys.data(), flags.data(), flags.size()), "mg_add_signatures_packed");
+    }
+    gpu(mg_finalize_alt(g.c), "mg_finalize_alt");
+    gpu(mg_import_set_bits(g.c, 1, ctx_bits.data(), ctx_bits.size()), "mg_import_set_bits");
+    gpu(mg_finalize_context(g.c), "mg_finalize_context");
+  }
+  pelapsed("Reference parsing");
+  std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
+  pelapsed("Reference processed");
+
+  // STEP 2: the sample k-mer scan (main.cpp:482-500).  Raw suffix records go through a ring of pinned buffers;
+  // the library copies and scans them asynchronously (double-buffered on its side), a buffer is refilled only
+  // after the event recorded behind its scan has completed.
+  pelapsed("KMC output processing");
+  {
+    gpu(mg_kmc_open(g.c, db.lut.data(), db.lut.size(), db.lut_prefix_len, db.kmer_len, db.counter_size, db.min_count,
+                    db.max_count),
+        "mg_kmc_open");
+    constexpr int RING = 4;
+    constexpr uint64_t CHUNK = 1ull << 22;  // records per buffer
+    uint8_t *buf[RING] = {};
+    bool used[RING] = {};
+    for (auto &b : buf) gpu(mg_host_alloc((void **)&b, CHUNK * db.record_bytes + 64), "mg_host_alloc");
+    uint64_t first = 0;
+    for (int slot = 0;; slot = (slot + 1) % RING) {
+      if (used[slot]) gpu(mg_event_sync(g.c, 32 + slot), "mg_event_sync");
+      uint64_t n = db.read_records(buf[slot], first, CHUNK);
+      if (n == 0) break;
+      gpu(mg_scan_kmc_records(g.c, buf[slot], first, n), "mg_scan_kmc_records");
+      gpu(mg_event_record(g.c, 32 + slot), "mg_event_record");
+      used[slot] = true;
+      first += n;
+    }
+    gpu(mg_sync(g.c), "mg_sync");
+    for (auto &b : buf) mg_host_free(b);
+    if (first != db.total_kmers)
+      throw std::runtime_error(o.kmc_path + ".kmc_suf is shorter than its header says");
+  }
+  pelapsed("BF weights created");
+
+  // STEP 3: genotype (main.cpp:504-581)
+  std::cout << stream.header().cleaned(o.verbose);
+  pelapsed("VCF parsing and genotyping");
+  std::vector<mh::VarBlock> blocks;
+  mh::SignatureCsr sigs;
+  std::vector<uint64_t> lik_off;
+  std::vector<uint32_t> cov;
+  std::vector<int32_t> n_gts, status, best, gq;
+  std::vector<double> lik;
+  std::vector<const mh::Variant *> order;
+  std::vector<std::string> text;
+  while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+    enumerate_batch(blocks, refs, o, sigs);
+    const uint64_t nv = sigs.n_variants();
+    if (nv == 0) continue;
+    lik_off.assign(nv + 1, 0);
+    for (uint64_t i = 0; i < nv; ++i) {
+      uint64_t n = sigs.var_allele_off[i + 1] - sigs.var_allele_off[i];
+      lik_off[i + 1] = lik_off[i] + std::max<uint64_t>(n, o.haploid ? n : n * (n + 1) / 2);
+    }
+    cov.resize(sigs.n_alleles());
+    n_gts.resize(nv), status.resize(nv), best.resize(nv), gq.resize(nv);
+    lik.resize(o.verbose ? lik_off[nv] : 0);
+    mg_variant_batch in = {nv,
+                           sigs.var_allele_off.data(),
+                           sigs.allele_sig_off.data(),
+                           sigs.sig_kmer_off.data(),
+                           sigs.kmer_off.data(),
+                           sigs.pool.data(),
+                           sigs.freq.data()};
+    mg_genotype_out res = {cov.data(),  n_gts.data(),   status.data(),
+                           best.data(), gq.data(),      lik_off.data(),
+                           o.verbose ? lik.data() : nullptr};
+    gpu(mg_genotype(g.c, &in, &res, o.error_rate, (int)o.max_coverage, o.haploid ? 1 : 0), "mg_genotype");
+    order.clear();
+    for (const auto &b : blocks)
+      for (size_t i = 0; i < b.size(); ++i) order.push_back(&b[i]);
+    const size_t chunk = 4096, n_chunks = (nv + chunk - 1) / chunk;
+    text.assign(n_chunks, std::string());
+    parallel_for(n_chunks, o.threads, [&](size_t c) {
+      for (size_t i = c * chunk; i < std::min<size_t>(nv, (c + 1) * chunk); ++i)
+        format_variant(*order[i], cov.data() + sigs.var_allele_off[i], n_gts[i], status[i], best[i], gq[i],
+                       o.verbose ? lik.data() + lik_off[i] : nullptr, o, text[c]);
+    });
+    for (const auto &t : text) fwrite(t.data(), 1, t.size(), stdout);
+  }
+  pelapsed("Processed " + std::to_string(stream.n_records) + " variants");
+  fflush(stdout);
+  pelapsed("Execution completed");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CPU-only: print the signatures of every block, for the parity tests of the host logic against the reference's
+// VB::extract_kmers.  One line per signature: contig \t 1-based pos \t block-local variant index \t allele \t kmers
+int signatures_main(int argc, char **argv) {
+  Options o;
+  if (!parse_arguments(argc, argv, o, 2)) return EXIT_FAILURE;
+  BlockStream stream(o, o.index_blocks);
+  if (stream.samples_code != 0) {
+    std::cerr << "ERROR: VCF samples subset (code: " << stream.samples_code << ")" << std::endl;
+    return 1;
+  }
+  std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
+  std::vector<mh::VarBlock> blocks;
+  mh::SignatureCsr sigs;
+  uint64_t block_no = 0;
+  while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+    enumerate_batch(blocks, refs, o, sigs);
+    uint64_t vi = 0;
+    for (const auto &b : blocks) {
+      for (size_t i = 0; i < b.size(); ++i, ++vi) {
+        const uint64_t a0 = sigs.var_allele_off[vi], a1 = sigs.var_allele_off[vi + 1];
+        for (uint64_t a = a0; a < a1; ++a)
+          for (uint64_t s = sigs.allele_sig_off[a]; s < sigs.allele_sig_off[a + 1]; ++s) {
+            std::cout << block_no << '\t' << b.contig << '\t' << b[i].ref_pos + 1 << '\t' << i << '\t' << (a - a0) << '\t';
+            for (uint64_t q = sigs.sig_kmer_off[s]; q < sigs.sig_kmer_off[s + 1]; ++q) {
+              if (q != sigs.sig_kmer_off[s]) std::cout << ',';
+              std::cout.write(sigs.pool.data() + sigs.kmer_off[q], (std::streamsize)(sigs.kmer_off[q + 1] - sigs.kmer_off[q]));
+            }
+            std::cout << '\n';
+          }
+      }
+      ++block_no;
+    }
+  }
+  std::cout << "#used";
+  for (const auto &n : stream.used_seq_names) std::cout << '\t' << n;
+  std::cout << '\n';
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    std::cerr << "malva missing arguments" << std::endl << USAGE << std::endl;
+    return 1;
+  }
+  try {
+    if (strncmp(argv[1], "index", 5) == 0) return index_main(argc - 1, argv + 1);
+    if (strncmp(argv[1], "call", 4) == 0) return call_main(argc - 1, argv + 1);
+    if (strcmp(argv[1], "signatures") == 0) return signatures_main(argc - 1, argv + 1);
+  } catch (const GpuError &e) {
+    std::cerr << "malva-geno: GPU error: " << e.what() << " (there is no CPU fallback)" << std::endl;
+    return 2;
+  } catch (const std::exception &e) {
+    std::cerr << "malva-geno: " << e.what() << std::endl;
+    return 1;
+  }
+  std::cerr << "Could not interpret command " << argv[1] << "." << std::endl;
+  std::cerr << "Accepted commands are index and call." << std::endl;
+  return 1;
+}

@@ -1,0 +1,353 @@
+// Host-kept part of malva-geno (north star: "the C++ host keeps VCF parsing, FASTA reading and var_block
+// signature enumeration").  This file: the variant record and the var_block signature enumerator, written
+// from scratch to emit the batch (CSR) layout the C ABI consumes directly -- not the reference's
+// map<int, map<int, vector<vector<string>>>> -- and to be run on many blocks in parallel (blocks are
+// independent).
+//
+// Behaviour follows the reference decision by decision:
+//   block membership ("near")       var_block.hpp:417-423   (single-precision compare, see near())
+//   overlap                         var_block.hpp:408-412
+//   neighbour chains                var_block.hpp:436-677
+//   haplotype allele combinations   var_block.hpp:709-786
+//   signature construction          var_block.hpp:95-219
+// What differs is only how the work is organised:
+//   * haplotypes are tuples of small allele ids, not vectors of string_view; an allele id is the index of the
+//     first allele of the variant with the same TEXT, which is exactly the identity the reference's
+//     unordered_set<vector<string_view>> and Variant::get_allele_index (variant.hpp:228-240) use;
+//   * identical per-sample genotype patterns are collapsed before unphased patterns are expanded into their
+//     2^n haplotypes (2,504 samples mostly share a handful of patterns);
+//   * duplicate signatures of an allele are dropped: the coverage of an allele is a max over its signatures
+//     (main.cpp:176-177) and filter/table inserts are idempotent, so results cannot change.
+// The order of the signatures of an allele is unspecified in the reference too (unordered_set iteration).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <string_view>
+#include <utility>
+#include <vector>
+
+namespace mh {
+
+struct Variant {
+  std::string seq_name;
+  int ref_pos = 0;  // 0-based
+  std::string idx;  // ID column
+  std::string ref_sub;
+  std::vector<std::string> alts;  // symbolic (<..>) alleles removed, upper-cased
+  float quality = 0;
+  std::vector<uint16_t> gt;     // two allele indices per kept sample (variant.hpp:158-211)
+  std::vector<uint8_t> phased;  // one flag per kept sample
+  int ref_size = 0, min_size = 0, max_size = 0;
+  bool has_alts = true, is_present = true;
+  std::vector<float> frequencies;
+  std::vector<uint16_t> text_id;  // allele index -> first allele index with the same text
+
+  int n_alleles() const { return (int)alts.size() + 1; }
+  size_t n_samples() const { return phased.size(); }
+  const std::string &allele(int i) const { return i == 0 ? ref_sub : alts[(size_t)i - 1]; }
+
+  void set_sizes() {  // variant.hpp:108-124
+    ref_size = (int)ref_sub.size();
+    if (alts.empty()) {
+      has_alts = false;
+      return;
+    }
+    min_size = max_size = ref_size;
+    for (const auto &a : alts) {
+      min_size = std::min(min_size, (int)a.size());
+      max_size = std::max(max_size, (int)a.size());
+    }
+    text_id.resize((size_t)n_alleles());
+    for (int i = 0; i < n_alleles(); ++i) {
+      int first = i;
+      for (int j = 0; j < i; ++j)
+        if (allele(j) == allele(i)) {
+          first = j;
+          break;
+        }
+      text_id[(size_t)i] = (uint16_t)first;
+    }
+  }
+  // a GT index past the kept ALTs is undefined behaviour in the reference (variant.hpp:221); clamp it
+  uint16_t gt_text_id(size_t sample, int which) const {
+    int a = gt[2 * sample + (size_t)which];
+    if (a >= n_alleles()) a = n_alleles() - 1;
+    return text_id[(size_t)a];
+  }
+};
+
+// Flattened signatures of a run of variants: variant -> allele slot -> signature -> k-mers.
+struct SignatureCsr {
+  std::string pool;
+  std::vector<uint64_t> kmer_off{0}, sig_kmer_off{0}, allele_sig_off{0}, var_allele_off{0};
+  std::vector<uint8_t> kmer_is_ref;
+  std::vector<float> freq;
+  uint64_t n_variants() const { return var_allele_off.size() - 1; }
+  uint64_t n_alleles() const { return allele_sig_off.size() - 1; }
+  uint64_t n_kmers() const { return kmer_off.size() - 1; }
+  void clear() {
+    pool.clear();
+    kmer_off.assign(1, 0);
+    sig_kmer_off.assign(1, 0);
+    allele_sig_off.assign(1, 0);
+    var_allele_off.assign(1, 0);
+    kmer_is_ref.clear();
+    freq.clear();
+  }
+  void append(const SignatureCsr &o) {
+    const uint64_t pb = pool.size(), kb = n_kmers(), sb = sig_kmer_off.size() - 1, ab = n_alleles();
+    pool += o.pool;
+    for (size_t i = 1; i < o.kmer_off.size(); ++i) kmer_off.push_back(pb + o.kmer_off[i]);
+    for (size_t i = 1; i < o.sig_kmer_off.size(); ++i) sig_kmer_off.push_back(kb + o.sig_kmer_off[i]);
+    for (size_t i = 1; i < o.allele_sig_off.size(); ++i) allele_sig_off.push_back(sb + o.allele_sig_off[i]);
+    for (size_t i = 1; i < o.var_allele_off.size(); ++i) var_allele_off.push_back(ab + o.var_allele_off[i]);
+    kmer_is_ref.insert(kmer_is_ref.end(), o.kmer_is_ref.begin(), o.kmer_is_ref.end());
+    freq.insert(freq.end(), o.freq.begin(), o.freq.end());
+  }
+};
+
+// var_block.hpp:417-423.  The reference adds ceil((float)k/2) to an int sum, so the whole comparison runs in
+// single precision: beyond 2^24 bases positions are rounded before they are compared.  Kept on purpose.
+inline bool variants_near(const Variant &a, const Variant &b, int k, int sum_to_add) {
+  float lhs = (float)(a.ref_pos + a.ref_size - a.min_size - 1 + sum_to_add) + std::ceil((float)k / 2);
+  return lhs >= (float)b.ref_pos;
+}
+
+class VarBlock {
+ public:
+  VarBlock() = default;
+  explicit VarBlock(int k) : k_(k) {}
+  bool empty() const { return vars_.empty(); }
+  void clear() { vars_.clear(); }
+  void add(Variant v) { vars_.push_back(std::move(v)); }
+  size_t size() const { return vars_.size(); }
+  const Variant &operator[](size_t i) const { return vars_[i]; }
+  bool is_near_to_last(const Variant &v) const { return variants_near(vars_.back(), v, k_, 0); }
+  std::string contig;  // name of the contig the block lies on (last_seq_name at flush time)
+
+  // Signatures of every variant of the block, appended to `out`: one variant entry per block member, in order;
+  // allele slot a = allele index a (slots of duplicate-text alleles stay empty, like in the reference).
+  void enumerate(const std::string &reference, bool haploid, SignatureCsr &out) const {
+    std::vector<std::vector<std::vector<std::string>>> per_allele;  // [allele][signature][k-mer]
+    for (size_t vi = 0; vi < vars_.size(); ++vi) {
+      const Variant &v = vars_[vi];
+      per_allele.assign((size_t)v.n_alleles(), {});
+      // var_block.hpp:104 -- no signatures for absent variants or variants within k of a contig end
+      if (v.is_present && v.ref_pos >= k_ && v.ref_pos <= (int)reference.size() - k_)
+        signatures_of((int)vi, reference, haploid, per_allele);
+      for (int a = 0; a < v.n_alleles(); ++a) {
+        auto &sigs = per_allele[(size_t)a];
+        std::sort(sigs.begin(), sigs.end());
+        sigs.erase(std::unique(sigs.begin(), sigs.end()), sigs.end());
+        for (const auto &sig : sigs) {
+          for (const auto &kmer : sig) {
+            out.pool += kmer;
+            out.kmer_off.push_back(out.pool.size());
+            out.kmer_is_ref.push_back(a == 0);
+          }
+          out.sig_kmer_off.push_back(out.kmer_off.size() - 1);
+        }
+        out.allele_sig_off.push_back(out.sig_kmer_off.size() - 1);
+        out.freq.push_back((size_t)a < v.frequencies.size() ? v.frequencies[(size_t)a] : 0.0f);
+      }
+      out.var_allele_off.push_back(out.allele_sig_off.size() - 1);
+    }
+  }
+
+ private:
+  using Chain = std::vector<int>;
+  using Hap = std::vector<uint16_t>;  // one allele text-id per chain member
+
+  static bool overlapping(const Variant &a, const Variant &b) {  // var_block.hpp:408-412
+    return a.ref_pos <= b.ref_pos && b.ref_pos < a.ref_pos + a.ref_size;
+  }
+
+  // var_block.hpp:436-525 (dir = +1) and 534-624 (dir = -1): every chain of mutually compatible neighbours that
+  // stays within reach of the mid variant.  Pairs are always tested in genomic order.
+  std::vector<Chain> side_chains(int i, int dir) const {
+    const Variant &mid = vars_[(size_t)i];
+    std::vector<Chain> chains;
+    std::vector<int> reach;  // bases the chain's deletions add to the reach of the mid variant
+    auto ovl = [&](int near_mid, int far) {
+      return dir > 0 ? overlapping(vars_[(size_t)near_mid], vars_[(size_t)far])
+                     : overlapping(vars_[(size_t)far], vars_[(size_t)near_mid]);
+    };
+    auto in_reach = [&](int j, int extra) {
+      return dir > 0 ? variants_near(mid, vars_[(size_t)j], k_, extra) : variants_near(vars_[(size_t)j], mid, k_, extra);
+    };
+    auto gain = [&](int j) { return vars_[(size_t)j].ref_size - vars_[(size_t)j].min_size; };
+    bool halt = false;
+    for (int j = i + dir; j >= 0 && j < (int)vars_.size() && !halt; j += dir) {
+      if (!vars_[(size_t)j].is_present || ovl(i, j)) continue;
+      if (chains.empty()) {
+        if (in_reach(j, 0)) {
+          chains.push_back(Chain{j});
+          reach.push_back(gain(j));
+        }
+        continue;
+      }
+      bool compatible = false;  // with the tail of at least one chain
+      for (size_t c = 0; c < chains.size(); ++c) {
+        if (ovl(chains[c].back(), j)) continue;
+        compatible = true;
+        if (in_reach(j, reach[c])) {
+          chains[c].push_back(j);
+          reach[c] += gain(j);
+        }
+      }
+      if (compatible) continue;
+      // it clashes with every tail: fork each chain, cut back to the part it is compatible with
+      std::vector<Chain> forks;
+      std::vector<int> fork_reach;
+      for (size_t c = 0; c < chains.size(); ++c) {
+        Chain f = chains[c];
+        int r = reach[c];
+        while (!f.empty() && ovl(f.back(), j)) {
+          r -= gain(f.back());
+          f.pop_back();
+        }
+        f.push_back(j);
+        if (in_reach(j, r)) {
+          forks.push_back(std::move(f));
+          fork_reach.push_back(r + gain(j));
+        }
+      }
+      if (forks.empty()) halt = true;  // too far for any chain: nothing further can be added (var_block.hpp:516-519)
+      for (size_t c = 0; c < forks.size(); ++c) {
+        chains.push_back(std::move(forks[c]));
+        reach.push_back(fork_reach[c]);
+      }
+    }
+    return chains;
+  }
+
+  // var_block.hpp:631-677: left chains (reversed into genomic order) x right chains around the mid variant
+  std::vector<Chain> full_chains(int i) const {
+    std::vector<Chain> right = side_chains(i, +1), left = side_chains(i, -1), out;
+    if (left.empty()) left.push_back(Chain{});
+    if (right.empty()) right.push_back(Chain{});
+    for (const Chain &l : left)
+      for (const Chain &r : right) {
+        Chain c(l.rbegin(), l.rend());
+        c.push_back(i);
+        c.insert(c.end(), r.begin(), r.end());
+        out.push_back(std::move(c));
+      }
+    return out;
+  }
+
+  // var_block.hpp:734-786: the distinct haplotypes (one allele per chain member) carried by the samples of the
+  // central variant.  Unphased patterns contribute every way of picking one of the two alleles at each site
+  // (combine_haplotypes, var_block.hpp:709-728).
+  void haplotypes(const Chain &chain, int central, bool haploid, std::vector<Hap> &out) const {
+    const size_t n = chain.size(), n_samples = vars_[(size_t)central].n_samples();
+    // per-sample pattern: [h1 ids | h2 ids | phased]
+    std::vector<Hap> patterns;
+    patterns.reserve(n_samples);
+    Hap p(2 * n + 1);
+    for (size_t s = 0; s < n_samples; ++s) {
+      bool ph = true;
+      for (size_t m = 0; m < n; ++m) {
+        const Variant &v = vars_[(size_t)chain[m]];
+        const bool has = s < v.n_samples();
+        p[m] = has ? v.gt_text_id(s, 0) : 0;
+        p[n + m] = haploid ? p[m] : (has ? v.gt_text_id(s, 1) : 0);
+        ph = ph && (!has || v.phased[s] != 0);
+      }
+      p[2 * n] = (haploid || ph) ? 1 : 0;
+      patterns.push_back(p);
+    }
+    std::sort(patterns.begin(), patterns.end());
+    patterns.erase(std::unique(patterns.begin(), patterns.end()), patterns.end());
+    out.clear();
+    for (const Hap &q : patterns) {
+      if (q[2 * n]) {
+        out.emplace_back(q.begin(), q.begin() + (long)n);
+        if (!haploid) out.emplace_back(q.begin() + (long)n, q.begin() + 2 * (long)n);
+      } else {
+        std::vector<size_t> het;  // sites where the two alleles differ
+        for (size_t m = 0; m < n; ++m)
+          if (q[m] != q[n + m]) het.push_back(m);
+        Hap h(q.begin(), q.begin() + (long)n);
+        for (uint64_t mask = 0; mask < (1ull << het.size()); ++mask) {
+          for (size_t b = 0; b < het.size(); ++b) h[het[b]] = ((mask >> b) & 1) ? q[n + het[b]] : q[het[b]];
+          out.push_back(h);
+        }
+      }
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+  }
+
+  static void append_clamped(std::string &dst, const std::string &s, long pos, long len) {
+    if (len <= 0 || pos < 0 || pos >= (long)s.size()) return;  // (the reference would throw on pos > size)
+    dst.append(s, (size_t)pos, (size_t)len);
+  }
+
+  // var_block.hpp:114-216
+  void signatures_of(int vi, const std::string &reference, bool haploid,
+                     std::vector<std::vector<std::vector<std::string>>> &per_allele) const {
+    const Variant &v = vars_[(size_t)vi];
+    std::vector<Hap> haps;
+    std::vector<std::string> between;
+    for (const Chain &chain : full_chains(vi)) {
+      // reference text between consecutive members of the chain (var_block.hpp:682-702)
+      between.clear();
+      size_t mid_slot = 0;
+      for (size_t m = 0; m < chain.size(); ++m) {
+        if (chain[m] == vi) mid_slot = m;
+        if (m == 0) continue;
+        const Variant &prev = vars_[(size_t)chain[m - 1]], &cur = vars_[(size_t)chain[m]];
+        std::string gap;
+        append_clamped(gap, reference, (long)prev.ref_pos + prev.ref_size, (long)cur.ref_pos - (prev.ref_pos + prev.ref_size));
+        between.push_back(std::move(gap));
+      }
+      haplotypes(chain, vi, haploid, haps);
+      for (const Hap &h : haps) {
+        std::vector<std::string> sig;
+        const int mid_id = h[mid_slot];
+        const std::string &mid_allele = v.allele(mid_id);
+        if (chain.size() == 1 && (int)mid_allele.size() >= k_) {
+          // an allele at least k long: every k-mer inside the allele itself (var_block.hpp:130-144)
+          for (size_t p = 0; p + (size_t)k_ <= mid_allele.size(); ++p) sig.emplace_back(mid_allele, p, (size_t)k_);
+        } else {
+          std::string kmer;
+          int mid_pos = 0;
+          for (size_t m = 0; m < chain.size(); ++m) {
+            if (m == mid_slot) mid_pos = (int)kmer.size();
+            kmer += vars_[(size_t)chain[m]].allele(h[m]);
+            if (m < between.size()) kmer += between[m];
+          }
+          const int first_part = mid_pos + (int)mid_allele.size() / 2;
+          const int second_part = (int)kmer.size() - first_part;
+          const int missing_prefix = k_ / 2 - first_part;
+          const int missing_suffix = (int)std::ceil((float)k_ / 2) - second_part;
+          if (missing_prefix >= 0) {
+            const Variant &first = vars_[(size_t)chain.front()];
+            std::string pre;
+            append_clamped(pre, reference, (long)first.ref_pos - missing_prefix, missing_prefix);
+            kmer.insert(0, pre);
+          } else {
+            kmer.erase(0, std::min<size_t>(kmer.size(), (size_t)(-missing_prefix)));
+          }
+          if (missing_suffix >= 0) {
+            const Variant &last = vars_[(size_t)chain.back()];
+            append_clamped(kmer, reference, (long)last.ref_pos + last.ref_size, missing_suffix);
+          } else {
+            const size_t cut = std::min<size_t>(kmer.size(), (size_t)(-missing_suffix));
+            kmer.erase(kmer.size() - cut, cut);
+          }
+          sig.push_back(std::move(kmer));
+        }
+        per_allele[(size_t)mid_id].push_back(std::move(sig));
+      }
+    }
+  }
+
+  int k_ = 35;
+  std::vector<Variant> vars_;
+};
+
+}  // namespace mh

@@ -1,0 +1,430 @@
+// Host-kept input side of malva-geno: gz-transparent line reader, FASTA reference, VCF header and record
+// decoding with the htslib conventions the reference's output depends on (htslib itself is not part of this
+// build: the records malva-geno needs are CHROM/POS/ID/REF/ALT/QUAL, one INFO float vector and the GT field):
+//   * header lines are kept in file order, de-duplicated by key (+ID); `##FILTER=<ID=PASS,...>` always exists;
+//     appending a line whose key/ID is already present is a no-op (bcf_hdr_append, main.cpp:190-204)
+//   * sample subsetting (-s): kept samples stay in header order (bcf_hdr_set_samples, main.cpp:266,514)
+//   * INFO floats are parsed with strtod and narrowed to float (variant.hpp:126-141)
+//   * GT decode: allele index, '.' -> 0, phase taken from the separator before the second allele
+//     (variant.hpp:158-211)
+// Record decoding is a pure function of one text line, so that batches of lines are decoded in parallel.
+#pragma once
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "signatures.hpp"
+
+namespace mh {
+
+class LineReader {
+ public:
+  explicit LineReader(const std::string &path) : fp_(gzopen(path.c_str(), "r")) {
+    if (!fp_) throw std::runtime_error("cannot open " + path);
+    gzbuffer(fp_, 1 << 20);
+    buf_.resize(1 << 20);
+  }
+  ~LineReader() {
+    if (fp_) gzclose(fp_);
+  }
+  LineReader(const LineReader &) = delete;
+  LineReader &operator=(const LineReader &) = delete;
+  bool next(std::string &line) {
+    line.clear();
+    bool any = false;
+    while (gzgets(fp_, buf_.data(), (int)buf_.size()) != nullptr) {
+      any = true;
+      size_t n = strlen(buf_.data());
+      if (n && buf_[n - 1] == '\n') {
+        line.append(buf_.data(), n - 1);
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return true;
+      }
+      line.append(buf_.data(), n);
+    }
+    return any;
+  }
+
+ private:
+  gzFile fp_;
+  std::vector<char> buf_;
+};
+
+// whole reference, upper-cased, name = first word of the header line, optional "chr" strip (main.cpp:283-295).
+// FASTA and FASTQ-style records are both accepted, like kseq does.
+inline std::map<std::string, std::string> read_fasta(const std::string &path, bool strip_chr) {
+  std::map<std::string, std::string> refs;
+  LineReader in(path);
+  std::string line;
+  std::string *cur = nullptr;
+  bool in_qual = false;
+  size_t qual_left = 0;
+  while (in.next(line)) {
+    if (in_qual) {  // FASTQ quality lines: as many symbols as the sequence had
+      qual_left = line.size() >= qual_left ? 0 : qual_left - line.size();
+      if (qual_left == 0) in_qual = false;
+      continue;
+    }
+    if (!line.empty() && (line[0] == '>' || line[0] == '@')) {
+      size_t e = line.find_first_of(" \t");
+      std::string name = line.substr(1, e == std::string::npos ? std::string::npos : e - 1);
+      if (strip_chr && name.compare(0, 3, "chr") == 0) name = name.substr(3);
+      cur = &refs[name];
+      cur->clear();
+    } else if (!line.empty() && line[0] == '+' && cur) {
+      in_qual = !cur->empty();
+      qual_left = cur->size();
+    } else if (cur) {
+      for (char c : line)
+        if (!isspace((unsigned char)c)) cur->push_back((char)toupper((unsigned char)c));
+    }
+  }
+  return refs;
+}
+
+struct HeaderLine {
+  std::string key, id, text;
+};
+
+class VcfHeader {
+ public:
+  std::vector<HeaderLine> lines;
+  std::vector<std::string> samples;  // as in the file
+  std::vector<int> keep;             // kept samples, header order
+
+  static bool parse(const std::string &text, HeaderLine &h) {
+    if (text.size() < 3 || text[0] != '#' || text[1] != '#') return false;
+    size_t eq = text.find('=');
+    if (eq == std::string::npos) return false;
+    h.key = text.substr(2, eq - 2);
+    h.text = text;
+    h.id.clear();
+    if (eq + 1 < text.size() && text[eq + 1] == '<') {
+      size_t p = text.find("ID=", eq);
+      if (p != std::string::npos) {
+        size_t e = text.find_first_of(",>", p);
+        h.id = text.substr(p + 3, e == std::string::npos ? std::string::npos : e - p - 3);
+      }
+    }
+    return true;
+  }
+  void append(const std::string &text) {
+    HeaderLine h;
+    if (!parse(text, h)) return;
+    for (const auto &o : lines) {
+      if (o.key != h.key) continue;
+      if (!h.id.empty() || !o.id.empty()) {
+        if (o.id == h.id) return;
+      } else if (o.text == h.text || h.key == "fileformat") {
+        return;
+      }
+    }
+    if (h.key == "fileformat")
+      lines.insert(lines.begin(), h);
+    else
+      lines.push_back(h);
+  }
+  bool has_info(const std::string &id) const {
+    for (const auto &l : lines)
+      if (l.key == "INFO" && l.id == id) return true;
+    return false;
+  }
+  // bcf_hdr_set_samples: "-" = all, otherwise a file with one name per line.
+  // Returns 0, or (index of the first listed name that is absent) + 1, or -1 if the file cannot be read.
+  int set_samples(const std::string &spec) {
+    keep.clear();
+    if (spec == "-") {
+      for (size_t i = 0; i < samples.size(); ++i) keep.push_back((int)i);
+      return 0;
+    }
+    std::vector<std::string> names;
+    try {
+      LineReader in(spec);
+      std::string l;
+      while (in.next(l)) {
+        size_t e = l.find_first_of(" \t");
+        if (e != std::string::npos) l = l.substr(0, e);
+        if (!l.empty()) names.push_back(l);
+      }
+    } catch (const std::exception &) {
+      return -1;
+    }
+    std::vector<char> want(samples.size(), 0);
+    int ret = 0;
+    for (size_t i = 0; i < names.size(); ++i) {
+      bool found = false;
+      for (size_t j = 0; j < samples.size(); ++j)
+        if (samples[j] == names[i]) {
+          want[j] = 1;
+          found = true;
+        }
+      if (!found && ret == 0) ret = (int)i + 1;
+    }
+    for (size_t j = 0; j < want.size(); ++j)
+      if (want[j]) keep.push_back((int)j);
+    return ret;
+  }
+  // print_cleaned_header (main.cpp:190-219): GT/GQ (+COVS/GTS) appended if new, all samples replaced by DONOR
+  std::string cleaned(bool verbose) const {
+    VcfHeader h = *this;
+    h.append("##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">");
+    h.append("##FORMAT=<ID=GQ,Number=1,Type=Integer,Description=\"Genotype Quality\">");
+    if (verbose) {
+      h.append("##INFO=<ID=COVS,Number=R,Type=Integer,Description=\"Allele coverages\">");
+      h.append("##INFO=<ID=GTS,Number=.,Type=String,Description=\"Genotypes Likelihood\">");
+    }
+    std::string out;
+    for (const auto &l : h.lines) out += l.text + "\n";
+    out += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tDONOR\n";
+    return out;
+  }
+};
+
+// Opens a VCF (plain or gz), reads the header; data lines are then pulled with next_line().
+class VcfReader {
+ public:
+  VcfHeader header;
+
+  explicit VcfReader(const std::string &path) : in_(path) {
+    header.append("##FILTER=<ID=PASS,Description=\"All filters passed\">");
+    std::string line;
+    while (in_.next(line)) {
+      if (line.size() >= 2 && line[0] == '#' && line[1] == '#') {
+        header.append(line);
+        continue;
+      }
+      if (!line.empty() && line[0] == '#') {
+        size_t col = 0, p = 0;
+        while (true) {
+          size_t t = line.find('\t', p);
+          std::string c = line.substr(p, t == std::string::npos ? std::string::npos : t - p);
+          if (col >= 9 && !c.empty()) header.samples.push_back(c);
+          ++col;
+          if (t == std::string::npos) break;
+          p = t + 1;
+        }
+        for (size_t i = 0; i < header.samples.size(); ++i) header.keep.push_back((int)i);
+        return;
+      }
+      pending_ = line;
+      has_pending_ = true;
+      return;
+    }
+  }
+
+  bool next_line(std::string &line) {
+    while (true) {
+      if (has_pending_) {
+        line.swap(pending_);
+        has_pending_ = false;
+      } else if (!in_.next(line)) {
+        return false;
+      }
+      if (!line.empty()) return true;
+    }
+  }
+
+ private:
+  LineReader in_;
+  std::string pending_;
+  bool has_pending_ = false;
+};
+
+namespace detail {
+struct Field {
+  const char *b, *e;
+  size_t size() const { return (size_t)(e - b); }
+  std::string str() const { return std::string(b, e); }
+  bool is(const char *s) const { return size() == strlen(s) && memcmp(b, s, size()) == 0; }
+};
+inline std::string upper(const char *b, const char *e) {
+  std::string s(b, e);
+  for (auto &ch : s) ch = (char)toupper((unsigned char)ch);
+  return s;
+}
+inline float missing_float() {  // bcf_float_missing: a NaN
+  return std::nanf("");
+}
+inline bool info_floats(const Field &info, const std::string &key, std::vector<float> &out) {
+  const char *p = info.b;
+  while (p < info.e) {
+    const char *e = (const char *)memchr(p, ';', (size_t)(info.e - p));
+    if (!e) e = info.e;
+    if ((size_t)(e - p) > key.size() && memcmp(p, key.data(), key.size()) == 0 && p[key.size()] == '=') {
+      const char *q = p + key.size() + 1;
+      while (q <= e) {
+        const char *t = (const char *)memchr(q, ',', (size_t)(e - q));
+        if (!t) t = e;
+        std::string tok(q, t);
+        out.push_back((tok == "." || tok.empty()) ? missing_float() : (float)strtod(tok.c_str(), nullptr));
+        q = t + 1;
+      }
+      return true;
+    }
+    p = e + 1;
+  }
+  return false;
+}
+}  // namespace detail
+
+// Variant(hdr, rec, freq_key, uniform), variant.hpp:66-103, from one VCF data line.
+inline Variant parse_record(const std::string &line, const VcfHeader &header, const std::string &freq_key, bool uniform,
+                            bool freq_key_declared) {
+  using detail::Field;
+  Field c[9];
+  int nf = 0;
+  const char *p = line.data(), *end = line.data() + line.size();
+  const char *samples_begin = nullptr;
+  while (nf < 9) {
+    const char *t = (const char *)memchr(p, '\t', (size_t)(end - p));
+    c[nf++] = Field{p, t ? t : end};
+    if (!t) break;
+    p = t + 1;
+    if (nf == 9) samples_begin = p;
+  }
+  if (nf < 8) throw std::runtime_error("malformed VCF record: " + line.substr(0, 60));
+  Variant v;
+  v.seq_name = c[0].str();
+  v.ref_pos = (int)(strtoll(c[1].str().c_str(), nullptr, 10) - 1);
+  v.idx = c[2].str();
+  v.ref_sub = detail::upper(c[3].b, c[3].e);
+  if (!c[4].is(".")) {
+    const char *a = c[4].b;
+    while (a <= c[4].e) {
+      const char *t = (const char *)memchr(a, ',', (size_t)(c[4].e - a));
+      if (!t) t = c[4].e;
+      if (!(t > a && a[0] == '<')) v.alts.push_back(detail::upper(a, t));  // symbolic alleles dropped (variant.hpp:82)
+      a = t + 1;
+    }
+  }
+  v.quality = c[5].is(".") ? detail::missing_float() : (float)strtod(c[5].str().c_str(), nullptr);
+  v.set_sizes();
+  if (!v.has_alts) return v;
+  // ---- extract_frequencies (variant.hpp:126-156) ----
+  if (!uniform) {
+    std::vector<float> af;
+    if (!freq_key_declared || !detail::info_floats(c[7], freq_key, af))
+      throw std::runtime_error("INFO key " + freq_key + " missing at " + v.seq_name + ":" + std::to_string(v.ref_pos + 1) +
+                               " (the reference dereferences NULL here; use -u or -f)");
+    v.frequencies.push_back(0.0f);
+    for (size_t i = 0; i < v.alts.size(); ++i) v.frequencies.push_back(i < af.size() ? af[i] : 0.0f);
+    double sum = 0.0;
+    for (float f : v.frequencies) sum += f;
+    v.frequencies[0] = (float)(1.0 - sum);
+    if (v.frequencies[0] < 0) v.frequencies[0] = 0.0f;
+  } else {
+    float u = (float)(1.0 / (double)(v.alts.size() + 1));
+    v.frequencies.assign(v.alts.size() + 1, u);
+  }
+  if (v.frequencies[0] == 1.0) v.is_present = false;
+  if (!v.is_present) return v;
+  // ---- extract_genotypes (variant.hpp:158-211) ----
+  int gt_field = -1;
+  if (nf > 8) {
+    int idx = 0;
+    const char *f = c[8].b;
+    while (f <= c[8].e) {
+      const char *t = (const char *)memchr(f, ':', (size_t)(c[8].e - f));
+      if (!t) t = c[8].e;
+      if (t - f == 2 && f[0] == 'G' && f[1] == 'T') {
+        gt_field = idx;
+        break;
+      }
+      ++idx;
+      f = t + 1;
+    }
+  }
+  if (gt_field < 0 || header.keep.empty()) {
+    v.has_alts = false;  // "The record doesn't contain GT information" (variant.hpp:170-175)
+    return v;
+  }
+  // raw codes per kept sample, htslib style: ((allele + 1) << 1) | phased; `first`/`second`/ploidy per sample
+  const size_t ns = header.keep.size();
+  std::vector<int32_t> g0(ns, 0), g1(ns, 0);
+  std::vector<uint8_t> ploidy(ns, 1);
+  size_t max_ploidy = 1;
+  {
+    size_t ki = 0;  // next kept sample to fill
+    int col = 0;
+    const char *s = samples_begin;
+    while (s && s <= end && ki < ns) {
+      const char *t = (const char *)memchr(s, '\t', (size_t)(end - s));
+      if (!t) t = end;
+      if (col == header.keep[ki]) {
+        const char *q = s;
+        for (int f = 0; f < gt_field && q; ++f) {
+          q = (const char *)memchr(q, ':', (size_t)(t - q));
+          if (q) ++q;
+        }
+        size_t n = 0;
+        if (q) {
+          const char *e = (const char *)memchr(q, ':', (size_t)(t - q));
+          if (!e) e = t;
+          int ph = 0;
+          while (q < e) {
+            int32_t code;
+            if (*q == '.') {
+              code = 0 | ph;
+              ++q;
+            } else {
+              int a = 0;
+              while (q < e && *q >= '0' && *q <= '9') a = a * 10 + (*q++ - '0');
+              code = ((a + 1) << 1) | ph;
+            }
+            if (n == 0) g0[ki] = code;
+            if (n == 1) g1[ki] = code;
+            ++n;
+            if (q < e) {
+              ph = *q == '|';
+              ++q;
+            }
+          }
+        }
+        if (n == 0) n = 1;  // an empty field counts as one missing allele
+        ploidy[ki] = (uint8_t)std::min<size_t>(n, 255);
+        max_ploidy = std::max(max_ploidy, n);
+        ++ki;
+      }
+      ++col;
+      s = t + 1;
+    }
+  }
+  const int32_t VECTOR_END = INT32_MIN + 1;
+  v.gt.resize(2 * ns);
+  v.phased.resize(ns);
+  for (size_t i = 0; i < ns; ++i) {
+    // the reference reads curr_gt[0] and curr_gt[1] of a row of max_ploidy entries; with ploidy 1 everywhere the
+    // second read lands on the NEXT sample's first entry (variant.hpp:184) -- reproduced; the last sample sees
+    // the end marker
+    int32_t a = g0[i], b;
+    if (max_ploidy >= 2)
+      b = ploidy[i] >= 2 ? g1[i] : VECTOR_END;
+    else
+      b = i + 1 < ns ? g0[i + 1] : VECTOR_END;
+    int a1, a2;
+    bool ph;
+    if (b == VECTOR_END) {
+      a1 = a2 = (a >> 1) - 1;
+      ph = true;
+    } else {
+      a1 = (a >> 1) - 1;
+      a2 = (b >> 1) - 1;
+      ph = (b & 1) != 0;
+    }
+    if (a1 < 0) a1 = 0;
+    if (a2 < 0) a2 = 0;
+    v.gt[2 * i] = (uint16_t)std::min(a1, 65535);
+    v.gt[2 * i + 1] = (uint16_t)std::min(a2, 65535);
+    v.phased[i] = ph ? 1 : 0;
+  }
+  return v;
+}
+
+}  // namespace mh

@@ -615,6 +615,56 @@ __global__ void __launch_bounds__(128) k_genotype(const uint32_t *__restrict__ c
 }
 
 // ---------------------------------------------------------------------------
+// index image export / import (the index file of `malva-geno index`, main.cpp:406-412, 455-461):
+// filters travel as sorted lists of set-bit indices, ref_bf as a list of packed keys
+// ---------------------------------------------------------------------------
+// one thread per 256-bit unit; offs = exclusive scan of the per-unit popcounts
+__global__ void __launch_bounds__(256) k_emit_bits(const uint32_t *__restrict__ words, uint64_t n_units, int stride_u32,
+                                                  const uint32_t *__restrict__ offs, uint64_t n_bits,
+                                                  uint64_t *__restrict__ out) {
+  uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  uint64_t o = offs[u];
+  for (int w = 0; w < 8; ++w) {
+    uint32_t x = words[u * (uint64_t)stride_u32 + (uint64_t)w];
+    while (x) {
+      int b = __ffs(x) - 1;
+      x &= x - 1;
+      uint64_t idx = u * 256 + (uint64_t)w * 32 + (uint64_t)b;
+      if (idx < n_bits) out[o++] = idx;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_set_bits(const uint64_t *__restrict__ idx, uint64_t n, uint64_t n_bits,
+                                                 uint32_t *words_rw, int as_lines) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t b = idx[i];
+  if (b >= n_bits) return;
+  uint32_t *w = as_lines ? words_rw + (b >> 8) * 32 + ((b & 255) >> 5) : words_rw + (b >> 5);
+  atomicOr(w, 1u << (b & 31));
+}
+// every non-empty key slot of the probe lines (n_slots = 6 * n_lines) or of the overflow table
+__global__ void __launch_bounds__(256) k_emit_keys(const uint4 *__restrict__ lines, uint64_t n_lines,
+                                                  const u128 *__restrict__ ovf_keys, uint64_t ovf_cap,
+                                                  unsigned long long *counter, u128 *__restrict__ out, uint64_t cap) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t n_slots = n_lines * LINE_KEYS;
+  u128 key;
+  if (i < n_slots) {
+    key = key_of(lines[(i / LINE_KEYS) * LINE_U4 + 2 + (i % LINE_KEYS)]);
+  } else if (i < n_slots + ovf_cap) {
+    key = ovf_keys[i - n_slots];
+    key.hi &= KEY_HI_MASK;
+  } else {
+    return;
+  }
+  if (key_empty(key)) return;
+  unsigned long long o = atomicAdd(counter, 1ull);
+  if (o < cap) out[o] = key;
+}
+
+// ---------------------------------------------------------------------------
 // roofline diagnostics: measured ceilings on this device (bench.py records them)
 //   k_diag_random  : independent random reads, `gran` separate 4-byte loads inside one aligned
 //                    gran*32-byte unit (1, 2 or 4 sectors)

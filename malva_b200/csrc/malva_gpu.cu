@@ -689,7 +689,6 @@ extern "C" int mg_genotype(mg_ctx *c, const mg_variant_batch *in, const mg_genot
            o_lik = o_i32 + al(nv * 16), total = o_lik + al(nl * 8) + 256;
   if (c->geno_arena_bytes < total) {  // grow-only device arena, reused across calls
     cudaFree(c->geno_arena);
-  cudaFree(c->kmc_lut);
     c->geno_arena = nullptr;
     c->geno_arena_bytes = 0;
     CU(cudaMalloc(&c->geno_arena, total + total / 4));
@@ -809,6 +808,80 @@ extern "C" int mg_counter_buffers(mg_ctx *c, void **d_ptr, uint64_t *n) {
   return MG_OK;
 }
 
+// ---- index image export / import ----
+extern "C" int mg_export_set_bits(mg_ctx *c, int which, uint64_t *out, uint64_t cap, uint64_t *n) {
+  if (!c || !n || which < 0 || which > 1 || (!out && cap)) return set_err(MG_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  int rc = mg_sync(c);
+  if (rc) return rc;
+  const uint32_t *words = which ? c->ctx_words : reinterpret_cast<const uint32_t *>(c->lines);
+  const int stride = which ? 8 : 32;
+  DevFree cnt, offs, tmp, idx;
+  CU(cudaMalloc(&cnt.p, (c->n_lines + 1) * 4));
+  CU(cudaMalloc(&offs.p, (c->n_lines + 1) * 4));
+  CU(cudaMemsetAsync((uint32_t *)cnt.p + c->n_lines, 0, 4, c->stream[0]));
+  unsigned long long ones = 0;
+  rc = count_ones(c, words, c->n_lines, stride, (uint32_t *)cnt.p, &ones);
+  if (rc) return rc;
+  *n = ones;
+  if (!out || cap < ones) return ones && out ? set_err(MG_ERR_ARG, "output buffer too small (%llu needed)", ones) : MG_OK;
+  if (ones == 0) return MG_OK;
+  if (ones > 0xFFFFFFFFull) return set_err(MG_ERR_ARG, "more than 2^32 set bits");
+  size_t tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)cnt.p, (uint32_t *)offs.p, (int64_t)(c->n_lines + 1), c->stream[0]));
+  CU(cudaMalloc(&tmp.p, tb ? tb : 1));
+  CU(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (uint32_t *)cnt.p, (uint32_t *)offs.p, (int64_t)(c->n_lines + 1), c->stream[0]));
+  CU(cudaMalloc(&idx.p, ones * 8));
+  c->launches += 2;
+  mg::k_emit_bits<<<grid_for(c->n_lines, 256), 256, 0, c->stream[0]>>>(words, c->n_lines, stride, (uint32_t *)offs.p,
+                                                                       c->bf_bits, (uint64_t *)idx.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, idx.p, ones * 8, cudaMemcpyDeviceToHost, c->stream[0]));
+  CU(cudaStreamSynchronize(c->stream[0]));
+  return MG_OK;
+}
+
+extern "C" int mg_import_set_bits(mg_ctx *c, int which, const uint64_t *idx, uint64_t n) {
+  if (!c || which < 0 || which > 1 || (!idx && n)) return set_err(MG_ERR_ARG, "bad argument");
+  if (which == 0 && c->alt_final) return set_err(MG_ERR_STATE, "bf is already finalized");
+  if (n == 0) return MG_OK;
+  CU(cudaSetDevice(c->device));
+  DevFree d;
+  CU(cudaMalloc(&d.p, n * 8));
+  CU(cudaMemcpyAsync(d.p, idx, n * 8, cudaMemcpyHostToDevice, c->stream[0]));
+  c->launches++;
+  mg::k_set_bits<<<grid_for(n, 256), 256, 0, c->stream[0]>>>(
+      (const uint64_t *)d.p, n, c->bf_bits, which ? c->ctx_words : reinterpret_cast<uint32_t *>(c->lines), which == 0);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream[0]));
+  return MG_OK;
+}
+
+extern "C" int mg_export_ref_keys(mg_ctx *c, uint64_t *lohi, uint64_t cap, uint64_t *n) {
+  if (!c || !n || (!lohi && cap)) return set_err(MG_ERR_ARG, "bad argument");
+  *n = c->n_keys;
+  if (!lohi) return MG_OK;
+  if (cap < c->n_keys) return set_err(MG_ERR_ARG, "output buffer too small (%llu needed)", (unsigned long long)c->n_keys);
+  if (c->n_keys == 0) return MG_OK;
+  CU(cudaSetDevice(c->device));
+  int rc = mg_sync(c);
+  if (rc) return rc;
+  DevFree d;
+  CU(cudaMalloc(&d.p, c->n_keys * 16));
+  CU(cudaMemsetAsync(c->d_scalars, 0, 8, c->stream[0]));
+  uint64_t ovf_cap = 1ull << c->ovf_log2, total = c->n_lines * mg::LINE_KEYS + ovf_cap;
+  c->launches++;
+  mg::k_emit_keys<<<grid_for(total, 256), 256, 0, c->stream[0]>>>(c->lines, c->n_lines, c->ovf_keys, ovf_cap, c->d_scalars,
+                                                                  (u128 *)d.p, c->n_keys);
+  CU(cudaGetLastError());
+  unsigned long long got = 0;
+  CU(cudaMemcpyAsync(&got, c->d_scalars, 8, cudaMemcpyDeviceToHost, c->stream[0]));
+  CU(cudaMemcpyAsync(lohi, d.p, c->n_keys * 16, cudaMemcpyDeviceToHost, c->stream[0]));
+  CU(cudaStreamSynchronize(c->stream[0]));
+  if (got != c->n_keys) return set_err(MG_ERR_STATE, "key count mismatch: %llu in the table, %llu recorded", got, (unsigned long long)c->n_keys);
+  return MG_OK;
+}
+
 // ---- timing on the library's own streams (torch.cuda.Event cannot see them) ----
 extern "C" int mg_event_record(mg_ctx *c, int idx) {
   if (!c || idx < 0 || idx >= 64) return set_err(MG_ERR_ARG, "bad event index");
@@ -828,6 +901,12 @@ extern "C" int mg_event_elapsed_ms(mg_ctx *c, int a, int b, float *ms) {
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->evs[b]));
   CU(cudaEventElapsedTime(ms, c->evs[a], c->evs[b]));
+  return MG_OK;
+}
+extern "C" int mg_event_sync(mg_ctx *c, int idx) {
+  if (!c || idx < 0 || idx >= 64 || !c->evs[idx]) return set_err(MG_ERR_ARG, "bad event index");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->evs[idx]));
   return MG_OK;
 }
 extern "C" int mg_genotype_kernel_ms(mg_ctx *c, float *ms3) {

@@ -1,0 +1,131 @@
+"""Host logic of the malva-geno CLI (malva_b200/csrc/host), checked on CPU against the reference's own
+VB::extract_kmers (oracle/_ref hook) and block grouping rules: `malva-geno signatures` prints what the CLI would
+send to the device for every var_block.  No GPU involved (the signatures sub-command never touches CUDA)."""
+import os
+import subprocess
+
+import pytest
+
+import synth
+import vcf_blocks
+from malva_b200 import build as mbuild
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "haploid")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    mbuild.build()
+    assert os.path.exists(mbuild.CLI)
+    return mbuild.CLI
+
+
+def cli_signatures(cli, fa, vcf, flags, index_mode):
+    cmd = [cli, "signatures"] + (["--index-blocks"] if index_mode else []) + list(flags) + [fa, vcf]
+    out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
+    blocks, used = {}, None
+    for l in out.split("\n"):
+        if not l:
+            continue
+        if l.startswith("#used"):
+            used = l.split("\t")[1:]
+            continue
+        b, contig, pos, vi, allele, kmers = l.split("\t")
+        blocks.setdefault(int(b), {}).setdefault((contig, int(pos), int(vi), int(allele)), set()).add(tuple(kmers.split(",")))
+    return blocks, used
+
+
+def expected_signatures(ref_lib, fa, vcf, k, haploid, freq_key, uniform, index_mode, strip_chr=False):
+    refs, name = {}, None
+    for l in open(fa):
+        l = l.rstrip("\n")
+        if l.startswith(">"):
+            name = l[1:].split()[0]
+            if strip_chr and name.startswith("chr"):
+                name = name[3:]
+            refs[name] = []
+        else:
+            refs[name].append(l.upper())
+    refs = {n: "".join(v) for n, v in refs.items()}
+    _, recs = vcf_blocks.read_vcf(vcf, freq_key, uniform)
+    blocks, used = {}, []
+    if recs:
+        used.append(recs[0].chrom)
+    for b, (contig, blk) in enumerate(vcf_blocks.blocks(recs, k, index_mode=index_mode)):
+        if contig not in used or used[-1] != contig:
+            used.append(contig)
+        nested = vcf_blocks.ref_extract(ref_lib, blk, refs.get(contig, ""), k, haploid)
+        for vi, v in enumerate(blk):
+            for a, sigs in enumerate(nested[vi]):
+                for s in sigs:
+                    blocks.setdefault(b, {}).setdefault((contig, v.pos0 + 1, vi, a), set()).add(tuple(s))
+    return blocks, used
+
+
+def test_signatures_haploid_example(cli, ref_lib):
+    fa, vcf = os.path.join(GOLD, "haploid.fa"), os.path.join(GOLD, "haploid.vcf.gz")
+    for index_mode in (True, False):
+        got, used = cli_signatures(cli, fa, vcf, ["-1"], index_mode)
+        exp, exp_used = expected_signatures(ref_lib, fa, vcf, 35, True, "AF", False, index_mode)
+        assert got == exp
+        assert used == exp_used
+
+
+@pytest.mark.parametrize("case", synth.CASES, ids=[c.name for c in synth.CASES])
+def test_signatures_synthetic(cli, ref_lib, case, tmp_path):
+    fa, vcf, _, _ = synth.build_case(case, str(tmp_path))
+    uniform = "-u" in case.flags
+    sig_flags = [f for f in case.flags]
+    # only the flags the enumeration depends on
+    keep, it = [], iter(sig_flags)
+    for f in it:
+        if f in ("-k", "-f", "-r", "-e", "-c"):
+            v = next(it)
+            if f in ("-k", "-f"):
+                keep += [f, v]
+        else:
+            keep.append(f)
+    for index_mode in (True, False):
+        got, used = cli_signatures(cli, fa, vcf, keep, index_mode)
+        exp, exp_used = expected_signatures(ref_lib, fa, vcf, case.k, case.haploid, case.freq_key, uniform, index_mode,
+                                            strip_chr=case.chr_prefix)
+        assert set(got) == set(exp), "different set of blocks with signatures"
+        for b in exp:
+            assert got[b] == exp[b], f"block {b} differs"
+        assert used == exp_used
+        assert sum(len(v) for v in exp.values()) > 100
+
+
+def test_cli_usage_errors(cli):
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 1 and "missing arguments" in r.stderr
+    r = subprocess.run([cli, "frobnicate"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Could not interpret command" in r.stderr
+    r = subprocess.run([cli, "call", "only_one.fa"], capture_output=True, text=True)
+    assert r.returncode == 1 and "missing arguments" in r.stderr
+    r = subprocess.run([cli, "index", "-h"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--bf-size" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["cfg4_wg_like_multiallelic", "haploid_af"])
+def test_cli_goldens_are_what_the_reference_prints(name, tmp_path):
+    """tests/golden/cli/*.expected.vcf.gz (used by the GPU end-to-end test) against the reference's own main.cpp
+    (oracle/_ref/malva-geno-ref) run now on the regenerated inputs; the other cases are pinned by the manifest."""
+    import gzip
+    import hashlib
+    import json
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_cli_golden as mk
+
+    if not os.path.exists(mk.REF_BIN):
+        pytest.skip("oracle/_ref/malva-geno-ref not built")
+    case = next(c for c in synth.CASES if c.name == name)
+    out, hashes, _ = mk.run_reference(case, str(tmp_path))
+    manifest = json.load(open(os.path.join(mk.OUT, "manifest.json")))
+    assert hashes == manifest[name]["inputs"]
+    assert out == gzip.open(os.path.join(mk.OUT, name + ".expected.vcf.gz")).read()
+    for n, m in manifest.items():
+        blob = gzip.open(os.path.join(mk.OUT, n + ".expected.vcf.gz")).read()
+        assert hashlib.sha256(blob).hexdigest() == m["expected_sha256"]
