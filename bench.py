@@ -150,7 +150,7 @@ def make_variant_batch(torch, nv, alt, ref, gen, dev):
     lik_slots = n_all * (n_all + 1) // 2
     lo = np.zeros(nv + 1, np.uint64)
     lo[1:] = np.cumsum(lik_slots)
-    return dict(vao=vao, aso=aso, sko=sko, koff=koff, pool=pool, freq=freq, lik_off=lo, dims=(nv, na, na, nk))
+    return dict(vao=vao, aso=aso, sko=sko, koff=koff, pool=pool, freq=freq, lik_off=lo, dims=(nv, na, na, nk, nk * K))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -395,7 +395,7 @@ def run_ours(args, wl, rank, local_rank, world):
     B = wl["batch"]
     batches = [make_sample_batch(torch, B, alt, ref, gen, dev) for _ in range(2)]
     vb = make_variant_batch(torch, wl["variants"], alt, ref, gen, dev)
-    nv, na, ns, nk = vb["dims"]
+    nv, na, ns, nk = vb["dims"][:4]
     d = {k2: torch.from_numpy(vb[k1]).to(dev) for k1, k2 in (("vao", "var_allele_off"), ("aso", "allele_sig_off"),
                                                               ("sko", "sig_kmer_off"), ("koff", "kmer_off"),
                                                               ("lik_off", "lik_off"), ("freq", "freq"))}

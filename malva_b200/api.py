@@ -301,7 +301,8 @@ class MalvaGpu:
                                   int(bool(haploid))))
 
     def genotype_device(self, ptrs: dict, dims: tuple, error_rate: float, max_coverage: int, haploid: bool) -> None:
-        """ptrs: device addresses keyed like mg_variant_batch / mg_genotype_out fields; dims = (nv, na, ns, nk)."""
+        """ptrs: device addresses keyed like mg_variant_batch / mg_genotype_out fields; dims = (nv, na, ns, nk)
+        or (nv, na, ns, nk, pool_bytes)."""
         c = lambda name, typ: C.cast(C.c_void_p(ptrs[name]), typ)
         vb = _lib.VariantBatch(dims[0], c("var_allele_off", _lib.u64p), c("allele_sig_off", _lib.u64p),
                                c("sig_kmer_off", _lib.u64p), c("kmer_off", _lib.u64p), C.c_void_p(ptrs["pool"]),
@@ -309,7 +310,7 @@ class MalvaGpu:
         out = _lib.GenotypeOut(c("cov", _lib.u32p), c("n_gts", _lib.i32p), c("status", _lib.i32p),
                                c("best_gt", _lib.i32p), c("gq", _lib.i32p), c("lik_off", _lib.u64p),
                                c("lik", _lib.f64p))
-        dm = _lib.BatchDims(*dims)
+        dm = _lib.BatchDims(*(tuple(dims) + (0,) * (5 - len(dims))))
         check(self._L.mg_genotype_device(self._h, C.byref(vb), C.byref(out), C.byref(dm), C.c_float(error_rate),
                                          int(max_coverage), int(bool(haploid))))
 

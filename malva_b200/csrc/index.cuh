@@ -19,6 +19,8 @@
 //   bf_counts[r]   u32 accumulator of the r-th set bit; read back & 0xFFFF (uint16 wrap-around)
 //   key_counts[6L + s]  u32 count of key slot s of line L   (KMAP value, 32-bit wrap-around)
 //   ctx_words      context_bf as a plain u32 bit array (consulted only on bf hits)
+//   occ            occupancy pre-filter: one bit per 2^occ_shift bf indices (<= 64 MB, kept resident in L2);
+//                  the scan and the reference pass consult it first and skip empty probe lines
 #pragma once
 #include <cstdint>
 
@@ -46,12 +48,28 @@ struct DevView {  // everything the kernels need, passed by value
   uint64_t bf_bits;
   uint64_t bf_mask;  // bf_bits-1 when bf_bits is a power of two, else 0
   int k, ref_k;
+  // occupancy pre-filter (L2-resident): bit (idx >> occ_shift) is set iff some bf bit or some ref key has its
+  // bf index in [idx >> occ_shift << occ_shift, +2^occ_shift).  A clear bit means the probe line holds nothing
+  // for this k-mer and the HBM access is skipped altogether.  nullptr = no pre-filter.
+  const uint32_t *occ;
+  int occ_shift;
 };
 
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ uint64_t bf_index(const DevView &v, uint64_t h) {
   return v.bf_mask ? (h & v.bf_mask) : (h % v.bf_bits);
+}
+__device__ __forceinline__ bool occ_test(const DevView &v, uint64_t idx) {
+  if (!v.occ) return true;
+  uint64_t o = idx >> v.occ_shift;
+  return (__ldg(v.occ + (o >> 5)) >> (o & 31)) & 1u;
+}
+__device__ __forceinline__ void occ_set(const DevView &v, uint32_t *occ_rw, uint64_t idx) {
+  if (!occ_rw) return;
+  uint64_t o = idx >> v.occ_shift;
+  uint32_t m = 1u << (o & 31);
+  if (!(occ_rw[o >> 5] & m)) atomicOr(occ_rw + (o >> 5), m);
 }
 __device__ __forceinline__ bool ctx_test(const DevView &v, uint64_t idx) {
   return (__ldg(v.ctx_words + (idx >> 5)) >> (idx & 31)) & 1u;

@@ -28,8 +28,10 @@ __device__ __forceinline__ uint64_t canon_hash_k(u128 x, int k, u128 *canon) {
 // ---------------------------------------------------------------------------
 // K3a: index-time inserts (add_kmers_to_bf, main.cpp:122-144)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void insert_ref_key(const DevView &v, uint4 *lines_rw, uint64_t h, u128 canon, uint64_t i,
-                                               unsigned long long *scalars, uint32_t *spill_idx) {
+__device__ __forceinline__ void insert_ref_key(const DevView &v, uint4 *lines_rw, uint32_t *occ_rw, uint64_t h,
+                                               u128 canon, uint64_t i, unsigned long long *scalars,
+                                               uint32_t *spill_idx) {
+  occ_set(v, occ_rw, bf_index(v, h));
   uint64_t line = bf_index(v, h) >> 8;
   int r = line_insert(lines_rw, line, canon);
   if (r == 1) {
@@ -40,8 +42,9 @@ __device__ __forceinline__ void insert_ref_key(const DevView &v, uint4 *lines_rw
     spill_idx[p] = (uint32_t)i;
   }
 }
-__device__ __forceinline__ void set_bf_bit(const DevView &v, uint4 *lines_rw, uint64_t h) {
+__device__ __forceinline__ void set_bf_bit(const DevView &v, uint4 *lines_rw, uint32_t *occ_rw, uint64_t h) {
   uint64_t idx = bf_index(v, h);
+  occ_set(v, occ_rw, idx);
   uint32_t *w = reinterpret_cast<uint32_t *>(lines_rw) + (idx >> 8) * 32 + ((idx & 255) >> 5);
   atomicOr(w, 1u << (idx & 31));
 }
@@ -49,7 +52,7 @@ __device__ __forceinline__ void set_bf_bit(const DevView &v, uint4 *lines_rw, ui
 __global__ void __launch_bounds__(128) k_add_signatures(const uint8_t *__restrict__ pool,
                                                        const uint64_t *__restrict__ off,
                                                        const uint8_t *__restrict__ is_ref, uint64_t n, DevView v,
-                                                       uint4 *lines_rw, unsigned long long *scalars,
+                                                       uint4 *lines_rw, uint32_t *occ_rw, unsigned long long *scalars,
                                                        uint32_t *irregular_idx, uint32_t *spill_idx) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -70,17 +73,17 @@ __global__ void __launch_bounds__(128) k_add_signatures(const uint8_t *__restric
       return;
     }
     uint64_t h = canon_hash_rt(x, v.k, &canon);
-    insert_ref_key(v, lines_rw, h, canon, i, scalars, spill_idx);
+    insert_ref_key(v, lines_rw, occ_rw, h, canon, i, scalars, spill_idx);
   } else {  // bf.add_key
     uint64_t h = regular ? canon_hash_rt(x, v.k, &canon) : hash_ascii(s, len);
-    set_bf_bit(v, lines_rw, h);
+    set_bf_bit(v, lines_rw, occ_rw, h);
   }
 }
 
 // same inserts for signature k-mers that arrive already packed (exactly k symbols of ACGT)
 __global__ void __launch_bounds__(256) k_add_packed(const uint4 *__restrict__ kmers, const uint8_t *__restrict__ is_ref,
-                                                   uint64_t n, DevView v, uint4 *lines_rw, unsigned long long *scalars,
-                                                   uint32_t *spill_idx) {
+                                                   uint64_t n, DevView v, uint4 *lines_rw, uint32_t *occ_rw,
+                                                   unsigned long long *scalars, uint32_t *spill_idx) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint4 q = kmers[i];
@@ -90,9 +93,9 @@ __global__ void __launch_bounds__(256) k_add_packed(const uint4 *__restrict__ km
   x = mask128(x, 2 * v.k);
   uint64_t h = canon_hash_rt(x, v.k, &canon);
   if (is_ref[i])
-    insert_ref_key(v, lines_rw, h, canon, i, scalars, spill_idx);
+    insert_ref_key(v, lines_rw, occ_rw, h, canon, i, scalars, spill_idx);
   else
-    set_bf_bit(v, lines_rw, h);
+    set_bf_bit(v, lines_rw, occ_rw, h);
 }
 
 // second pass over the keys whose line was full: insert into the overflow table.
@@ -265,7 +268,8 @@ __global__ void __launch_bounds__(RP_THREADS) k_refpass(const uint8_t *__restric
       }
       h35 = hash_ascii(s, k);
     }
-    if (!bf_test(v, bf_index(v, h35))) continue;
+    const uint64_t i35 = bf_index(v, h35);
+    if (!occ_test(v, i35) || !bf_test(v, i35)) continue;
     uint64_t h43;
     if ((bad & m43) == 0) {
       u128 canon;
@@ -311,8 +315,36 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+// canon_hash<K> (xxh3.cuh) with the 2-bit -> ASCII expansion done by a 256-entry shared-memory table (4 bases per
+// look-up) instead of shift/mask/PRMT sequences: the scan kernel is bound by the ALU pipe (LOP3/SHF/PRMT issue at
+// half rate), shared-memory loads go through the otherwise idle LSU pipe.  tab[v] = expand4(v).
+template <int K>
+__device__ __forceinline__ uint64_t canon_hash_lut(u128 x, u128 *canon, const uint32_t *tab) {
+  u128 rc = revcomp(x, K);
+  bool fwd = less128(x, rc);
+  u128 c = fwd ? x : rc, other = fwd ? rc : x;
+  u128 r;
+  r.lo = ~other.lo;
+  r.hi = ~other.hi;
+  r = mask128(r, 2 * K);  // LSB-first image of the canonical k-mer
+  constexpr int NW = (K + 7) / 8;
+  uint64_t w[NW + 1];
+  const uint32_t rw[4] = {(uint32_t)r.lo, (uint32_t)(r.lo >> 32), (uint32_t)r.hi, (uint32_t)(r.hi >> 32)};
+#pragma unroll
+  for (int j = 0; j < NW; ++j) {  // ASCII bytes 8j .. 8j+7 = bases held by bytes 2j and 2j+1 of r
+    const uint32_t word = rw[j >> 1];
+    uint32_t lo = tab[__byte_perm(word, 0u, (j & 1) ? 0x4442u : 0x4440u)], hi = 0;
+    if (8 * j + 4 < K) hi = tab[__byte_perm(word, 0u, (j & 1) ? 0x4443u : 0x4441u)];
+    w[j] = (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  w[NW] = 0;
+  *canon = c;
+  return xxh3_64_words(w, K);
+}
+
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_SMEM = (SCAN_THREADS / 32) * 32 * 128;  // one 4 KB tile per warp
+// per warp: a 4 KB tile + 32 row indices; per CTA: the 1 KB expansion table
+constexpr int SCAN_SMEM = (SCAN_THREADS / 32) * (32 * 128 + 32 * 4) + 256 * 4;
 
 // Where the sample k-mers come from.  MODE 0: packed {lo,hi} words + u32 counts.  MODE 1: raw records of a
 // KMC database suffix file (.kmc_suf): (ref_k - p)/4 suffix bytes (2-bit codes, first base most significant)
@@ -351,11 +383,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, 
   const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
   uint4 *tile = scan_sm + (threadIdx.x >> 5) * 256;  // 32 lines x 8 uint4
   const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t base = warp * 32; base < n; base += n_warps * 32) {
-    const uint64_t i = base + lane;
-    bool live = i < n;
+  uint32_t *rows = reinterpret_cast<uint32_t *>(scan_sm + (SCAN_THREADS / 32) * 256) + (threadIdx.x >> 5) * 32;
+  uint32_t *tab = reinterpret_cast<uint32_t *>(scan_sm + (SCAN_THREADS / 32) * 256) + (SCAN_THREADS / 32) * 32;
+  if constexpr (K > 0) {
+    static_assert(SCAN_THREADS == 256, "one table entry per thread");
+    tab[threadIdx.x] = expand4(threadIdx.x);
+    __syncthreads();
+  }
+  // 32-bit indices: the host never launches more than 2^31 k-mers at once
+  const uint32_t n32 = (uint32_t)n;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t step = ((gridDim.x * blockDim.x) >> 5) * 32;
+  for (uint32_t base = warp * 32; base < n32; base += step) {
+    const uint32_t i = base + lane;
+    bool live = i < n32;
     uint32_t cnt;
     u128 x43, canon;
     if constexpr (MODE == 0) {
@@ -366,7 +407,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, 
     } else {
       // stage the warp's 32 records (contiguous bytes) in its shared-memory tile, then decode one per lane
       const int rec = src.suf_bytes + src.counter_size;
-      const uint64_t byte0 = base * (uint64_t)rec, start = byte0 & ~3ull;
+      const uint64_t byte0 = (uint64_t)base * (uint64_t)rec, start = byte0 & ~3ull;
       const int n_words = (int)((byte0 - start) + 32u * (uint32_t)rec + 3u) >> 2;
       __syncwarp();
       uint32_t *stage = reinterpret_cast<uint32_t *>(tile);
@@ -384,7 +425,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, 
       // prefix of each record: one LUT search per warp in the common case (a prefix bucket spans many records)
       const uint64_t g = src.first_rec + i;
       const uint64_t g_first = src.first_rec + base;
-      const uint64_t g_last = src.first_rec + (base + 31 < n ? base + 31 : n - 1);
+      const uint64_t g_last = src.first_rec + (base + 31 < n32 ? base + 31 : n32 - 1);
       uint32_t pj = lut_bucket(src.lut, src.n_lut, g_first);
       if (__ldg(src.lut + pj + 1) <= g_last) pj = lut_bucket(src.lut, src.n_lut, live ? g : g_first);
       u128 pre = {(uint64_t)(pj & src.prefix_mask), 0};
@@ -403,37 +444,52 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, 
       cnt = (uint32_t)c64;
     }
     u128 x35 = mask128(shr128(x43, 2 * tail), 2 * k);
-    uint64_t h = canon_hash_k<K>(x35, k, &canon);
+    uint64_t h;
+    if constexpr (K > 0)
+      h = canon_hash_lut<K>(x35, &canon, tab);
+    else
+      h = canon_hash_rt(x35, k, &canon);
     uint64_t idx = bf_index(v, h);
     uint32_t line = (uint32_t)(idx >> 8);  // n_lines < 2^32 (bf_bits < 2^40)
     uint32_t bit = (uint32_t)(idx & 255);
-    __syncwarp();  // the previous iteration's reads of the tile are done
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    // occupancy pre-filter (L2): most probe lines hold nothing for a given k-mer; those are never fetched
+    const bool need = live && occ_test(v, idx);
+    const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
+    const int n_need = __popc(need_mask);
+    const int rank = __popc(need_mask & ((1u << lane) - 1u));  // row of this lane's line in the tile
+    __syncwarp();  // the previous iteration's reads of the tile and of the row list are done
+    if (need) rows[rank] = line;
+    __syncwarp();
+    for (int r = 0; 4 * r < n_need; ++r) {
       const int L = 4 * r + grp;
-      uint32_t l = __shfl_sync(0xffffffffu, line, L);
-      cp_async16(tile_addr + (uint32_t)((L * 8 + (sub ^ (L & 7))) * 16), v.lines + (uint64_t)l * LINE_U4 + sub);
+      if (L < n_need)
+        cp_async16(tile_addr + (uint32_t)((L * 8 + (sub ^ (L & 7))) * 16), v.lines + (uint64_t)rows[L] * LINE_U4 + sub);
     }
     cp_async_wait_all();
     __syncwarp();
-    // ---- every lane now owns line `lane` of the tile ----
-    const uint4 *mine = tile + lane * 8;
-    const int sw = lane & 7;
+    if (!need) continue;
+    // ---- every needing lane now owns row `rank` of the tile ----
+    const uint4 *mine = tile + rank * 8;
+    const int sw = rank & 7;
     uint32_t wsel = bit >> 5;  // which of the 8 filter words
     uint32_t fw = reinterpret_cast<const uint32_t *>(mine + ((wsel >> 2) ^ sw))[wsel & 3];
     bool bf_hit = (fw >> (bit & 31u)) & 1u;
     const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
                    c3 = (uint32_t)(canon.hi >> 32);
-    int slot = -1;
-    uint32_t last_w = 0;
+    // the low word of each key slot first (one 4-byte shared load per slot); the other three words only when it
+    // matches (a ref-key hit, ~3 % of the k-mers, or a 2^-32 coincidence)
+    bool low_match = false;
 #pragma unroll
-    for (int s = 0; s < LINE_KEYS; ++s) {
-      uint4 p = mine[(2 + s) ^ sw];
-      uint32_t diff = (p.x ^ c0) | (p.y ^ c1) | (p.z ^ c2) | ((p.w & (uint32_t)(KEY_HI_MASK >> 32)) ^ c3);
-      if (diff == 0) slot = s;
-      if (s == LINE_KEYS - 1) last_w = p.w;
+    for (int s = 0; s < LINE_KEYS; ++s) low_match |= reinterpret_cast<const uint32_t *>(mine + ((2 + s) ^ sw))[0] == c0;
+    int slot = -1;
+    if (low_match) {
+#pragma unroll 1
+      for (int s = 0; s < LINE_KEYS; ++s) {
+        uint4 p = mine[(2 + s) ^ sw];
+        if (((p.x ^ c0) | (p.y ^ c1) | (p.z ^ c2) | ((p.w & (uint32_t)(KEY_HI_MASK >> 32)) ^ c3)) == 0) slot = s;
+      }
     }
-    if (!live) continue;
+    const uint32_t last_w = reinterpret_cast<const uint32_t *>(mine + ((2 + LINE_KEYS - 1) ^ sw))[3];
     // ---- ref_bf.increment ----
     if (slot >= 0) {
       atomicAdd(v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot, cnt);
@@ -452,7 +508,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, 
     // ---- bf.increment unless the context filter vetoes it ----
     if (bf_hit) {
       u128 c43;
-      uint64_t h43 = canon_hash_k<REFK>(x43, ref_k, &c43);
+      uint64_t h43;
+      if constexpr (REFK > 0)
+        h43 = canon_hash_lut<REFK>(x43, &c43, tab);
+      else
+        h43 = canon_hash_rt(x43, ref_k, &c43);
       if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + bf_rank_of(v, idx), cnt);
     }
   }
@@ -478,9 +538,11 @@ __global__ void __launch_bounds__(256) k_mark_ref(const uint64_t *__restrict__ v
 // mode 1: test_key on filter/table `which` (0 bf, 1 context_bf, 2 ref_bf; out = 0/1, -1 = irregular KMAP key)
 __global__ void __launch_bounds__(128) k_lookup(const uint8_t *__restrict__ pool, const uint64_t *__restrict__ off,
                                                const uint8_t *__restrict__ is_ref, uint64_t n, DevView v, int mode,
-                                               int which, int32_t *__restrict__ out, unsigned long long *scalars) {
+                                               int which, int32_t *__restrict__ out, unsigned long long *scalars,
+                                               const uint8_t *__restrict__ only_flagged) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (only_flagged && !only_flagged[i]) return;  // second pass after k_lookup_fast: the k-mers it deferred
   uint64_t b = off[i], e = off[i + 1];
   int len = (int)(e - b);
   if (len > 128) {
@@ -514,6 +576,48 @@ __global__ void __launch_bounds__(128) k_lookup(const uint8_t *__restrict__ pool
     out[i] = set;
   } else {
     out[i] = (set && v.rank) ? (int32_t)(v.bf_counts[bf_rank_of(v, idx)] & 0xFFFFu) : 0;
+  }
+}
+
+// Fast path of mode 0 for the compiled k: signature k-mers that are exactly K bytes long are read as aligned
+// 32-bit words, packed to 2-bit codes four bases at a time and validated by re-expanding the codes to ASCII
+// (pack_words, xxh3.cuh); anything that is not K symbols of ACGT, and the few k-mers at the very end of the
+// pool, take the generic byte path above.  ~10x fewer instructions per k-mer than the generic kernel.
+template <int K>
+__global__ void __launch_bounds__(128) k_lookup_fast(const uint8_t *__restrict__ pool, uint64_t pool_bytes,
+                                                    const uint64_t *__restrict__ off,
+                                                    const uint8_t *__restrict__ is_ref, uint64_t n, DevView v,
+                                                    int32_t *__restrict__ out, uint8_t *__restrict__ slow_flag) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int NW = (K + 3) / 4;  // 4-base groups
+  const uint64_t b = off[i], e = off[i + 1];
+  const uint64_t a0 = b & ~3ull;
+  if (e - b != (uint64_t)K || a0 + 4ull * (NW + 1) > pool_bytes) {
+    slow_flag[i] = 1;
+    return;
+  }
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>(pool + a0);
+  const uint32_t sh = (uint32_t)(b & 3) * 8;
+  uint32_t raw[NW + 1], t[NW];
+#pragma unroll
+  for (int j = 0; j <= NW; ++j) raw[j] = __ldg(wp + j);
+#pragma unroll
+  for (int j = 0; j < NW; ++j) t[j] = __funnelshift_r(raw[j], raw[j + 1], sh);  // bases 4j..4j+3, first base low
+  u128 x;
+  const uint32_t bad = pack_words<K>(t, &x);
+  if (bad) {
+    slow_flag[i] = 1;
+    return;
+  }
+  u128 canon;
+  uint64_t h = canon_hash<K>(x, &canon);
+  uint64_t idx = bf_index(v, h);
+  if (is_ref[i]) {
+    int64_t loc = key_locate(v, h, idx, canon);
+    out[i] = loc != -1 ? (int32_t)*count_ptr(v, loc) : 0;
+  } else {
+    out[i] = (bf_test(v, idx) && v.rank) ? (int32_t)(v.bf_counts[bf_rank_of(v, idx)] & 0xFFFFu) : 0;
   }
 }
 
@@ -636,11 +740,12 @@ __global__ void __launch_bounds__(256) k_emit_bits(const uint32_t *__restrict__ 
   }
 }
 __global__ void __launch_bounds__(256) k_set_bits(const uint64_t *__restrict__ idx, uint64_t n, uint64_t n_bits,
-                                                 uint32_t *words_rw, int as_lines) {
+                                                 uint32_t *words_rw, int as_lines, DevView v, uint32_t *occ_rw) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t b = idx[i];
   if (b >= n_bits) return;
+  if (as_lines) occ_set(v, occ_rw, b);
   uint32_t *w = as_lines ? words_rw + (b >> 8) * 32 + ((b & 255) >> 5) : words_rw + (b >> 5);
   atomicOr(w, 1u << (b & 31));
 }

@@ -62,6 +62,9 @@ struct mg_ctx {
   uint64_t bf_bits = 0, n_lines = 0, n_ctx_words = 0;
   uint4 *lines = nullptr;          // n_lines x 128 B
   uint32_t *ctx_words = nullptr;   // context_bf bits
+  uint32_t *occ = nullptr;         // occupancy pre-filter (index.cuh), one bit per 2^occ_shift bf indices
+  uint64_t n_occ_words = 0;
+  int occ_shift = 0;
   uint32_t *rank = nullptr;        // n_lines + 1
   uint32_t *bf_counts = nullptr;   // one per set bit of bf
   uint32_t *key_counts = nullptr;  // n_lines x 6
@@ -78,7 +81,7 @@ struct mg_ctx {
   void *d_stage_k[2] = {nullptr, nullptr};
   uint32_t *d_stage_c[2] = {nullptr, nullptr};
   int next_stage = 0;
-  int scan_ctas_per_sm = 8;
+  int scan_ctas_per_sm = 128;  // grid cap of the scan kernel, in CTAs per SM (measured optimum 64..256, profiles/)
   uint64_t *kmc_lut = nullptr;  // device copy of the KMC prefix LUT (+ guard)
   uint32_t kmc_n_lut = 0, kmc_min = 0;
   uint64_t kmc_max = 0;
@@ -108,6 +111,8 @@ struct mg_ctx {
     v.bf_mask = (bf_bits & (bf_bits - 1)) == 0 ? bf_bits - 1 : 0;
     v.k = k;
     v.ref_k = ref_k;
+    v.occ = occ;
+    v.occ_shift = occ_shift;
     return v;
   }
 };
@@ -173,7 +178,7 @@ extern "C" int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sms = prop.multiProcessorCount;
-  if (const char *e = getenv("MG_SCAN_CTAS_PER_SM")) c->scan_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 8;
+  if (const char *e = getenv("MG_SCAN_CTAS_PER_SM")) c->scan_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 128;
   for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
   CU(cudaMalloc(&c->lines, c->n_lines * 128));
   CU(cudaMalloc(&c->ctx_words, c->n_ctx_words * 4));
@@ -183,6 +188,19 @@ extern "C" int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf
   CU(cudaGetLastError());
   CU(cudaMemsetAsync(c->ctx_words, 0, c->n_ctx_words * 4, c->stream[0]));
   CU(cudaMemsetAsync(c->key_counts, 0, c->n_lines * mg::LINE_KEYS * 4, c->stream[0]));
+  // occupancy pre-filter: at most 2^MG_OCC_LOG2_BITS bits (default 2^29 = 64 MB: half of the 126 MB L2, the measured optimum)
+  {
+    int cap_log2 = 29;
+    if (const char *e = getenv("MG_OCC_LOG2_BITS")) cap_log2 = atoi(e);
+    if (cap_log2 > 0) {
+      if (cap_log2 < 10) cap_log2 = 10;
+      if (cap_log2 > 34) cap_log2 = 34;
+      while (((bf_bits - 1) >> c->occ_shift) + 1 > (1ull << cap_log2)) ++c->occ_shift;
+      c->n_occ_words = ((((bf_bits - 1) >> c->occ_shift) + 1) + 31) / 32;
+      CU(cudaMalloc(&c->occ, c->n_occ_words * 4));
+      CU(cudaMemsetAsync(c->occ, 0, c->n_occ_words * 4, c->stream[0]));
+    }
+  }
   CU(cudaMalloc(&c->d_scalars, 8 * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), c->stream[0]));
   c->ovf_log2 = 10;
@@ -199,6 +217,7 @@ extern "C" void mg_destroy(mg_ctx *c) {
   cudaDeviceSynchronize();
   cudaFree(c->lines);
   cudaFree(c->ctx_words);
+  cudaFree(c->occ);
   cudaFree(c->rank);
   cudaFree(c->bf_counts);
   cudaFree(c->key_counts);
@@ -303,7 +322,7 @@ extern "C" int mg_add_signatures(mg_ctx *c, const char *pool, const uint64_t *of
   CU(cudaMalloc(&spill.p, (n_ref ? n_ref : 1) * 4));
   CU(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), c->stream[0]));
   c->launches++;
-  mg::k_add_signatures<<<grid_for(n, 128), 128, 0, c->stream[0]>>>(b.pool, b.off, b.flags, n, c->view(), c->lines,
+  mg::k_add_signatures<<<grid_for(n, 128), 128, 0, c->stream[0]>>>(b.pool, b.off, b.flags, n, c->view(), c->lines, c->occ,
                                                                    c->d_scalars, (uint32_t *)irr.p, (uint32_t *)spill.p);
   CU(cudaGetLastError());
   unsigned long long n_irr = 0;
@@ -339,7 +358,7 @@ extern "C" int mg_add_signatures_packed(mg_ctx *c, const uint64_t *lohi, const u
   CU(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), c->stream[0]));
   c->launches++;
   mg::k_add_packed<<<grid_for(n, 256), 256, 0, c->stream[0]>>>((const uint4 *)dk.p, (const uint8_t *)df.p, n, c->view(),
-                                                               c->lines, c->d_scalars, (uint32_t *)spill.p);
+                                                               c->lines, c->occ, c->d_scalars, (uint32_t *)spill.p);
   CU(cudaGetLastError());
   return finish_inserts(c, (const uint32_t *)spill.p, nullptr, nullptr, (const uint4 *)dk.p, nullptr);
 }
@@ -352,6 +371,28 @@ static int count_ones(mg_ctx *c, const uint32_t *words, uint64_t n_units, int st
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ones, c->d_scalars + 2, 8, cudaMemcpyDeviceToHost, c->stream[0]));
   CU(cudaStreamSynchronize(c->stream[0]));
+  return MG_OK;
+}
+
+// Keep the occupancy pre-filter resident in L2 while the probe lines stream through it: a persisting
+// access-policy window on both of the context's streams (MG_L2_PERSIST=0 disables it).
+static int pin_occ_in_l2(mg_ctx *c) {
+  if (!c->occ) return MG_OK;
+  if (const char *e = getenv("MG_L2_PERSIST"))
+    if (atoi(e) == 0) return MG_OK;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c->device));
+  size_t bytes = c->n_occ_words * 4;
+  if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return MG_OK;
+  size_t carve = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+  CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+  cudaStreamAttrValue attr = {};
+  attr.accessPolicyWindow.base_ptr = c->occ;
+  attr.accessPolicyWindow.num_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+  attr.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)((double)carve / (double)bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  for (int i = 0; i < 2; ++i) CU(cudaStreamSetAttribute(c->stream[i], cudaStreamAttributeAccessPolicyWindow, &attr));
   return MG_OK;
 }
 
@@ -379,7 +420,7 @@ extern "C" int mg_finalize_alt(mg_ctx *c) {
   CU(cudaMalloc(&c->bf_counts, (ones ? ones : 1) * 4));
   CU(cudaMemset(c->bf_counts, 0, (ones ? ones : 1) * 4));
   c->alt_final = true;
-  return MG_OK;
+  return pin_occ_in_l2(c);
 }
 
 template <int K, int REFK>
@@ -452,10 +493,15 @@ static int scan_src(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t 
 }
 
 static int scan_device(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n, cudaStream_t st) {
-  mg::ScanSrc src = {};
-  src.kmers = reinterpret_cast<const uint4 *>(d_lohi);
-  src.counts = reinterpret_cast<const uint32_t *>(d_counts);
-  return scan_src<0>(c, src, n, st);
+  const uint64_t MAX_LAUNCH = 1ull << 30;  // the kernel indexes k-mers with 32 bits
+  for (uint64_t o = 0; o < n; o += MAX_LAUNCH) {
+    mg::ScanSrc src = {};
+    src.kmers = reinterpret_cast<const uint4 *>(d_lohi) + o;
+    src.counts = reinterpret_cast<const uint32_t *>(d_counts) + o;
+    int rc = scan_src<0>(c, src, n - o < MAX_LAUNCH ? n - o : MAX_LAUNCH, st);
+    if (rc) return rc;
+  }
+  return MG_OK;
 }
 
 extern "C" int mg_scan_sample_kmers_device(mg_ctx *c, const void *d_lohi, const void *d_counts, uint64_t n) {
@@ -573,7 +619,7 @@ static int lookup_common(mg_ctx *c, const char *pool, const uint64_t *off, const
   CU(cudaMalloc(&d_out.p, (n ? n : 1) * 4));
   c->launches++;
   mg::k_lookup<<<grid_for(n, 128), 128, 0, c->stream[0]>>>(b.pool, b.off, b.flags, n, c->view(), mode, which,
-                                                           (int32_t *)d_out.p, c->d_scalars);
+                                                           (int32_t *)d_out.p, c->d_scalars, nullptr);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out_host, d_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream[0]));
   CU(cudaStreamSynchronize(c->stream[0]));
@@ -611,7 +657,7 @@ static int genotype_on_device(mg_ctx *c, const mg_variant_batch *in, const mg_ge
                               const mg_batch_dims *dm, float error_rate, int max_coverage, int haploid) {
   cudaStream_t st = c->stream[0];
   uint64_t nv = dm->n_variants, na = dm->n_alleles, nk = dm->n_kmers;
-  uint64_t need = (nk ? nk : 1) * 5;
+  uint64_t need = (nk ? nk : 1) * 6;  // i32 weight + ref flag + deferred flag per k-mer
   if (c->geno_scratch_bytes < need) {
     cudaFree(c->geno_scratch);
     c->geno_scratch = nullptr;
@@ -630,10 +676,26 @@ static int genotype_on_device(mg_ctx *c, const mg_variant_batch *in, const mg_ge
     mg::k_mark_ref<<<grid_for(nv, 256), 256, 0, st>>>(in->var_allele_off, in->allele_sig_off, in->sig_kmer_off, nv,
                                                       d_flags);
     CU(cudaGetLastError());
-    c->launches++;
-    mg::k_lookup<<<grid_for(nk, 128), 128, 0, st>>>(reinterpret_cast<const uint8_t *>(in->pool), in->kmer_off, d_flags,
-                                                    nk, c->view(), 0, 0, d_w, c->d_scalars);
-    CU(cudaGetLastError());
+    const uint8_t *d_pool = reinterpret_cast<const uint8_t *>(in->pool);
+    if (c->k == 35 && dm->pool_bytes && (reinterpret_cast<uintptr_t>(d_pool) & 3) == 0) {
+      // fast path for well-formed 35-mers; whatever it defers (odd lengths, non-ACGT, pool tail) goes through
+      // the generic kernel, which is skipped when nothing was deferred
+      uint8_t *d_slow = d_flags + nk;
+      CU(cudaMemsetAsync(d_slow, 0, nk, st));
+      c->launches++;
+      mg::k_lookup_fast<35><<<grid_for(nk, 128), 128, 0, st>>>(d_pool, dm->pool_bytes, in->kmer_off, d_flags, nk,
+                                                               c->view(), d_w, d_slow);
+      CU(cudaGetLastError());
+      c->launches++;
+      mg::k_lookup<<<grid_for(nk, 128), 128, 0, st>>>(d_pool, in->kmer_off, d_flags, nk, c->view(), 0, 0, d_w,
+                                                      c->d_scalars, d_slow);
+      CU(cudaGetLastError());
+    } else {
+      c->launches++;
+      mg::k_lookup<<<grid_for(nk, 128), 128, 0, st>>>(d_pool, in->kmer_off, d_flags, nk, c->view(), 0, 0, d_w,
+                                                      c->d_scalars, nullptr);
+      CU(cudaGetLastError());
+    }
   }
   CU(cudaEventRecord(c->ge[1], st));
   c->launches++;
@@ -678,6 +740,7 @@ extern "C" int mg_genotype(mg_ctx *c, const mg_variant_batch *in, const mg_genot
   dm.n_alleles = in->var_allele_off[nv];
   dm.n_sigs = in->allele_sig_off[dm.n_alleles];
   dm.n_kmers = in->sig_kmer_off[dm.n_sigs];
+  dm.pool_bytes = in->kmer_off[dm.n_kmers];
   uint64_t na = dm.n_alleles, ns = dm.n_sigs, nk = dm.n_kmers, nl = out->lik_off[nv];
   uint64_t pool_bytes = in->kmer_off[nk];
   cudaStream_t st = c->stream[0];
@@ -851,7 +914,8 @@ extern "C" int mg_import_set_bits(mg_ctx *c, int which, const uint64_t *idx, uin
   CU(cudaMemcpyAsync(d.p, idx, n * 8, cudaMemcpyHostToDevice, c->stream[0]));
   c->launches++;
   mg::k_set_bits<<<grid_for(n, 256), 256, 0, c->stream[0]>>>(
-      (const uint64_t *)d.p, n, c->bf_bits, which ? c->ctx_words : reinterpret_cast<uint32_t *>(c->lines), which == 0);
+      (const uint64_t *)d.p, n, c->bf_bits, which ? c->ctx_words : reinterpret_cast<uint32_t *>(c->lines), which == 0,
+      c->view(), c->occ);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream[0]));
   return MG_OK;
@@ -1003,6 +1067,15 @@ extern "C" uint64_t mg_selftest_hash_packed_k43(uint64_t lo, uint64_t hi) {
 }
 extern "C" uint64_t mg_selftest_hash_ascii(const char *s, int len) {
   return mg::hash_ascii(reinterpret_cast<const uint8_t *>(s), len);
+}
+extern "C" int mg_selftest_pack35(const char *s35, uint64_t *lo, uint64_t *hi) {
+  uint32_t t[9] = {0};
+  memcpy(t, s35, 35);
+  u128 x;
+  uint32_t bad = mg::pack_words<35>(t, &x);
+  if (lo) *lo = x.lo;
+  if (hi) *hi = x.hi;
+  return bad ? 0 : 1;
 }
 extern "C" float mg_selftest_logf(float x) { return mg::glibc_logf(x); }
 extern "C" int mg_selftest_genotype(const uint32_t *cov, const float *freq, int n_alleles, float error_rate,

@@ -64,7 +64,12 @@ MG_HD uint64_t bswap64(uint64_t v) {
 }
 MG_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 
-MG_HD uint64_t mul128_fold64(uint64_t a, uint64_t b) { return (a * b) ^ mulhi64(a, b); }
+// low ^ high half of the 128-bit product (XXH3_mul128_fold64, xxhash.h:3708-3762); one 128-bit multiply lets
+// the compiler share the four 32x32 partial products between the two halves
+MG_HD uint64_t mul128_fold64(uint64_t a, uint64_t b) {
+  unsigned __int128 p = (unsigned __int128)a * b;
+  return (uint64_t)p ^ (uint64_t)(p >> 64);
+}
 MG_HD uint64_t xxh3_avalanche(uint64_t h) {
   h ^= h >> 37;
   h *= 0x165667919E3779F9ULL;
@@ -202,6 +207,28 @@ MG_HD uint32_t expand4(uint32_t v) {
 #endif
 }
 
+MG_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, b, sel);
+#else
+  const uint64_t pool = (uint64_t)a | ((uint64_t)b << 32);
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7))) & 0xFFu) << (8 * i);
+  return r;
+#endif
+}
+// 8 bases = one 16-bit half of `word` (HALF 0: bits 0..15, HALF 1: bits 16..31; base 0 in the low 2 bits)
+// -> 8 ASCII bytes.  The two bytes are first moved to byte lanes 0 and 2 (one PRMT), the 2-bit codes are then
+// spread to nibbles in two shift-or-mask steps, and each nibble indexes the byte table "ACGT" (PRMT).
+template <int HALF>
+MG_HD uint64_t expand8(uint32_t word) {
+  uint32_t t = prmt(word, 0u, HALF ? 0x4342u : 0x4140u);  // {b0, 0, b1, 0}
+  t = (t | (t << 4)) & 0x0F0F0F0Fu;
+  t = (t | (t << 2)) & 0x33333333u;
+  const uint32_t lo = prmt(0x54474341u, 0u, t), hi = prmt(0x54474341u, 0u, t >> 16);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
 // ASCII bytes of a k-mer (given in LSB-first layout) as LE u64 words; bytes
 // past k are unspecified but never read by xxh3_64_words(w, K).
 template <int K>
@@ -209,10 +236,8 @@ MG_HD void ascii_words(u128 r, uint64_t *w) {
   constexpr int NW = (K + 7) / 8;
 #pragma unroll
   for (int j = 0; j < NW; ++j) {
-    uint32_t bits16 = (j < 4) ? (uint32_t)(r.lo >> (16 * j)) : (uint32_t)(r.hi >> (16 * (j - 4)));
-    uint32_t lo = expand4(bits16 & 0xFFu);
-    uint32_t hi = expand4((bits16 >> 8) & 0xFFu);
-    w[j] = (uint64_t)lo | ((uint64_t)hi << 32);
+    const uint32_t word = (j < 4) ? (uint32_t)(r.lo >> (32 * (j >> 1))) : (uint32_t)(r.hi >> (32 * ((j - 4) >> 1)));
+    w[j] = (j & 1) ? expand8<1>(word) : expand8<0>(word);
   }
   w[NW] = 0;
 }
@@ -326,6 +351,44 @@ MG_HD bool pack_ascii(const uint8_t *s, int len, int k, u128 *out) {
   }
   *out = x;
   return true;
+}
+
+// Pack a K-byte ASCII k-mer given as little-endian 32-bit words (first base in the low byte of t[0]) and
+// validate it at the same time: returns 0 iff every one of the K bytes is one of A, C, G, T.
+//   code of an ASCII base: ((c >> 1) ^ (c >> 2)) & 3  ->  A=0 C=1 G=2 T=3; re-expanding the codes through the
+//   byte table "ACGT" and comparing with the input catches every other byte value.
+template <int K>
+MG_HD uint32_t pack_words(const uint32_t *t, u128 *out) {
+  constexpr int NW = (K + 3) / 4;
+  constexpr int REM = K - 4 * (NW - 1);  // bases in the last group
+  u128 x;
+  x.lo = 0;
+  x.hi = 0;
+  uint32_t bad = 0;
+#pragma unroll
+  for (int j = 0; j < NW; ++j) {
+    const uint32_t c = ((t[j] >> 1) ^ (t[j] >> 2)) & 0x03030303u;
+    const uint32_t sel = (c & 0x3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
+#if defined(__CUDA_ARCH__)
+    const uint32_t back = __byte_perm(0x54474341u, 0u, sel);
+#else
+    uint32_t back = 0;
+    for (int q = 0; q < 4; ++q) back |= ((0x54474341u >> (8 * ((sel >> (4 * q)) & 3))) & 0xFFu) << (8 * q);
+#endif
+    const uint32_t m = (j == NW - 1 && REM < 4) ? ((1u << (8 * (REM & 3))) - 1u) : 0xFFFFFFFFu;
+    bad |= (back ^ t[j]) & m;
+    uint32_t x8 = (c * 0x40100401u) >> 24;  // b0<<6 | b1<<4 | b2<<2 | b3
+    if (j == NW - 1 && REM < 4) {
+      x8 >>= 2 * (4 - REM);
+      x.hi = (x.hi << (2 * REM)) | (x.lo >> (64 - 2 * REM));
+      x.lo = (x.lo << (2 * REM)) | x8;
+    } else {
+      x.hi = (x.hi << 8) | (x.lo >> 56);
+      x.lo = (x.lo << 8) | x8;
+    }
+  }
+  *out = x;
+  return bad;
 }
 
 }  // namespace mg
