@@ -383,10 +383,12 @@ def run_ours(args, wl, rank, local_rank, world):
     ref_seq[(ppos[:, None] + torch.arange(K, device=dev)[None, :]).reshape(-1)] = plant.reshape(-1)
     ref_host = ref_seq.cpu().numpy().tobytes()
     del ref_seq
+    g.scan_reference(ref_host)   # cold call (allocation, first touch of the pageable host buffer)
     g.event_record(0)
-    g.scan_reference(ref_host)   # includes the H2D copy of the contig
+    g.scan_reference(ref_host)   # idempotent (bits are only ever set): the warm call is the one timed
     g.event_record(1)
-    refpass_ms = g.event_elapsed_ms(0, 1)
+    refpass_ms = g.event_elapsed_ms(0, 1)           # includes the H2D copy of the contig from pageable memory
+    refpass_kernel_ms = g.refpass_kernel_ms()       # the rolling-pass kernel alone
     del ref_host
     g.finalize_context()
     pop_alt, pop_ctx, n_keys = g.popcount(0), g.popcount(1), g.kmap_size()
@@ -409,7 +411,8 @@ def run_ours(args, wl, rank, local_rank, world):
     del alt, ref
     torch.cuda.synchronize()
     log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s: bf ones {pop_alt}, context ones {pop_ctx}, ref keys {n_keys}, "
-        f"K2 reference pass {wl['ref_bases'] / refpass_ms / 1e6:.1f} Gbases/s incl. H2D")
+        f"K2 reference pass {wl['ref_bases'] / refpass_kernel_ms / 1e6:.1f} Gbases/s (kernel), "
+        f"{wl['ref_bases'] / refpass_ms / 1e6:.1f} Gbases/s incl. H2D")
 
     # ---- host-side inputs of the e2e leg, all in pinned memory ----
     #  (a) the batch as raw KMC suffix records (+ prefix LUT): what malva-geno call reads from <db>.kmc_suf
@@ -550,7 +553,8 @@ def run_ours(args, wl, rank, local_rank, world):
         "variants_per_sec": world * nv / (sum(geno_ms) * 1e-3),
         "variants_per_sec_note": "K4+K5 kernels only (signature look-ups, coverage, likelihood), device-resident CSR",
         "kernel_ms": {"k1_scan": k1_ms, "k4_lookup": geno_ms[0], "k4_coverage": geno_ms[1], "k5_genotype": geno_ms[2],
-                      "k2_reference_pass_incl_h2d": refpass_ms},
+                      "k2_reference_pass": refpass_kernel_ms, "k2_reference_pass_incl_h2d": refpass_ms},
+        "ref_bases_per_sec": wl["ref_bases"] / (refpass_kernel_ms * 1e-3),
         "ref_bases_per_sec_incl_h2d": wl["ref_bases"] / (refpass_ms * 1e-3),
         "index": {"bf_ones": pop_alt, "context_ones": pop_ctx, "ref_keys": n_keys},
         "e2e": None if e2e_ms is None else {

@@ -153,6 +153,8 @@ int mg_event_elapsed_ms(mg_ctx *ctx, int a, int b, float *ms);
 int mg_event_sync(mg_ctx *ctx, int idx);
 /* device time of the last mg_genotype call: {signature look-ups, coverage, likelihood} kernels, ms */
 int mg_genotype_kernel_ms(mg_ctx *ctx, float *ms3);
+/* device time of the rolling-pass kernel of the last mg_scan_reference call (contigs >= ref_k), ms */
+int mg_refpass_kernel_ms(mg_ctx *ctx, float *ms);
 /* kernels launched by this context so far */
 int mg_launch_count(mg_ctx *ctx, uint64_t *n);
 /* measured ceilings over `bytes` of HBM, GB/s of useful bytes, best of reps: mode 0 / 2 / 3 = independent

@@ -91,6 +91,7 @@ SYMBOLS = {
     "mg_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, f32p]),
     "mg_event_sync": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_genotype_kernel_ms": (C.c_int, [C.c_void_p, f32p]),
+    "mg_refpass_kernel_ms": (C.c_int, [C.c_void_p, f32p]),
     "mg_launch_count": (C.c_int, [C.c_void_p, u64p]),
     "mg_diag_bandwidth": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, f64p]),
     "mg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

@@ -319,6 +319,11 @@ class MalvaGpu:
         check(self._L.mg_genotype_kernel_ms(self._h, ms))
         return list(ms)
 
+    def refpass_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        check(self._L.mg_refpass_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def launch_count(self) -> int:
         v = C.c_uint64(0)
         check(self._L.mg_launch_count(self._h, C.byref(v)))

@@ -71,6 +71,7 @@ struct Options {
   uint64_t bf_size = 1ull << 35;
   bool strip_chr = false, uniform = false, verbose = false, haploid = false, index_blocks = false;
   int threads = 0, device = 0;
+  bool trace = false;  // --trace: per-batch host/device timings on stderr
   std::string fasta_path, vcf_path, kmc_path;
 };
 
@@ -93,6 +94,7 @@ bool parse_arguments(int argc, char **argv, Options &o, int n_positional) {
                                     {"threads", required_argument, nullptr, 1000},
                                     {"device", required_argument, nullptr, 1001},
                                     {"index-blocks", no_argument, nullptr, 1002},
+                                    {"trace", no_argument, nullptr, 1003},
                                     {nullptr, 0, nullptr, 0}};
   bool die = false;
   optind = 1;
@@ -116,6 +118,7 @@ bool parse_arguments(int argc, char **argv, Options &o, int n_positional) {
       case 1000: arg >> o.threads; break;
       case 1001: arg >> o.device; break;
       case 1002: o.index_blocks = true; break;
+      case 1003: o.trace = true; break;
       case '?': die = true; break;
       case 'h':
         std::cout << USAGE;
@@ -163,6 +166,16 @@ void pelapsed(const std::string &s, bool rollback = false) {
   std::cerr << buf;
   g_last = Clock::now();
 }
+
+struct Stopwatch {
+  Clock::time_point t = Clock::now();
+  double lap() {
+    auto n = Clock::now();
+    double s = std::chrono::duration<double>(n - t).count();
+    t = n;
+    return s * 1e3;
+  }
+};
 
 void parallel_for(size_t n, int threads, const std::function<void(size_t)> &fn) {
   if (n == 0) return;
@@ -312,14 +325,22 @@ int index_main(int argc, char **argv) {
 
   pelapsed("VCF parsing (Bloom Filter construction)");
   Ctx g;
+  Stopwatch sw;
   gpu(mg_create(&g.c, o.device, (int)o.k, (int)o.ref_k, o.bf_size), "mg_create");
+  if (o.trace) fprintf(stderr, "[trace] mg_create (CUDA start-up + empty index) %.1f ms\n", sw.lap());
   std::vector<mh::VarBlock> blocks;
   mh::SignatureCsr sigs;
   while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+    const double t_parse = sw.lap();
     enumerate_batch(blocks, refs, o, sigs);
+    const double t_enum = sw.lap();
     // add_kmers_to_bf (main.cpp:122-144): allele 0 -> ref_bf, others -> bf
     gpu(mg_add_signatures(g.c, sigs.pool.data(), sigs.kmer_off.data(), sigs.kmer_is_ref.data(), sigs.n_kmers()),
         "mg_add_signatures");
+    if (o.trace)
+      fprintf(stderr, "[trace] index batch: %zu blocks, %llu k-mers: read+decode %.1f ms, enumerate %.1f ms, device %.1f ms\n",
+              blocks.size(), (unsigned long long)sigs.n_kmers(), t_parse, t_enum, sw.lap());
+    sw.lap();
   }
   pelapsed("Processed " + std::to_string(stream.n_records) + " variants");
   gpu(mg_finalize_alt(g.c), "mg_finalize_alt");  // bf.switch_mode()
@@ -499,8 +520,11 @@ int call_main(int argc, char **argv) {
   std::vector<double> lik;
   std::vector<const mh::Variant *> order;
   std::vector<std::string> text;
+  Stopwatch sw;
   while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+    const double t_parse = sw.lap();
     enumerate_batch(blocks, refs, o, sigs);
+    const double t_enum = sw.lap();
     const uint64_t nv = sigs.n_variants();
     if (nv == 0) continue;
     lik_off.assign(nv + 1, 0);
@@ -522,6 +546,7 @@ int call_main(int argc, char **argv) {
                            best.data(), gq.data(),      lik_off.data(),
                            o.verbose ? lik.data() : nullptr};
     gpu(mg_genotype(g.c, &in, &res, o.error_rate, (int)o.max_coverage, o.haploid ? 1 : 0), "mg_genotype");
+    const double t_dev = sw.lap();
     order.clear();
     for (const auto &b : blocks)
       for (size_t i = 0; i < b.size(); ++i) order.push_back(&b[i]);
@@ -533,6 +558,10 @@ int call_main(int argc, char **argv) {
                        o.verbose ? lik.data() + lik_off[i] : nullptr, o, text[c]);
     });
     for (const auto &t : text) fwrite(t.data(), 1, t.size(), stdout);
+    if (o.trace)
+      fprintf(stderr, "[trace] call batch: %llu variants, %llu k-mers: read+decode %.1f ms, enumerate %.1f ms, device %.1f ms, print %.1f ms\n",
+              (unsigned long long)nv, (unsigned long long)sigs.n_kmers(), t_parse, t_enum, t_dev, sw.lap());
+    sw.lap();
   }
   pelapsed("Processed " + std::to_string(stream.n_records) + " variants");
   fflush(stdout);

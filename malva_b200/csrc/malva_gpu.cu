@@ -89,6 +89,7 @@ struct mg_ctx {
   uint64_t launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
   cudaEvent_t tj = nullptr;
   cudaEvent_t ge[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t rpe[2] = {nullptr, nullptr};  // around the last reference-pass kernel
   void *geno_scratch = nullptr;  // per-k-mer weights + ref flags of mg_genotype
   uint64_t geno_scratch_bytes = 0;
   void *geno_arena = nullptr;  // device image of the last mg_genotype batch (grow-only)
@@ -235,6 +236,8 @@ extern "C" void mg_destroy(mg_ctx *c) {
   if (c->tj) cudaEventDestroy(c->tj);
   for (int i = 0; i < 4; ++i)
     if (c->ge[i]) cudaEventDestroy(c->ge[i]);
+  for (int i = 0; i < 2; ++i)
+    if (c->rpe[i]) cudaEventDestroy(c->rpe[i]);
   for (int i = 0; i < 64; ++i)
     if (c->evs[i]) cudaEventDestroy(c->evs[i]);
   delete c;
@@ -454,12 +457,16 @@ extern "C" int mg_scan_reference(mg_ctx *c, const char *seq, uint64_t len) {
   }
   CU(cudaMalloc(&ds.p, len));
   CU(cudaMemcpyAsync(ds.p, seq, len, cudaMemcpyHostToDevice, c->stream[0]));
+  for (int i = 0; i < 2; ++i)
+    if (!c->rpe[i]) CU(cudaEventCreate(&c->rpe[i]));
+  CU(cudaEventRecord(c->rpe[0], c->stream[0]));
   cudaError_t e;
   if (c->k == 35 && c->ref_k == 43)
     e = launch_refpass<35, 43>(c, (const uint8_t *)ds.p, len);
   else
     e = launch_refpass<0, 0>(c, (const uint8_t *)ds.p, len);
   if (e != cudaSuccess) return set_err(MG_ERR_CUDA, "k_refpass launch -> %s", cudaGetErrorString(e));
+  CU(cudaEventRecord(c->rpe[1], c->stream[0]));
   CU(cudaStreamSynchronize(c->stream[0]));
   return MG_OK;
 }
@@ -978,6 +985,13 @@ extern "C" int mg_genotype_kernel_ms(mg_ctx *c, float *ms3) {
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->ge[3]));
   for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms3[i], c->ge[i], c->ge[i + 1]));
+  return MG_OK;
+}
+extern "C" int mg_refpass_kernel_ms(mg_ctx *c, float *ms) {
+  if (!c || !ms || !c->rpe[1]) return set_err(MG_ERR_ARG, "no mg_scan_reference call to report");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->rpe[1]));
+  CU(cudaEventElapsedTime(ms, c->rpe[0], c->rpe[1]));
   return MG_OK;
 }
 extern "C" int mg_launch_count(mg_ctx *c, uint64_t *n) {

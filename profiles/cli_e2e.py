@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Whole-program comparison on one machine: the reference `malva-geno` (oracle/_ref/malva-geno-ref: the reference's
+own main.cpp, CPU, single-threaded like the original) against this repository's `malva-geno` (C++ host + B200
+kernels) on the same synthetic chromosome-arm-sized inputs; outputs must be byte-identical.
+
+    python profiles/cli_e2e.py [Mbp=5] [samples=32] > gpurun_out/cli_e2e.json
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np  # noqa: E402
+
+import synth  # noqa: E402
+from malva_b200 import build as mbuild  # noqa: E402
+from malva_b200 import kmc  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "malva-geno-ref")
+
+
+def fast_write_kmc(prefix, keys, counts, k, p=7):
+    """numpy version of kmc.write_kmc_db for millions of records (KMC2 layout, counter_size 1)."""
+    import struct
+    lo, hi = keys["lo"], keys["hi"]
+    suf_syms = k - p
+    assert suf_syms % 4 == 0 and 64 < 2 * suf_syms < 128
+    sb = suf_syms // 4
+    pref = (hi >> np.uint64(2 * suf_syms - 64)).astype(np.int64)
+    lut = np.zeros(4 ** p + 1, np.uint64)
+    lut[1:] = np.cumsum(np.bincount(pref, minlength=4 ** p)).astype(np.uint64)
+    rec = np.empty((len(lo), sb + 1), np.uint8)
+    hi_bytes = sb - 8
+    for j in range(hi_bytes):
+        rec[:, j] = ((hi >> np.uint64(8 * (hi_bytes - 1 - j))) & np.uint64(0xFF)).astype(np.uint8)
+    for j in range(8):
+        rec[:, hi_bytes + j] = ((lo >> np.uint64(56 - 8 * j)) & np.uint64(0xFF)).astype(np.uint8)
+    rec[:, sb] = counts.astype(np.uint8)
+    with open(prefix + ".kmc_suf", "wb") as fh:
+        fh.write(b"KMCS")
+        fh.write(rec.tobytes())
+        fh.write(b"KMCS")
+    sig_len = 5
+    hdr = struct.pack("<7IQB", k, 0, 1, p, sig_len, 2, 255, len(lo), 0)
+    hdr += b"\0" * (60 - len(hdr)) + struct.pack("<I", 0x200)
+    with open(prefix + ".kmc_pre", "wb") as fh:
+        fh.write(b"KMCP")
+        fh.write(lut.astype("<u8").tobytes())
+        fh.write(b"\0" * ((4 ** sig_len + 1) * 4))
+        fh.write(hdr + struct.pack("<I", len(hdr)) + b"KMCP")
+
+
+def phases(stderr):
+    out = {}
+    for m in re.finditer(r"\[malva-geno/([^\]]+)\] Execution Time ([0-9.e+-]+)s", stderr):
+        out[m.group(1)] = float(m.group(2))
+    return out
+
+
+def main():
+    mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
+    n_samples = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    mbuild.build()
+    case = synth.Case("cli_e2e", 20261018 + 42, [("1", int(mbp * 1e6))], mean_gap=41, n_samples=n_samples)
+    synth_write = kmc.write_kmc_db
+    kmc.write_kmc_db = lambda prefix, uk, uc, k, **kw: fast_write_kmc(prefix, uk, uc, k)
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.time()
+        fa, vcf, prefix, n_kmers = synth.build_case(case, d)
+        kmc.write_kmc_db = synth_write
+        n_var = sum(1 for l in open(vcf) if not l.startswith("#"))
+        res = {"reference_bases": int(mbp * 1e6), "variants": n_var, "panel_samples": n_samples, "sample_kmers": n_kmers,
+               "generate_s": round(time.time() - t0, 1), "host_cores": os.cpu_count()}
+        outs = {}
+        for name, exe in (("reference_cpu", REF), ("malva_b200", mbuild.CLI)):
+            r = {}
+            for sub in ("index", "call"):
+                t = time.time()
+                extra = ["--trace"] if name == "malva_b200" else []
+                p = subprocess.run([exe, sub, "-k", "35", "-r", "43", "-b", "1"] + extra + [fa, vcf, prefix], capture_output=True, text=True)
+                if extra:
+                    r[sub + "_trace"] = [l for l in p.stderr.split("\n") if l.startswith("[trace]")]
+                r[sub + "_wall_s"] = round(time.time() - t, 3)
+                assert p.returncode == 0, p.stderr[-2000:]
+                r[sub + "_phases_s"] = phases(p.stderr)
+                if sub == "call":
+                    outs[name] = p.stdout
+            os.remove(vcf + ".c43.k35.malvax.zst")
+            res[name] = r
+        res["outputs_identical"] = outs["reference_cpu"] == outs["malva_b200"]
+        a, b = res["reference_cpu"], res["malva_b200"]
+        scan_ref = a["call_phases_s"].get("BF weights created")
+        scan_ours = b["call_phases_s"].get("BF weights created")
+        res["summary"] = {
+            "total_speedup": round((a["index_wall_s"] + a["call_wall_s"]) / (b["index_wall_s"] + b["call_wall_s"]), 1),
+            "kmc_scan_s": [scan_ref, scan_ours],
+            "reference_pass_s": [a["index_phases_s"].get("Reference BF creation complete"),
+                                 b["index_phases_s"].get("Reference BF creation complete")],
+        }
+        print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
