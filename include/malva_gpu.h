@@ -110,6 +110,27 @@ typedef struct {
 int mg_genotype_device(mg_ctx *ctx, const mg_variant_batch *in, const mg_genotype_out *out, const mg_batch_dims *dims,
                        float error_rate, int max_coverage, int haploid);
 
+/* -------------------- k-mer counting (the step before the path) ---------- */
+/* What the wrapper script obtains from `kmc -k<ref_k> -ci2 -cs255` (MALVA:107) and malva-geno lists through the KMC
+ * API (main.cpp:482-490): canonical k-mers of the reads, windows with a non-ACGT symbol skipped, k-mers seen fewer
+ * than min_count times (or more than max_count) dropped, counts saturated at counter_max, ascending order.
+ * mg_count_add takes read bytes in HOST memory, records separated by any non-ACGT byte (e.g. '\n'); a k-mer never
+ * spans two calls.  For inputs whose distinct k-mers exceed device memory, run several passes over the reads with
+ * mg_count_set_partition (only canonical k-mers whose top part_bits bits lie in [part_lo, part_hi) are counted;
+ * passes in ascending prefix order yield the listing order) and mg_count_reset between them. */
+typedef struct mg_counter mg_counter;
+int mg_count_create(mg_counter **out, int device, int k);
+void mg_count_destroy(mg_counter *c);
+int mg_count_set_partition(mg_counter *c, int part_bits, uint32_t part_lo, uint32_t part_hi);
+int mg_count_reset(mg_counter *c);
+int mg_count_add(mg_counter *c, const char *bases, uint64_t n);
+int mg_count_finish(mg_counter *c, uint32_t min_count, uint32_t counter_max, uint64_t max_count, uint64_t *n_kmers);
+int mg_count_download(mg_counter *c, uint64_t *lohi, uint32_t *counts, uint64_t cap);
+/* {distinct k-mers in the table, k-mer instances counted, table capacity, kernels launched}; n >= 4 */
+int mg_count_stats(mg_counter *c, uint64_t *stats, int n);
+/* the counted k-mers straight into the sample scan (same device): no database file, no host round trip */
+int mg_scan_counted(mg_ctx *ctx, mg_counter *c);
+
 /* ------------------------- batch queries (BF / KMAP) --------------------- */
 /* which: 0 = bf, 1 = context_bf, 2 = ref_bf (KMAP).  BF::test_key / KMAP::test_key */
 int mg_test_keys(mg_ctx *ctx, int which, const char *pool, const uint64_t *kmer_off, uint64_t n, uint8_t *out);

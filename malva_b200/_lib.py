@@ -76,6 +76,15 @@ SYMBOLS = {
                               C.c_int]),
     "mg_genotype_device": (C.c_int, [C.c_void_p, C.POINTER(VariantBatch), C.POINTER(GenotypeOut),
                                      C.POINTER(BatchDims), C.c_float, C.c_int, C.c_int]),
+    "mg_count_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "mg_count_destroy": (None, [C.c_void_p]),
+    "mg_count_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]),
+    "mg_count_reset": (C.c_int, [C.c_void_p]),
+    "mg_count_add": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
+    "mg_count_finish": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, u64p]),
+    "mg_count_download": (C.c_int, [C.c_void_p, u64p, u32p, C.c_uint64]),
+    "mg_count_stats": (C.c_int, [C.c_void_p, u64p, C.c_int]),
+    "mg_scan_counted": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_test_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, u64p, C.c_uint64, u8p]),
     "mg_get_counts": (C.c_int, [C.c_void_p, C.c_char_p, u64p, u8p, C.c_uint64, i32p]),
     "mg_bf_popcount": (C.c_int, [C.c_void_p, C.c_int, u64p]),

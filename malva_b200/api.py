@@ -314,6 +314,11 @@ class MalvaGpu:
         check(self._L.mg_genotype_device(self._h, C.byref(vb), C.byref(out), C.byref(dm), C.c_float(error_rate),
                                          int(max_coverage), int(bool(haploid))))
 
+    def scan_counted(self, counter: "KmerCounter") -> None:
+        """the counted k-mers of a finished KmerCounter straight into the sample scan (no database file)"""
+        check(self._L.mg_scan_counted(self._h, counter._h))
+        self.sync()
+
     def genotype_kernel_ms(self):
         ms = (C.c_float * 3)()
         check(self._L.mg_genotype_kernel_ms(self._h, ms))
@@ -342,6 +347,52 @@ class MalvaGpu:
         check(self._L.mg_index_stats(self._h, s, 6))
         return dict(zip(("probe_lines", "bf_ones", "ref_keys", "overflow_keys", "overflow_capacity",
                          "irregular_ref_keys"), [int(x) for x in s]))
+
+
+class KmerCounter:
+    """Canonical k-mer counting on the device (``mg_count_*``): the ``kmc -k<k> -ci2 -cs255`` step of the MALVA
+    wrapper (MALVA:107).  ``add(reads)`` takes upper-case read bytes, records separated by any non-ACGT byte."""
+
+    def __init__(self, k: int = 43, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.k = k
+        check(self._L.mg_count_create(C.byref(self._h), device, k))
+
+    def close(self):
+        if self._h:
+            self._L.mg_count_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_partition(self, part_bits: int, lo: int, hi: int):
+        check(self._L.mg_count_set_partition(self._h, part_bits, lo, hi))
+
+    def reset(self):
+        check(self._L.mg_count_reset(self._h))
+
+    def add(self, reads) -> None:
+        b = reads if isinstance(reads, (bytes, bytearray)) else "\n".join(reads).encode()
+        check(self._L.mg_count_add(self._h, bytes(b), len(b)))
+
+    def finish(self, min_count: int = 2, counter_max: int = 255, max_count: int = 10 ** 9):
+        """-> (packed k-mers in ascending order, u32 counts)"""
+        n = C.c_uint64(0)
+        check(self._L.mg_count_finish(self._h, min_count, counter_max, max_count, C.byref(n)))
+        keys = np.zeros(n.value, dtype=KMER_DTYPE)
+        counts = np.zeros(n.value, dtype=np.uint32)
+        check(self._L.mg_count_download(self._h, keys.ctypes.data_as(_lib.u64p), _p(counts, _lib.u32p), n.value))
+        return keys, counts
+
+    def stats(self) -> dict:
+        s = (C.c_uint64 * 4)()
+        check(self._L.mg_count_stats(self._h, s, 4))
+        return dict(zip(("distinct", "instances", "capacity", "launches"), [int(x) for x in s]))
 
 
 def diag_bandwidth(device: int, mode: int, nbytes: int, reps: int = 3) -> float:

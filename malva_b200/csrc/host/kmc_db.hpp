@@ -106,4 +106,95 @@ struct KmcDb {
   }
 };
 
+// Writer of the same two files (KMC2 "0x200" layout, counter_size 1): what `malva-geno count` produces in place of
+// `kmc`.  Records must arrive in ascending k-mer order (append() may be called several times).
+class KmcWriter {
+ public:
+  // the prefix length the Python twin (malva_b200/kmc.py) picks: the largest p <= 13 with (k - p) % 4 == 0 and
+  // 4^p <= max(64, n); the smallest valid p if there is none
+  static uint32_t choose_prefix_len(uint32_t k, uint64_t n) {
+    int best = -1;
+    for (uint32_t p = 1; p <= (k < 13 ? k : 13); ++p) {
+      if ((k - p) % 4) continue;
+      if (best < 0 || (1ull << (2 * p)) <= (n > 64 ? n : 64)) best = (int)p;
+    }
+    if (best < 0) throw std::runtime_error("no LUT prefix length with (k-p)%4==0 for this k");
+    return (uint32_t)best;
+  }
+
+  KmcWriter(const std::string &prefix, uint32_t k, uint32_t lut_prefix_len, uint32_t min_count, uint32_t counter_max)
+      : prefix_(prefix), k_(k), p_(lut_prefix_len), min_count_(min_count), counter_max_(counter_max) {
+    if ((k_ - p_) % 4 || p_ >= k_) throw std::runtime_error("(k - lut_prefix_len) must be a positive multiple of 4");
+    suf_ = fopen((prefix + ".kmc_suf").c_str(), "wb");
+    if (!suf_) throw std::runtime_error("cannot write " + prefix + ".kmc_suf");
+    fwrite("KMCS", 1, 4, suf_);
+    bins_.assign((((size_t)1) << (2 * p_)) + 1, 0);
+  }
+  ~KmcWriter() {
+    if (suf_) fclose(suf_);
+  }
+  // n records {lo, hi} (packed canonical k-mers, right-aligned) + counts
+  void append(const uint64_t *lohi, const uint32_t *counts, uint64_t n) {
+    const uint32_t suf_syms = k_ - p_, sb = suf_syms / 4;
+    std::vector<uint8_t> buf;
+    buf.reserve((size_t)((n < (1u << 20) ? n : (1u << 20)) * (sb + 1)));
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t lo = lohi[2 * i], hi = lohi[2 * i + 1];
+      // prefix = the top p symbols
+      const uint32_t sh = 2 * suf_syms;
+      const uint64_t pre = sh >= 64 ? (hi >> (sh - 64)) : ((lo >> sh) | (sh ? hi << (64 - sh) : 0));
+      bins_[(size_t)pre + 1]++;
+      for (uint32_t j = 0; j < sb; ++j) {  // suffix bytes, most significant first
+        const uint32_t bit = 8 * (sb - 1 - j);
+        uint64_t byte = bit >= 64 ? (hi >> (bit - 64)) : ((lo >> bit) | (bit && bit > 56 ? hi << (64 - bit) : 0));
+        buf.push_back((uint8_t)(byte & 0xFF));
+      }
+      buf.push_back((uint8_t)(counts[i] > 255 ? 255 : counts[i]));
+      if (buf.size() >= (1u << 24)) flush(buf);
+    }
+    flush(buf);
+    total_ += n;
+  }
+  void close() {
+    fwrite("KMCS", 1, 4, suf_);
+    if (fclose(suf_) != 0) {
+      suf_ = nullptr;
+      throw std::runtime_error("error closing " + prefix_ + ".kmc_suf");
+    }
+    suf_ = nullptr;
+    for (size_t i = 1; i < bins_.size(); ++i) bins_[i] += bins_[i - 1];  // bins_[i] = records with prefix < i
+    FILE *fp = fopen((prefix_ + ".kmc_pre").c_str(), "wb");
+    if (!fp) throw std::runtime_error("cannot write " + prefix_ + ".kmc_pre");
+    fwrite("KMCP", 1, 4, fp);
+    fwrite(bins_.data(), 8, bins_.size(), fp);
+    const uint32_t sig_len = 5;
+    std::vector<uint32_t> sigmap((((size_t)1) << (2 * sig_len)) + 1, 0);
+    fwrite(sigmap.data(), 4, sigmap.size(), fp);
+    uint8_t hdr[64] = {0};
+    auto put32 = [&](size_t o, uint32_t v) { memcpy(hdr + o, &v, 4); };
+    put32(0, k_), put32(4, 0), put32(8, 1), put32(12, p_), put32(16, sig_len), put32(20, min_count_), put32(24, counter_max_);
+    memcpy(hdr + 28, &total_, 8);
+    hdr[36] = 0;           // both strands (stored inverted)
+    put32(60, 0x200);      // KMC2 layout
+    fwrite(hdr, 1, 64, fp);
+    const uint32_t hoff = 64;
+    fwrite(&hoff, 4, 1, fp);
+    fwrite("KMCP", 1, 4, fp);
+    if (fclose(fp) != 0) throw std::runtime_error("error closing " + prefix_ + ".kmc_pre");
+  }
+  uint64_t total() const { return total_; }
+
+ private:
+  void flush(std::vector<uint8_t> &buf) {
+    if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), suf_) != buf.size())
+      throw std::runtime_error("short write on " + prefix_ + ".kmc_suf");
+    buf.clear();
+  }
+  std::string prefix_;
+  uint32_t k_, p_, min_count_, counter_max_;
+  FILE *suf_ = nullptr;
+  std::vector<uint64_t> bins_;
+  uint64_t total_ = 0;
+};
+
 }  // namespace mh

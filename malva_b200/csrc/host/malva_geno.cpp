@@ -16,8 +16,12 @@
 //     mg_scan_kmc_records;
 //   * the index file holds sparse lists (index_file.hpp).
 //
-// Extra (non-reference) flags: --threads N, --device N.  Extra sub-command for the CPU-only tests:
-//   malva-geno signatures [--index-blocks] [flags] <reference.fa> <variants.vcf>     (no GPU involved)
+// Extra (non-reference) flags: --threads N, --device N, --trace.  Extra sub-commands:
+//   malva-geno count [-k43 -ci2 -cs255 ...] <reads.fq|fa[.gz]> <kmc_output_prefix> [tmp_dir]
+//        the `kmc` step of the MALVA wrapper (MALVA:107) on the GPU: same command-line shape as kmc, writes a KMC
+//        database that `index` / `call` (and the reference) read
+//   malva-geno kmc-dump <kmc_output_prefix>                 lists a database as text (no GPU involved)
+//   malva-geno signatures [--index-blocks] [flags] <reference.fa> <variants.vcf>     (no GPU involved; CPU tests)
 #include <getopt.h>
 #include <sys/resource.h>
 
@@ -30,6 +34,7 @@
 #include <functional>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -609,6 +614,163 @@ int signatures_main(int argc, char **argv) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// `kmc -k43 -ci2 -cs255 -m4 -t1 -fm <sample> <out_prefix> <tmp>` (MALVA:107) on the GPU.  Flags come joined to their
+// value like kmc's (-k43) or separated (-k 43); -m / -t / -f* / the tmp directory are accepted and ignored (the file
+// format is detected from its first byte).  --passes N counts in N prefix-partitioned passes over the reads for
+// inputs whose distinct k-mers do not fit device memory at once.
+struct ReadFeeder {
+  // sequences of a FASTA / FASTQ file (plain or gz), upper-cased, '\n' between records, in chunks of whole records
+  explicit ReadFeeder(const std::string &path) : in_(path) {}
+  bool next_chunk(std::string &out, size_t target) {
+    out.clear();
+    std::string line;
+    while (out.size() < target) {
+      if (!have_) {
+        if (!in_.next(line_)) break;
+        have_ = true;
+      }
+      if (line_.empty()) {
+        have_ = false;
+        continue;
+      }
+      if (line_[0] == '@' && !in_fasta_) {  // FASTQ record: header, sequence, '+', qualities
+        have_ = false;
+        if (!in_.next(line)) break;
+        append_seq(out, line);
+        out.push_back('\n');
+        if (in_.next(line) && !line.empty() && line[0] == '+') in_.next(line);
+      } else if (line_[0] == '>') {  // FASTA record: the sequence may span lines
+        in_fasta_ = true;
+        have_ = false;
+        while (in_.next(line_)) {
+          if (!line_.empty() && line_[0] == '>') {
+            have_ = true;
+            break;
+          }
+          append_seq(out, line_);
+        }
+        out.push_back('\n');
+      } else {
+        have_ = false;  // stray line
+      }
+    }
+    return !out.empty();
+  }
+
+ private:
+  static void append_seq(std::string &out, const std::string &l) {
+    for (char ch : l)
+      if (!isspace((unsigned char)ch)) out.push_back((char)toupper((unsigned char)ch));
+  }
+  mh::LineReader in_;
+  std::string line_;
+  bool have_ = false, in_fasta_ = false;
+};
+
+struct Counter {
+  mg_counter *c = nullptr;
+  ~Counter() { mg_count_destroy(c); }
+};
+
+int count_main(int argc, char **argv) {
+  unsigned k = 43, ci = 2, cs = 255, passes = 1;
+  unsigned long long cx = 1000000000ull;
+  int device = 0;
+  std::vector<std::string> pos;
+  auto value = [&](const std::string &a, size_t skip, int &i) -> std::string {
+    if (a.size() > skip) return a.substr(skip);
+    if (i + 1 < argc) return argv[++i];
+    throw std::runtime_error("missing value for " + a);
+  };
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "--passes") passes = (unsigned)atoi(value(a, a.size(), i).c_str());
+    else if (a == "--device") device = atoi(value(a, a.size(), i).c_str());
+    else if (a.compare(0, 3, "-ci") == 0) ci = (unsigned)atoi(value(a, 3, i).c_str());
+    else if (a.compare(0, 3, "-cs") == 0) cs = (unsigned)atoi(value(a, 3, i).c_str());
+    else if (a.compare(0, 3, "-cx") == 0) cx = strtoull(value(a, 3, i).c_str(), nullptr, 10);
+    else if (a.compare(0, 2, "-k") == 0) k = (unsigned)atoi(value(a, 2, i).c_str());
+    else if (a.compare(0, 2, "-m") == 0 || a.compare(0, 2, "-t") == 0) (void)value(a, 2, i);
+    else if (a.compare(0, 2, "-f") == 0 || a == "-v" || a.compare(0, 2, "-p") == 0 || a.compare(0, 2, "-s") == 0 ||
+             a.compare(0, 2, "-n") == 0 || a == "-r") continue;
+    else if (a == "-b") throw std::runtime_error("-b (non-canonical counting) is not supported: MALVA needs canonical k-mers");
+    else if (!a.empty() && a[0] == '-') throw std::runtime_error("unknown option " + a);
+    else pos.push_back(a);
+  }
+  if (pos.size() < 2 || passes < 1 || passes > 256) {
+    std::cerr << "Usage: malva-geno count [-k43] [-ci2] [-cs255] [-cx1000000000] [--passes N] [--device N] "
+                 "<reads.fq|fa[.gz]> <kmc_output_prefix> [tmp_dir]\n";
+    return 1;
+  }
+  if (cs > 255) throw std::runtime_error("-cs above 255 is not supported (one counter byte per record)");
+  pelapsed("k-mer counting");
+  Counter cn;
+  gpu(mg_count_create(&cn.c, device, (int)k), "mg_count_create");
+  std::unique_ptr<mh::KmcWriter> w;
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> counts;
+  uint64_t instances = 0, distinct = 0, total_bases = 0;
+  for (unsigned p = 0; p < passes; ++p) {
+    if (passes > 1) {
+      gpu(mg_count_reset(cn.c), "mg_count_reset");
+      gpu(mg_count_set_partition(cn.c, 8, p * 256 / passes, (p + 1) * 256 / passes), "mg_count_set_partition");
+    }
+    ReadFeeder feed(pos[0]);
+    std::string chunk;
+    while (feed.next_chunk(chunk, 64u << 20)) {
+      if (p == 0) total_bases += chunk.size();
+      gpu(mg_count_add(cn.c, chunk.data(), chunk.size()), "mg_count_add");
+    }
+    uint64_t n = 0, st[4];
+    gpu(mg_count_finish(cn.c, ci, cs, cx, &n), "mg_count_finish");
+    gpu(mg_count_stats(cn.c, st, 4), "mg_count_stats");
+    distinct += st[0];
+    instances += st[1];
+    keys.resize(2 * n);
+    counts.resize(n);
+    gpu(mg_count_download(cn.c, keys.data(), counts.data(), n), "mg_count_download");
+    if (!w) w.reset(new mh::KmcWriter(pos[1], k, passes == 1 ? mh::KmcWriter::choose_prefix_len(k, n)
+                                                             : mh::KmcWriter::choose_prefix_len(k, 1ull << 40), ci, cs));
+    w->append(keys.data(), counts.data(), n);
+  }
+  w->close();
+  std::cerr << "[malva-geno/count] " << total_bases << " read bytes, " << instances << " k-mer instances, " << distinct
+            << " distinct, " << w->total() << " written (count >= " << ci << ", capped at " << cs << ")" << std::endl;
+  pelapsed("k-mer counting complete");
+  return 0;
+}
+
+// `kmc_dump`-like listing: "<k-mer>\t<count>" per record passing the database's count filter (host only)
+int kmc_dump_main(int argc, char **argv) {
+  if (argc != 2) {
+    std::cerr << "Usage: malva-geno kmc-dump <kmc_output_prefix>\n";
+    return 1;
+  }
+  mh::KmcDb db;
+  std::string why;
+  if (!db.open(argv[1], why)) {
+    std::cerr << "ERROR: " << why << std::endl;
+    return 1;
+  }
+  const uint32_t p = db.lut_prefix_len, sb = (db.kmer_len - p) / 4, single = 1u << (2 * p);
+  std::vector<uint8_t> rec(db.record_bytes);
+  std::string kmer(db.kmer_len, 'A');
+  size_t pi = 0;
+  for (uint64_t i = 0; i < db.total_kmers; ++i) {
+    while (pi + 1 < db.lut.size() && db.lut[pi + 1] <= i) ++pi;
+    if (db.read_records(rec.data(), i, 1) != 1) throw std::runtime_error("suffix file truncated");
+    uint64_t c = db.counter_size ? 0 : 1;
+    for (uint32_t b = 0; b < db.counter_size; ++b) c |= (uint64_t)rec[sb + b] << (8 * b);
+    if (c < db.min_count || c > db.max_count) continue;
+    const uint32_t pfx = (uint32_t)(pi % single);
+    for (uint32_t j = 0; j < p; ++j) kmer[j] = "ACGT"[(pfx >> (2 * (p - 1 - j))) & 3];
+    for (uint32_t j = 0; j < 4 * sb; ++j) kmer[p + j] = "ACGT"[(rec[j >> 2] >> (2 * (3 - (j & 3)))) & 3];
+    std::cout << kmer << '\t' << c << '\n';
+  }
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -620,6 +782,8 @@ int main(int argc, char **argv) {
     if (strncmp(argv[1], "index", 5) == 0) return index_main(argc - 1, argv + 1);
     if (strncmp(argv[1], "call", 4) == 0) return call_main(argc - 1, argv + 1);
     if (strcmp(argv[1], "signatures") == 0) return signatures_main(argc - 1, argv + 1);
+    if (strcmp(argv[1], "count") == 0) return count_main(argc - 1, argv + 1);
+    if (strcmp(argv[1], "kmc-dump") == 0) return kmc_dump_main(argc - 1, argv + 1);
   } catch (const GpuError &e) {
     std::cerr << "malva-geno: GPU error: " << e.what() << " (there is no CPU fallback)" << std::endl;
     return 2;

@@ -4,6 +4,7 @@
 // There is no CPU fallback anywhere: every entry point fails with MG_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <cmath>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "../../include/malva_gpu.h"
+#include "count.cuh"
 #include "kernels.cuh"
 
 using mg::DevView;
@@ -951,6 +953,230 @@ extern "C" int mg_export_ref_keys(mg_ctx *c, uint64_t *lohi, uint64_t cap, uint6
   CU(cudaStreamSynchronize(c->stream[0]));
   if (got != c->n_keys) return set_err(MG_ERR_STATE, "key count mismatch: %llu in the table, %llu recorded", got, (unsigned long long)c->n_keys);
   return MG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K6: canonical k-mer counting (the `kmc` step of the pipeline, MALVA:107) -- count.cuh
+// ---------------------------------------------------------------------------
+struct mg_counter {
+  int device = 0, k = 0, log2cap = 0, part_bits = 0;
+  uint32_t part_lo = 0, part_hi = 0;
+  cudaStream_t st = nullptr;
+  mg::CountSlot *table = nullptr;
+  unsigned long long *d_scalars = nullptr;  // [0] distinct keys in the table [1] instances counted [2] emit cursor
+  uint8_t *d_seq = nullptr;
+  uint64_t seq_cap = 0, n_out = 0, launches = 0;
+  u128 *out_keys = nullptr;
+  uint32_t *out_counts = nullptr;
+  bool finished = false;
+};
+constexpr uint64_t COUNT_CHUNK = 1ull << 26;  // read bytes per kernel launch
+
+static int counter_alloc_table(mg_counter *c, int log2cap, mg::CountSlot **t) {
+  uint64_t cap = 1ull << log2cap;
+  CU(cudaMalloc(t, cap * sizeof(mg::CountSlot)));
+  c->launches++;
+  mg::k_count_clear<<<grid_for(cap, 256), 256, 0, c->st>>>(*t, cap);
+  CU(cudaGetLastError());
+  return MG_OK;
+}
+
+extern "C" int mg_count_create(mg_counter **out, int device, int k) {
+  if (!out) return set_err(MG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (k < 1 || k > 63) return set_err(MG_ERR_ARG, "unsupported k=%d (need 1 <= k <= 63)", k);
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return set_err(MG_ERR_CUDA, "device %d not available (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  mg_counter *c = new mg_counter();
+  c->device = device;
+  c->k = k;
+  CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CU(cudaMalloc(&c->d_scalars, 4 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(unsigned long long), c->st));
+  c->log2cap = 16;
+  int rc = counter_alloc_table(c, c->log2cap, &c->table);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->st));
+  *out = c;
+  return MG_OK;
+}
+
+extern "C" void mg_count_destroy(mg_counter *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  cudaFree(c->table);
+  cudaFree(c->d_scalars);
+  cudaFree(c->d_seq);
+  cudaFree(c->out_keys);
+  cudaFree(c->out_counts);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+extern "C" int mg_count_set_partition(mg_counter *c, int part_bits, uint32_t part_lo, uint32_t part_hi) {
+  if (!c || part_bits < 0 || part_bits > 30 || part_bits > 2 * c->k) return set_err(MG_ERR_ARG, "bad partition");
+  c->part_bits = part_bits;
+  c->part_lo = part_lo;
+  c->part_hi = part_hi;
+  return MG_OK;
+}
+
+// empty table, same capacity: the next prefix-partitioned pass
+extern "C" int mg_count_reset(mg_counter *c) {
+  if (!c) return set_err(MG_ERR_ARG, "NULL counter");
+  CU(cudaSetDevice(c->device));
+  uint64_t cap = 1ull << c->log2cap;
+  c->launches++;
+  mg::k_count_clear<<<grid_for(cap, 256), 256, 0, c->st>>>(c->table, cap);
+  CU(cudaGetLastError());
+  CU(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(unsigned long long), c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->finished = false;
+  return MG_OK;
+}
+
+static int counter_reserve(mg_counter *c, uint64_t more) {
+  unsigned long long nd = 0;
+  CU(cudaMemcpyAsync(&nd, c->d_scalars, 8, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  uint64_t need = (nd + more) * 2;
+  if (need <= (1ull << c->log2cap)) return MG_OK;
+  int nl = c->log2cap;
+  while ((1ull << nl) < need) ++nl;
+  mg::CountSlot *nt = nullptr;
+  int rc = counter_alloc_table(c, nl, &nt);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(c->d_scalars, 0, 8, c->st));
+  uint64_t ocap = 1ull << c->log2cap;
+  c->launches++;
+  mg::k_count_rehash<<<grid_for(ocap, 256), 256, 0, c->st>>>(c->table, ocap, nt, (1ull << nl) - 1, c->d_scalars);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaFree(c->table));
+  c->table = nt;
+  c->log2cap = nl;
+  return MG_OK;
+}
+
+extern "C" int mg_count_add(mg_counter *c, const char *bases, uint64_t n) {
+  if (!c || (!bases && n)) return set_err(MG_ERR_ARG, "NULL argument");
+  if (c->finished) return set_err(MG_ERR_STATE, "mg_count_add after mg_count_finish (call mg_count_reset)");
+  CU(cudaSetDevice(c->device));
+  const uint64_t halo = (uint64_t)(c->k - 1);
+  if (n <= halo) return MG_OK;
+  if (!c->d_seq) {
+    uint64_t cap = COUNT_CHUNK;
+    if (const char *e = getenv("MG_COUNT_CHUNK"))  // (tests shrink it to exercise the sub-chunk seams)
+      if (strtoull(e, nullptr, 10) > 2 * halo + 1) cap = strtoull(e, nullptr, 10);
+    CU(cudaMalloc(&c->d_seq, cap + 64));
+    c->seq_cap = cap;
+  }
+  // sub-chunks overlap by k-1 bytes: a launch counts the windows that END inside its own part
+  for (uint64_t start = 0; start + halo < n;) {
+    const uint64_t len = n - start < c->seq_cap ? n - start : c->seq_cap;
+    int rc = counter_reserve(c, len);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_seq, bases + start, len, cudaMemcpyHostToDevice, c->st));
+    const uint64_t n_pos = len - halo;
+    const int grid = (int)((n_pos + mg::CNT_TILE - 1) / mg::CNT_TILE);
+    const size_t smem = mg::CNT_TILE + 64;
+    const uint64_t mask = (1ull << c->log2cap) - 1;
+    c->launches++;
+    if (c->k == 43)
+      mg::k_count_kmers<43><<<grid, mg::CNT_THREADS, smem, c->st>>>(c->d_seq, len, c->k, c->table, mask, c->part_bits,
+                                                                    c->part_lo, c->part_hi, c->d_scalars, c->d_scalars + 1);
+    else
+      mg::k_count_kmers<0><<<grid, mg::CNT_THREADS, smem, c->st>>>(c->d_seq, len, c->k, c->table, mask, c->part_bits,
+                                                                   c->part_lo, c->part_hi, c->d_scalars, c->d_scalars + 1);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->st));  // d_seq is reused by the next sub-chunk
+    if (start + len >= n) break;
+    start += len - halo;  // the next part re-sends the last k-1 bytes as its halo
+  }
+  return MG_OK;
+}
+
+extern "C" int mg_count_finish(mg_counter *c, uint32_t min_count, uint32_t counter_max, uint64_t max_count,
+                               uint64_t *n_kmers) {
+  if (!c) return set_err(MG_ERR_ARG, "NULL counter");
+  CU(cudaSetDevice(c->device));
+  cudaFree(c->out_keys);
+  cudaFree(c->out_counts);
+  c->out_keys = nullptr;
+  c->out_counts = nullptr;
+  c->n_out = 0;
+  const uint64_t cap = 1ull << c->log2cap;
+  unsigned long long n = 0;
+  CU(cudaMemsetAsync(c->d_scalars + 2, 0, 8, c->st));
+  c->launches++;
+  mg::k_count_emit<<<grid_for(cap, 256), 256, 0, c->st>>>(c->table, cap, min_count, counter_max, max_count,
+                                                          c->d_scalars + 2, nullptr, nullptr);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(&n, c->d_scalars + 2, 8, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (n) {
+    DevFree k0, v0, tmp;
+    CU(cudaMalloc(&k0.p, n * 16));
+    CU(cudaMalloc(&v0.p, n * 4));
+    CU(cudaMalloc(&c->out_keys, n * 16));
+    CU(cudaMalloc(&c->out_counts, n * 4));
+    CU(cudaMemsetAsync(c->d_scalars + 2, 0, 8, c->st));
+    c->launches++;
+    mg::k_count_emit<<<grid_for(cap, 256), 256, 0, c->st>>>(c->table, cap, min_count, counter_max, max_count,
+                                                            c->d_scalars + 2, (u128 *)k0.p, (uint32_t *)v0.p);
+    CU(cudaGetLastError());
+    // KMC lists k-mers in ascending order (prefix bins, sorted suffixes): sort the kept entries by key
+    size_t tb = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, (u128 *)k0.p, c->out_keys, (uint32_t *)v0.p, c->out_counts, (int64_t)n,
+                                       mg::KmerDecomposer{}, 0, 2 * c->k, c->st));
+    CU(cudaMalloc(&tmp.p, tb ? tb : 1));
+    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tb, (u128 *)k0.p, c->out_keys, (uint32_t *)v0.p, c->out_counts, (int64_t)n,
+                                       mg::KmerDecomposer{}, 0, 2 * c->k, c->st));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->st));
+  }
+  c->n_out = n;
+  c->finished = true;
+  if (n_kmers) *n_kmers = n;
+  return MG_OK;
+}
+
+extern "C" int mg_count_download(mg_counter *c, uint64_t *lohi, uint32_t *counts, uint64_t cap) {
+  if (!c || ((!lohi || !counts) && cap)) return set_err(MG_ERR_ARG, "NULL argument");
+  if (!c->finished) return set_err(MG_ERR_STATE, "mg_count_download before mg_count_finish");
+  if (cap < c->n_out) return set_err(MG_ERR_ARG, "output buffers too small (%llu needed)", (unsigned long long)c->n_out);
+  if (!c->n_out) return MG_OK;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(lohi, c->out_keys, c->n_out * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(counts, c->out_counts, c->n_out * 4, cudaMemcpyDeviceToHost));
+  return MG_OK;
+}
+
+extern "C" int mg_count_stats(mg_counter *c, uint64_t *stats, int n) {
+  if (!c || !stats || n < 4) return set_err(MG_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  unsigned long long sc[2];
+  CU(cudaMemcpy(sc, c->d_scalars, 16, cudaMemcpyDeviceToHost));
+  stats[0] = sc[0];
+  stats[1] = sc[1];
+  stats[2] = 1ull << c->log2cap;
+  stats[3] = c->launches;
+  return MG_OK;
+}
+
+// the counted k-mers go straight into the sample scan: no KMC database, no host round trip
+extern "C" int mg_scan_counted(mg_ctx *ctx, mg_counter *c) {
+  if (!ctx || !c) return set_err(MG_ERR_ARG, "NULL argument");
+  if (!c->finished) return set_err(MG_ERR_STATE, "mg_scan_counted before mg_count_finish");
+  if (c->device != ctx->device) return set_err(MG_ERR_ARG, "counter and context live on different devices");
+  if (c->k != ctx->ref_k) return set_err(MG_ERR_ARG, "counter holds %d-mers but ref_k is %d", c->k, ctx->ref_k);
+  if (!ctx->alt_final) return set_err(MG_ERR_STATE, "scan before mg_finalize_alt (BF::increment is a no-op in write mode)");
+  if (!c->n_out) return MG_OK;
+  CU(cudaSetDevice(ctx->device));
+  return scan_device(ctx, c->out_keys, c->out_counts, c->n_out, ctx->stream[0]);
 }
 
 // ---- timing on the library's own streams (torch.cuda.Event cannot see them) ----

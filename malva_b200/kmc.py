@@ -130,7 +130,7 @@ def read_fastx(path: str) -> list:
 
 def _choose_lut_prefix_len(k: int, n: int) -> int:
     best = None
-    for p in range(1, min(k, 15) + 1):
+    for p in range(1, min(k, 13) + 1):   # (same rule as csrc/host/kmc_db.hpp: KmcWriter::choose_prefix_len)
         if (k - p) % 4:
             continue
         if best is None or (4 ** p) <= max(64, n):

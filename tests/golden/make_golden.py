@@ -6,7 +6,7 @@ Run in the build container only (needs /root/reference and oracle/_ref):
 
 Inputs  : /root/reference/example/haploid.tar.gz (haploid.fa, haploid.fq, haploid.vcf)
           /root/reference/example/haploid.malva.vcf (the reference's shipped golden)
-Outputs : haploid.fa, haploid.vcf.gz            -- inputs of the example, verbatim
+Outputs : haploid.fa, haploid.vcf.gz, haploid.fq.gz -- inputs of the example, verbatim
           haploid.kmc_pre/.kmc_suf             -- reads counted as `kmc -k43 -ci2 -cs255` does
                                                   (malva_b200.kmc.count_kmers)
           haploid.malva.vcf                    -- shipped golden (GT:GQ only)
@@ -50,6 +50,9 @@ def main():
         with open(os.path.join(tmp, "haploid.vcf"), "rb") as src, \
                 gzip.GzipFile(os.path.join(OUT, "haploid.vcf.gz"), "wb", mtime=0) as dst:
             dst.write(src.read())
+        with open(os.path.join(tmp, "haploid.fq"), "rb") as src, \
+                gzip.GzipFile(os.path.join(OUT, "haploid.fq.gz"), "wb", mtime=0) as dst:
+            dst.write(src.read())   # the reads themselves: input of the GPU k-mer counter test
         for ext in (".kmc_pre", ".kmc_suf"):
             shutil.copy(os.path.join(tmp, "haploid" + ext), OUT)
         open(os.path.join(OUT, "haploid.malva.vcf"), "wb").write(shipped)

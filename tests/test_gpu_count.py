@@ -1,0 +1,162 @@
+"""K6, canonical k-mer counting on the GPU (the `kmc` step in front of malva-geno), against the Python
+restatement of KMC's defaults (malva_b200.kmc.count_kmers: canonical k-mers, windows with non-ACGT skipped, -ci2,
+-cs255) that reproduces the reference's shipped golden, and end to end: reads -> `malva-geno count` -> `index` ->
+`call` must give the VCF the reference ships for its haploid example."""
+import gzip
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from malva_b200 import KmerCounter, MalvaGpu, kmc
+from malva_b200 import build as mbuild
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "haploid")
+
+
+def random_reads(rng, n_reads, genome_len=20000, read_len=(60, 260), n_rate=0.002):
+    genome = "".join(rng.choice("ACGT") for _ in range(genome_len))
+    reads = []
+    for _ in range(n_reads):
+        ln = rng.randrange(*read_len)
+        p = rng.randrange(0, genome_len - ln)
+        r = list(genome[p:p + ln])
+        if rng.random() < 0.5:
+            r = [{"A": "T", "C": "G", "G": "C", "T": "A"}[c] for c in reversed(r)]
+        for i in range(len(r)):
+            u = rng.random()
+            if u < n_rate:
+                r[i] = "N"
+            elif u < n_rate + 0.003:
+                r[i] = rng.choice("ACGT")
+        reads.append("".join(r))
+    reads += ["ACGT" * 5, "", "A" * 300, "N" * 50, genome[:42], genome[:43], genome[100:143] + "N" + genome[100:143]]
+    return reads
+
+
+@pytest.mark.parametrize("k", [43, 31, 21, 63])
+def test_counts_match_the_kmc_restatement(k):
+    rng = random.Random(100 + k)
+    reads = random_reads(rng, 1500)
+    exp_k, exp_c = kmc.count_kmers(reads, k, min_count=2, counter_max=255)
+    c = KmerCounter(k)
+    try:
+        c.add(reads)
+        got_k, got_c = c.finish(2, 255)
+        assert np.array_equal(got_k, exp_k) and np.array_equal(got_c, exp_c)
+        st = c.stats()
+        assert st["instances"] == sum(max(0, len(s) - k + 1) for r in reads for s in r.split("N"))
+        # other thresholds on the same table: -ci1 with a counter cap of 3, -ci5
+        for ci, cs in ((1, 3), (5, 255)):
+            e_k, e_c = kmc.count_kmers(reads, k, min_count=ci, counter_max=cs)
+            g_k, g_c = c.finish(ci, cs)
+            assert np.array_equal(g_k, e_k) and np.array_equal(g_c, e_c)
+    finally:
+        c.close()
+
+
+def test_many_calls_small_chunks_and_partitioned_passes(monkeypatch):
+    """records fed one call at a time, device sub-chunks of 1 KiB (k-1 overlap at every seam), and three
+    prefix-partitioned passes concatenated: all give the single-pass result"""
+    k = 43
+    rng = random.Random(7)
+    reads = random_reads(rng, 600, read_len=(100, 3000))
+    exp_k, exp_c = kmc.count_kmers(reads, k, min_count=2, counter_max=255)
+    monkeypatch.setenv("MG_COUNT_CHUNK", "1024")
+    c = KmerCounter(k)
+    try:
+        for r in reads:
+            c.add([r])
+        got_k, got_c = c.finish(2, 255)
+        assert np.array_equal(got_k, exp_k) and np.array_equal(got_c, exp_c)
+        parts_k, parts_c = [], []
+        for lo, hi in ((0, 70), (70, 71), (71, 256)):
+            c.reset()
+            c.set_partition(8, lo, hi)
+            c.add(reads)
+            pk, pc = c.finish(2, 255)
+            parts_k.append(pk)
+            parts_c.append(pc)
+        assert np.array_equal(np.concatenate(parts_k), exp_k) and np.array_equal(np.concatenate(parts_c), exp_c)
+    finally:
+        c.close()
+
+
+def test_empty_and_too_short_inputs():
+    c = KmerCounter(43)
+    try:
+        c.add([""])
+        c.add(["ACGT" * 10])
+        k, n = c.finish(1, 255)
+        assert len(k) == 0 and len(n) == 0
+    finally:
+        c.close()
+
+
+def test_counted_kmers_go_straight_into_the_scan():
+    """mg_scan_counted == writing the database and scanning it"""
+    import parity_util as util
+
+    rng = random.Random(11)
+    k, ref_k, bits = 35, 43, 1 << 22
+    genome = util.make_genome(rng, 20000)
+    nested, _ = util.synth_signatures(rng, genome, k, 300)
+    ks, fl = util.flatten(nested)
+    words, _, _ = util.synth_sample(rng, genome, nested, k, ref_k, 6000)   # 43-mers carrying alt alleles, both strands
+    reads = [genome[p:p + 150] for p in range(0, len(genome) - 150, 37)] * 3 + [w for w in words for _ in range(2)]
+    a, b = MalvaGpu(k=k, ref_k=ref_k, bf_bits=bits), MalvaGpu(k=k, ref_k=ref_k, bf_bits=bits)
+    c = KmerCounter(ref_k)
+    try:
+        for g in (a, b):
+            g.add_signatures(ks, fl)
+            g.finalize_alt()
+            g.scan_reference(genome)
+            g.finalize_context()
+        c.add(reads)
+        packed, counts = c.finish(2, 255)
+        assert len(packed) > 1000
+        a.scan_sample_kmers(packed, counts)
+        b.scan_counted(c)
+        assert np.array_equal(a.bf_counts(), b.bf_counts())
+        assert a.bf_counts().sum() > 0
+        ref_kmers = [x for x, f in zip(ks, fl) if f]
+        assert np.array_equal(a.get_counts(ref_kmers, [1] * len(ref_kmers)), b.get_counts(ref_kmers, [1] * len(ref_kmers)))
+    finally:
+        a.close(), b.close(), c.close()
+
+
+def test_cli_count_reproduces_the_database_and_the_shipped_golden(tmp_path):
+    """README.md:137 from the reads on: `MALVA -1 -k 35 -r 43 -b 1 -f AF haploid.fa haploid.vcf haploid.fq` with
+    `malva-geno count` in the place of `kmc -m4 -k43 -t1 -fm` (MALVA:107) -> example/haploid.malva.vcf"""
+    mbuild.build()
+    cli = mbuild.CLI
+    fq = tmp_path / "haploid.fq"
+    fq.write_bytes(gzip.open(os.path.join(GOLD, "haploid.fq.gz")).read())
+    for f in ("haploid.fa", "haploid.vcf.gz"):
+        os.symlink(os.path.join(GOLD, f), tmp_path / f)
+    prefix = str(tmp_path / "haploid.fq_malva43.kmercount")
+    r = subprocess.run([cli, "count", "-m4", "-k43", "-t1", "-fm", str(fq), prefix, str(tmp_path / "tmp")], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    for ext in (".kmc_pre", ".kmc_suf"):
+        assert open(prefix + ext, "rb").read() == open(os.path.join(GOLD, "haploid" + ext), "rb").read(), ext
+    # gz input, flags separated from their values: same database
+    r = subprocess.run([cli, "count", "-k", "43", "-ci", "2", "-cs", "255", os.path.join(GOLD, "haploid.fq.gz"),
+                        str(tmp_path / "again")], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert open(str(tmp_path / "again") + ".kmc_suf", "rb").read() == open(prefix + ".kmc_suf", "rb").read()
+    # three partitioned passes: same listing (the LUT prefix length differs, the records do not)
+    r = subprocess.run([cli, "count", "-k43", "--passes", "3", str(fq), str(tmp_path / "p3")], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    d1 = subprocess.run([cli, "kmc-dump", prefix], capture_output=True, check=True).stdout
+    d3 = subprocess.run([cli, "kmc-dump", str(tmp_path / "p3")], capture_output=True, check=True).stdout
+    assert d1 == d3 and d1.count(b"\n") == 4503
+    flags = ["-1", "-k", "35", "-r", "43", "-b", "1", "-f", "AF"]
+    args = [str(tmp_path / "haploid.fa"), str(tmp_path / "haploid.vcf.gz"), prefix]
+    r = subprocess.run([cli, "index"] + flags + args, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    r = subprocess.run([cli, "call"] + flags + args, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert r.stdout == open(os.path.join(GOLD, "haploid.malva.vcf"), "rb").read()

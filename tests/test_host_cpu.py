@@ -129,3 +129,34 @@ def test_cli_goldens_are_what_the_reference_prints(name, tmp_path):
     for n, m in manifest.items():
         blob = gzip.open(os.path.join(mk.OUT, n + ".expected.vcf.gz")).read()
         assert hashlib.sha256(blob).hexdigest() == m["expected_sha256"]
+
+
+def test_kmc_dump_lists_what_the_python_reader_lists(cli, tmp_path):
+    """csrc/host/kmc_db.hpp (the reader `call` uses) against malva_b200.kmc on the haploid database and on random
+    databases in both prefix-file layouts"""
+    import random
+
+    import numpy as np
+
+    from malva_b200 import kmc
+
+    def dump(prefix):
+        out = subprocess.run([cli, "kmc-dump", prefix], capture_output=True, text=True, check=True).stdout
+        rows = [l.split("\t") for l in out.split("\n") if l]
+        return [r[0] for r in rows], [int(r[1]) for r in rows]
+
+    packed, counts, k = kmc.read_kmc_db(os.path.join(GOLD, "haploid"))
+    ks, cs = dump(os.path.join(GOLD, "haploid"))
+    assert ks == kmc.packed_to_strings(packed, k) and cs == counts.tolist() and len(ks) == 4503
+    rng = random.Random(3)
+    for k, version, p, csz in ((43, 0x200, 7, 1), (43, 0, 3, 2), (31, 0x200, 3, 1), (21, 0, 5, 4)):
+        vals = sorted({rng.getrandbits(2 * k) for _ in range(3000)})
+        cts = np.array([rng.randrange(1, 300 if csz > 1 else 256) for _ in vals], dtype=np.uint32)
+        prefix = str(tmp_path / f"db_{k}_{version}_{p}")
+        kmc.write_kmc_db(prefix, kmc.ints_to_packed(vals), cts, k, lut_prefix_len=p, version=version, counter_size=csz,
+                         min_count=2, max_count=255)
+        ks, cs = dump(prefix)
+        keep = [(v, int(c)) for v, c in zip(vals, cts) if 2 <= c <= 255]
+        assert ks == [kmc.unpack_kmer(v, k) for v, _ in keep] and cs == [c for _, c in keep]
+    r = subprocess.run([cli, "kmc-dump", str(tmp_path / "nope")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
