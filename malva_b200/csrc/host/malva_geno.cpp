@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <future>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -285,6 +286,33 @@ class BlockStream {
   std::vector<std::string> lines_;
 };
 
+// Reads and decodes batch i+1 on a background thread while batch i is enumerated, sent to the device and printed.
+class BatchPrefetcher {
+ public:
+  BatchPrefetcher(BlockStream &stream, size_t max_lines) : stream_(stream), max_lines_(max_lines) { launch(); }
+  // false when the VCF is exhausted; otherwise `out` holds the next batch of flushed blocks (possibly empty)
+  bool next(std::vector<mh::VarBlock> &out) {
+    if (!pending_.valid()) return false;
+    auto got = pending_.get();
+    if (!got.first) return false;
+    out = std::move(got.second);
+    launch();
+    return true;
+  }
+
+ private:
+  void launch() {
+    pending_ = std::async(std::launch::async, [this] {
+      std::vector<mh::VarBlock> b;
+      bool ok = stream_.next_batch(b, max_lines_);
+      return std::make_pair(ok, std::move(b));
+    });
+  }
+  BlockStream &stream_;
+  size_t max_lines_;
+  std::future<std::pair<bool, std::vector<mh::VarBlock>>> pending_;
+};
+
 // signatures of a batch of blocks, enumerated in parallel, concatenated in block order
 void enumerate_batch(const std::vector<mh::VarBlock> &blocks, std::map<std::string, std::string> &refs, const Options &o,
                      mh::SignatureCsr &out) {
@@ -324,6 +352,9 @@ int index_main(int argc, char **argv) {
       return 1;
     }
   }
+  // (the first batch of VCF records is read and decoded in the background while the reference is loaded and the
+  // device starts up)
+  BatchPrefetcher index_batches(stream, LINES_PER_BATCH);
   pelapsed("Reference parsing");
   std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
   pelapsed("Reference processed");
@@ -335,7 +366,7 @@ int index_main(int argc, char **argv) {
   if (o.trace) fprintf(stderr, "[trace] mg_create (CUDA start-up + empty index) %.1f ms\n", sw.lap());
   std::vector<mh::VarBlock> blocks;
   mh::SignatureCsr sigs;
-  while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+  while (index_batches.next(blocks)) {
     const double t_parse = sw.lap();
     enumerate_batch(blocks, refs, o, sigs);
     const double t_enum = sw.lap();
@@ -343,7 +374,7 @@ int index_main(int argc, char **argv) {
     gpu(mg_add_signatures(g.c, sigs.pool.data(), sigs.kmer_off.data(), sigs.kmer_is_ref.data(), sigs.n_kmers()),
         "mg_add_signatures");
     if (o.trace)
-      fprintf(stderr, "[trace] index batch: %zu blocks, %llu k-mers: read+decode %.1f ms, enumerate %.1f ms, device %.1f ms\n",
+      fprintf(stderr, "[trace] index batch: %zu blocks, %llu k-mers: wait for read+decode %.1f ms, enumerate %.1f ms, device %.1f ms\n",
               blocks.size(), (unsigned long long)sigs.n_kmers(), t_parse, t_enum, sw.lap());
     sw.lap();
   }
@@ -459,6 +490,7 @@ int call_main(int argc, char **argv) {
       return 1;
     }
   }
+  BatchPrefetcher call_batches(stream, LINES_PER_BATCH);  // first VCF batch decoded while the index loads and the scan runs
   Ctx g;
   {  // load the index: context_bf, bf, ref_bf (main.cpp:455-461)
     mh::IndexReader r(o.vcf_path + ".c" + std::to_string(o.ref_k) + ".k" + std::to_string(o.k) + ".malvax.zst");
@@ -526,7 +558,7 @@ int call_main(int argc, char **argv) {
   std::vector<const mh::Variant *> order;
   std::vector<std::string> text;
   Stopwatch sw;
-  while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+  while (call_batches.next(blocks)) {
     const double t_parse = sw.lap();
     enumerate_batch(blocks, refs, o, sigs);
     const double t_enum = sw.lap();
@@ -564,7 +596,7 @@ int call_main(int argc, char **argv) {
     });
     for (const auto &t : text) fwrite(t.data(), 1, t.size(), stdout);
     if (o.trace)
-      fprintf(stderr, "[trace] call batch: %llu variants, %llu k-mers: read+decode %.1f ms, enumerate %.1f ms, device %.1f ms, print %.1f ms\n",
+      fprintf(stderr, "[trace] call batch: %llu variants, %llu k-mers: wait for read+decode %.1f ms, enumerate %.1f ms, device %.1f ms, print %.1f ms\n",
               (unsigned long long)nv, (unsigned long long)sigs.n_kmers(), t_parse, t_enum, t_dev, sw.lap());
     sw.lap();
   }

@@ -160,3 +160,20 @@ def test_cli_count_reproduces_the_database_and_the_shipped_golden(tmp_path):
     r = subprocess.run([cli, "call"] + flags + args, capture_output=True)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     assert r.stdout == open(os.path.join(GOLD, "haploid.malva.vcf"), "rb").read()
+
+
+def test_wrapper_script_runs_the_whole_pipeline(tmp_path):
+    """README.md:137 verbatim: MALVA -1 -k 35 -r 43 -b 1 -f AF haploid.fa haploid.vcf haploid.fq > out.vcf"""
+    mbuild.build()
+    wrapper = os.path.join(os.path.dirname(mbuild.CLI), "MALVA")
+    (tmp_path / "haploid.fq").write_bytes(gzip.open(os.path.join(GOLD, "haploid.fq.gz")).read())
+    (tmp_path / "haploid.vcf").write_bytes(gzip.open(os.path.join(GOLD, "haploid.vcf.gz")).read())
+    os.symlink(os.path.join(GOLD, "haploid.fa"), tmp_path / "haploid.fa")
+    cmd = [wrapper, "-1", "-k", "35", "-r", "43", "-b", "1", "-f", "AF", "haploid.fa", "haploid.vcf", "haploid.fq"]
+    r = subprocess.run(cmd, capture_output=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert r.stdout == open(os.path.join(GOLD, "haploid.malva.vcf"), "rb").read()
+    assert os.path.exists(tmp_path / "haploid.fq_malva43.kmercount.kmc_suf")
+    assert os.path.exists(tmp_path / "haploid.vcf.c43.k35.malvax.zst")
+    r2 = subprocess.run(cmd, capture_output=True, cwd=tmp_path)   # second run reuses the database and the index
+    assert r2.returncode == 0 and r2.stdout == r.stdout and b"Index file exists already" in r2.stderr
