@@ -45,6 +45,12 @@ struct DevView {  // everything the kernels need, passed by value
   uint32_t *ovf_counts;
   uint64_t ovf_mask;  // capacity-1
   int ovf_shift;      // 64 - log2(capacity)
+  // after mg_finalize_alt the overflow keys are a SORTED array of ovf_n entries (binary search): the index image
+  // -- key slots sorted within every line, the six smallest keys of a crowded line in the line, the rest here in
+  // ascending order -- is then a function of the key SET alone, not of the order or the races of the inserts,
+  // so that replicas built independently are identical and their counter arrays add up element by element
+  uint64_t ovf_n;
+  int ovf_sorted;
   uint64_t bf_bits;
   uint64_t bf_mask;  // bf_bits-1 when bf_bits is a power of two, else 0
   int k, ref_k;
@@ -118,6 +124,30 @@ __device__ __forceinline__ u128 cas128(u128 *addr, u128 cmp, u128 val) {
 
 __device__ __forceinline__ uint64_t ovf_slot0(const DevView &v, uint64_t h) { return (h * GOLD) >> v.ovf_shift; }
 
+// slot of `canon` in the overflow structure, or -1
+__device__ __forceinline__ int64_t ovf_find(const DevView &v, uint64_t h, u128 canon) {
+  if (v.ovf_sorted) {
+    uint64_t lo = 0, hi = v.ovf_n;  // first entry >= canon
+    while (lo < hi) {
+      uint64_t mid = (lo + hi) >> 1;
+      u128 key = key_of(__ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + mid)));
+      if (less128(key, canon))
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo < v.ovf_n && key_eq(key_of(__ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + lo))), canon)) return (int64_t)lo;
+    return -1;
+  }
+  uint64_t slot = ovf_slot0(v, h);
+  while (true) {
+    u128 key = key_of(__ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + slot)));
+    if (key_eq(key, canon)) return (int64_t)slot;
+    if (key_empty(key)) return -1;
+    slot = (slot + 1) & v.ovf_mask;
+  }
+}
+
 // Where the count of canonical key `canon` (hash h, bf index idx) lives:
 //   >= 0            index into key_counts
 //   <= -2           -(2 + slot) in ovf_counts
@@ -132,14 +162,8 @@ __device__ __forceinline__ int64_t key_locate(const DevView &v, uint64_t h, uint
   for (int s = 0; s < LINE_KEYS; ++s)
     if (key_eq(key_of(q[s]), canon)) return (int64_t)(line * LINE_KEYS + (uint64_t)s);
   if (!(q[LINE_KEYS - 1].w & OVF_FLAG_W)) return -1;
-  uint64_t slot = ovf_slot0(v, h);
-  while (true) {
-    uint4 o = __ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + slot));
-    u128 key = key_of(o);
-    if (key_eq(key, canon)) return -(int64_t)(2 + slot);
-    if (key_empty(key)) return -1;
-    slot = (slot + 1) & v.ovf_mask;
-  }
+  int64_t slot = ovf_find(v, h, canon);
+  return slot < 0 ? -1 : -(2 + slot);
 }
 __device__ __forceinline__ uint32_t *count_ptr(const DevView &v, int64_t loc) {
   return loc >= 0 ? v.key_counts + loc : v.ovf_counts + (uint64_t)(-loc - 2);

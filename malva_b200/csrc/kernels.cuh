@@ -161,6 +161,49 @@ __global__ void k_rehash(const u128 *old_keys, const uint32_t *old_counts, uint6
 }
 
 // ---------------------------------------------------------------------------
+// K3c: canonical index image (run by mg_finalize_alt, before any count exists): the key slots of every line in
+// ascending order, empty slots last.  Which slot a key took during the build depended on the order (and the races)
+// of the inserts; after this pass it depends on the key set only.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sort_line_keys(uint4 *lines, uint64_t n_lines) {
+  uint64_t line = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= n_lines) return;
+  uint4 *p = lines + line * LINE_U4 + 2;
+  uint4 q[LINE_KEYS];
+#pragma unroll
+  for (int s = 0; s < LINE_KEYS; ++s) q[s] = p[s];
+  if (key_empty(key_of(q[1]))) return;  // zero or one key: already canonical (slots fill from the front)
+  const uint32_t flag = q[LINE_KEYS - 1].w & OVF_FLAG_W;
+  q[LINE_KEYS - 1].w &= ~OVF_FLAG_W;
+#pragma unroll
+  for (int a = 1; a < LINE_KEYS; ++a) {  // insertion sort on (hi, lo); an empty slot is the largest value
+#pragma unroll
+    for (int b = a; b > 0; --b) {
+      u128 x = key_of(q[b - 1]), y = key_of(q[b]);
+      if (less128(y, x)) {
+        uint4 t = q[b - 1];
+        q[b - 1] = q[b];
+        q[b] = t;
+      }
+    }
+  }
+  q[LINE_KEYS - 1].w |= flag;
+#pragma unroll
+  for (int s = 0; s < LINE_KEYS; ++s) p[s] = q[s];
+}
+// the six key slots of the listed lines, to / from a dense array (overflow canonicalisation on the host)
+__global__ void k_gather_line_keys(const uint4 *lines, const uint64_t *ids, uint64_t n, uint4 *out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * LINE_KEYS) return;
+  out[i] = lines[ids[i / LINE_KEYS] * LINE_U4 + 2 + (i % LINE_KEYS)];
+}
+__global__ void k_scatter_line_keys(uint4 *lines, const uint64_t *ids, uint64_t n, const uint4 *in) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * LINE_KEYS) return;
+  lines[ids[i / LINE_KEYS] * LINE_U4 + 2 + (i % LINE_KEYS)] = in[i];
+}
+
+// ---------------------------------------------------------------------------
 // K3b: switch_mode (bloom_filter.hpp:93-98): ones per probe line (then an exclusive scan -> rank)
 // also used on a plain bit array (stride_u32 = 8) for context_bf statistics
 // ---------------------------------------------------------------------------
@@ -493,17 +536,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, 
     // ---- ref_bf.increment ----
     if (slot >= 0) {
       atomicAdd(v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot, cnt);
-    } else if (last_w & OVF_FLAG_W) {  // line overflowed at index time: the key may live in the overflow table
-      uint64_t os = ovf_slot0(v, h);
-      while (true) {
-        u128 key = key_of(__ldg(reinterpret_cast<const uint4 *>(v.ovf_keys + os)));
-        if (key_eq(key, canon)) {
-          atomicAdd(v.ovf_counts + os, cnt);
-          break;
-        }
-        if (key_empty(key)) break;
-        os = (os + 1) & v.ovf_mask;
-      }
+    } else if (last_w & OVF_FLAG_W) {  // line overflowed at index time: the key may live in the overflow array
+      const int64_t os = ovf_find(v, h, canon);
+      if (os >= 0) atomicAdd(v.ovf_counts + os, cnt);
     }
     // ---- bf.increment unless the context filter vetoes it ----
     if (bf_hit) {

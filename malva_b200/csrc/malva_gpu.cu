@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -74,6 +75,7 @@ struct mg_ctx {
   uint32_t *ovf_counts = nullptr;
   int ovf_log2 = 0;
   uint64_t ovf_n = 0;  // keys in the overflow table
+  bool ovf_sorted = false;  // after mg_finalize_alt: a sorted array instead of a hash table (index.cuh)
   uint64_t bf_ones = 0;
   uint64_t n_keys = 0;  // distinct packed ref keys (lines + overflow)
   bool alt_final = false, ctx_final = false;
@@ -110,6 +112,8 @@ struct mg_ctx {
     v.ovf_counts = ovf_counts;
     v.ovf_mask = (1ull << ovf_log2) - 1;
     v.ovf_shift = 64 - ovf_log2;
+    v.ovf_n = ovf_n;
+    v.ovf_sorted = ovf_sorted ? 1 : 0;
     v.bf_bits = bf_bits;
     v.bf_mask = (bf_bits & (bf_bits - 1)) == 0 ? bf_bits - 1 : 0;
     v.k = k;
@@ -379,6 +383,94 @@ static int count_ones(mg_ctx *c, const uint32_t *words, uint64_t n_units, int st
   return MG_OK;
 }
 
+// The canonical index image (index.cuh): key slots sorted within every line; for the (rare) lines that took more
+// than six keys, the six smallest stay in the line and the rest go to a sorted overflow array.  The handful of
+// crowded lines is fixed up on the host.
+static int canonicalize_keys(mg_ctx *c) {
+  c->launches++;
+  mg::k_sort_line_keys<<<grid_for(c->n_lines, 256), 256, 0, c->stream[0]>>>(c->lines, c->n_lines);
+  CU(cudaGetLastError());
+  const uint64_t cap = 1ull << c->ovf_log2;
+  std::vector<u128> ovk;
+  if (c->ovf_n) {
+    std::vector<u128> raw(cap);
+    CU(cudaMemcpyAsync(raw.data(), c->ovf_keys, cap * sizeof(u128), cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    for (auto &k : raw) {
+      k.hi &= mg::KEY_HI_MASK;
+      if (!(k.lo == ~0ull && k.hi == mg::KEY_HI_MASK)) ovk.push_back(k);
+    }
+  }
+  auto less = [](const u128 &a, const u128 &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); };
+  if (!ovk.empty()) {
+    // line of every overflow key (same hash, same modulo as the device)
+    const uint64_t mask = (c->bf_bits & (c->bf_bits - 1)) == 0 ? c->bf_bits - 1 : 0;
+    std::vector<std::pair<uint64_t, u128>> by_line;
+    for (const auto &k : ovk) {
+      u128 canon;
+      uint64_t h = mg::canon_hash_rt(k, c->k, &canon);
+      by_line.push_back({(mask ? (h & mask) : (h % c->bf_bits)) >> 8, k});
+    }
+    std::sort(by_line.begin(), by_line.end(), [&](const auto &a, const auto &b) {
+      return a.first < b.first || (a.first == b.first && less(a.second, b.second));
+    });
+    std::vector<uint64_t> ids;
+    for (const auto &e : by_line)
+      if (ids.empty() || ids.back() != e.first) ids.push_back(e.first);
+    DevFree d_ids, d_keys;
+    CU(cudaMalloc(&d_ids.p, ids.size() * 8));
+    CU(cudaMalloc(&d_keys.p, ids.size() * mg::LINE_KEYS * 16));
+    CU(cudaMemcpyAsync(d_ids.p, ids.data(), ids.size() * 8, cudaMemcpyHostToDevice, c->stream[0]));
+    c->launches++;
+    mg::k_gather_line_keys<<<grid_for(ids.size() * mg::LINE_KEYS, 256), 256, 0, c->stream[0]>>>(
+        c->lines, (const uint64_t *)d_ids.p, ids.size(), (uint4 *)d_keys.p);
+    CU(cudaGetLastError());
+    std::vector<u128> slots(ids.size() * mg::LINE_KEYS);
+    CU(cudaMemcpyAsync(slots.data(), d_keys.p, slots.size() * 16, cudaMemcpyDeviceToHost, c->stream[0]));
+    CU(cudaStreamSynchronize(c->stream[0]));
+    ovk.clear();
+    size_t e = 0;
+    for (size_t i = 0; i < ids.size(); ++i) {
+      std::vector<u128> all;
+      for (int s = 0; s < mg::LINE_KEYS; ++s) {
+        u128 k = slots[i * mg::LINE_KEYS + s];
+        k.hi &= mg::KEY_HI_MASK;
+        if (!(k.lo == ~0ull && k.hi == mg::KEY_HI_MASK)) all.push_back(k);
+      }
+      for (; e < by_line.size() && by_line[e].first == ids[i]; ++e) all.push_back(by_line[e].second);
+      std::sort(all.begin(), all.end(), less);
+      const u128 empty = {~0ull, mg::KEY_HI_MASK};
+      for (size_t s = 0; s < (size_t)mg::LINE_KEYS; ++s) slots[i * mg::LINE_KEYS + s] = s < all.size() ? all[s] : empty;
+      slots[i * mg::LINE_KEYS + mg::LINE_KEYS - 1].hi |= 1ull << 63;  // the overflow flag stays
+      if (all.size() > (size_t)mg::LINE_KEYS) ovk.insert(ovk.end(), all.begin() + mg::LINE_KEYS, all.end());
+    }
+    CU(cudaMemcpyAsync(d_keys.p, slots.data(), slots.size() * 16, cudaMemcpyHostToDevice, c->stream[0]));
+    c->launches++;
+    mg::k_scatter_line_keys<<<grid_for(ids.size() * mg::LINE_KEYS, 256), 256, 0, c->stream[0]>>>(
+        c->lines, (const uint64_t *)d_ids.p, ids.size(), (const uint4 *)d_keys.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream[0]));
+    std::sort(ovk.begin(), ovk.end(), less);
+  }
+  // the overflow keys as a sorted array (padded with empty entries to a power of two), counts zeroed
+  int nl = 0;
+  while ((1ull << nl) < (ovk.size() ? ovk.size() : 1)) ++nl;
+  u128 *nk = nullptr;
+  uint32_t *nc = nullptr;
+  int rc = ovf_alloc(c, nl, &nk, &nc);
+  if (rc) return rc;
+  if (!ovk.empty()) CU(cudaMemcpyAsync(nk, ovk.data(), ovk.size() * sizeof(u128), cudaMemcpyHostToDevice, c->stream[0]));
+  CU(cudaStreamSynchronize(c->stream[0]));
+  CU(cudaFree(c->ovf_keys));
+  CU(cudaFree(c->ovf_counts));
+  c->ovf_keys = nk;
+  c->ovf_counts = nc;
+  c->ovf_log2 = nl;
+  c->ovf_n = ovk.size();
+  c->ovf_sorted = true;
+  return MG_OK;
+}
+
 // Keep the occupancy pre-filter resident in L2 while the probe lines stream through it: a persisting
 // access-policy window on both of the context's streams (MG_L2_PERSIST=0 disables it).
 static int pin_occ_in_l2(mg_ctx *c) {
@@ -424,6 +516,8 @@ extern "C" int mg_finalize_alt(mg_ctx *c) {
   c->bf_ones = ones;
   CU(cudaMalloc(&c->bf_counts, (ones ? ones : 1) * 4));
   CU(cudaMemset(c->bf_counts, 0, (ones ? ones : 1) * 4));
+  rc = canonicalize_keys(c);
+  if (rc) return rc;
   c->alt_final = true;
   return pin_occ_in_l2(c);
 }

@@ -236,3 +236,66 @@ def test_kmc_records_decoded_on_device(oracle_lib, tmp_path, version, p, k, ref_
     finally:
         g.close()
         o.close()
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u4", "data": (ptr, False), "version": 2}
+
+
+def _counter_arrays(g):
+    """the three u32 counter arrays of a context (what a multi-GPU run sum-reduces), as host arrays"""
+    import torch
+
+    g.sync()
+    out = []
+    for ptr, n in g.counter_buffers():
+        out.append(torch.as_tensor(_DevArray(ptr, n), device="cuda:0").cpu().numpy().copy() if n else np.zeros(0, np.uint32))
+    return out
+
+
+@pytest.mark.parametrize("bf_bits", [1 << 13, 1 << 22])
+def test_replicas_built_in_any_order_have_one_image_and_their_counters_add_up(oracle_lib, bf_bits):
+    """Multi-GPU contract: every replica builds the index on its own, scans a share of the stream, and the
+    counter arrays are added ELEMENT BY ELEMENT.  That is only exact if the index image does not depend on the order
+    (or the races) of the inserts.  2^13 bits = 32 probe lines for ~1,000 ref keys: every line overflows."""
+    k, ref_k = 35, 43
+    rng = random.Random(99)
+    genome = util.make_genome(rng, 30000)
+    nested, _ = util.synth_signatures(rng, genome, k, 700)
+    ks, fl = util.flatten(nested)
+    words, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, 30000)
+    order = list(range(len(ks)))
+    rng.shuffle(order)
+    a, b, whole = (MalvaGpu(k=k, ref_k=ref_k, bf_bits=bf_bits) for _ in range(3))
+    o = util.OracleRun(oracle_lib, k, ref_k, bf_bits)
+    try:
+        a.add_signatures(ks, fl)                                   # one batch, file order
+        for s in range(0, len(order), 97):                         # shuffled, many small batches
+            idx = order[s:s + 97]
+            b.add_signatures([ks[i] for i in idx], [fl[i] for i in idx])
+        whole.add_signatures(list(reversed(ks)), list(reversed(fl)))
+        o.add_signatures(ks, fl)
+        for x in (a, b, whole, o):
+            x.finalize_alt()
+            x.scan_reference(genome)
+            x.finalize_context()
+        if bf_bits == 1 << 13:
+            assert a.index_stats()["overflow_keys"] > 100
+        assert a.index_stats() == b.index_stats() == whole.index_stats()
+        half = len(packed) // 2
+        a.scan_sample_kmers(packed[:half], counts[:half])
+        b.scan_sample_kmers(packed[half:], counts[half:])
+        whole.scan_sample_kmers(packed, counts)
+        o.scan_sample_kmers(packed, counts)
+        ca, cb, cw = _counter_arrays(a), _counter_arrays(b), _counter_arrays(whole)
+        for i, name in enumerate(("bf counters", "line key counts", "overflow counts")):
+            assert len(ca[i]) == len(cb[i]) == len(cw[i]), name
+            assert np.array_equal(ca[i] + cb[i], cw[i]), name
+        assert cw[1].sum() + cw[2].sum() > 0
+        # and the single-replica answers are the reference's
+        assert np.array_equal(whole.get_counts(ks, fl), o.get_counts(ks, fl))
+        assert np.array_equal(whole.bf_counts(), o.bf_counts())
+    finally:
+        for x in (a, b, whole, o):
+            x.close()
