@@ -155,6 +155,11 @@ int mg_index_stats(mg_ctx *ctx, uint64_t *stats, int n);
  * replicas: [0] one per set bit of bf, [1] one per key slot of the probe lines, [2] overflow table */
 int mg_counter_buffers(mg_ctx *ctx, void **d_ptr /*[3]*/, uint64_t *n /*[3]*/);
 
+/* Replicas inside one process: ctx[0..n-1] hold the same index (on any devices) and each scanned a share of the
+ * sample stream; adds the counter arrays of ctx[1..n-1] into ctx[0] (NVLink peer copies + an add kernel).  After it
+ * ctx[0] answers mg_genotype / mg_get_counts for the whole stream. */
+int mg_reduce_counts(mg_ctx **ctx, int n);
+
 /* index image for the index file (BF::operator>> / KMAP::operator>>, main.cpp:406-412; loading :455-461).
  * Filters travel as sorted lists of set-bit indices (the reference writes the raw 2 x bf_bits/8 bytes), ref_bf
  * as its packed canonical keys.  Call with out == NULL to get the count first.  Import the bits of bf (which=0)

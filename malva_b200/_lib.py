@@ -93,6 +93,7 @@ SYMBOLS = {
     "mg_kmap_size": (C.c_int, [C.c_void_p, u64p]),
     "mg_index_stats": (C.c_int, [C.c_void_p, u64p, C.c_int]),
     "mg_counter_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
+    "mg_reduce_counts": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "mg_export_set_bits": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64, u64p]),
     "mg_import_set_bits": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64]),
     "mg_export_ref_keys": (C.c_int, [C.c_void_p, u64p, C.c_uint64, u64p]),

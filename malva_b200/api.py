@@ -349,6 +349,12 @@ class MalvaGpu:
                          "irregular_ref_keys"), [int(x) for x in s]))
 
 
+def reduce_counts(contexts) -> None:
+    """adds the counters of contexts[1:] into contexts[0] (replicas of one index that scanned shares of the stream)"""
+    arr = (C.c_void_p * len(contexts))(*[c._h.value for c in contexts])
+    check(_lib.load().mg_reduce_counts(arr, len(contexts)))
+
+
 class KmerCounter:
     """Canonical k-mer counting on the device (``mg_count_*``): the ``kmc -k<k> -ci2 -cs255`` step of the MALVA
     wrapper (MALVA:107).  ``add(reads)`` takes upper-case read bytes, records separated by any non-ACGT byte."""

@@ -67,6 +67,8 @@ const char *USAGE =
     "      -1, --haploid                     run MALVA in haploid mode (default: false)\n"
     "          --threads N                   host threads for VCF decoding / signature enumeration (default: all)\n"
     "          --device N                    CUDA device (default: 0)\n"
+    "          --devices A,B,..              call: replicate the index on these devices, deal the KMC records\n"
+    "                                        round-robin, add the counters up on the first one\n"
     "\n";
 
 struct Options {
@@ -78,6 +80,7 @@ struct Options {
   bool strip_chr = false, uniform = false, verbose = false, haploid = false, index_blocks = false;
   int threads = 0, device = 0;
   bool trace = false;  // --trace: per-batch host/device timings on stderr
+  std::vector<int> devices;  // --devices a,b,..: `call` replicates the index and deals the KMC records round-robin
   std::string fasta_path, vcf_path, kmc_path;
 };
 
@@ -101,6 +104,7 @@ bool parse_arguments(int argc, char **argv, Options &o, int n_positional) {
                                     {"device", required_argument, nullptr, 1001},
                                     {"index-blocks", no_argument, nullptr, 1002},
                                     {"trace", no_argument, nullptr, 1003},
+                                    {"devices", required_argument, nullptr, 1004},
                                     {nullptr, 0, nullptr, 0}};
   bool die = false;
   optind = 1;
@@ -125,6 +129,12 @@ bool parse_arguments(int argc, char **argv, Options &o, int n_positional) {
       case 1001: arg >> o.device; break;
       case 1002: o.index_blocks = true; break;
       case 1003: o.trace = true; break;
+      case 1004: {
+        std::string tok;
+        while (std::getline(arg, tok, ','))
+          if (!tok.empty()) o.devices.push_back(atoi(tok.c_str()));
+        break;
+      }
       case '?': die = true; break;
       case 'h':
         std::cout << USAGE;
@@ -146,6 +156,8 @@ bool parse_arguments(int argc, char **argv, Options &o, int n_positional) {
   o.vcf_path = argv[optind++];
   if (n_positional > 2) o.kmc_path = argv[optind++];
   if (o.threads <= 0) o.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  if (o.devices.empty()) o.devices.push_back(o.device);
+  o.device = o.devices[0];
   return true;
 }
 
@@ -491,58 +503,71 @@ int call_main(int argc, char **argv) {
     }
   }
   BatchPrefetcher call_batches(stream, LINES_PER_BATCH);  // first VCF batch decoded while the index loads and the scan runs
-  Ctx g;
-  {  // load the index: context_bf, bf, ref_bf (main.cpp:455-461)
+  const int n_dev = (int)o.devices.size();
+  std::vector<Ctx> gs((size_t)n_dev);
+  Ctx &g = gs[0];  // the context that answers after the reduce
+  {  // load the index: context_bf, bf, ref_bf (main.cpp:455-461) -- once from the file, then onto every device
     mh::IndexReader r(o.vcf_path + ".c" + std::to_string(o.ref_k) + ".k" + std::to_string(o.k) + ".malvax.zst");
     if (r.k != o.k || r.ref_k != o.ref_k)
       throw std::runtime_error("the index was built with -k " + std::to_string(r.k) + " -r " + std::to_string(r.ref_k));
-    // the filter size travels with the index, like the reference's serialised bit vectors (-b matters at index time)
-    gpu(mg_create(&g.c, o.device, (int)o.k, (int)o.ref_k, r.bf_bits), "mg_create");
-    std::vector<uint64_t> ctx_bits = r.read_bits();
-    {
-      std::vector<uint64_t> bf_bits = r.read_bits();
-      gpu(mg_import_set_bits(g.c, 0, bf_bits.data(), bf_bits.size()), "mg_import_set_bits");
+    std::vector<uint64_t> ctx_bits = r.read_bits(), bf_bits = r.read_bits(), keys = r.read_keys();
+    std::vector<uint8_t> flags(keys.size() / 2, 1);
+    for (int d = 0; d < n_dev; ++d) {
+      // the filter size travels with the index, like the reference's serialised bit vectors (-b matters at index time)
+      gpu(mg_create(&gs[(size_t)d].c, o.devices[(size_t)d], (int)o.k, (int)o.ref_k, r.bf_bits), "mg_create");
+      mg_ctx *c = gs[(size_t)d].c;
+      gpu(mg_import_set_bits(c, 0, bf_bits.data(), bf_bits.size()), "mg_import_set_bits");
+      gpu(mg_add_signatures_packed(c, keys.data(), flags.data(), flags.size()), "mg_add_signatures_packed");
+      gpu(mg_finalize_alt(c), "mg_finalize_alt");
+      gpu(mg_import_set_bits(c, 1, ctx_bits.data(), ctx_bits.size()), "mg_import_set_bits");
+      gpu(mg_finalize_context(c), "mg_finalize_context");
     }
-    {
-      std::vector<uint64_t> keys = r.read_keys();
-      std::vector<uint8_t> flags(keys.size() / 2, 1);
-      gpu(mg_add_signatures_packed(g.c, keys.data(), flags.data(), flags.size()), "mg_add_signatures_packed");
-    }
-    gpu(mg_finalize_alt(g.c), "mg_finalize_alt");
-    gpu(mg_import_set_bits(g.c, 1, ctx_bits.data(), ctx_bits.size()), "mg_import_set_bits");
-    gpu(mg_finalize_context(g.c), "mg_finalize_context");
   }
   pelapsed("Reference parsing");
   std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
   pelapsed("Reference processed");
 
-  // STEP 2: the sample k-mer scan (main.cpp:482-500).  Raw suffix records go through a ring of pinned buffers;
-  // the library copies and scans them asynchronously (double-buffered on its side), a buffer is refilled only
-  // after the event recorded behind its scan has completed.
+  // STEP 2: the sample k-mer scan (main.cpp:482-500).  Raw suffix records go through rings of pinned buffers, one
+  // ring per device, chunks dealt round-robin; the library copies and scans them asynchronously (double-buffered on
+  // its side), a buffer is refilled only after the event recorded behind its scan has completed.  With several
+  // devices the counters are then added up on the first one (all updates are commutative adds, main.cpp:495-499).
   pelapsed("KMC output processing");
   {
-    gpu(mg_kmc_open(g.c, db.lut.data(), db.lut.size(), db.lut_prefix_len, db.kmer_len, db.counter_size, db.min_count,
-                    db.max_count),
-        "mg_kmc_open");
     constexpr int RING = 4;
     constexpr uint64_t CHUNK = 1ull << 22;  // records per buffer
-    uint8_t *buf[RING] = {};
-    bool used[RING] = {};
-    for (auto &b : buf) gpu(mg_host_alloc((void **)&b, CHUNK * db.record_bytes + 64), "mg_host_alloc");
+    std::vector<uint8_t *> buf((size_t)(n_dev * RING), nullptr);
+    std::vector<char> used((size_t)(n_dev * RING), 0);
+    for (int d = 0; d < n_dev; ++d) {
+      gpu(mg_kmc_open(gs[(size_t)d].c, db.lut.data(), db.lut.size(), db.lut_prefix_len, db.kmer_len, db.counter_size,
+                      db.min_count, db.max_count),
+          "mg_kmc_open");
+      for (int s = 0; s < RING; ++s) gpu(mg_host_alloc((void **)&buf[(size_t)(d * RING + s)], CHUNK * db.record_bytes + 64), "mg_host_alloc");
+    }
     uint64_t first = 0;
-    for (int slot = 0;; slot = (slot + 1) % RING) {
-      if (used[slot]) gpu(mg_event_sync(g.c, 32 + slot), "mg_event_sync");
-      uint64_t n = db.read_records(buf[slot], first, CHUNK);
+    for (uint64_t chunk = 0;; ++chunk) {
+      const int d = (int)(chunk % (uint64_t)n_dev), slot = d * RING + (int)((chunk / (uint64_t)n_dev) % RING);
+      mg_ctx *c = gs[(size_t)d].c;
+      if (used[(size_t)slot]) gpu(mg_event_sync(c, 32 + slot % RING), "mg_event_sync");
+      uint64_t n = db.read_records(buf[(size_t)slot], first, CHUNK);
       if (n == 0) break;
-      gpu(mg_scan_kmc_records(g.c, buf[slot], first, n), "mg_scan_kmc_records");
-      gpu(mg_event_record(g.c, 32 + slot), "mg_event_record");
-      used[slot] = true;
+      gpu(mg_scan_kmc_records(c, buf[(size_t)slot], first, n), "mg_scan_kmc_records");
+      gpu(mg_event_record(c, 32 + slot % RING), "mg_event_record");
+      used[(size_t)slot] = 1;
       first += n;
     }
-    gpu(mg_sync(g.c), "mg_sync");
+    for (auto &x : gs) gpu(mg_sync(x.c), "mg_sync");
     for (auto &b : buf) mg_host_free(b);
     if (first != db.total_kmers)
       throw std::runtime_error(o.kmc_path + ".kmc_suf is shorter than its header says");
+    if (n_dev > 1) {
+      std::vector<mg_ctx *> all;
+      for (auto &x : gs) all.push_back(x.c);
+      gpu(mg_reduce_counts(all.data(), n_dev), "mg_reduce_counts");
+      for (size_t d = 1; d < gs.size(); ++d) {  // the replicas are no longer needed
+        mg_destroy(gs[d].c);
+        gs[d].c = nullptr;
+      }
+    }
   }
   pelapsed("BF weights created");
 

@@ -804,6 +804,18 @@ __global__ void __launch_bounds__(256) k_emit_keys(const uint4 *__restrict__ lin
   if (o < cap) out[o] = key;
 }
 
+// dst[i] += src[i] (u32, wrap-around): the counter reduce of replicated contexts (mg_reduce_counts)
+__global__ void __launch_bounds__(256) k_add_u32(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint64_t n) {
+  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    uint4 a = *reinterpret_cast<const uint4 *>(dst + i), b = *reinterpret_cast<const uint4 *>(src + i);
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    *reinterpret_cast<uint4 *>(dst + i) = a;
+  } else {
+    for (; i < n; ++i) dst[i] += src[i];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // roofline diagnostics: measured ceilings on this device (bench.py records them)
 //   k_diag_random  : independent random reads, `gran` separate 4-byte loads inside one aligned

@@ -974,6 +974,45 @@ extern "C" int mg_counter_buffers(mg_ctx *c, void **d_ptr, uint64_t *n) {
   return MG_OK;
 }
 
+// Replicate-and-reduce inside one process: ctx[0..n-1] hold the same index (any devices, the same
+// device included), each scanned its share of the sample stream; the three counter arrays of ctx[1..] are added
+// into ctx[0] -- peer copies over NVLink into a staging buffer on ctx[0]'s device, then an add kernel.  Exact
+// because the index image is canonical (identical layouts) and the updates are modular adds.
+extern "C" int mg_reduce_counts(mg_ctx **ctx, int n) {
+  if (!ctx || n < 1) return set_err(MG_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    if (!ctx[i]) return set_err(MG_ERR_ARG, "NULL context");
+    if (!ctx[i]->alt_final) return set_err(MG_ERR_STATE, "mg_reduce_counts before mg_finalize_alt");
+    if (ctx[i]->bf_bits != ctx[0]->bf_bits || ctx[i]->bf_ones != ctx[0]->bf_ones || ctx[i]->n_keys != ctx[0]->n_keys ||
+        ctx[i]->ovf_n != ctx[0]->ovf_n || ctx[i]->ovf_log2 != ctx[0]->ovf_log2 || ctx[i]->k != ctx[0]->k)
+      return set_err(MG_ERR_ARG, "context %d does not hold the same index as context 0", i);
+    for (int j = 0; j < i; ++j)
+      if (ctx[j] == ctx[i]) return set_err(MG_ERR_ARG, "context %d listed twice", i);
+    int rc = mg_sync(ctx[i]);
+    if (rc) return rc;
+  }
+  mg_ctx *c0 = ctx[0];
+  CU(cudaSetDevice(c0->device));
+  const uint64_t CH = 1ull << 26;  // u32 elements per staging chunk (256 MB)
+  DevFree stage;
+  CU(cudaMalloc(&stage.p, CH * 4));
+  for (int i = 1; i < n; ++i) {
+    uint32_t *dst[3] = {c0->bf_counts, c0->key_counts, c0->ovf_counts};
+    uint32_t *src[3] = {ctx[i]->bf_counts, ctx[i]->key_counts, ctx[i]->ovf_counts};
+    uint64_t len[3] = {c0->bf_ones, c0->n_lines * mg::LINE_KEYS, 1ull << c0->ovf_log2};
+    for (int a = 0; a < 3; ++a)
+      for (uint64_t o = 0; o < len[a]; o += CH) {
+        uint64_t m = len[a] - o < CH ? len[a] - o : CH;
+        CU(cudaMemcpyPeerAsync(stage.p, c0->device, src[a] + o, ctx[i]->device, m * 4, c0->stream[0]));
+        c0->launches++;
+        mg::k_add_u32<<<grid_for((m + 3) / 4, 256), 256, 0, c0->stream[0]>>>(dst[a] + o, (const uint32_t *)stage.p, m);
+        CU(cudaGetLastError());
+      }
+  }
+  CU(cudaStreamSynchronize(c0->stream[0]));
+  return MG_OK;
+}
+
 // ---- index image export / import ----
 extern "C" int mg_export_set_bits(mg_ctx *c, int which, uint64_t *out, uint64_t cap, uint64_t *n) {
   if (!c || !n || which < 0 || which > 1 || (!out && cap)) return set_err(MG_ERR_ARG, "bad argument");

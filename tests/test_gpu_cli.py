@@ -83,3 +83,26 @@ def test_cli_threads_and_errors(cli, tmp_path):
     assert r.returncode == 1 and "index" in r.stderr
     r = subprocess.run([cli, "index", "-b", "1", "-f", "NOPE_AF", fa, vcf, prefix], capture_output=True, text=True)
     assert r.returncode == 1 and "NOPE_AF" in r.stderr
+
+
+def _n_gpus():
+    from malva_b200 import _lib
+
+    return _lib.load().mg_device_count()
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0", "0,1"])
+def test_cli_call_over_replicated_contexts(cli, devices, tmp_path):
+    """`call --devices a,b,..`: the index replicated per context, KMC chunks dealt round-robin, counters added up with
+    mg_reduce_counts -- same bytes as the single-context run (contexts may share a device)"""
+    if max(int(d) for d in devices.split(",")) >= _n_gpus():
+        pytest.skip("needs more GPUs")
+    case = synth.CASES[3]
+    fa, vcf, prefix, _ = synth.build_case(case, str(tmp_path))
+    expected = gzip.open(os.path.join(GOLD, "cli", case.name + ".expected.vcf.gz")).read()
+    flags = mk.cli_flags(case)
+    r = subprocess.run([cli, "index"] + flags + [fa, vcf, prefix], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    r = subprocess.run([cli, "call", "-v", "--devices", devices] + flags + [fa, vcf, prefix], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert r.stdout == expected, first_diff(r.stdout, expected)
