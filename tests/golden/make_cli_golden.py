@@ -34,20 +34,20 @@ def input_hashes(fa, vcf, prefix):
     return {"fasta": sha(fa), "vcf": sha(vcf), "kmc_pre": sha(prefix + ".kmc_pre"), "kmc_suf": sha(prefix + ".kmc_suf")}
 
 
-def cli_flags(case):
-    """flags common to both programs: -k/-r/-b 1 + the case's own"""
+def cli_flags(case, workdir=None):
+    """flags common to both programs: -k/-r/-b 1 + the case's own ("@SAMPLES" -> <workdir>/samples.txt)"""
     fl, it = [], iter(case.flags)
     for f in it:
         if f in ("-k", "-r"):
             next(it)
             continue
-        fl.append(f)
+        fl.append(os.path.join(workdir, "samples.txt") if f == "@SAMPLES" else f)
     return ["-k", str(case.k), "-r", str(case.ref_k), "-b", "1"] + fl
 
 
 def run_reference(case, workdir, verbose=True):
     fa, vcf, prefix, n = synth.build_case(case, workdir)
-    flags = cli_flags(case)
+    flags = cli_flags(case, workdir)
     subprocess.run([REF_BIN, "index"] + flags + [fa, vcf, prefix], check=True, capture_output=True)
     r = subprocess.run([REF_BIN, "call"] + (["-v"] if verbose else []) + flags + [fa, vcf, prefix], check=True,
                        capture_output=True)

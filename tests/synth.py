@@ -282,7 +282,8 @@ class Case:
     mean_cov: float = 30.0
     k: int = 35
     ref_k: int = 43
-    flags: tuple = ()              # extra CLI flags (both programs)
+    flags: tuple = ()              # extra CLI flags (both programs); "@SAMPLES" = path of the sample-list file
+    sample_subset: tuple = ()      # indices of the panel samples listed in that file (file order is NOT header order)
     freq_key: str = "AF"
     gz: bool = False
     chr_prefix: bool = False
@@ -299,6 +300,10 @@ def build_case(case: Case, outdir: str):
     vcf = os.path.join(outdir, "vars.vcf" + (".gz" if case.gz else ""))
     write_fasta(fa, refs, chr_prefix=case.chr_prefix)
     write_vcf(vcf, refs, recs, case.n_samples, case.haploid, case.lower_case_frac, rng, freq_key=case.freq_key)
+    if case.sample_subset:
+        with open(os.path.join(outdir, "samples.txt"), "w") as fh:
+            for i in case.sample_subset:
+                fh.write(f"S{i}\n")
     haps = donor_haplotypes(rng, refs, recs, case.haploid)
     prefix = os.path.join(outdir, "sample")
     n = sample_kmc_db(rng, prefix, haps, case.ref_k, case.mean_cov)
@@ -321,4 +326,6 @@ CASES = [
          chr_prefix=True, flags=("-p", "-e", "0.01", "-c", "25")),
     Case("k31_r39", 20261018 + 9, [("1", 50_000)], mean_gap=30, n_samples=5, k=31, ref_k=39,
          flags=("-k", "31", "-r", "39")),
+    Case("samples_subset_uniform", 20261018 + 10, [("3", 40_000)], mean_gap=28, n_samples=12,
+         flags=("-s", "@SAMPLES", "-u"), sample_subset=(7, 2, 9, 3)),
 ]

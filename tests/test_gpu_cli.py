@@ -53,7 +53,7 @@ def test_cli_vcf_is_byte_identical_to_the_reference(cli, case, tmp_path):
     fa, vcf, prefix, _ = synth.build_case(case, str(tmp_path))
     assert mk.input_hashes(fa, vcf, prefix) == manifest["inputs"], "synthetic inputs differ from the ones the golden was made from"
     expected = gzip.open(os.path.join(GOLD, "cli", case.name + ".expected.vcf.gz")).read()
-    got = run_ours(cli, mk.cli_flags(case), fa, vcf, prefix, verbose=True)
+    got = run_ours(cli, mk.cli_flags(case, str(tmp_path)), fa, vcf, prefix, verbose=True)
     assert got == expected, first_diff(got, expected)
 
 

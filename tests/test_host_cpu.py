@@ -75,6 +75,8 @@ def test_signatures_haploid_example(cli, ref_lib):
 def test_signatures_synthetic(cli, ref_lib, case, tmp_path):
     fa, vcf, _, _ = synth.build_case(case, str(tmp_path))
     uniform = "-u" in case.flags
+    if case.sample_subset:
+        pytest.skip("sample subsetting is covered end to end (tests/test_gpu_cli.py); the Python twin reads all samples")
     sig_flags = [f for f in case.flags]
     # only the flags the enumeration depends on
     keep, it = [], iter(sig_flags)
