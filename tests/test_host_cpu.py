@@ -162,3 +162,26 @@ def test_kmc_dump_lists_what_the_python_reader_lists(cli, tmp_path):
         assert ks == [kmc.unpack_kmer(v, k) for v, _ in keep] and cs == [c for _, c in keep]
     r = subprocess.run([cli, "kmc-dump", str(tmp_path / "nope")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+def test_signatures_fuzz_small_blocks(cli, ref_lib, tmp_path):
+    """many small random VCFs (dense clusters, 20 % multi-allelic, symbolic and long alleles, 1-9 samples, haploid and
+    diploid, k from 15 to 35): enumeration == VB::extract_kmers in both grouping modes"""
+    import random
+
+    for seed in range(24):
+        rng = random.Random(7000 + seed)
+        haploid = rng.random() < 0.3
+        k = rng.choice([35, 35, 31, 21, 15])
+        contigs = [("1", rng.randrange(1500, 6000)), ("2", rng.randrange(800, 3000))]
+        refs = synth.make_reference(rng, contigs, n_run_every=1700)
+        recs = synth.make_variants(rng, refs, rng.choice([7, 10, 20, 30]), rng.choice([1, 2, 5, 9]), haploid, multi_frac=0.2,
+                                   sym_frac=0.03, long_frac=0.02, k=k)
+        fa, vcf = str(tmp_path / f"r{seed}.fa"), str(tmp_path / f"v{seed}.vcf")
+        synth.write_fasta(fa, refs)
+        synth.write_vcf(vcf, refs, recs, len(recs[0].gts) if recs else 1, haploid, 0.05, rng)
+        flags = (["-1"] if haploid else []) + ["-k", str(k)]
+        for index_mode in (True, False):
+            got, used = cli_signatures(cli, fa, vcf, flags, index_mode)
+            exp, exp_used = expected_signatures(ref_lib, fa, vcf, k, haploid, "AF", False, index_mode)
+            assert got == exp and used == exp_used, f"seed {seed} index_mode {index_mode}"
