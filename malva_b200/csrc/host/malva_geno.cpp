@@ -243,16 +243,13 @@ class BlockStream {
   bool next_batch(std::vector<mh::VarBlock> &out, size_t max_lines) {
     out.clear();
     if (done_) return false;
-    lines_.clear();
-    std::string line;
-    size_t bytes = 0;
-    while (lines_.size() < max_lines && bytes < (256u << 20) && reader_.next_line(line)) {
-      bytes += line.size();
-      lines_.push_back(std::move(line));
-    }
+    // a block of whole lines (no per-line allocation), decoded in parallel
+    const bool more = reader_.next_lines(store_, lines_, max_lines, 32u << 20);
     std::vector<mh::Variant> vars(lines_.size());
-    parallel_for(lines_.size(), o_.threads, [&](size_t i) {
-      vars[i] = mh::parse_record(lines_[i], reader_.header, o_.freq_key, o_.uniform, freq_declared_);
+    const size_t grain = 256, n_tasks = (lines_.size() + grain - 1) / grain;
+    parallel_for(n_tasks, o_.threads, [&](size_t t) {
+      for (size_t i = t * grain; i < std::min(lines_.size(), (t + 1) * grain); ++i)
+        vars[i] = mh::parse_record(lines_[i].b, lines_[i].e, reader_.header, o_.freq_key, o_.uniform, freq_declared_);
     });
     for (auto &v : vars) {
       ++n_records;
@@ -277,7 +274,7 @@ class BlockStream {
       }
       vb_.add(std::move(v));
     }
-    if (lines_.size() < max_lines && bytes < (256u << 20)) {  // end of file
+    if (!more) {  // end of file
       done_ = true;
       if (!vb_.empty()) flush(out);
     }
@@ -295,7 +292,8 @@ class BlockStream {
   mh::VcfReader reader_;
   mh::VarBlock vb_;
   std::string last_seq_name_;
-  std::vector<std::string> lines_;
+  std::vector<char> store_;
+  std::vector<mh::BlockLineReader::View> lines_;
 };
 
 // Reads and decodes batch i+1 on a background thread while batch i is enumerated, sent to the device and printed.

@@ -57,6 +57,92 @@ class LineReader {
   std::vector<char> buf_;
 };
 
+// Block-wise reader: whole lines of a plain or gz file, many at a time, as views into one buffer (no per-line
+// allocation; the VCF decode that follows runs on the views in parallel).
+class BlockLineReader {
+ public:
+  struct View {
+    const char *b, *e;
+  };
+  explicit BlockLineReader(const std::string &path) : fp_(gzopen(path.c_str(), "r")) {
+    if (!fp_) throw std::runtime_error("cannot open " + path);
+    gzbuffer(fp_, 1 << 20);
+  }
+  ~BlockLineReader() {
+    if (fp_) gzclose(fp_);
+  }
+  BlockLineReader(const BlockLineReader &) = delete;
+  BlockLineReader &operator=(const BlockLineReader &) = delete;
+
+  // one line (header parsing); false at end of file
+  bool next(std::string &line) {
+    while (true) {
+      const char *nl = pos_ < buf_.size() ? (const char *)memchr(buf_.data() + pos_, '\n', buf_.size() - pos_) : nullptr;
+      if (nl || (eof_ && pos_ < buf_.size())) {
+        const char *b = buf_.data() + pos_, *e = nl ? nl : buf_.data() + buf_.size();
+        pos_ = nl ? (size_t)(nl - buf_.data()) + 1 : buf_.size();
+        if (e > b && e[-1] == '\r') --e;
+        line.assign(b, e);
+        return true;
+      }
+      if (eof_) return false;
+      fill(1 << 20);
+    }
+  }
+  // up to max_lines non-empty lines / ~target bytes into `store` (which keeps the views alive); false when nothing is left
+  bool next_block(std::vector<char> &store, std::vector<View> &lines, size_t max_lines, size_t target) {
+    lines.clear();
+    while (!eof_ && buf_.size() - pos_ < target) fill(target - (buf_.size() - pos_) + (1 << 16));
+    // cut after the last complete line within reach
+    size_t end = buf_.size();
+    if (!eof_) {
+      const char *last = nullptr;
+      for (size_t i = buf_.size(); i > pos_; --i)
+        if (buf_[i - 1] == '\n') {
+          last = buf_.data() + i;
+          break;
+        }
+      if (!last) {  // one line longer than the target: keep reading
+        while (!eof_ && !memchr(buf_.data() + pos_, '\n', buf_.size() - pos_)) fill(target);
+        return next_block(store, lines, max_lines, target);
+      }
+      end = (size_t)(last - buf_.data());
+    }
+    store.assign(buf_.begin() + (long)pos_, buf_.begin() + (long)end);
+    size_t used = 0;
+    const char *p = store.data(), *stop = store.data() + store.size();
+    while (p < stop && lines.size() < max_lines) {
+      const char *nl = (const char *)memchr(p, '\n', (size_t)(stop - p));
+      const char *e = nl ? nl : stop;
+      const char *next = nl ? nl + 1 : stop;
+      if (e > p && e[-1] == '\r') --e;
+      if (e > p) lines.push_back(View{p, e});
+      p = next;
+      used = (size_t)(p - store.data());
+    }
+    pos_ += used;
+    if (pos_ > (8u << 20)) {  // drop what has been handed out
+      buf_.erase(buf_.begin(), buf_.begin() + (long)pos_);
+      pos_ = 0;
+    }
+    return !lines.empty() || pos_ < buf_.size() || !eof_;
+  }
+
+ private:
+  void fill(size_t want) {
+    size_t old = buf_.size();
+    buf_.resize(old + want);
+    int got = gzread(fp_, buf_.data() + old, (unsigned)want);
+    if (got < 0) throw std::runtime_error("read error");
+    buf_.resize(old + (size_t)got);
+    if ((size_t)got < want) eof_ = true;
+  }
+  gzFile fp_;
+  std::vector<char> buf_;
+  size_t pos_ = 0;
+  bool eof_ = false;
+};
+
 // whole reference, upper-cased, name = first word of the header line, optional "chr" strip (main.cpp:283-295).
 // FASTA and FASTQ-style records are both accepted, like kseq does.
 inline std::map<std::string, std::string> read_fasta(const std::string &path, bool strip_chr) {
@@ -187,7 +273,7 @@ class VcfHeader {
   }
 };
 
-// Opens a VCF (plain or gz), reads the header; data lines are then pulled with next_line().
+// Opens a VCF (plain or gz), reads the header; data lines are then pulled in blocks with next_lines().
 class VcfReader {
  public:
   VcfHeader header;
@@ -213,27 +299,28 @@ class VcfReader {
         for (size_t i = 0; i < header.samples.size(); ++i) header.keep.push_back((int)i);
         return;
       }
-      pending_ = line;
+      pending_ = line;  // a data line before any #CHROM line: headerless VCF
       has_pending_ = true;
       return;
     }
   }
 
-  bool next_line(std::string &line) {
-    while (true) {
-      if (has_pending_) {
-        line.swap(pending_);
-        has_pending_ = false;
-      } else if (!in_.next(line)) {
-        return false;
-      }
-      if (!line.empty()) return true;
+  // the next data lines (views into `store`); false at the end of the file
+  bool next_lines(std::vector<char> &store, std::vector<BlockLineReader::View> &lines, size_t max_lines, size_t target) {
+    bool more = in_.next_block(store, lines, max_lines, target);
+    if (has_pending_) {
+      has_pending_ = false;
+      pending_store_.assign(pending_.begin(), pending_.end());
+      lines.insert(lines.begin(), BlockLineReader::View{pending_store_.data(), pending_store_.data() + pending_store_.size()});
+      return true;
     }
+    return more;
   }
 
  private:
-  LineReader in_;
+  BlockLineReader in_;
   std::string pending_;
+  std::vector<char> pending_store_;
   bool has_pending_ = false;
 };
 
@@ -275,12 +362,12 @@ inline bool info_floats(const Field &info, const std::string &key, std::vector<f
 }  // namespace detail
 
 // Variant(hdr, rec, freq_key, uniform), variant.hpp:66-103, from one VCF data line.
-inline Variant parse_record(const std::string &line, const VcfHeader &header, const std::string &freq_key, bool uniform,
-                            bool freq_key_declared) {
+inline Variant parse_record(const char *line_begin, const char *line_end, const VcfHeader &header,
+                            const std::string &freq_key, bool uniform, bool freq_key_declared) {
   using detail::Field;
   Field c[9];
   int nf = 0;
-  const char *p = line.data(), *end = line.data() + line.size();
+  const char *p = line_begin, *end = line_end;
   const char *samples_begin = nullptr;
   while (nf < 9) {
     const char *t = (const char *)memchr(p, '\t', (size_t)(end - p));
@@ -289,7 +376,8 @@ inline Variant parse_record(const std::string &line, const VcfHeader &header, co
     p = t + 1;
     if (nf == 9) samples_begin = p;
   }
-  if (nf < 8) throw std::runtime_error("malformed VCF record: " + line.substr(0, 60));
+  if (nf < 8)
+    throw std::runtime_error("malformed VCF record: " + std::string(line_begin, std::min<size_t>(60, (size_t)(line_end - line_begin))));
   Variant v;
   v.seq_name = c[0].str();
   v.ref_pos = (int)(strtoll(c[1].str().c_str(), nullptr, 10) - 1);
