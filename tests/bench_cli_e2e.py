@@ -3,7 +3,9 @@
 own main.cpp, CPU, single-threaded like the original) against this repository's `malva-geno` (C++ host + B200
 kernels) on the same synthetic chromosome-arm-sized inputs; outputs must be byte-identical.
 
-    python profiles/cli_e2e.py [Mbp=5] [samples=32] > gpurun_out/cli_e2e.json
+    python tests/bench_cli_e2e.py [Mbp=5] [samples=32] > gpurun_out/cli_e2e.json
+
+(lives under tests/ because it executes the oracle build of the reference; not collected by pytest)
 """
 import json
 import os
