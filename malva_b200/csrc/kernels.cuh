@@ -419,7 +419,7 @@ __device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_l
 }
 
 template <int K, int REFK, int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, DevView v) {
+__global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t n, DevView v) {
   extern __shared__ uint4 scan_sm[];
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
@@ -507,6 +507,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanSrc src, uint64_t n, 
       const int L = 4 * r + grp;
       if (L < n_need)
         cp_async16(tile_addr + (uint32_t)((L * 8 + (sub ^ (L & 7))) * 16), v.lines + (uint64_t)rows[L] * LINE_U4 + sub);
+    }
+    if constexpr (MODE == 0) {
+      // while the lines are in flight: the warp's next batch (512 B of k-mers + 128 B of counts) into L2
+      if (lane < 5 && base + step < n32) {
+        const char *pf = lane < 4 ? reinterpret_cast<const char *>(src.kmers + base + step) + lane * 128
+                                  : reinterpret_cast<const char *>(src.counts + base + step);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      }
     }
     cp_async_wait_all();
     __syncwarp();
