@@ -393,7 +393,9 @@ def run_ours(args, wl, rank, local_rank, world):
     g.finalize_context()
     pop_alt, pop_ctx, n_keys = g.popcount(0), g.popcount(1), g.kmap_size()
     # sample batches, device resident (2 batches rotate so that no step re-reads the previous step's lines)
-    gen.manual_seed(SEED + 100 + rank)  # every rank scans its own share of the stream
+    # every rank scans its own share of the stream (--verify: the same share, so that the reduced counters must be
+    # exactly world x one rank's)
+    gen.manual_seed(SEED + 100 + (0 if args.verify else rank))
     B = wl["batch"]
     batches = [make_sample_batch(torch, B, alt, ref, gen, dev) for _ in range(2)]
     vb = make_variant_batch(torch, wl["variants"], alt, ref, gen, dev)
@@ -462,8 +464,11 @@ def run_ours(args, wl, rank, local_rank, world):
         g.scan_sample_kmers_ptr(kk.data_ptr(), cc.data_ptr(), B, device=True)
         g.event_record(11 + 2 * (i % 8))
         g.genotype_device(ptrs, vb["dims"], 0.001, 200, False)
+    before = None
     if world > 1:
         g.sync()  # the library's streams -> torch's stream, then the NCCL sum-reduce of both counter arrays
+        if args.verify:
+            before = [t.clone() for t in counters]
         for t in counters:
             dist.reduce(t, dst=0)
         torch.cuda.synchronize()
@@ -478,6 +483,12 @@ def run_ours(args, wl, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     region_ms = float(tm.item())
+    verified = None
+    if before is not None and rank == 0:
+        # identical replicas (canonical index image) that scanned identical batches: sum over ranks == world x mine
+        verified = all(bool(torch.equal(t, b * world)) for t, b in zip(counters, before)) and \
+            any(int(b.sum().item()) != 0 for b in before)
+        log(f"[verify] reduced counters == {world} x rank 0's own counters: {verified}")
     ms_per_step = region_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -568,6 +579,7 @@ def run_ours(args, wl, rank, local_rank, world):
                           "note": "same step with host-decoded {lo,hi} words + u32 counts (20 B per 43-mer) through "
                                   "mg_scan_sample_kmers"}},
         "gpu_launches": launches,
+        **({"verify_reduce_exact": verified} if verified is not None else {}),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_scan<35,43>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -594,6 +606,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     ap.add_argument("--no-diag", action="store_true", help="skip the bandwidth microbenchmarks (profiling runs)")
+    ap.add_argument("--verify", action="store_true",
+                    help="N > 1: every rank scans the same batches; checks that the NCCL-reduced counters are exactly "
+                         "N x one rank's (replicas are identical, the reduce is exact)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
