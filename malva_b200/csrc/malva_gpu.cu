@@ -164,6 +164,7 @@ static int ovf_reserve(mg_ctx *c, uint64_t extra) {
   return MG_OK;
 }
 
+static int ctx_init(mg_ctx *c);
 extern "C" int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf_bits) {
   if (!out) return set_err(MG_ERR_ARG, "out is NULL");
   *out = nullptr;
@@ -180,6 +181,21 @@ extern "C" int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf
   c->k = k;
   c->ref_k = ref_k;
   c->bf_bits = bf_bits;
+  int rc = ctx_init(c);
+  if (rc) {  // (e.g. out of device memory for a large -b): nothing is left behind
+    char msg[sizeof(g_err)];
+    memcpy(msg, g_err, sizeof(msg));
+    mg_destroy(c);
+    memcpy(g_err, msg, sizeof(msg));
+    return rc;
+  }
+  *out = c;
+  return MG_OK;
+}
+
+static int ctx_init(mg_ctx *c) {
+  const int device = c->device;
+  const uint64_t bf_bits = c->bf_bits;
   c->n_lines = (bf_bits + 255) / 256;
   c->n_ctx_words = c->n_lines * 8;
   cudaDeviceProp prop;
@@ -214,7 +230,6 @@ extern "C" int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf
   int rc = ovf_alloc(c, c->ovf_log2, &c->ovf_keys, &c->ovf_counts);
   if (rc) return rc;
   CU(cudaStreamSynchronize(c->stream[0]));
-  *out = c;
   return MG_OK;
 }
 
@@ -1114,6 +1129,7 @@ static int counter_alloc_table(mg_counter *c, int log2cap, mg::CountSlot **t) {
   return MG_OK;
 }
 
+extern "C" void mg_count_destroy(mg_counter *c);
 extern "C" int mg_count_create(mg_counter **out, int device, int k) {
   if (!out) return set_err(MG_ERR_ARG, "out is NULL");
   *out = nullptr;
@@ -1125,13 +1141,24 @@ extern "C" int mg_count_create(mg_counter **out, int device, int k) {
   mg_counter *c = new mg_counter();
   c->device = device;
   c->k = k;
-  CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-  CU(cudaMalloc(&c->d_scalars, 4 * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(unsigned long long), c->st));
-  c->log2cap = 16;
-  int rc = counter_alloc_table(c, c->log2cap, &c->table);
-  if (rc) return rc;
-  CU(cudaStreamSynchronize(c->st));
+  auto init = [&]() -> int {
+    CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->d_scalars, 4 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(c->d_scalars, 0, 4 * sizeof(unsigned long long), c->st));
+    c->log2cap = 16;
+    int rc = counter_alloc_table(c, c->log2cap, &c->table);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    return MG_OK;
+  };
+  int rc = init();
+  if (rc) {
+    char msg[sizeof(g_err)];
+    memcpy(msg, g_err, sizeof(msg));
+    mg_count_destroy(c);
+    memcpy(g_err, msg, sizeof(msg));
+    return rc;
+  }
   *out = c;
   return MG_OK;
 }
