@@ -30,3 +30,12 @@ def ref_lib():
     if not pyoracle.have_ref():
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     return pyoracle.ref()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_in_tree():
+    """libmalva_gpu.so and malva-geno are built in-tree (git-ignored); make sure they exist and are current before
+    any test loads them (a no-op when they are up to date)"""
+    from malva_b200 import build as mbuild
+
+    mbuild.build()
