@@ -675,52 +675,74 @@ int signatures_main(int argc, char **argv) {
 // format is detected from its first byte).  --passes N counts in N prefix-partitioned passes over the reads for
 // inputs whose distinct k-mers do not fit device memory at once.
 struct ReadFeeder {
-  // sequences of a FASTA / FASTQ file (plain or gz), upper-cased, '\n' between records, in chunks of whole records
+  // sequences of a FASTA / FASTQ file (plain or gz), upper-cased, '\n' between records, in chunks of whole records.
+  // Lines are taken block-wise as views (no per-line allocation); FASTQ records are four lines (header, sequence,
+  // '+', qualities), FASTA sequences may span lines.
   explicit ReadFeeder(const std::string &path) : in_(path) {}
   bool next_chunk(std::string &out, size_t target) {
     out.clear();
-    std::string line;
     while (out.size() < target) {
-      if (!have_) {
-        if (!in_.next(line_)) break;
-        have_ = true;
+      if (li_ == lines_.size()) {
+        if (done_) break;
+        li_ = 0;
+        if (!in_.next_block(store_, lines_, 1u << 20, 32u << 20, true)) done_ = true;
+        if (lines_.empty()) continue;
       }
-      if (line_.empty()) {
-        have_ = false;
-        continue;
-      }
-      if (line_[0] == '@' && !in_fasta_) {  // FASTQ record: header, sequence, '+', qualities
-        have_ = false;
-        if (!in_.next(line)) break;
-        append_seq(out, line);
-        out.push_back('\n');
-        if (in_.next(line) && !line.empty() && line[0] == '+') in_.next(line);
-      } else if (line_[0] == '>') {  // FASTA record: the sequence may span lines
-        in_fasta_ = true;
-        have_ = false;
-        while (in_.next(line_)) {
-          if (!line_.empty() && line_[0] == '>') {
-            have_ = true;
-            break;
-          }
-          append_seq(out, line_);
+      for (; li_ < lines_.size() && out.size() < target; ++li_) {
+        const char *b = lines_[li_].b, *e = lines_[li_].e;
+        if (format_ == 0) {
+          if (b == e) continue;                   // blank lines before the first record
+          format_ = *b == '>' ? 1 : 2;            // by the first byte of the file, whatever -f says
         }
-        out.push_back('\n');
-      } else {
-        have_ = false;  // stray line
+        if (format_ == 1 && b == e) continue;     // blank line inside a FASTA file
+        if (format_ == 2) {  // FASTQ
+          if (phase_ == 1) {
+            append_upper(out, b, e);
+            out.push_back('\n');
+          }
+          phase_ = (phase_ + 1) & 3;
+        } else if (*b == '>') {  // FASTA header: the previous record ends here
+          if (open_) out.push_back('\n');
+          open_ = true;
+        } else {
+          append_upper(out, b, e);
+        }
       }
+      if (format_ == 1 && open_ && out.size() >= target) {  // a FASTA record larger than a chunk is cut with k-mers
+        // lost at the seam only if a chunk ends inside it: keep going to the end of the record instead
+        while (true) {
+          if (li_ == lines_.size()) {
+            if (done_) break;
+            li_ = 0;
+            if (!in_.next_block(store_, lines_, 1u << 20, 32u << 20, true)) done_ = true;
+            if (lines_.empty()) continue;
+          }
+          if (lines_[li_].b != lines_[li_].e && *lines_[li_].b == '>') break;
+          append_upper(out, lines_[li_].b, lines_[li_].e);
+          ++li_;
+        }
+      }
+    }
+    if (done_ && li_ == lines_.size() && open_) {
+      out.push_back('\n');
+      open_ = false;
     }
     return !out.empty();
   }
 
  private:
-  static void append_seq(std::string &out, const std::string &l) {
-    for (char ch : l)
-      if (!isspace((unsigned char)ch)) out.push_back((char)toupper((unsigned char)ch));
+  static void append_upper(std::string &out, const char *b, const char *e) {
+    const size_t o = out.size();
+    out.resize(o + (size_t)(e - b));
+    char *d = &out[o];
+    for (const char *p = b; p < e; ++p) *d++ = (char)(*p & 0xDF);  // a-z -> A-Z; nothing else can become A, C, G or T
   }
-  mh::LineReader in_;
-  std::string line_;
-  bool have_ = false, in_fasta_ = false;
+  mh::BlockLineReader in_;
+  std::vector<char> store_;
+  std::vector<mh::BlockLineReader::View> lines_;
+  size_t li_ = 0;
+  int format_ = 0, phase_ = 0;
+  bool done_ = false, open_ = false;
 };
 
 struct Counter {

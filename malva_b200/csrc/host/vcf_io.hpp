@@ -89,8 +89,10 @@ class BlockLineReader {
       fill(1 << 20);
     }
   }
-  // up to max_lines non-empty lines / ~target bytes into `store` (which keeps the views alive); false when nothing is left
-  bool next_block(std::vector<char> &store, std::vector<View> &lines, size_t max_lines, size_t target) {
+  // up to max_lines lines (empty ones dropped unless keep_empty) / ~target bytes into `store` (which keeps the views
+  // alive); false when nothing is left
+  bool next_block(std::vector<char> &store, std::vector<View> &lines, size_t max_lines, size_t target,
+                  bool keep_empty = false) {
     lines.clear();
     while (!eof_ && buf_.size() - pos_ < target) fill(target - (buf_.size() - pos_) + (1 << 16));
     // cut after the last complete line within reach
@@ -104,7 +106,7 @@ class BlockLineReader {
         }
       if (!last) {  // one line longer than the target: keep reading
         while (!eof_ && !memchr(buf_.data() + pos_, '\n', buf_.size() - pos_)) fill(target);
-        return next_block(store, lines, max_lines, target);
+        return next_block(store, lines, max_lines, target, keep_empty);
       }
       end = (size_t)(last - buf_.data());
     }
@@ -116,7 +118,7 @@ class BlockLineReader {
       const char *e = nl ? nl : stop;
       const char *next = nl ? nl + 1 : stop;
       if (e > p && e[-1] == '\r') --e;
-      if (e > p) lines.push_back(View{p, e});
+      if (e > p || keep_empty) lines.push_back(View{p, e});
       p = next;
       used = (size_t)(p - store.data());
     }

@@ -177,3 +177,37 @@ def test_wrapper_script_runs_the_whole_pipeline(tmp_path):
     assert os.path.exists(tmp_path / "haploid.vcf.c43.k35.malvax.zst")
     r2 = subprocess.run(cmd, capture_output=True, cwd=tmp_path)   # second run reuses the database and the index
     assert r2.returncode == 0 and r2.stdout == r.stdout and b"Index file exists already" in r2.stderr
+
+
+def test_cli_count_reads_fasta_and_fastq_layouts(tmp_path):
+    """multi-line FASTA (lower case, blank lines, CRLF), FASTQ with an empty read and '@' as the first quality symbol,
+    gz: the database lists what the KMC restatement counts on the parsed sequences"""
+    mbuild.build()
+    cli = mbuild.CLI
+    rng = random.Random(21)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(rng.randrange(50, 400))) for _ in range(60)]
+    seqs[5] = seqs[5][:100] + "N" + seqs[5][100:]
+    seqs += seqs[:40]                                # so that some k-mers reach -ci2
+    fa = tmp_path / "reads.fa"
+    with open(fa, "w", newline="") as fh:
+        fh.write("\r\n")
+        for i, s in enumerate(seqs):
+            fh.write(f">r{i} some text\r\n")
+            body = s.lower() if i % 3 == 0 else s
+            for o in range(0, len(body), 61):
+                fh.write(body[o:o + 61] + "\r\n")
+            if i % 7 == 0:
+                fh.write("\r\n")
+    fq = tmp_path / "reads.fq.gz"
+    with gzip.open(fq, "wt") as fh:
+        for i, s in enumerate(seqs + [""]):
+            fh.write(f"@r{i}\n{s}\n+\n{'@' * len(s)}\n")
+    exp_k, exp_c = kmc.count_kmers(seqs, 43, min_count=2, counter_max=255)
+    exp = [f"{a}\t{b}" for a, b in zip(kmc.packed_to_strings(exp_k, 43), exp_c.tolist())]
+    assert len(exp) > 1000
+    for src in (fa, fq):
+        out = str(tmp_path / (src.name + ".db"))
+        r = subprocess.run([cli, "count", "-k43", str(src), out], capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        got = subprocess.run([cli, "kmc-dump", out], capture_output=True, text=True, check=True).stdout.split("\n")
+        assert [l for l in got if l] == exp, src.name
