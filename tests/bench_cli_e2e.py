@@ -3,7 +3,7 @@
 own main.cpp, CPU, single-threaded like the original) against this repository's `malva-geno` (C++ host + B200
 kernels) on the same synthetic chromosome-arm-sized inputs; outputs must be byte-identical.
 
-    python tests/bench_cli_e2e.py [Mbp=5] [samples=32] > gpurun_out/cli_e2e.json
+    python tests/bench_cli_e2e.py [Mbp=5] [samples=32] [bf_gb=1] > gpurun_out/cli_e2e.json
 
 (lives under tests/ because it executes the oracle build of the reference; not collected by pytest)
 """
@@ -68,6 +68,7 @@ def phases(stderr):
 def main():
     mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
     n_samples = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    bf_gb = sys.argv[3] if len(sys.argv) > 3 else "1"          # -b: filter size in GB (reference default: 4)
     mbuild.build()
     case = synth.Case("cli_e2e", 20261018 + 42, [("1", int(mbp * 1e6))], mean_gap=41, n_samples=n_samples)
     synth_write = kmc.write_kmc_db
@@ -78,14 +79,14 @@ def main():
         kmc.write_kmc_db = synth_write
         n_var = sum(1 for l in open(vcf) if not l.startswith("#"))
         res = {"reference_bases": int(mbp * 1e6), "variants": n_var, "panel_samples": n_samples, "sample_kmers": n_kmers,
-               "generate_s": round(time.time() - t0, 1), "host_cores": os.cpu_count()}
+               "generate_s": round(time.time() - t0, 1), "host_cores": os.cpu_count(), "bf_gb": bf_gb}
         outs = {}
         for name, exe in (("reference_cpu", REF), ("malva_b200", mbuild.CLI)):
             r = {}
             for sub in ("index", "call"):
                 t = time.time()
                 extra = ["--trace"] if name == "malva_b200" else []
-                p = subprocess.run([exe, sub, "-k", "35", "-r", "43", "-b", "1"] + extra + [fa, vcf, prefix], capture_output=True, text=True)
+                p = subprocess.run([exe, sub, "-k", "35", "-r", "43", "-b", bf_gb] + extra + [fa, vcf, prefix], capture_output=True, text=True)
                 if extra:
                     r[sub + "_trace"] = [l for l in p.stderr.split("\n") if l.startswith("[trace]")]
                 r[sub + "_wall_s"] = round(time.time() - t, 3)
