@@ -186,6 +186,44 @@ def write_kmc_db(prefix: str, kmers: np.ndarray, counts: np.ndarray, k: int, *,
         fh.write(suf)
 
 
+def write_kmc_db_binned(prefix: str, kmers: np.ndarray, counts: np.ndarray, k: int, bin_of, n_bins: int, *,
+                        lut_prefix_len: int, counter_size: int = 1, min_count: int = 2, max_count: int = 255,
+                        signature_len: int = 5) -> None:
+    """KMC2 layout with SEVERAL bins, as the real tool writes it: one prefix LUT of 4^p entries per bin, the records
+    of bin 0 first (sorted), then bin 1, ...; ``bin_of(value) -> bin`` stands in for KMC's minimiser-signature map.
+    The listing order of such a database is NOT globally sorted (it is sorted within each bin)."""
+    vals = packed_to_ints(kmers)
+    cts = [int(c) for c in counts]
+    p = lut_prefix_len
+    suf_syms = k - p
+    suf_bytes = suf_syms // 4
+    smask = (1 << (2 * suf_syms)) - 1
+    bins = [[] for _ in range(n_bins)]
+    for v, c in sorted(zip(vals, cts)):
+        bins[bin_of(v)].append((v, c))
+    lut, suf, n = [], bytearray(b"KMCS"), 0
+    for b in bins:
+        per = [0] * (4 ** p)
+        for v, _ in b:
+            per[v >> (2 * suf_syms)] += 1
+        for cnt in per:
+            lut.append(n)
+            n += cnt
+        for v, c in b:
+            suf += (v & smask).to_bytes(suf_bytes, "big") + int(c).to_bytes(counter_size, "little")
+    lut.append(n)
+    suf += b"KMCS"
+    pre = bytearray(b"KMCP") + struct.pack(f"<{len(lut)}Q", *lut)
+    pre += struct.pack(f"<{4 ** signature_len + 1}I", *([0] * (4 ** signature_len + 1)))
+    hdr = struct.pack("<7IQB", k, 0, counter_size, p, signature_len, min_count, max_count & 0xFFFFFFFF, n, 0)
+    hdr += b"\0" * (60 - len(hdr)) + struct.pack("<I", 0x200)
+    pre += hdr + struct.pack("<I", len(hdr)) + b"KMCP"
+    with open(prefix + ".kmc_pre", "wb") as fh:
+        fh.write(pre)
+    with open(prefix + ".kmc_suf", "wb") as fh:
+        fh.write(suf)
+
+
 def read_kmc_db(prefix: str) -> Tuple[np.ndarray, np.ndarray, int]:
     """List a KMC database: (packed k-mers, u32 counts, k); count filter applied."""
     pre = open(prefix + ".kmc_pre", "rb").read()

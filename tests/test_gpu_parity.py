@@ -299,3 +299,47 @@ def test_replicas_built_in_any_order_have_one_image_and_their_counters_add_up(or
     finally:
         for x in (a, b, whole, o):
             x.close()
+
+
+def test_kmc_database_with_several_bins(oracle_lib, tmp_path):
+    """the layout real KMC2 files have: one prefix LUT per bin, records sorted within a bin only.  The device finds
+    the prefix of a record from its global index through the concatenated LUT."""
+    k, ref_k, bits, p = 35, 43, 1 << 20, 3
+    rng = random.Random(515)
+    genome = util.make_genome(rng, 20000)
+    nested, _ = util.synth_signatures(rng, genome, k, 300)
+    ks, fl = util.flatten(nested)
+    _, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, 6000)
+    counts = np.minimum(counts, 255).astype(np.uint32)
+    # one record per distinct k-mer (a KMC database never lists a k-mer twice)
+    vals = kmc.packed_to_ints(packed)
+    first = {}
+    for i, v in enumerate(vals):
+        first.setdefault(v, i)
+    keep = sorted(first.values())
+    packed, counts = packed[keep], counts[keep]
+    prefix = str(tmp_path / "binned")
+    kmc.write_kmc_db_binned(prefix, packed, counts, ref_k, bin_of=lambda v: (v * 2654435761 >> 7) % 5, n_bins=5,
+                            lut_prefix_len=p)
+    listed, lcounts, kk = kmc.read_kmc_db(prefix)
+    assert kk == ref_k and len(listed) == len(packed)
+    assert sorted(kmc.packed_to_ints(listed)) == sorted(kmc.packed_to_ints(packed))
+    assert kmc.packed_to_ints(listed) != sorted(kmc.packed_to_ints(listed)), "bins should break the global order"
+    db = kmc.open_kmc_db(prefix)
+    assert len(db["lut"]) == 5 * 4 ** p
+    g, o = MalvaGpu(k=k, ref_k=ref_k, bf_bits=bits), util.OracleRun(oracle_lib, k, ref_k, bits)
+    try:
+        for x in (g, o):
+            x.add_signatures(ks, fl)
+            x.finalize_alt()
+            x.scan_reference(genome)
+            x.finalize_context()
+        o.scan_sample_kmers(listed, lcounts)
+        g.kmc_open(db)
+        g.scan_kmc_records(db["records"], 0, db["total"])
+        assert np.array_equal(g.bf_counts(), o.bf_counts())
+        assert np.array_equal(g.get_counts(ks, [1] * len(ks)), o.get_counts(ks, [1] * len(ks)))
+        assert o.bf_counts().sum() > 0
+    finally:
+        g.close()
+        o.close()

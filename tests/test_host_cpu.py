@@ -160,6 +160,15 @@ def test_kmc_dump_lists_what_the_python_reader_lists(cli, tmp_path):
         ks, cs = dump(prefix)
         keep = [(v, int(c)) for v, c in zip(vals, cts) if 2 <= c <= 255]
         assert ks == [kmc.unpack_kmer(v, k) for v, _ in keep] and cs == [c for _, c in keep]
+    # several bins (what real KMC2 files look like): sorted within a bin only
+    vals = sorted({rng.getrandbits(86) for _ in range(2000)})
+    cts = np.array([rng.randrange(2, 200) for _ in vals], dtype=np.uint32)
+    prefix = str(tmp_path / "binned")
+    kmc.write_kmc_db_binned(prefix, kmc.ints_to_packed(vals), cts, 43, bin_of=lambda v: (v >> 3) % 4, n_bins=4,
+                            lut_prefix_len=3)
+    listed, lc, _ = kmc.read_kmc_db(prefix)
+    ks, cs = dump(prefix)
+    assert ks == kmc.packed_to_strings(listed, 43) and cs == lc.tolist() and sorted(kmc.packed_to_ints(listed)) == vals
     r = subprocess.run([cli, "kmc-dump", str(tmp_path / "nope")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stderr
 
