@@ -527,18 +527,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t 
     bool bf_hit = (fw >> (bit & 31u)) & 1u;
     const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
                    c3 = (uint32_t)(canon.hi >> 32);
-    // the low word of each key slot first (one 4-byte shared load per slot); the other three words only when it
-    // matches (a ref-key hit, ~3 % of the k-mers, or a 2^-32 coincidence)
-    bool low_match = false;
+    // the low word of each key slot first (one 4-byte shared load per slot); the other three words only of the
+    // slots where it matches (a ref-key hit, ~3 % of the k-mers, or a 2^-32 coincidence)
+    uint32_t low_match = 0;  // bit s: the low word of slot s equals the k-mer's
 #pragma unroll
-    for (int s = 0; s < LINE_KEYS; ++s) low_match |= reinterpret_cast<const uint32_t *>(mine + ((2 + s) ^ sw))[0] == c0;
+    for (int s = 0; s < LINE_KEYS; ++s)
+      low_match |= (uint32_t)(reinterpret_cast<const uint32_t *>(mine + ((2 + s) ^ sw))[0] == c0) << s;
     int slot = -1;
-    if (low_match) {
-#pragma unroll 1
-      for (int s = 0; s < LINE_KEYS; ++s) {
-        uint4 p = mine[(2 + s) ^ sw];
-        if (((p.x ^ c0) | (p.y ^ c1) | (p.z ^ c2) | ((p.w & (uint32_t)(KEY_HI_MASK >> 32)) ^ c3)) == 0) slot = s;
-      }
+    while (low_match) {  // (some lane of the warp gets here in most iterations: keep it to the matching slot)
+      const int s = __ffs(low_match) - 1;
+      low_match &= low_match - 1;
+      uint4 p = mine[(2 + s) ^ sw];
+      if (((p.y ^ c1) | (p.z ^ c2) | ((p.w & (uint32_t)(KEY_HI_MASK >> 32)) ^ c3)) == 0) slot = s;
     }
     const uint32_t last_w = reinterpret_cast<const uint32_t *>(mine + ((2 + LINE_KEYS - 1) ^ sw))[3];
     // ---- ref_bf.increment ----
