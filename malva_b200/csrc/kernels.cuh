@@ -387,7 +387,7 @@ __device__ __forceinline__ uint64_t canon_hash_lut(u128 x, u128 *canon, const ui
 
 constexpr int SCAN_THREADS = 256;
 // per warp: a 4 KB tile + 32 row indices; per CTA: the 1 KB expansion table
-constexpr int SCAN_SMEM = (SCAN_THREADS / 32) * (32 * 128 + 32 * 4) + 256 * 4;
+constexpr int SCAN_SMEM = (SCAN_THREADS / 32) * (32 * 128 + 32 * 4 + 4) + 256 * 4;  // (+ a hit counter per warp)
 
 // Where the sample k-mers come from.  MODE 0: packed {lo,hi} words + u32 counts.  MODE 1: raw records of a
 // KMC database suffix file (.kmc_suf): (ref_k - p)/4 suffix bytes (2-bit codes, first base most significant)
@@ -404,6 +404,14 @@ struct ScanSrc {
   int prefix_len, suf_bytes, counter_size;
   uint32_t min_count;
   uint64_t max_count;
+  // Deferred filter hits.  A k-mer whose bf bit is set needs a second XXH3 (the 43-mer, for the context filter): rare
+  // per k-mer (~0.7 %) but not per warp (one iteration in five), and while one lane runs it 31 idle.  The scan
+  // therefore only records the hit -- {context k-mer, bf index, count}, 32 bytes, in the warp's own segment of
+  // hit_buf -- and k_scan_hits works all of them off afterwards with full warps.  A full segment falls back to the
+  // in-line path.  hit_buf == nullptr: always in line.
+  uint4 *hit_buf;
+  uint32_t *hit_counts;  // per warp of the scan grid
+  uint32_t seg_cap;      // entries per warp segment
 };
 
 __device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_lut, uint64_t g) {
@@ -428,11 +436,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t 
   const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
   uint32_t *rows = reinterpret_cast<uint32_t *>(scan_sm + (SCAN_THREADS / 32) * 256) + (threadIdx.x >> 5) * 32;
   uint32_t *tab = reinterpret_cast<uint32_t *>(scan_sm + (SCAN_THREADS / 32) * 256) + (SCAN_THREADS / 32) * 32;
+  uint32_t *hitc = tab + 256 + (threadIdx.x >> 5);  // this warp's deferred-hit counter
+  if (lane == 0) *hitc = 0;
   if constexpr (K > 0) {
     static_assert(SCAN_THREADS == 256, "one table entry per thread");
     tab[threadIdx.x] = expand4(threadIdx.x);
     __syncthreads();
+  } else {
+    __syncwarp();
   }
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   // 32-bit indices: the host never launches more than 2^31 k-mers at once
   const uint32_t n32 = (uint32_t)n;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -550,15 +563,48 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t 
     }
     // ---- bf.increment unless the context filter vetoes it ----
     if (bf_hit) {
-      u128 c43;
-      uint64_t h43;
-      if constexpr (REFK > 0)
-        h43 = canon_hash_lut<REFK>(x43, &c43, tab);
-      else
-        h43 = canon_hash_rt(x43, ref_k, &c43);
-      if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + bf_rank_of(v, idx), cnt);
+      const uint32_t pos = src.hit_buf ? atomicAdd(hitc, 1u) : 0xFFFFFFFFu;
+      if (pos < src.seg_cap) {  // recorded; k_scan_hits finishes it
+        uint4 *e = src.hit_buf + ((uint64_t)warp_id * src.seg_cap + pos) * 2;
+        e[0] = make_uint4((uint32_t)x43.lo, (uint32_t)(x43.lo >> 32), (uint32_t)x43.hi, (uint32_t)(x43.hi >> 32));
+        e[1] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), cnt, 0u);
+      } else {
+        u128 c43;
+        uint64_t h43;
+        if constexpr (REFK > 0)
+          h43 = canon_hash_lut<REFK>(x43, &c43, tab);
+        else
+          h43 = canon_hash_rt(x43, ref_k, &c43);
+        if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + bf_rank_of(v, idx), cnt);
+      }
     }
   }
+  if (src.hit_buf) {
+    __syncwarp();
+    if (lane == 0) src.hit_counts[warp_id] = *hitc < src.seg_cap ? *hitc : src.seg_cap;
+  }
+}
+
+// second half of the scan for the recorded filter hits: 43-mer hash -> context filter -> rank -> counter
+template <int REFK>
+__global__ void __launch_bounds__(256) k_scan_hits(const uint4 *__restrict__ hit_buf, const uint32_t *__restrict__ hit_counts,
+                                                  uint32_t n_warps, uint32_t seg_cap, DevView v) {
+  __shared__ uint32_t tab[256];
+  tab[threadIdx.x] = expand4(threadIdx.x);
+  __syncthreads();
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t w = (uint32_t)(t / seg_cap), slot = (uint32_t)(t % seg_cap);
+  if (w >= n_warps || slot >= __ldg(hit_counts + w)) return;
+  const uint4 a = __ldg(hit_buf + t * 2), b = __ldg(hit_buf + t * 2 + 1);
+  u128 x43 = {(uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32)}, c43;
+  const uint64_t idx = (uint64_t)b.x | ((uint64_t)b.y << 32);
+  const uint32_t r = bf_rank_of(v, idx);  // (independent of the hash: these loads overlap with it)
+  uint64_t h43;
+  if constexpr (REFK > 0)
+    h43 = canon_hash_lut<REFK>(x43, &c43, tab);
+  else
+    h43 = canon_hash_rt(x43, v.ref_k, &c43);
+  if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + r, b.z);
 }
 
 // ---------------------------------------------------------------------------

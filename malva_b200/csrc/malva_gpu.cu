@@ -85,6 +85,10 @@ struct mg_ctx {
   void *d_stage_k[2] = {nullptr, nullptr};
   uint32_t *d_stage_c[2] = {nullptr, nullptr};
   int next_stage = 0;
+  uint4 *hit_buf[2] = {nullptr, nullptr};  // deferred filter hits of the scan, one set per stream (grow-only)
+  uint32_t *hit_counts[2] = {nullptr, nullptr};
+  uint64_t hit_entries[2] = {0, 0}, hit_warps[2] = {0, 0};
+  bool defer_hits = true;
   int scan_ctas_per_sm = 128;  // grid cap of the scan kernel, in CTAs per SM (measured optimum 64..256, profiles/)
   uint64_t *kmc_lut = nullptr;  // device copy of the KMC prefix LUT (+ guard)
   uint32_t kmc_n_lut = 0, kmc_min = 0;
@@ -202,6 +206,7 @@ static int ctx_init(mg_ctx *c) {
   CU(cudaGetDeviceProperties(&prop, device));
   c->sms = prop.multiProcessorCount;
   if (const char *e = getenv("MG_SCAN_CTAS_PER_SM")) c->scan_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 128;
+  if (const char *e = getenv("MG_SCAN_DEFER_HITS")) c->defer_hits = atoi(e) != 0;
   for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
   CU(cudaMalloc(&c->lines, c->n_lines * 128));
   CU(cudaMalloc(&c->ctx_words, c->n_ctx_words * 4));
@@ -250,6 +255,8 @@ extern "C" void mg_destroy(mg_ctx *c) {
   cudaFree(c->geno_arena);
   cudaFree(c->kmc_lut);
   for (int i = 0; i < 2; ++i) {
+    cudaFree(c->hit_buf[i]);
+    cudaFree(c->hit_counts[i]);
     cudaFree(c->d_stage_k[i]);
     cudaFree(c->d_stage_c[i]);
     if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
@@ -589,13 +596,47 @@ extern "C" int mg_finalize_context(mg_ctx *c) {
 }
 
 template <int K, int REFK, int MODE>
-static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t st) {
+static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n, cudaStream_t st) {
   uint64_t want = (n + 255) / 256;  // one warp per 32 k-mers, 8 warps per CTA
   uint64_t cap = (uint64_t)c->sms * (uint64_t)c->scan_ctas_per_sm;
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
+  mg::ScanSrc src = src_in;
+  const int si = st == c->stream[1] ? 1 : 0;
+  const uint64_t n_warps = (uint64_t)grid * (mg::SCAN_THREADS / 32);
+  if (c->defer_hits) {
+    // a segment per warp of the grid, sized for one k-mer in 32 hitting the filter (expected: < 1 in 100; whatever
+    // exceeds a segment is finished in line by the scan itself)
+    const uint64_t per_warp = ((n + n_warps * 32 - 1) / (n_warps * 32)) * 32;
+    const uint64_t seg = per_warp / 32 > 8 ? per_warp / 32 : 8;
+    if (c->hit_entries[si] < n_warps * seg) {
+      cudaFree(c->hit_buf[si]);
+      c->hit_buf[si] = nullptr;
+      c->hit_entries[si] = 0;
+      cudaError_t e = cudaMalloc(&c->hit_buf[si], n_warps * seg * 32);
+      if (e != cudaSuccess) return e;
+      c->hit_entries[si] = n_warps * seg;
+    }
+    if (c->hit_warps[si] < n_warps) {
+      cudaFree(c->hit_counts[si]);
+      c->hit_counts[si] = nullptr;
+      c->hit_warps[si] = 0;
+      cudaError_t e = cudaMalloc(&c->hit_counts[si], n_warps * 4);
+      if (e != cudaSuccess) return e;
+      c->hit_warps[si] = n_warps;
+    }
+    src.hit_buf = c->hit_buf[si];
+    src.hit_counts = c->hit_counts[si];
+    src.seg_cap = (uint32_t)seg;
+  }
   c->launches++;
   mg::k_scan<K, REFK, MODE><<<grid, mg::SCAN_THREADS, mg::SCAN_SMEM, st>>>(src, n, c->view());
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !src.hit_buf) return e;
+  const uint64_t threads = n_warps * src.seg_cap;
+  c->launches++;
+  mg::k_scan_hits<REFK><<<grid_for(threads, 256), 256, 0, st>>>(src.hit_buf, src.hit_counts, (uint32_t)n_warps, src.seg_cap,
+                                                               c->view());
   return cudaGetLastError();
 }
 
