@@ -40,6 +40,10 @@ int mg_version(void);
 /* number of CUDA devices visible; <0 on failure (used to fail loudly) */
 int mg_device_count(void);
 
+/* initialises CUDA on `device` (driver + primary context, 0.5-5 s on a cold box); optional -- meant to be called from
+ * a background thread while the host reads its input files */
+int mg_warmup(int device);
+
 /* BF bf(size); KMAP ref_bf; BF context_bf(size)      main.cpp:300-302, 451-453 */
 int mg_create(mg_ctx **out, int device, int k, int ref_k, uint64_t bf_bits);
 void mg_destroy(mg_ctx *ctx);

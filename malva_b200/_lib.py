@@ -59,6 +59,7 @@ SYMBOLS = {
     "mg_last_error": (C.c_char_p, []),
     "mg_version": (C.c_int, []),
     "mg_device_count": (C.c_int, []),
+    "mg_warmup": (C.c_int, [C.c_int]),
     "mg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "mg_destroy": (None, [C.c_void_p]),
     "mg_add_signatures": (C.c_int, [C.c_void_p, C.c_char_p, u64p, u8p, C.c_uint64]),

@@ -349,6 +349,7 @@ struct Ctx {
 int index_main(int argc, char **argv) {
   Options o;
   if (!parse_arguments(argc, argv, o, 3)) return EXIT_FAILURE;
+  auto cuda_up = std::async(std::launch::async, [&] { return mg_warmup(o.device); });  // overlaps with the file reading
   BlockStream stream(o, true);
   if (stream.samples_code != 0) {
     std::cerr << "ERROR: VCF samples subset (code: " << stream.samples_code << ")" << std::endl;
@@ -487,6 +488,8 @@ void format_variant(const mh::Variant &v, const uint32_t *cov, int n_gts, int st
 int call_main(int argc, char **argv) {
   Options o;
   if (!parse_arguments(argc, argv, o, 3)) return EXIT_FAILURE;
+  std::vector<std::future<int>> cuda_up;  // CUDA start-up on every device, overlapped with the file reading
+  for (int d : o.devices) cuda_up.push_back(std::async(std::launch::async, [d] { return mg_warmup(d); }));
   BlockStream stream(o, false);
   if (stream.samples_code != 0) {
     std::cerr << "ERROR: VCF samples subset (code: " << stream.samples_code << ")" << std::endl;

@@ -55,6 +55,14 @@ extern "C" int mg_device_count(void) {
   return n;
 }
 
+// CUDA start-up (driver initialisation + primary context) costs 0.5-5 s on a cold box: a host program calls this
+// from a background thread first thing, so that it overlaps with reading its input files.
+extern "C" int mg_warmup(int device) {
+  CU(cudaSetDevice(device));
+  CU(cudaFree(nullptr));
+  return MG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
