@@ -130,7 +130,8 @@ int mg_count_reset(mg_counter *c);
 int mg_count_add(mg_counter *c, const char *bases, uint64_t n);
 int mg_count_finish(mg_counter *c, uint32_t min_count, uint32_t counter_max, uint64_t max_count, uint64_t *n_kmers);
 int mg_count_download(mg_counter *c, uint64_t *lohi, uint32_t *counts, uint64_t cap);
-/* {distinct k-mers in the table, k-mer instances counted, table capacity, kernels launched}; n >= 4 */
+/* {distinct k-mers in the table, k-mer instances counted, table capacity, kernels launched[, device time of the
+ * counting kernels in microseconds]}; n >= 4 */
 int mg_count_stats(mg_counter *c, uint64_t *stats, int n);
 /* the counted k-mers straight into the sample scan (same device): no database file, no host round trip */
 int mg_scan_counted(mg_ctx *ctx, mg_counter *c);

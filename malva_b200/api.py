@@ -396,9 +396,9 @@ class KmerCounter:
         return keys, counts
 
     def stats(self) -> dict:
-        s = (C.c_uint64 * 4)()
-        check(self._L.mg_count_stats(self._h, s, 4))
-        return dict(zip(("distinct", "instances", "capacity", "launches"), [int(x) for x in s]))
+        s = (C.c_uint64 * 5)()
+        check(self._L.mg_count_stats(self._h, s, 5))
+        return dict(zip(("distinct", "instances", "capacity", "launches", "kernel_us"), [int(x) for x in s]))
 
 
 def diag_bandwidth(device: int, mode: int, nbytes: int, reps: int = 3) -> float:

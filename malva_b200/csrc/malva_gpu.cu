@@ -1166,6 +1166,8 @@ struct mg_counter {
   u128 *out_keys = nullptr;
   uint32_t *out_counts = nullptr;
   bool finished = false;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double kernel_ms = 0;  // device time of the counting kernels so far
 };
 constexpr uint64_t COUNT_CHUNK = 1ull << 26;  // read bytes per kernel launch
 
@@ -1221,6 +1223,8 @@ extern "C" void mg_count_destroy(mg_counter *c) {
   cudaFree(c->d_seq);
   cudaFree(c->out_keys);
   cudaFree(c->out_counts);
+  for (int i = 0; i < 2; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -1294,6 +1298,9 @@ extern "C" int mg_count_add(mg_counter *c, const char *bases, uint64_t n) {
     const size_t smem = mg::CNT_TILE + 64;
     const uint64_t mask = (1ull << c->log2cap) - 1;
     c->launches++;
+    for (int i = 0; i < 2; ++i)
+      if (!c->ev[i]) CU(cudaEventCreate(&c->ev[i]));
+    CU(cudaEventRecord(c->ev[0], c->st));
     if (c->k == 43)
       mg::k_count_kmers<43><<<grid, mg::CNT_THREADS, smem, c->st>>>(c->d_seq, len, c->k, c->table, mask, c->part_bits,
                                                                     c->part_lo, c->part_hi, c->d_scalars, c->d_scalars + 1);
@@ -1301,7 +1308,11 @@ extern "C" int mg_count_add(mg_counter *c, const char *bases, uint64_t n) {
       mg::k_count_kmers<0><<<grid, mg::CNT_THREADS, smem, c->st>>>(c->d_seq, len, c->k, c->table, mask, c->part_bits,
                                                                    c->part_lo, c->part_hi, c->d_scalars, c->d_scalars + 1);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev[1], c->st));
     CU(cudaStreamSynchronize(c->st));  // d_seq is reused by the next sub-chunk
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    c->kernel_ms += ms;
     if (start + len >= n) break;
     start += len - halo;  // the next part re-sends the last k-1 bytes as its halo
   }
@@ -1373,6 +1384,7 @@ extern "C" int mg_count_stats(mg_counter *c, uint64_t *stats, int n) {
   stats[1] = sc[1];
   stats[2] = 1ull << c->log2cap;
   stats[3] = c->launches;
+  if (n >= 5) stats[4] = (uint64_t)(c->kernel_ms * 1e3);
   return MG_OK;
 }
 

@@ -51,7 +51,8 @@ def main():
     keys, counts = c.finish(2, 255)
     t_fin = time.perf_counter() - t1
     out.update({"read_bytes": total, "instances": st["instances"], "distinct": st["distinct"], "kept_ci2": int(len(keys)),
-                "table_capacity": st["capacity"], "count_s": round(t_add, 3), "finish_sort_download_s": round(t_fin, 3),
+                "table_capacity": st["capacity"], "count_s": round(t_add, 3), "count_kernels_s": round(st["kernel_us"] / 1e6, 4),
+                "instances_per_s_kernels_only": st["instances"] / max(st["kernel_us"] / 1e6, 1e-9), "finish_sort_download_s": round(t_fin, 3),
                 "bases_per_s": total / t_add, "instances_per_s": st["instances"] / t_add,
                 "note": "count_s includes the H2D copies of the reads (pageable host memory) and every table growth + rehash; "
                         "one random 32-byte slot access (+ one atomic) per k-mer instance"})
