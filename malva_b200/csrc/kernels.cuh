@@ -516,10 +516,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t 
     __syncwarp();  // the previous iteration's reads of the tile and of the row list are done
     if (need) rows[rank] = line;
     __syncwarp();
-    for (int r = 0; 4 * r < n_need; ++r) {
-      const int L = 4 * r + grp;
-      if (L < n_need)
-        cp_async16(tile_addr + (uint32_t)((L * 8 + (sub ^ (L & 7))) * 16), v.lines + (uint64_t)rows[L] * LINE_U4 + sub);
+    {
+      // row L = grp, grp + 4, ...: uint4 `sub` of line rows[L] goes to column sub ^ (L & 7) of tile row L.  L & 7
+      // alternates between grp and grp + 4, i.e. the column toggles bit 2 from one round to the next.
+      uint32_t dst = tile_addr + (uint32_t)(grp * 128 + ((sub ^ grp) * 16));
+      int toggle = ((sub ^ grp) & 4) ? -64 : 64;
+      const uint32_t *rp = rows + grp;
+      const char *src0 = reinterpret_cast<const char *>(v.lines) + sub * 16;
+#pragma unroll 1
+      for (int L = grp; L < n_need; L += 4) {
+        cp_async16(dst, src0 + (uint64_t)(*rp) * 128);
+        rp += 4;
+        dst += 512 + toggle;
+        toggle = -toggle;
+      }
     }
     if constexpr (MODE == 0) {
       // while the lines are in flight: the warp's next batch (512 B of k-mers + 128 B of counts) into L2
