@@ -7,11 +7,15 @@
 // Nothing is decoded on the host: the prefix LUT goes to the device once (mg_kmc_open) and the suffix records
 // are streamed as they lie in the file (mg_scan_kmc_records), 10 bytes per 43-mer.
 #pragma once
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace mh {
@@ -22,10 +26,10 @@ struct KmcDb {
   bool both_strands = true;
   std::vector<uint64_t> lut;  // n_lut entries (a multiple of 4^lut_prefix_len): records before each prefix
   uint32_t record_bytes = 0;
-  FILE *suf = nullptr;
+  int suf_fd = -1;  // <db>.kmc_suf; records start at byte 4
 
   ~KmcDb() {
-    if (suf) fclose(suf);
+    if (suf_fd >= 0) close(suf_fd);
   }
   KmcDb() = default;
   KmcDb(const KmcDb &) = delete;
@@ -88,21 +92,48 @@ struct KmcDb {
     lut.resize(n_lut);
     for (size_t i = 0; i < n_lut; ++i) lut[i] = rd64(&pre[4 + 8 * i]);
     record_bytes = (kmer_len - lut_prefix_len) / 4 + counter_size;
-    suf = fopen((prefix + ".kmc_suf").c_str(), "rb");
+    suf_fd = ::open((prefix + ".kmc_suf").c_str(), O_RDONLY);
     char m[4];
-    if (!suf || fread(m, 1, 4, suf) != 4 || memcmp(m, "KMCS", 4) != 0) {
+    if (suf_fd < 0 || pread(suf_fd, m, 4, 0) != 4 || memcmp(m, "KMCS", 4) != 0) {
       why = "cannot open " + prefix + ".kmc_suf";
       return false;
     }
     return true;
   }
 
-  // next `max_records` whole records into dst; returns the number read (0 at the end)
-  uint64_t read_records(uint8_t *dst, uint64_t first_record, uint64_t max_records) {
+  // up to `max_records` whole records starting at record `first_record` into dst; returns the number read (0 at the
+  // end).  Large requests are split over a few threads (pread): copying out of the page cache is the bottleneck of
+  // the whole scan once the device side runs at PCIe speed.
+  uint64_t read_records(uint8_t *dst, uint64_t first_record, uint64_t max_records, int threads = 4) {
     if (first_record >= total_kmers) return 0;
-    uint64_t want = total_kmers - first_record < max_records ? total_kmers - first_record : max_records;
-    size_t got = fread(dst, record_bytes, (size_t)want, suf);
-    return (uint64_t)got;
+    const uint64_t want = total_kmers - first_record < max_records ? total_kmers - first_record : max_records;
+    const uint64_t bytes = want * record_bytes, off0 = 4 + first_record * record_bytes;
+    auto read_all = [&](uint64_t b, uint64_t e) -> uint64_t {  // bytes [b, e) of the request
+      uint64_t done = b;
+      while (done < e) {
+        ssize_t r = pread(suf_fd, dst + done, (size_t)(e - done), (off_t)(off0 + done));
+        if (r <= 0) break;
+        done += (uint64_t)r;
+      }
+      return done - b;
+    };
+    if (threads < 2 || bytes < (8u << 20)) return read_all(0, bytes) / record_bytes;
+    std::vector<uint64_t> got((size_t)threads, 0);
+    std::vector<std::thread> pool;
+    const uint64_t piece = (bytes + (uint64_t)threads - 1) / (uint64_t)threads;
+    for (int t = 0; t < threads; ++t)
+      pool.emplace_back([&, t] {
+        uint64_t b = (uint64_t)t * piece, e = b + piece < bytes ? b + piece : bytes;
+        if (b < e) got[(size_t)t] = read_all(b, e);
+      });
+    for (auto &th : pool) th.join();
+    uint64_t total = 0;  // contiguous prefix actually read
+    for (int t = 0; t < threads; ++t) {
+      uint64_t b = (uint64_t)t * piece, e = b + piece < bytes ? b + piece : bytes;
+      total += got[(size_t)t];
+      if (b < e && got[(size_t)t] < e - b) break;
+    }
+    return total / record_bytes;
   }
 };
 

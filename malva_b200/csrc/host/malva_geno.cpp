@@ -834,12 +834,15 @@ int kmc_dump_main(int argc, char **argv) {
     return 1;
   }
   const uint32_t p = db.lut_prefix_len, sb = (db.kmer_len - p) / 4, single = 1u << (2 * p);
-  std::vector<uint8_t> rec(db.record_bytes);
+  constexpr uint64_t BLOCK = 1 << 16;
+  std::vector<uint8_t> block(BLOCK * db.record_bytes);
   std::string kmer(db.kmer_len, 'A');
   size_t pi = 0;
   for (uint64_t i = 0; i < db.total_kmers; ++i) {
     while (pi + 1 < db.lut.size() && db.lut[pi + 1] <= i) ++pi;
-    if (db.read_records(rec.data(), i, 1) != 1) throw std::runtime_error("suffix file truncated");
+    if (i % BLOCK == 0 && db.read_records(block.data(), i, BLOCK, 1) != std::min<uint64_t>(BLOCK, db.total_kmers - i))
+      throw std::runtime_error("suffix file truncated");
+    const uint8_t *rec = block.data() + (i % BLOCK) * db.record_bytes;
     uint64_t c = db.counter_size ? 0 : 1;
     for (uint32_t b = 0; b < db.counter_size; ++b) c |= (uint64_t)rec[sb + b] << (8 * b);
     if (c < db.min_count || c > db.max_count) continue;
