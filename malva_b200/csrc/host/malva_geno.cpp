@@ -647,8 +647,18 @@ int signatures_main(int argc, char **argv) {
   std::vector<mh::VarBlock> blocks;
   mh::SignatureCsr sigs;
   uint64_t block_no = 0;
-  while (stream.next_batch(blocks, LINES_PER_BATCH)) {
+  const bool quiet = getenv("MALVA_SIGNATURES_QUIET") != nullptr;  // (timing runs: enumerate, print nothing)
+  Stopwatch sw;
+  double t_batch = 0, t_enum = 0;
+  while (true) {
+    sw.lap();
+    const bool more = stream.next_batch(blocks, LINES_PER_BATCH);
+    t_batch += sw.lap();
+    if (!more) break;
     enumerate_batch(blocks, refs, o, sigs);
+    t_enum += sw.lap();
+    if (o.trace) fprintf(stderr, "[trace] read+decode+group %.1f ms, enumerate %.1f ms (cumulative)\n", t_batch, t_enum);
+    if (quiet) continue;
     uint64_t vi = 0;
     for (const auto &b : blocks) {
       for (size_t i = 0; i < b.size(); ++i, ++vi) {
