@@ -245,6 +245,7 @@ class BlockStream {
     freq_declared_ = reader_.header.has_info(o.freq_key);
   }
   int samples_code = 0;
+  double t_read = 0, t_decode = 0, t_group = 0;  // ms spent reading lines / decoding records / grouping blocks
   std::vector<std::string> used_seq_names;  // main.cpp:304-306, 323-328, 352-356
   uint64_t n_records = 0;
   const mh::VcfHeader &header() const { return reader_.header; }
@@ -254,13 +255,16 @@ class BlockStream {
     out.clear();
     if (done_) return false;
     // a block of whole lines (no per-line allocation), decoded in parallel
-    const bool more = reader_.next_lines(store_, lines_, max_lines, 32u << 20);
+    Stopwatch sw;
+    const bool more = reader_.next_lines(store_, lines_, max_lines, 12u << 20);
+    t_read += sw.lap();
     std::vector<mh::Variant> vars(lines_.size());
     const size_t grain = 256, n_tasks = (lines_.size() + grain - 1) / grain;
     parallel_for(n_tasks, o_.threads, [&](size_t t) {
       for (size_t i = t * grain; i < std::min(lines_.size(), (t + 1) * grain); ++i)
         vars[i] = mh::parse_record(lines_[i].b, lines_[i].e, reader_.header, o_.freq_key, o_.uniform, freq_declared_);
     });
+    t_decode += sw.lap();
     for (auto &v : vars) {
       ++n_records;
       if (n_records % 5000 == 0) pelapsed("Processed " + std::to_string(n_records) + " variants", true);
@@ -288,6 +292,7 @@ class BlockStream {
       done_ = true;
       if (!vb_.empty()) flush(out);
     }
+    t_group += sw.lap();
     return !out.empty() || !done_;
   }
 
@@ -348,7 +353,7 @@ void enumerate_batch(const std::vector<mh::VarBlock> &blocks, std::map<std::stri
   for (const auto &p : parts) out.append(p);
 }
 
-constexpr size_t LINES_PER_BATCH = 1 << 16;
+constexpr size_t LINES_PER_BATCH = 1 << 17;  // (a batch is ~12 MB of VCF text, at most this many records)
 
 struct Ctx {
   mg_ctx *c = nullptr;
@@ -666,7 +671,9 @@ int signatures_main(int argc, char **argv) {
     if (!more) break;
     enumerate_batch(blocks, refs, o, sigs);
     t_enum += sw.lap();
-    if (o.trace) fprintf(stderr, "[trace] read+decode+group %.1f ms, enumerate %.1f ms (cumulative)\n", t_batch, t_enum);
+    if (o.trace)
+      fprintf(stderr, "[trace] read %.1f + decode %.1f + group %.1f ms, enumerate %.1f ms (cumulative)\n", stream.t_read,
+              stream.t_decode, stream.t_group, t_enum);
     if (quiet) continue;
     uint64_t vi = 0;
     for (const auto &b : blocks) {

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <string_view>
 #include <utility>
@@ -130,20 +131,32 @@ class VarBlock {
   // Signatures of every variant of the block, appended to `out`: one variant entry per block member, in order;
   // allele slot a = allele index a (slots of duplicate-text alleles stay empty, like in the reference).
   void enumerate(const std::string &reference, bool haploid, SignatureCsr &out) const {
-    std::vector<std::vector<std::vector<std::string>>> per_allele;  // [allele][signature][k-mer]
+    Scratch sc;  // reused by every variant of the block
     for (size_t vi = 0; vi < vars_.size(); ++vi) {
       const Variant &v = vars_[vi];
-      per_allele.assign((size_t)v.n_alleles(), {});
+      sc.text.clear();
+      sc.sigs.clear();
       // var_block.hpp:104 -- no signatures for absent variants or variants within k of a contig end
       if (v.is_present && v.ref_pos >= k_ && v.ref_pos <= (int)reference.size() - k_)
-        signatures_of((int)vi, reference, haploid, per_allele);
+        signatures_of((int)vi, reference, haploid, sc);
+      // by allele, duplicates dropped (equal text + equal k-mer count = equal k-mer list: every k-mer of a
+      // multi-k-mer signature is k long)
+      auto text_of = [&](const SigRec &r) { return std::string_view(sc.text.data() + r.text_off, r.text_len); };
+      std::sort(sc.sigs.begin(), sc.sigs.end(), [&](const SigRec &x, const SigRec &y) {
+        if (x.allele != y.allele) return x.allele < y.allele;
+        if (x.n_kmers != y.n_kmers) return x.n_kmers < y.n_kmers;
+        return text_of(x) < text_of(y);
+      });
+      size_t si = 0;
       for (int a = 0; a < v.n_alleles(); ++a) {
-        auto &sigs = per_allele[(size_t)a];
-        std::sort(sigs.begin(), sigs.end());
-        sigs.erase(std::unique(sigs.begin(), sigs.end()), sigs.end());
-        for (const auto &sig : sigs) {
-          for (const auto &kmer : sig) {
-            out.pool += kmer;
+        const SigRec *prev = nullptr;
+        for (; si < sc.sigs.size() && sc.sigs[si].allele == (uint32_t)a; ++si) {
+          const SigRec &r = sc.sigs[si];
+          if (prev && prev->n_kmers == r.n_kmers && text_of(*prev) == text_of(r)) continue;
+          prev = &r;
+          const size_t klen = r.n_kmers > 1 ? (size_t)k_ : r.text_len;
+          for (uint32_t q = 0; q < r.n_kmers; ++q) {
+            out.pool.append(sc.text, r.text_off + q * klen, klen);
             out.kmer_off.push_back(out.pool.size());
             out.kmer_is_ref.push_back(a == 0);
           }
@@ -158,7 +171,31 @@ class VarBlock {
 
  private:
   using Chain = std::vector<int>;
-  using Hap = std::vector<uint16_t>;  // one allele text-id per chain member
+  // flat work arrays (rows of uint16 allele text-ids) kept across the variants of a block: no allocation per sample
+  struct SigRec {  // one signature of the current variant: its k-mers lie back to back in Scratch::text
+    uint32_t allele, text_off, text_len, n_kmers;
+  };
+  struct Scratch {
+    std::vector<uint16_t> pat, cand, haps;
+    std::vector<uint32_t> order;
+    size_t n_haps = 0;
+    std::string text, kmer;                // signature text of the current variant; the k-mer being built
+    std::vector<SigRec> sigs;              // its signatures
+    std::vector<std::string> between;      // reference text between the members of the current chain
+  };
+  // sorts row indices by content (any total order will do: equal rows only have to end up adjacent) and keeps one
+  // index per distinct row
+  static void distinct_rows(const std::vector<uint16_t> &rows, size_t n_rows, size_t width, std::vector<uint32_t> &order) {
+    order.resize(n_rows);
+    for (size_t i = 0; i < n_rows; ++i) order[i] = (uint32_t)i;
+    const uint16_t *base = rows.data();
+    const size_t bytes = width * sizeof(uint16_t);
+    std::sort(order.begin(), order.end(),
+              [&](uint32_t a, uint32_t b) { return memcmp(base + a * width, base + b * width, bytes) < 0; });
+    order.erase(std::unique(order.begin(), order.end(),
+                            [&](uint32_t a, uint32_t b) { return memcmp(base + a * width, base + b * width, bytes) == 0; }),
+                order.end());
+  }
 
   static bool overlapping(const Variant &a, const Variant &b) {  // var_block.hpp:408-412
     return a.ref_pos <= b.ref_pos && b.ref_pos < a.ref_pos + a.ref_size;
@@ -239,46 +276,52 @@ class VarBlock {
   }
 
   // var_block.hpp:734-786: the distinct haplotypes (one allele per chain member) carried by the samples of the
-  // central variant.  Unphased patterns contribute every way of picking one of the two alleles at each site
-  // (combine_haplotypes, var_block.hpp:709-728).
-  void haplotypes(const Chain &chain, int central, bool haploid, std::vector<Hap> &out) const {
-    const size_t n = chain.size(), n_samples = vars_[(size_t)central].n_samples();
+  // central variant, as sc.n_haps rows of chain.size() text-ids in sc.haps.  Unphased patterns contribute every way
+  // of picking one of the two alleles at each site (combine_haplotypes, var_block.hpp:709-728).
+  void haplotypes(const Chain &chain, int central, bool haploid, Scratch &sc) const {
+    const size_t n = chain.size(), n_samples = vars_[(size_t)central].n_samples(), W = 2 * n + 1;
     // per-sample pattern: [h1 ids | h2 ids | phased]
-    std::vector<Hap> patterns;
-    patterns.reserve(n_samples);
-    Hap p(2 * n + 1);
-    for (size_t s = 0; s < n_samples; ++s) {
-      bool ph = true;
-      for (size_t m = 0; m < n; ++m) {
-        const Variant &v = vars_[(size_t)chain[m]];
-        const bool has = s < v.n_samples();
-        p[m] = has ? v.gt_text_id(s, 0) : 0;
-        p[n + m] = haploid ? p[m] : (has ? v.gt_text_id(s, 1) : 0);
-        ph = ph && (!has || v.phased[s] != 0);
+    sc.pat.resize(n_samples * W);
+    for (size_t m = 0; m < n; ++m) {
+      const Variant &v = vars_[(size_t)chain[m]];
+      const size_t have = std::min(n_samples, v.n_samples());
+      uint16_t *p = sc.pat.data() + m;
+      for (size_t s = 0; s < have; ++s, p += W) {
+        p[0] = v.gt_text_id(s, 0);
+        p[n] = haploid ? p[0] : v.gt_text_id(s, 1);
+        const uint16_t ph = (haploid || v.phased[s] != 0) ? 1 : 0;
+        p[2 * n - m] = m == 0 ? ph : (uint16_t)(p[2 * n - m] & ph);
       }
-      p[2 * n] = (haploid || ph) ? 1 : 0;
-      patterns.push_back(p);
+      for (size_t s = have; s < n_samples; ++s, p += W) {  // (a variant that carries fewer samples: reference, phased)
+        p[0] = p[n] = 0;
+        if (m == 0) p[2 * n - m] = 1;
+      }
     }
-    std::sort(patterns.begin(), patterns.end());
-    patterns.erase(std::unique(patterns.begin(), patterns.end()), patterns.end());
-    out.clear();
-    for (const Hap &q : patterns) {
+    distinct_rows(sc.pat, n_samples, W, sc.order);
+    sc.cand.clear();
+    for (uint32_t row : sc.order) {
+      const uint16_t *q = sc.pat.data() + (size_t)row * W;
       if (q[2 * n]) {
-        out.emplace_back(q.begin(), q.begin() + (long)n);
-        if (!haploid) out.emplace_back(q.begin() + (long)n, q.begin() + 2 * (long)n);
+        sc.cand.insert(sc.cand.end(), q, q + n);
+        if (!haploid) sc.cand.insert(sc.cand.end(), q + n, q + 2 * n);
       } else {
-        std::vector<size_t> het;  // sites where the two alleles differ
-        for (size_t m = 0; m < n; ++m)
-          if (q[m] != q[n + m]) het.push_back(m);
-        Hap h(q.begin(), q.begin() + (long)n);
-        for (uint64_t mask = 0; mask < (1ull << het.size()); ++mask) {
-          for (size_t b = 0; b < het.size(); ++b) h[het[b]] = ((mask >> b) & 1) ? q[n + het[b]] : q[het[b]];
-          out.push_back(h);
+        size_t het[64], n_het = 0;  // sites where the two alleles differ
+        for (size_t m = 0; m < n && n_het < 64; ++m)
+          if (q[m] != q[n + m]) het[n_het++] = m;
+        for (uint64_t mask = 0; mask < (1ull << n_het); ++mask) {
+          const size_t o = sc.cand.size();
+          sc.cand.insert(sc.cand.end(), q, q + n);
+          for (size_t b = 0; b < n_het; ++b)
+            if ((mask >> b) & 1) sc.cand[o + het[b]] = q[n + het[b]];
         }
       }
     }
-    std::sort(out.begin(), out.end());
-    out.erase(std::unique(out.begin(), out.end()), out.end());
+    const size_t n_cand = sc.cand.size() / n;
+    distinct_rows(sc.cand, n_cand, n, sc.order);
+    sc.haps.resize(sc.order.size() * n);
+    for (size_t i = 0; i < sc.order.size(); ++i)
+      memcpy(sc.haps.data() + i * n, sc.cand.data() + (size_t)sc.order[i] * n, n * sizeof(uint16_t));
+    sc.n_haps = sc.order.size();
   }
 
   static void append_clamped(std::string &dst, const std::string &s, long pos, long len) {
@@ -287,61 +330,64 @@ class VarBlock {
   }
 
   // var_block.hpp:114-216
-  void signatures_of(int vi, const std::string &reference, bool haploid,
-                     std::vector<std::vector<std::vector<std::string>>> &per_allele) const {
+  void signatures_of(int vi, const std::string &reference, bool haploid, Scratch &sc) const {
     const Variant &v = vars_[(size_t)vi];
-    std::vector<Hap> haps;
-    std::vector<std::string> between;
     for (const Chain &chain : full_chains(vi)) {
       // reference text between consecutive members of the chain (var_block.hpp:682-702)
-      between.clear();
-      size_t mid_slot = 0;
+      if (sc.between.size() < chain.size()) sc.between.resize(chain.size());
+      size_t mid_slot = 0, n_between = 0;
       for (size_t m = 0; m < chain.size(); ++m) {
         if (chain[m] == vi) mid_slot = m;
         if (m == 0) continue;
         const Variant &prev = vars_[(size_t)chain[m - 1]], &cur = vars_[(size_t)chain[m]];
-        std::string gap;
+        std::string &gap = sc.between[n_between++];
+        gap.clear();
         append_clamped(gap, reference, (long)prev.ref_pos + prev.ref_size, (long)cur.ref_pos - (prev.ref_pos + prev.ref_size));
-        between.push_back(std::move(gap));
       }
-      haplotypes(chain, vi, haploid, haps);
-      for (const Hap &h : haps) {
-        std::vector<std::string> sig;
+      haplotypes(chain, vi, haploid, sc);
+      for (size_t hi = 0; hi < sc.n_haps; ++hi) {
+        const uint16_t *h = sc.haps.data() + hi * chain.size();
         const int mid_id = h[mid_slot];
         const std::string &mid_allele = v.allele(mid_id);
+        SigRec rec{(uint32_t)mid_id, (uint32_t)sc.text.size(), 0, 0};
         if (chain.size() == 1 && (int)mid_allele.size() >= k_) {
           // an allele at least k long: every k-mer inside the allele itself (var_block.hpp:130-144)
-          for (size_t p = 0; p + (size_t)k_ <= mid_allele.size(); ++p) sig.emplace_back(mid_allele, p, (size_t)k_);
+          for (size_t p = 0; p + (size_t)k_ <= mid_allele.size(); ++p) {
+            sc.text.append(mid_allele, p, (size_t)k_);
+            ++rec.n_kmers;
+          }
         } else {
-          std::string kmer;
+          std::string &kmer = sc.kmer;
+          kmer.clear();
           int mid_pos = 0;
           for (size_t m = 0; m < chain.size(); ++m) {
             if (m == mid_slot) mid_pos = (int)kmer.size();
             kmer += vars_[(size_t)chain[m]].allele(h[m]);
-            if (m < between.size()) kmer += between[m];
+            if (m < n_between) kmer += sc.between[m];
           }
           const int first_part = mid_pos + (int)mid_allele.size() / 2;
           const int second_part = (int)kmer.size() - first_part;
           const int missing_prefix = k_ / 2 - first_part;
           const int missing_suffix = (int)std::ceil((float)k_ / 2) - second_part;
+          // extend with reference text / cut, left then right; the result goes straight into sc.text
           if (missing_prefix >= 0) {
             const Variant &first = vars_[(size_t)chain.front()];
-            std::string pre;
-            append_clamped(pre, reference, (long)first.ref_pos - missing_prefix, missing_prefix);
-            kmer.insert(0, pre);
+            append_clamped(sc.text, reference, (long)first.ref_pos - missing_prefix, missing_prefix);
           } else {
             kmer.erase(0, std::min<size_t>(kmer.size(), (size_t)(-missing_prefix)));
           }
           if (missing_suffix >= 0) {
+            sc.text += kmer;
             const Variant &last = vars_[(size_t)chain.back()];
-            append_clamped(kmer, reference, (long)last.ref_pos + last.ref_size, missing_suffix);
+            append_clamped(sc.text, reference, (long)last.ref_pos + last.ref_size, missing_suffix);
           } else {
             const size_t cut = std::min<size_t>(kmer.size(), (size_t)(-missing_suffix));
-            kmer.erase(kmer.size() - cut, cut);
+            sc.text.append(kmer, 0, kmer.size() - cut);
           }
-          sig.push_back(std::move(kmer));
+          rec.n_kmers = 1;
         }
-        per_allele[(size_t)mid_id].push_back(std::move(sig));
+        rec.text_len = (uint32_t)(sc.text.size() - rec.text_off);
+        sc.sigs.push_back(rec);
       }
     }
   }

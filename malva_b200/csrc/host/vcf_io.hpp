@@ -89,30 +89,33 @@ class BlockLineReader {
       fill(1 << 20);
     }
   }
-  // up to max_lines lines (empty ones dropped unless keep_empty) / ~target bytes into `store` (which keeps the views
-  // alive); false when nothing is left
+  // whole lines, ~target bytes of them (at most max_lines; empty ones dropped unless keep_empty), read straight into
+  // `store` (which keeps the views alive) -- one copy from the file, none per line; false when nothing is left
   bool next_block(std::vector<char> &store, std::vector<View> &lines, size_t max_lines, size_t target,
                   bool keep_empty = false) {
     lines.clear();
-    while (!eof_ && buf_.size() - pos_ < target) fill(target - (buf_.size() - pos_) + (1 << 16));
-    // cut after the last complete line within reach
-    size_t end = buf_.size();
-    if (!eof_) {
-      const char *last = nullptr;
-      for (size_t i = buf_.size(); i > pos_; --i)
-        if (buf_[i - 1] == '\n') {
-          last = buf_.data() + i;
-          break;
-        }
-      if (!last) {  // one line longer than the target: keep reading
-        while (!eof_ && !memchr(buf_.data() + pos_, '\n', buf_.size() - pos_)) fill(target);
-        return next_block(store, lines, max_lines, target, keep_empty);
+    // what next() left in its own buffer (header parsing) goes first
+    store.assign(buf_.begin() + (long)pos_, buf_.end());
+    buf_.clear();
+    pos_ = 0;
+    while (true) {
+      while (!eof_ && store.size() < target) {
+        const size_t old = store.size(), want = target - old + (1 << 16);
+        store.resize(old + want);
+        int got = gzread(fp_, store.data() + old, (unsigned)want);
+        if (got < 0) throw std::runtime_error("read error");
+        store.resize(old + (size_t)got);
+        if ((size_t)got < want) eof_ = true;
       }
-      end = (size_t)(last - buf_.data());
+      if (eof_ || memchr(store.data(), '\n', store.size())) break;
+      target *= 2;  // one line longer than the target: keep reading
     }
-    store.assign(buf_.begin() + (long)pos_, buf_.begin() + (long)end);
-    size_t used = 0;
-    const char *p = store.data(), *stop = store.data() + store.size();
+    // cut after the last complete line; the rest waits in buf_ for the next call
+    size_t end = store.size();
+    if (!eof_) {
+      while (end > 0 && store[end - 1] != '\n') --end;
+    }
+    const char *p = store.data(), *stop = store.data() + end;
     while (p < stop && lines.size() < max_lines) {
       const char *nl = (const char *)memchr(p, '\n', (size_t)(stop - p));
       const char *e = nl ? nl : stop;
@@ -120,14 +123,9 @@ class BlockLineReader {
       if (e > p && e[-1] == '\r') --e;
       if (e > p || keep_empty) lines.push_back(View{p, e});
       p = next;
-      used = (size_t)(p - store.data());
     }
-    pos_ += used;
-    if (pos_ > (8u << 20)) {  // drop what has been handed out
-      buf_.erase(buf_.begin(), buf_.begin() + (long)pos_);
-      pos_ = 0;
-    }
-    return !lines.empty() || pos_ < buf_.size() || !eof_;
+    buf_.assign(p, (const char *)store.data() + store.size());  // unconsumed lines + the partial last one
+    return !lines.empty() || !buf_.empty() || !eof_;
   }
 
  private:
