@@ -380,7 +380,14 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
     throw std::runtime_error("malformed VCF record: " + std::string(line_begin, std::min<size_t>(60, (size_t)(line_end - line_begin))));
   Variant v;
   v.seq_name = c[0].str();
-  v.ref_pos = (int)(strtoll(c[1].str().c_str(), nullptr, 10) - 1);
+  {  // POS: decimal digits (strtoll semantics: optional sign, stops at the first non-digit)
+    const char *q = c[1].b;
+    bool neg = false;
+    if (q < c[1].e && (*q == '-' || *q == '+')) neg = *q++ == '-';
+    long long pos = 0;
+    while (q < c[1].e && *q >= '0' && *q <= '9') pos = pos * 10 + (*q++ - '0');
+    v.ref_pos = (int)((neg ? -pos : pos) - 1);
+  }
   v.idx = c[2].str();
   v.ref_sub = detail::upper(c[3].b, c[3].e);
   if (!c[4].is(".")) {
@@ -435,8 +442,11 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
   }
   // raw codes per kept sample, htslib style: ((allele + 1) << 1) | phased; `first`/`second`/ploidy per sample
   const size_t ns = header.keep.size();
-  std::vector<int32_t> g0(ns, 0), g1(ns, 0);
-  std::vector<uint8_t> ploidy(ns, 1);
+  static thread_local std::vector<int32_t> g0, g1;  // scratch, one set per decoding thread
+  static thread_local std::vector<uint8_t> ploidy;
+  g0.assign(ns, 0);
+  g1.assign(ns, 0);
+  ploidy.assign(ns, 1);
   size_t max_ploidy = 1;
   {
     size_t ki = 0;  // next kept sample to fill
