@@ -194,3 +194,41 @@ def test_signatures_fuzz_small_blocks(cli, ref_lib, tmp_path):
             got, used = cli_signatures(cli, fa, vcf, flags, index_mode)
             exp, exp_used = expected_signatures(ref_lib, fa, vcf, k, haploid, "AF", False, index_mode)
             assert got == exp and used == exp_used, f"seed {seed} index_mode {index_mode}"
+
+
+def test_index_file_roundtrip(tmp_path):
+    """csrc/host/index_file.hpp: sorted set-bit lists (delta-coded) and packed keys survive the zstd-chunked file,
+    including sections larger than one chunk and empty sections; a foreign file is refused with a clear message"""
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "index_file.hpp"
+#include <cstdio>
+#include <random>
+int main(int argc, char **argv) {
+  std::mt19937_64 g(7);
+  std::vector<uint64_t> a, b, keys;
+  uint64_t x = 0;
+  for (int i = 0; i < 9000000; ++i) { x += 1 + g() % 4000; a.push_back(x); }   // 72 MB raw: two chunks
+  for (int i = 0; i < 1000; ++i) keys.push_back(g());
+  std::vector<uint64_t> a0 = a, b0 = b, k0 = keys;
+  { mh::IndexWriter w(argv[1], 35, 43, 1ull << 35); w.write_bits(a); w.write_bits(b); w.write_keys(keys); w.close(); }
+  mh::IndexReader r(argv[1]);
+  if (r.k != 35 || r.ref_k != 43 || r.bf_bits != (1ull << 35)) return 2;
+  if (r.read_bits() != a0) return 3;
+  if (r.read_bits() != b0) return 4;
+  if (r.read_keys() != k0) return 5;
+  try { mh::IndexReader bad(argv[2]); return 6; } catch (const std::exception &e) { if (!strstr(e.what(), "not an index")) return 7; }
+  puts("ok");
+  return 0;
+}
+''')
+    exe = tmp_path / "t"
+    host = os.path.join(os.path.dirname(mbuild.CLI), "csrc", "host")
+    zstd = next(p for p in ("/usr/lib/x86_64-linux-gnu/libzstd.so.1", "/lib/x86_64-linux-gnu/libzstd.so.1") if os.path.exists(p))
+    stdcxx = next(p for p in ("/usr/lib/x86_64-linux-gnu/libstdc++.so.6", "/lib/x86_64-linux-gnu/libstdc++.so.6") if os.path.exists(p))
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", host, "-o", str(exe), str(src), zstd, "-nostdlib++", stdcxx, "-lm"], check=True)
+    other = tmp_path / "other.zst"
+    other.write_bytes(b"\x28\xb5\x2f\xfd" + b"\0" * 64)      # (a zstd frame magic: what a CPU-built index starts with)
+    r = subprocess.run([str(exe), str(tmp_path / "idx.zst"), str(other)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stderr)
+    assert os.path.getsize(tmp_path / "idx.zst") < 30_000_000   # 72 MB of indices -> deltas -> zstd
