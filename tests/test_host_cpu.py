@@ -232,3 +232,24 @@ int main(int argc, char **argv) {
     r = subprocess.run([str(exe), str(tmp_path / "idx.zst"), str(other)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stderr)
     assert os.path.getsize(tmp_path / "idx.zst") < 30_000_000   # 72 MB of indices -> deltas -> zstd
+
+
+def test_sample_list_errors_and_subset(cli, tmp_path):
+    """-s: an unknown name stops the run with the reference's message and htslib's code (index of the name + 1,
+    main.cpp:266-271); a valid list keeps the listed samples in HEADER order whatever the order in the file"""
+    case = next(c for c in synth.CASES if c.name == "samples_subset_uniform")
+    fa, vcf, _, _ = synth.build_case(case, str(tmp_path))
+    bad = tmp_path / "bad.txt"
+    bad.write_text("S2\nNOPE\nS1\n")
+    r = subprocess.run([cli, "signatures", "-s", str(bad), fa, vcf], capture_output=True, text=True)
+    assert r.returncode == 1 and "ERROR: VCF samples subset (code: 2)" in r.stderr
+    r = subprocess.run([cli, "signatures", "-s", str(tmp_path / "missing.txt"), fa, vcf], capture_output=True, text=True)
+    assert r.returncode == 1 and "ERROR: VCF samples subset" in r.stderr
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    a.write_text("S7\nS2\nS9\nS3\n")
+    b.write_text("S2\nS3\nS7\nS9\n")
+    out = [subprocess.run([cli, "signatures", "-s", str(f), fa, vcf], capture_output=True, text=True, check=True).stdout
+           for f in (a, b)]
+    assert out[0] == out[1] and out[0].count("\n") > 500
+    all_samples = subprocess.run([cli, "signatures", fa, vcf], capture_output=True, text=True, check=True).stdout
+    assert all_samples != out[0]      # the subset really changes the haplotypes seen
