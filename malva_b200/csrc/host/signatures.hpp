@@ -177,24 +177,50 @@ class VarBlock {
   };
   struct Scratch {
     std::vector<uint16_t> pat, cand, haps;
-    std::vector<uint32_t> order;
+    std::vector<uint32_t> order, table;
     size_t n_haps = 0;
     std::string text, kmer;                // signature text of the current variant; the k-mer being built
     std::vector<SigRec> sigs;              // its signatures
     std::vector<std::string> between;      // reference text between the members of the current chain
   };
-  // sorts row indices by content (any total order will do: equal rows only have to end up adjacent) and keeps one
-  // index per distinct row
-  static void distinct_rows(const std::vector<uint16_t> &rows, size_t n_rows, size_t width, std::vector<uint32_t> &order) {
-    order.resize(n_rows);
-    for (size_t i = 0; i < n_rows; ++i) order[i] = (uint32_t)i;
+  // one index per distinct row, in order of first occurrence.  Thousands of panel samples share a handful of
+  // genotype patterns, so this is a small open-addressing hash set keyed by row content, not a sort.
+  static void distinct_rows(const std::vector<uint16_t> &rows, size_t n_rows, size_t width, std::vector<uint32_t> &order,
+                            std::vector<uint32_t> &table) {
+    order.clear();
     const uint16_t *base = rows.data();
     const size_t bytes = width * sizeof(uint16_t);
-    std::sort(order.begin(), order.end(),
-              [&](uint32_t a, uint32_t b) { return memcmp(base + a * width, base + b * width, bytes) < 0; });
-    order.erase(std::unique(order.begin(), order.end(),
-                            [&](uint32_t a, uint32_t b) { return memcmp(base + a * width, base + b * width, bytes) == 0; }),
-                order.end());
+    size_t cap = 64;
+    table.assign(cap, 0xFFFFFFFFu);
+    auto hash_row = [&](const uint16_t *r) {
+      uint64_t h = 0xCBF29CE484222325ull;
+      for (size_t i = 0; i < width; ++i) h = (h ^ r[i]) * 0x100000001B3ull;
+      return h ^ (h >> 29);
+    };
+    for (size_t i = 0; i < n_rows; ++i) {
+      const uint16_t *r = base + i * width;
+      size_t slot = (size_t)hash_row(r) & (cap - 1);
+      bool found = false;
+      while (table[slot] != 0xFFFFFFFFu) {
+        if (memcmp(base + (size_t)table[slot] * width, r, bytes) == 0) {
+          found = true;
+          break;
+        }
+        slot = (slot + 1) & (cap - 1);
+      }
+      if (found) continue;
+      table[slot] = (uint32_t)i;
+      order.push_back((uint32_t)i);
+      if (order.size() * 2 > cap) {  // grow and re-insert the distinct rows
+        cap *= 4;
+        table.assign(cap, 0xFFFFFFFFu);
+        for (uint32_t j : order) {
+          size_t s2 = (size_t)hash_row(base + (size_t)j * width) & (cap - 1);
+          while (table[s2] != 0xFFFFFFFFu) s2 = (s2 + 1) & (cap - 1);
+          table[s2] = j;
+        }
+      }
+    }
   }
 
   static bool overlapping(const Variant &a, const Variant &b) {  // var_block.hpp:408-412
@@ -297,7 +323,7 @@ class VarBlock {
         if (m == 0) p[2 * n - m] = 1;
       }
     }
-    distinct_rows(sc.pat, n_samples, W, sc.order);
+    distinct_rows(sc.pat, n_samples, W, sc.order, sc.table);
     sc.cand.clear();
     for (uint32_t row : sc.order) {
       const uint16_t *q = sc.pat.data() + (size_t)row * W;
@@ -317,7 +343,7 @@ class VarBlock {
       }
     }
     const size_t n_cand = sc.cand.size() / n;
-    distinct_rows(sc.cand, n_cand, n, sc.order);
+    distinct_rows(sc.cand, n_cand, n, sc.order, sc.table);
     sc.haps.resize(sc.order.size() * n);
     for (size_t i = 0; i < sc.order.size(); ++i)
       memcpy(sc.haps.data() + i * n, sc.cand.data() + (size_t)sc.order[i] * n, n * sizeof(uint16_t));

@@ -453,8 +453,24 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
     int col = 0;
     const char *s = samples_begin;
     while (s && s <= end && ki < ns) {
-      const char *t = (const char *)memchr(s, '\t', (size_t)(end - s));
-      if (!t) t = end;
+      // (sample columns are a few bytes long: plain loops beat memchr here)
+      if (gt_field == 0 && end - s >= 4 && (s[3] == '\t' || s[3] == ':') && s[0] >= '0' && s[0] <= '9' && s[2] >= '0' &&
+          s[2] <= '9' && (s[1] == '|' || s[1] == '/')) {  // "a|b" / "a/b" with one-digit alleles, GT first
+        if (col == header.keep[ki]) {
+          g0[ki] = ((s[0] - '0') + 1) << 1;
+          g1[ki] = (((s[2] - '0') + 1) << 1) | (s[1] == '|');
+          ploidy[ki] = 2;
+          max_ploidy = std::max<size_t>(max_ploidy, 2);
+          ++ki;
+        }
+        s += 3;
+        while (s < end && *s != '\t') ++s;
+        ++col;
+        ++s;
+        continue;
+      }
+      const char *t = s;
+      while (t < end && *t != '\t') ++t;
       if (col == header.keep[ki]) {
         const char *q = s;
         for (int f = 0; f < gt_field && q; ++f) {
