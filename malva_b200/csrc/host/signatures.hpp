@@ -132,6 +132,7 @@ class VarBlock {
   // allele slot a = allele index a (slots of duplicate-text alleles stay empty, like in the reference).
   void enumerate(const std::string &reference, bool haploid, SignatureCsr &out) const {
     Scratch sc;  // reused by every variant of the block
+    sample_classes(sc);
     for (size_t vi = 0; vi < vars_.size(); ++vi) {
       const Variant &v = vars_[vi];
       sc.text.clear();
@@ -178,6 +179,8 @@ class VarBlock {
   struct Scratch {
     std::vector<uint16_t> pat, cand, haps;
     std::vector<uint32_t> order, table;
+    std::vector<uint32_t> reps;  // one representative per class of panel samples with identical genotypes in the block
+    std::vector<uint16_t> block_rows;
     size_t n_haps = 0;
     std::string text, kmer;                // signature text of the current variant; the k-mer being built
     std::vector<SigRec> sigs;              // its signatures
@@ -301,29 +304,57 @@ class VarBlock {
     return out;
   }
 
+  // Panel samples whose genotypes agree at every variant of the block contribute the same haplotypes to every chain
+  // of the block: one pass over the block finds one representative per class (a few dozen for 2,504 samples), and
+  // the per-chain work below runs over the representatives only.
+  void sample_classes(Scratch &sc) const {
+    size_t ns = 0, nv = 0;
+    for (const Variant &v : vars_)
+      if (v.is_present) {
+        ns = std::max(ns, v.n_samples());
+        ++nv;
+      }
+    sc.reps.clear();
+    if (ns == 0) return;
+    const size_t W = 3 * nv;
+    sc.block_rows.assign(ns * W, 0);
+    size_t col = 0;
+    for (const Variant &v : vars_) {
+      if (!v.is_present) continue;
+      uint16_t *p = sc.block_rows.data() + 3 * col++;
+      const size_t have = std::min(ns, v.n_samples());
+      for (size_t smp = 0; smp < have; ++smp, p += W) {
+        p[0] = v.gt_text_id(smp, 0);
+        p[1] = v.gt_text_id(smp, 1);
+        p[2] = v.phased[smp] != 0;
+      }
+      for (size_t smp = have; smp < ns; ++smp, p += W) p[2] = 1;  // (fewer samples: reference, phased)
+    }
+    distinct_rows(sc.block_rows, ns, W, sc.reps, sc.table);
+  }
+
   // var_block.hpp:734-786: the distinct haplotypes (one allele per chain member) carried by the samples of the
   // central variant, as sc.n_haps rows of chain.size() text-ids in sc.haps.  Unphased patterns contribute every way
   // of picking one of the two alleles at each site (combine_haplotypes, var_block.hpp:709-728).
   void haplotypes(const Chain &chain, int central, bool haploid, Scratch &sc) const {
-    const size_t n = chain.size(), n_samples = vars_[(size_t)central].n_samples(), W = 2 * n + 1;
-    // per-sample pattern: [h1 ids | h2 ids | phased]
-    sc.pat.resize(n_samples * W);
-    for (size_t m = 0; m < n; ++m) {
-      const Variant &v = vars_[(size_t)chain[m]];
-      const size_t have = std::min(n_samples, v.n_samples());
-      uint16_t *p = sc.pat.data() + m;
-      for (size_t s = 0; s < have; ++s, p += W) {
-        p[0] = v.gt_text_id(s, 0);
-        p[n] = haploid ? p[0] : v.gt_text_id(s, 1);
-        const uint16_t ph = (haploid || v.phased[s] != 0) ? 1 : 0;
-        p[2 * n - m] = m == 0 ? ph : (uint16_t)(p[2 * n - m] & ph);
+    const size_t n = chain.size(), central_samples = vars_[(size_t)central].n_samples(), W = 2 * n + 1;
+    // pattern of each sample class that the central variant carries: [h1 ids | h2 ids | phased]
+    size_t n_rows = 0;
+    sc.pat.resize(sc.reps.size() * W);
+    for (uint32_t smp : sc.reps) {
+      if (smp >= central_samples) continue;  // (the reference walks the samples of the central variant)
+      uint16_t *p = sc.pat.data() + n_rows++ * W;
+      uint16_t ph = 1;
+      for (size_t m = 0; m < n; ++m) {
+        const Variant &v = vars_[(size_t)chain[m]];
+        const bool has = smp < v.n_samples();
+        p[m] = has ? v.gt_text_id(smp, 0) : 0;
+        p[n + m] = haploid ? p[m] : (has ? v.gt_text_id(smp, 1) : 0);
+        if (has && v.phased[smp] == 0) ph = 0;
       }
-      for (size_t s = have; s < n_samples; ++s, p += W) {  // (a variant that carries fewer samples: reference, phased)
-        p[0] = p[n] = 0;
-        if (m == 0) p[2 * n - m] = 1;
-      }
+      p[2 * n] = haploid ? 1 : ph;
     }
-    distinct_rows(sc.pat, n_samples, W, sc.order, sc.table);
+    distinct_rows(sc.pat, n_rows, W, sc.order, sc.table);
     sc.cand.clear();
     for (uint32_t row : sc.order) {
       const uint16_t *q = sc.pat.data() + (size_t)row * W;
