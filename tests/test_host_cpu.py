@@ -253,3 +253,45 @@ def test_sample_list_errors_and_subset(cli, tmp_path):
     assert out[0] == out[1] and out[0].count("\n") > 500
     all_samples = subprocess.run([cli, "signatures", fa, vcf], capture_output=True, text=True, check=True).stdout
     assert all_samples != out[0]      # the subset really changes the haplotypes seen
+
+
+@pytest.mark.parametrize("haploid", [False, True])
+def test_signatures_many_samples(cli, ref_lib, tmp_path, haploid):
+    """400 panel samples (hundreds of distinct genotype patterns per block: the sample-class hash set grows), dense
+    variants, unphased and missing genotypes"""
+    import random
+
+    rng = random.Random(31337 + haploid)
+    refs = synth.make_reference(rng, [("1", 12_000)], n_run_every=5000)
+    recs = synth.make_variants(rng, refs, 9, 400, haploid, multi_frac=0.15, sym_frac=0.02, long_frac=0.01, k=35)
+    for r in recs:                      # common variants: many different haplotypes among the samples
+        r.af = [min(0.45, 0.1 + 0.35 * rng.random()) / max(1, len(r.af)) for _ in r.af]
+    recs2 = []
+    for r in recs:                      # redraw the genotypes with the new frequencies
+        n_real = len([a for a in r.alts if not a.startswith("<")])
+        gts = []
+        for _ in range(400):
+            def draw():
+                u, acc = rng.random(), 0.0
+                for i in range(n_real):
+                    acc += r.af[i]
+                    if u < acc:
+                        return i + 1
+                return 0
+            if n_real == 0:
+                gts.append("0" if haploid else "0|0")
+            elif haploid:
+                gts.append(str(draw()))
+            else:
+                gts.append(f"{draw()}{'|' if rng.random() < 0.8 else '/'}{draw()}")
+        r.gts = gts
+        recs2.append(r)
+    fa, vcf = str(tmp_path / "r.fa"), str(tmp_path / "v.vcf")
+    synth.write_fasta(fa, refs)
+    synth.write_vcf(vcf, refs, recs2, 400, haploid, 0.02, rng)
+    flags = ["-1"] if haploid else []
+    for index_mode in (True, False):
+        got, used = cli_signatures(cli, fa, vcf, flags, index_mode)
+        exp, exp_used = expected_signatures(ref_lib, fa, vcf, 35, haploid, "AF", False, index_mode)
+        assert got == exp and used == exp_used
+        assert sum(len(v) for b in exp.values() for v in b.values()) > 2000
