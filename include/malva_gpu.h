@@ -114,6 +114,37 @@ typedef struct {
 int mg_genotype_device(mg_ctx *ctx, const mg_variant_batch *in, const mg_genotype_out *out, const mg_batch_dims *dims,
                        float error_rate, int max_coverage, int haploid);
 
+/* The same step for signature k-mers the host already packed -- what the C++ host (csrc/host/) sends: 16 B per
+ * k-mer instead of k ASCII bytes + an 8-byte offset, u32 offsets, no likelihood traffic unless asked for.
+ * kmers[i] = {lo, hi} word of a signature k-mer that is exactly k symbols of ACGT (format of the sample stream);
+ *   hi bit 62 set: the k-mer belongs to allele slot 0 and is looked up in ref_bf (KMAP::get_count), else in bf;
+ *   hi bit 63 set: IRREGULAR k-mer (shorter than k at a contig end, or holding N / IUPAC symbols,
+ *                  var_block.hpp:178-193): its text is irr_pool[irr_off[j] .. irr_off[j+1]) where irr_kmer[j] == i,
+ *                  and it is hashed byte-exactly like BF::_get_hash would (bloom_filter.hpp:58-74).
+ * out->lik == NULL (and then out->lik_off may be NULL): likelihoods are not returned.                          */
+typedef struct {
+  uint64_t n_variants;
+  const uint32_t *var_allele_off; /* [n_variants+1]                                                          */
+  const uint32_t *allele_sig_off; /* [n_alleles+1]                                                           */
+  const uint32_t *sig_kmer_off;   /* [n_sigs+1]                                                              */
+  const uint64_t *kmers;          /* [n_kmers] x {lo, hi}                                                    */
+  const float *freq;              /* [n_alleles]                                                             */
+  uint64_t n_irregular;
+  const uint64_t *irr_off;        /* [n_irregular+1] byte ranges in irr_pool                                 */
+  const char *irr_pool;
+  const uint32_t *irr_kmer;       /* [n_irregular] index in kmers[] of each irregular k-mer                  */
+} mg_packed_batch;
+int mg_genotype_packed(mg_ctx *ctx, const mg_packed_batch *in, const mg_genotype_out *out, float error_rate,
+                       int max_coverage, int haploid);
+typedef struct {
+  uint64_t n_variants, n_alleles, n_sigs, n_kmers;
+  uint64_t irr_pool_bytes;
+  uint64_t lik_slots; /* sum over variants of max(n, haploid ? n : n(n+1)/2): likelihood slots of the batch */
+} mg_packed_dims;
+/* every array of in/out DEVICE-resident (enqueued on the context's stream; mg_sync completes it) */
+int mg_genotype_packed_device(mg_ctx *ctx, const mg_packed_batch *in, const mg_genotype_out *out,
+                              const mg_packed_dims *dims, float error_rate, int max_coverage, int haploid);
+
 /* -------------------- k-mer counting (the step before the path) ---------- */
 /* What the wrapper script obtains from `kmc -k<ref_k> -ci2 -cs255` (MALVA:107) and malva-geno lists through the KMC
  * API (main.cpp:482-490): canonical k-mers of the reads, windows with a non-ACGT symbol skipped, k-mers seen fewer
@@ -156,13 +187,19 @@ int mg_kmap_size(mg_ctx *ctx, uint64_t *n);
  * irregular (non-ACGT / short) ref keys}; n >= 6 */
 int mg_index_stats(mg_ctx *ctx, uint64_t *stats, int n);
 
-/* device pointers + lengths of the three u32 counter arrays, for an external (NCCL) sum-reduce across
- * replicas: [0] one per set bit of bf, [1] one per key slot of the probe lines, [2] overflow table */
+/* The live counters sit inside the probe lines (one HBM line per k-mer).  For a sum-reduce across replicas
+ * (NCCL between processes) they are gathered into DENSE u32 arrays -- mg_counters_gather -- whose device pointers
+ * and lengths mg_counter_buffers returns: [0] one per set bit of bf (rank order), [1] one per ref key held by the
+ * probe lines (line order), [2] overflow table.  After the reduce the destination rank calls mg_counters_scatter
+ * to write the sums back into its probe lines. */
+int mg_counters_gather(mg_ctx *ctx);
 int mg_counter_buffers(mg_ctx *ctx, void **d_ptr /*[3]*/, uint64_t *n /*[3]*/);
+int mg_counters_scatter(mg_ctx *ctx);
 
 /* Replicas inside one process: ctx[0..n-1] hold the same index (on any devices) and each scanned a share of the
- * sample stream; adds the counter arrays of ctx[1..n-1] into ctx[0] (NVLink peer copies + an add kernel).  After it
- * ctx[0] answers mg_genotype / mg_get_counts for the whole stream. */
+ * sample stream; adds the counters of ctx[1..n-1] into ctx[0] (gather on every device, one N-way sum kernel that
+ * reads the peers' dense arrays in place over NVLink, scatter on ctx[0]).  After it ctx[0] answers mg_genotype /
+ * mg_get_counts for the whole stream. */
 int mg_reduce_counts(mg_ctx **ctx, int n);
 
 /* index image for the index file (BF::operator>> / KMAP::operator>>, main.cpp:406-412; loading :455-461).

@@ -54,6 +54,26 @@ class BatchDims(C.Structure):
                 ("n_kmers", C.c_uint64), ("pool_bytes", C.c_uint64)]
 
 
+class PackedBatch(C.Structure):
+    _fields_ = [
+        ("n_variants", C.c_uint64),
+        ("var_allele_off", u32p),
+        ("allele_sig_off", u32p),
+        ("sig_kmer_off", u32p),
+        ("kmers", C.c_void_p),
+        ("freq", f32p),
+        ("n_irregular", C.c_uint64),
+        ("irr_off", u64p),
+        ("irr_pool", C.c_void_p),
+        ("irr_kmer", u32p),
+    ]
+
+
+class PackedDims(C.Structure):
+    _fields_ = [("n_variants", C.c_uint64), ("n_alleles", C.c_uint64), ("n_sigs", C.c_uint64),
+                ("n_kmers", C.c_uint64), ("irr_pool_bytes", C.c_uint64), ("lik_slots", C.c_uint64)]
+
+
 # every symbol include/malva_gpu.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mg_last_error": (C.c_char_p, []),
@@ -65,7 +85,7 @@ SYMBOLS = {
     "mg_add_signatures": (C.c_int, [C.c_void_p, C.c_char_p, u64p, u8p, C.c_uint64]),
     "mg_add_signatures_packed": (C.c_int, [C.c_void_p, C.c_void_p, u8p, C.c_uint64]),
     "mg_finalize_alt": (C.c_int, [C.c_void_p]),
-    "mg_scan_reference": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
+    "mg_scan_reference": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "mg_finalize_context": (C.c_int, [C.c_void_p]),
     "mg_scan_sample_kmers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "mg_scan_sample_kmers_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -77,6 +97,10 @@ SYMBOLS = {
                               C.c_int]),
     "mg_genotype_device": (C.c_int, [C.c_void_p, C.POINTER(VariantBatch), C.POINTER(GenotypeOut),
                                      C.POINTER(BatchDims), C.c_float, C.c_int, C.c_int]),
+    "mg_genotype_packed": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.POINTER(GenotypeOut), C.c_float, C.c_int,
+                                     C.c_int]),
+    "mg_genotype_packed_device": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.POINTER(GenotypeOut),
+                                            C.POINTER(PackedDims), C.c_float, C.c_int, C.c_int]),
     "mg_count_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "mg_count_destroy": (None, [C.c_void_p]),
     "mg_count_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]),
@@ -93,6 +117,8 @@ SYMBOLS = {
     "mg_bf_download_counts": (C.c_int, [C.c_void_p, u16p, C.c_uint64]),
     "mg_kmap_size": (C.c_int, [C.c_void_p, u64p]),
     "mg_index_stats": (C.c_int, [C.c_void_p, u64p, C.c_int]),
+    "mg_counters_gather": (C.c_int, [C.c_void_p]),
+    "mg_counters_scatter": (C.c_int, [C.c_void_p]),
     "mg_counter_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
     "mg_reduce_counts": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "mg_export_set_bits": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64, u64p]),

@@ -83,6 +83,54 @@ class SignatureBatch:
                               np.array(sko, dtype=np.uint64), koff, pool, np.array(fr, dtype=np.float32))
 
 
+IRREGULAR_BIT, REF_ALLELE_BIT = 1 << 63, 1 << 62
+
+
+@dataclass
+class PackedSignatureBatch:
+    """The batch form the C++ host sends (mg_packed_batch): k-mers that are exactly k symbols of ACGT as 2-bit words,
+    the others ("irregular": shorter at a contig end, or holding N / IUPAC symbols) as text in a side pool."""
+    var_allele_off: np.ndarray   # u32
+    allele_sig_off: np.ndarray   # u32
+    sig_kmer_off: np.ndarray     # u32
+    kmers: np.ndarray            # KMER_DTYPE; hi bit 62 = ref allele, hi bit 63 = irregular
+    freq: np.ndarray
+    irr_off: np.ndarray          # u64 [n_irregular + 1]
+    irr_pool: bytes
+    irr_kmer: np.ndarray         # u32 [n_irregular]
+
+    @property
+    def n_variants(self) -> int:
+        return len(self.var_allele_off) - 1
+
+    @staticmethod
+    def from_batch(b: "SignatureBatch", k: int) -> "PackedSignatureBatch":
+        """re-encodes an ASCII SignatureBatch (test helper: the product's packer is csrc/host/signatures.hpp)"""
+        from .kmc import ints_to_packed, pack_kmer
+        nk = len(b.kmer_off) - 1
+        is_ref = np.zeros(nk, bool)
+        for v in range(b.n_variants):
+            a0 = int(b.var_allele_off[v])
+            if int(b.var_allele_off[v + 1]) > a0:
+                s0, s1 = int(b.allele_sig_off[a0]), int(b.allele_sig_off[a0 + 1])
+                is_ref[int(b.sig_kmer_off[s0]):int(b.sig_kmer_off[s1])] = True
+        texts = [b.pool[int(b.kmer_off[i]):int(b.kmer_off[i + 1])] for i in range(nk)]
+        regular = np.array([len(t) == k and set(t) <= set(b"ACGT") for t in texts], bool) if nk else np.zeros(0, bool)
+        kmers = np.zeros(nk, dtype=KMER_DTYPE)
+        if regular.any():
+            kmers[regular] = ints_to_packed([pack_kmer(texts[i].decode()) for i in np.nonzero(regular)[0]])
+        irr = np.nonzero(~regular)[0]
+        hi = kmers["hi"].copy()
+        lo = kmers["lo"].copy()
+        hi[irr] = IRREGULAR_BIT
+        lo[irr] = np.arange(len(irr), dtype=np.uint64)
+        hi[is_ref] |= np.uint64(REF_ALLELE_BIT)
+        kmers["hi"], kmers["lo"] = hi, lo
+        pool, off = make_pool([texts[i] for i in irr])
+        return PackedSignatureBatch(b.var_allele_off.astype(np.uint32), b.allele_sig_off.astype(np.uint32),
+                                    b.sig_kmer_off.astype(np.uint32), kmers, b.freq, off, pool, irr.astype(np.uint32))
+
+
 @dataclass
 class GenotypeResult:
     cov: np.ndarray       # u32 per allele slot
@@ -176,6 +224,10 @@ class MalvaGpu:
     def scan_reference(self, seq) -> None:
         s = _as_bytes(seq)
         check(self._L.mg_scan_reference(self._h, s, len(s)))
+
+    def scan_reference_ptr(self, ptr: int, n: int) -> None:
+        """contig bytes at a host address (pinned memory is copied from directly, without staging)"""
+        check(self._L.mg_scan_reference(self._h, C.c_void_p(ptr), n))
 
     def finalize_context(self) -> None:
         check(self._L.mg_finalize_context(self._h))
@@ -300,6 +352,63 @@ class MalvaGpu:
         check(self._L.mg_genotype(self._h, C.byref(vb), C.byref(out), C.c_float(error_rate), int(max_coverage),
                                   int(bool(haploid))))
 
+    def genotype_packed(self, batch: "PackedSignatureBatch", error_rate: float = 0.001, max_coverage: int = 200,
+                        haploid: bool = False, want_lik: bool = True) -> GenotypeResult:
+        """mg_genotype_packed: the batch form the C++ host sends (2-bit k-mer words, u32 offsets)."""
+        nv = batch.n_variants
+        na = int(batch.var_allele_off[-1]) if nv else 0
+        nall = np.diff(batch.var_allele_off.astype(np.int64))
+        slots = np.maximum(nall if haploid else nall * (nall + 1) // 2, nall)
+        lik_off = np.zeros(nv + 1, dtype=np.uint64)
+        lik_off[1:] = np.cumsum(slots, dtype=np.uint64)
+        res = GenotypeResult(np.zeros(max(na, 1), np.uint32), np.zeros(nv, np.int32), np.zeros(nv, np.int32),
+                             np.zeros(nv, np.int32), np.zeros(nv, np.int32), lik_off,
+                             np.zeros(int(lik_off[-1]) if want_lik else 0, np.float64))
+        if nv == 0:
+            res.cov = res.cov[:0]
+            return res
+        pb = _lib.PackedBatch(nv, _p(batch.var_allele_off, _lib.u32p), _p(batch.allele_sig_off, _lib.u32p),
+                              _p(batch.sig_kmer_off, _lib.u32p), batch.kmers.ctypes.data, _p(batch.freq, _lib.f32p),
+                              len(batch.irr_kmer), _p(batch.irr_off, _lib.u64p),
+                              C.cast(C.c_char_p(batch.irr_pool), C.c_void_p), _p(batch.irr_kmer, _lib.u32p))
+        out = _lib.GenotypeOut(_p(res.cov, _lib.u32p), _p(res.n_gts, _lib.i32p), _p(res.status, _lib.i32p),
+                               _p(res.best_gt, _lib.i32p), _p(res.gq, _lib.i32p),
+                               _p(lik_off, _lib.u64p) if want_lik else None,
+                               _p(res.lik, _lib.f64p) if want_lik and len(res.lik) else None)
+        if want_lik and not len(res.lik):
+            out.lik_off = None
+        check(self._L.mg_genotype_packed(self._h, C.byref(pb), C.byref(out), C.c_float(error_rate), int(max_coverage),
+                                         int(bool(haploid))))
+        res.cov = res.cov[:na]
+        return res
+
+    def genotype_packed_device(self, ptrs: dict, dims: tuple, error_rate: float, max_coverage: int, haploid: bool) -> None:
+        """ptrs: device addresses keyed like mg_packed_batch / mg_genotype_out fields ("lik"/"lik_off" may be 0);
+        dims = (nv, na, ns, nk, n_irregular, irr_pool_bytes, lik_slots)."""
+        c = lambda name, typ: C.cast(C.c_void_p(ptrs.get(name) or None), typ)
+        nv, na, ns, nk, ni, ipb, slots = dims
+        pb = _lib.PackedBatch(nv, c("var_allele_off", _lib.u32p), c("allele_sig_off", _lib.u32p),
+                              c("sig_kmer_off", _lib.u32p), C.c_void_p(ptrs["kmers"]), c("freq", _lib.f32p), ni,
+                              c("irr_off", _lib.u64p), C.c_void_p(ptrs.get("irr_pool") or None), c("irr_kmer", _lib.u32p))
+        out = _lib.GenotypeOut(c("cov", _lib.u32p), c("n_gts", _lib.i32p), c("status", _lib.i32p),
+                               c("best_gt", _lib.i32p), c("gq", _lib.i32p), c("lik_off", _lib.u64p), c("lik", _lib.f64p))
+        dm = _lib.PackedDims(nv, na, ns, nk, ipb, slots)
+        check(self._L.mg_genotype_packed_device(self._h, C.byref(pb), C.byref(out), C.byref(dm), C.c_float(error_rate),
+                                                int(max_coverage), int(bool(haploid))))
+
+    def genotype_packed_host(self, ptrs: dict, n_variants: int, n_irregular: int, error_rate: float, max_coverage: int,
+                             haploid: bool) -> None:
+        """mg_genotype_packed on caller-owned HOST buffers given by address (e.g. pinned memory)."""
+        c = lambda name, typ: C.cast(C.c_void_p(ptrs.get(name) or None), typ)
+        pb = _lib.PackedBatch(n_variants, c("var_allele_off", _lib.u32p), c("allele_sig_off", _lib.u32p),
+                              c("sig_kmer_off", _lib.u32p), C.c_void_p(ptrs["kmers"]), c("freq", _lib.f32p),
+                              n_irregular, c("irr_off", _lib.u64p), C.c_void_p(ptrs.get("irr_pool") or None),
+                              c("irr_kmer", _lib.u32p))
+        out = _lib.GenotypeOut(c("cov", _lib.u32p), c("n_gts", _lib.i32p), c("status", _lib.i32p),
+                               c("best_gt", _lib.i32p), c("gq", _lib.i32p), c("lik_off", _lib.u64p), c("lik", _lib.f64p))
+        check(self._L.mg_genotype_packed(self._h, C.byref(pb), C.byref(out), C.c_float(error_rate), int(max_coverage),
+                                         int(bool(haploid))))
+
     def genotype_device(self, ptrs: dict, dims: tuple, error_rate: float, max_coverage: int, haploid: bool) -> None:
         """ptrs: device addresses keyed like mg_variant_batch / mg_genotype_out fields; dims = (nv, na, ns, nk)
         or (nv, na, ns, nk, pool_bytes)."""
@@ -334,9 +443,20 @@ class MalvaGpu:
         check(self._L.mg_launch_count(self._h, C.byref(v)))
         return v.value
 
-    def counter_buffers(self):
-        """[(device ptr, n_u32)] x 3 -- bf counters, probe-line key counts, overflow counts -- for an
-        external NCCL sum-reduce across replicas."""
+    def counters_gather(self) -> None:
+        """the counters that live inside the probe lines -> the dense arrays counter_buffers() points at"""
+        check(self._L.mg_counters_gather(self._h))
+
+    def counters_scatter(self) -> None:
+        """the dense arrays (e.g. after an NCCL sum-reduce into this rank) -> back into the probe lines"""
+        check(self._L.mg_counters_scatter(self._h))
+
+    def counter_buffers(self, gather: bool = True):
+        """[(device ptr, n_u32)] x 3 -- bf counters (rank order), key counts of the probe lines (line order),
+        overflow counts -- for an external NCCL sum-reduce across replicas: gather, reduce, counters_scatter()
+        on the destination rank."""
+        if gather:
+            self.counters_gather()
         p = (C.c_void_p * 3)()
         n = (C.c_uint64 * 3)()
         check(self._L.mg_counter_buffers(self._h, p, n))

@@ -1,9 +1,10 @@
 // Hand-written sm_100a kernels of the MALVA hot path (see index.cuh for the data layout).
 //   K3  k_add_signatures / k_add_packed / k_add_spill / k_line_popc    index-time inserts + switch_mode
 //   K2  k_refpass / k_refpass_short                                    reference rolling pass
-//   K1  k_scan                                                         sample k-mer scan
-//   K4  k_mark_ref / k_lookup / k_coverage                             coverage read-back
+//   K1  k_scan / k_scan_hits                                           sample k-mer scan
+//   K4  k_lookup_packed / k_lookup_fast / k_lookup / k_coverage        coverage read-back
 //   K5  k_genotype                                                     likelihoods + posterior arg-max
+//       k_counters_xfer / k_sum_peers                                  dense counter image for the multi-GPU reduce
 #pragma once
 #include <cuda_runtime.h>
 
@@ -23,36 +24,44 @@ __device__ __forceinline__ uint64_t canon_hash_k(u128 x, int k, u128 *canon) {
     return canon_hash_rt(x, k, canon);
   }
 }
+__device__ __forceinline__ u128 u128_of(uint4 q) {
+  u128 r;
+  r.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+  r.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+  return r;
+}
+__device__ __forceinline__ uint4 uint4_of(u128 x) {
+  return make_uint4((uint32_t)x.lo, (uint32_t)(x.lo >> 32), (uint32_t)x.hi, (uint32_t)(x.hi >> 32));
+}
 
-// scalars: [0] new keys, [1] irregular ref keys, [2] popcount, [3] error flag, [4] spilled keys
+// scalars: [0] new keys, [1] irregular ref keys, [2] popcount, [3] error flag, [4] spilled keys, [5] scratch cursor
 // ---------------------------------------------------------------------------
 // K3a: index-time inserts (add_kmers_to_bf, main.cpp:122-144)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void insert_ref_key(const DevView &v, uint4 *lines_rw, uint32_t *occ_rw, uint64_t h,
-                                               u128 canon, uint64_t i, unsigned long long *scalars,
-                                               uint32_t *spill_idx) {
-  occ_set(v, occ_rw, bf_index(v, h));
-  uint64_t line = bf_index(v, h) >> 8;
-  int r = line_insert(lines_rw, line, canon);
+__device__ __forceinline__ void insert_ref_key(const DevView &v, uint32_t *occ_rw, uint64_t h, u128 canon, uint64_t i,
+                                               unsigned long long *scalars, uint32_t *spill_idx) {
+  const uint64_t idx = bf_index(v, h);
+  occ_set(v, occ_rw, idx);
+  const uint64_t line = idx >> 8;
+  int r = line_insert(v, line, canon);
   if (r == 1) {
     atomicAdd(&scalars[0], 1ull);
   } else if (r < 0) {  // line full: flag it and leave the key for the overflow pass
-    line_set_overflow(lines_rw, line);
+    line_set_overflow(v, line);
     unsigned long long p = atomicAdd(&scalars[4], 1ull);
     spill_idx[p] = (uint32_t)i;
   }
 }
-__device__ __forceinline__ void set_bf_bit(const DevView &v, uint4 *lines_rw, uint32_t *occ_rw, uint64_t h) {
+__device__ __forceinline__ void set_bf_bit(const DevView &v, uint32_t *occ_rw, uint64_t h) {
   uint64_t idx = bf_index(v, h);
   occ_set(v, occ_rw, idx);
-  uint32_t *w = reinterpret_cast<uint32_t *>(lines_rw) + (idx >> 8) * 32 + ((idx & 255) >> 5);
-  atomicOr(w, 1u << (idx & 31));
+  atomicOr(line_words(v, idx >> 8) + ((idx & 255) >> 5), 1u << (idx & 31));
 }
 
 __global__ void __launch_bounds__(128) k_add_signatures(const uint8_t *__restrict__ pool,
                                                        const uint64_t *__restrict__ off,
                                                        const uint8_t *__restrict__ is_ref, uint64_t n, DevView v,
-                                                       uint4 *lines_rw, uint32_t *occ_rw, unsigned long long *scalars,
+                                                       uint32_t *occ_rw, unsigned long long *scalars,
                                                        uint32_t *irregular_idx, uint32_t *spill_idx) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -73,29 +82,25 @@ __global__ void __launch_bounds__(128) k_add_signatures(const uint8_t *__restric
       return;
     }
     uint64_t h = canon_hash_rt(x, v.k, &canon);
-    insert_ref_key(v, lines_rw, occ_rw, h, canon, i, scalars, spill_idx);
+    insert_ref_key(v, occ_rw, h, canon, i, scalars, spill_idx);
   } else {  // bf.add_key
     uint64_t h = regular ? canon_hash_rt(x, v.k, &canon) : hash_ascii(s, len);
-    set_bf_bit(v, lines_rw, occ_rw, h);
+    set_bf_bit(v, occ_rw, h);
   }
 }
 
 // same inserts for signature k-mers that arrive already packed (exactly k symbols of ACGT)
 __global__ void __launch_bounds__(256) k_add_packed(const uint4 *__restrict__ kmers, const uint8_t *__restrict__ is_ref,
-                                                   uint64_t n, DevView v, uint4 *lines_rw, uint32_t *occ_rw,
+                                                   uint64_t n, DevView v, uint32_t *occ_rw,
                                                    unsigned long long *scalars, uint32_t *spill_idx) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint4 q = kmers[i];
-  u128 x, canon;
-  x.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
-  x.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
-  x = mask128(x, 2 * v.k);
+  u128 x = mask128(u128_of(kmers[i]), 2 * v.k), canon;
   uint64_t h = canon_hash_rt(x, v.k, &canon);
   if (is_ref[i])
-    insert_ref_key(v, lines_rw, occ_rw, h, canon, i, scalars, spill_idx);
+    insert_ref_key(v, occ_rw, h, canon, i, scalars, spill_idx);
   else
-    set_bf_bit(v, lines_rw, occ_rw, h);
+    set_bf_bit(v, occ_rw, h);
 }
 
 // second pass over the keys whose line was full: insert into the overflow table.
@@ -115,49 +120,35 @@ __global__ void __launch_bounds__(128) k_add_spill(const uint32_t *__restrict__ 
     for (int t = 0; t < len && t < 64; ++t) s[t] = pool[b + t];
     pack_ascii(s, len, v.k, &x);
   } else {
-    uint4 q = packed[i];
-    x.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
-    x.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
-    x = mask128(x, 2 * v.k);
+    x = mask128(u128_of(packed[i]), 2 * v.k);
   }
-  uint64_t h = canon_hash_rt(x, v.k, &canon);
-  if (ovf_insert(v, ovf_keys_rw, h, canon) == 1) atomicAdd(&scalars[0], 1ull);
+  canon_hash_rt(x, v.k, &canon);
+  if (ovf_insert(v, ovf_keys_rw, canon) == 1) atomicAdd(&scalars[0], 1ull);
 }
 
-__global__ void k_fill_keys(u128 *keys, uint64_t n) {
+__global__ void k_fill_keys(u128 *keys, uint64_t n, uint64_t hi_mask) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     keys[i].lo = ~0ull;
-    keys[i].hi = KEY_HI_MASK;
+    keys[i].hi = hi_mask;
   }
 }
-// a fresh probe-line array: filter bits 0, key slots empty
-__global__ void k_init_lines(uint4 *lines, uint64_t n_lines) {
+// a fresh probe-line array: filter bits 0, key slots empty, rank and counters 0
+__global__ void k_init_lines(uint4 *lines, uint64_t n_lines, uint64_t hi_mask) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one uint4 per thread
   if (i >= n_lines * LINE_U4) return;
-  uint32_t hi = (uint32_t)(KEY_HI_MASK >> 32);
-  lines[i] = (i & 7) < 2 ? make_uint4(0, 0, 0, 0) : make_uint4(~0u, ~0u, ~0u, hi);
+  const int q = (int)(i & 7);
+  lines[i] = (q < 2 || q == 7) ? make_uint4(0, 0, 0, 0) : make_uint4(~0u, ~0u, (uint32_t)hi_mask, (uint32_t)(hi_mask >> 32));
 }
 
-// re-insert every key of an old overflow table into a larger one (counts carried over)
-__global__ void k_rehash(const u128 *old_keys, const uint32_t *old_counts, uint64_t old_cap, DevView v,
-                         u128 *ovf_keys_rw) {
+// re-insert every key of an old overflow table into a larger one (index-build time: counts are all zero)
+__global__ void k_rehash(const u128 *old_keys, uint64_t old_cap, DevView v, u128 *ovf_keys_rw) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= old_cap) return;
   u128 key = old_keys[i];
-  key.hi &= KEY_HI_MASK;
-  if (key_empty(key)) return;
-  u128 canon;
-  uint64_t h = canon_hash_rt(key, v.k, &canon);  // keys are canonical: canon == key
-  const u128 empty = {~0ull, KEY_HI_MASK};
-  uint64_t slot = ovf_slot0(v, h);
-  while (true) {
-    u128 old = cas128(ovf_keys_rw + slot, empty, key);
-    old.hi &= KEY_HI_MASK;
-    if (key_empty(old)) break;
-    slot = (slot + 1) & v.ovf_mask;
-  }
-  v.ovf_counts[slot] = old_counts[i];
+  key.hi &= v.key_hi_mask;
+  if (key_empty(v, key)) return;
+  ovf_insert(v, ovf_keys_rw, key);
 }
 
 // ---------------------------------------------------------------------------
@@ -165,33 +156,33 @@ __global__ void k_rehash(const u128 *old_keys, const uint32_t *old_counts, uint6
 // ascending order, empty slots last.  Which slot a key took during the build depended on the order (and the races)
 // of the inserts; after this pass it depends on the key set only.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sort_line_keys(uint4 *lines, uint64_t n_lines) {
+__global__ void __launch_bounds__(256) k_sort_line_keys(DevView v) {
   uint64_t line = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (line >= n_lines) return;
-  uint4 *p = lines + line * LINE_U4 + 2;
-  uint4 q[LINE_KEYS];
+  if (line >= v.n_lines) return;
+  uint4 *p = v.lines + line * LINE_U4 + 2;
+  u128 q[LINE_KEYS];
 #pragma unroll
-  for (int s = 0; s < LINE_KEYS; ++s) q[s] = p[s];
-  if (key_empty(key_of(q[1]))) return;  // zero or one key: already canonical (slots fill from the front)
-  const uint32_t flag = q[LINE_KEYS - 1].w & OVF_FLAG_W;
-  q[LINE_KEYS - 1].w &= ~OVF_FLAG_W;
+  for (int s = 0; s < LINE_KEYS; ++s) q[s] = u128_of(p[s]);
+  const uint64_t flag = q[LINE_KEYS - 1].hi & v.ovf_flag_hi;
+#pragma unroll
+  for (int s = 0; s < LINE_KEYS; ++s) q[s].hi &= v.key_hi_mask;
+  if (key_empty(v, q[1])) return;  // zero or one key: already canonical (slots fill from the front)
 #pragma unroll
   for (int a = 1; a < LINE_KEYS; ++a) {  // insertion sort on (hi, lo); an empty slot is the largest value
 #pragma unroll
     for (int b = a; b > 0; --b) {
-      u128 x = key_of(q[b - 1]), y = key_of(q[b]);
-      if (less128(y, x)) {
-        uint4 t = q[b - 1];
+      if (less128(q[b], q[b - 1])) {
+        u128 t = q[b - 1];
         q[b - 1] = q[b];
         q[b] = t;
       }
     }
   }
-  q[LINE_KEYS - 1].w |= flag;
+  q[LINE_KEYS - 1].hi |= flag;
 #pragma unroll
-  for (int s = 0; s < LINE_KEYS; ++s) p[s] = q[s];
+  for (int s = 0; s < LINE_KEYS; ++s) p[s] = uint4_of(q[s]);
 }
-// the six key slots of the listed lines, to / from a dense array (overflow canonicalisation on the host)
+// the five key slots of the listed lines, to / from a dense array (overflow canonicalisation on the host)
 __global__ void k_gather_line_keys(const uint4 *lines, const uint64_t *ids, uint64_t n, uint4 *out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * LINE_KEYS) return;
@@ -204,8 +195,8 @@ __global__ void k_scatter_line_keys(uint4 *lines, const uint64_t *ids, uint64_t 
 }
 
 // ---------------------------------------------------------------------------
-// K3b: switch_mode (bloom_filter.hpp:93-98): ones per probe line (then an exclusive scan -> rank)
-// also used on a plain bit array (stride_u32 = 8) for context_bf statistics
+// K3b: switch_mode (bloom_filter.hpp:93-98): ones per probe line (then an exclusive scan -> rank, written into
+// word 28 of every line); also used on a plain bit array (stride_u32 = 8) for context_bf statistics
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_line_popc(const uint32_t *__restrict__ words, uint64_t n_units, int stride_u32,
                                                   uint32_t *__restrict__ unit_count, unsigned long long *total) {
@@ -229,6 +220,21 @@ __global__ void __launch_bounds__(256) k_line_popc(const uint32_t *__restrict__ 
     if (threadIdx.x == 0 && s) atomicAdd(total, (unsigned long long)s);
   }
 }
+__global__ void __launch_bounds__(256) k_write_rank(DevView v, const uint32_t *__restrict__ rank) {
+  uint64_t line = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= v.n_lines) return;
+  v.lines[line * LINE_U4 + 7] = make_uint4(rank[line], 0u, 0u, 0u);
+}
+// keys held by the five slots of every line (empty slots come last once the image is canonical)
+__global__ void __launch_bounds__(256) k_line_keycount(DevView v, uint32_t *__restrict__ cnt) {
+  uint64_t line = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= v.n_lines) return;
+  const uint4 *p = v.lines + line * LINE_U4 + 2;
+  uint32_t c = 0;
+#pragma unroll
+  for (int s = 0; s < LINE_KEYS; ++s) c += key_empty(v, key_of(v, p[s])) ? 0u : 1u;
+  cnt[line] = c;
+}
 // the 256 filter bits of every probe line, gathered into a plain bit array (state download)
 __global__ void k_extract_bits(const uint4 *__restrict__ lines, uint64_t n_lines, uint4 *__restrict__ out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one uint4 (128 bits) per thread
@@ -237,10 +243,74 @@ __global__ void k_extract_bits(const uint4 *__restrict__ lines, uint64_t n_lines
 }
 
 // ---------------------------------------------------------------------------
+// Dense counter image (the multi-GPU reduce, the counter download): the counters that live inside the probe lines
+// copied to / from dense arrays -- bf_counts[rank + j] for the inline alt counters (j < 3), key_dense[key_rank[L] + s]
+// for the key counts.  Eight lanes per line, one uint4 each: the line array is read once, fully coalesced.
+// ---------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_counters_xfer(DevView v, const uint32_t *__restrict__ key_rank,
+                                                      uint32_t *__restrict__ key_dense) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t line = t >> 3;
+  const int sub = (int)(t & 7);
+  const bool ok = line < v.n_lines;
+  const uint4 q = ok ? v.lines[line * LINE_U4 + (uint64_t)sub] : make_uint4(0, 0, 0, 0);
+  const uint32_t pc = sub < 2 ? (uint32_t)(__popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w)) : 0u;
+  const int g0 = (int)(threadIdx.x & 24);
+  const uint32_t n_alt = __shfl_sync(0xffffffffu, pc, g0) + __shfl_sync(0xffffffffu, pc, g0 + 1);
+  if (!ok) return;
+  uint32_t *w = line_words(v, line);
+  if (sub == 7) {
+    const uint32_t c[3] = {q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < LINE_INLINE_ALT; ++j)
+      if ((uint32_t)j < n_alt) {
+        if (SCATTER)
+          w[LINE_W_RANK + 1 + j] = v.bf_counts[(uint64_t)q.x + (uint64_t)j];
+        else
+          v.bf_counts[(uint64_t)q.x + (uint64_t)j] = c[j];
+      }
+  } else if (sub >= 2) {
+    const int s = sub - 2;
+    if (key_empty(v, key_of(v, q))) return;
+    const uint64_t d = (uint64_t)key_rank[line] + (uint64_t)s;
+    uint32_t *cp = v.inline_counts ? w + 8 + 4 * s + 3 : v.key_counts + line * LINE_KEYS + (uint64_t)s;
+    if (SCATTER)
+      *cp = key_dense[d];
+    else
+      key_dense[d] = v.inline_counts ? q.w : *cp;
+  }
+}
+// dst[i] += sum over peers of src[p][i] (u32, wrap-around): the counter reduce of replicated contexts inside one
+// process; the peers' arrays are read in place over NVLink (peer access), no staging copy
+struct PeerPtrs {
+  const uint32_t *p[15];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_sum_peers(uint32_t *__restrict__ dst, PeerPtrs peers, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      uint4 a = *reinterpret_cast<const uint4 *>(dst + i);
+      for (int p = 0; p < peers.n; ++p) {
+        const uint4 b = *reinterpret_cast<const uint4 *>(peers.p[p] + i);
+        a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+      }
+      *reinterpret_cast<uint4 *>(dst + i) = a;
+    } else {
+      for (uint64_t j = i; j < n; ++j)
+        for (int p = 0; p < peers.n; ++p) dst[j] += peers.p[p][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K2: reference rolling pass (main.cpp:385-400)
-// Each CTA stages a tile of the contig in shared memory (with a ref_k-1 halo); each thread rolls RP_RUN
-// consecutive windows through 2-bit registers.  Windows that contain a non-ACGT symbol take the
+// Each CTA stages a tile of the contig in shared memory (with a ref_k-1 halo, 16-byte loads); each thread rolls
+// RP_RUN consecutive windows through 2-bit registers.  Windows that contain a non-ACGT symbol take the
 // byte-exact ASCII path (the RCN table maps IUPAC symbols to NUL, bloom_filter.hpp:36-50).
+// The contig arrives in chunks (double-buffered H2D copies, malva_gpu.cu): `chunk` holds the bytes
+// [chunk_base, ...) of the contig, the launch covers the window end positions [p_begin, p_end).
 // ---------------------------------------------------------------------------
 constexpr int RP_THREADS = 256;
 constexpr int RP_RUN = 16;
@@ -251,18 +321,27 @@ __device__ __forceinline__ uint32_t base_code(uint8_t c) {  // 0..3, or 4 for an
 }
 
 template <int K, int REFK>
-__global__ void __launch_bounds__(RP_THREADS) k_refpass(const uint8_t *__restrict__ seq, uint64_t len, DevView v,
+__global__ void __launch_bounds__(RP_THREADS) k_refpass(const uint8_t *__restrict__ chunk, uint64_t chunk_base,
+                                                        uint64_t p_begin, uint64_t p_end, DevView v,
                                                         uint32_t *ctx_words_rw) {
-  extern __shared__ uint8_t sm[];
+  extern __shared__ uint4 rp_sm4[];
+  uint8_t *sm = reinterpret_cast<uint8_t *>(rp_sm4);
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int d = (ref_k - k) / 2;
   const bool odd = ((ref_k - k) & 1) != 0;
   // window end positions handled by this CTA: [p0, p1)
-  uint64_t p0 = (uint64_t)(ref_k - 1) + (uint64_t)blockIdx.x * RP_TILE;
-  uint64_t p1 = p0 + RP_TILE < len ? p0 + RP_TILE : len;
-  uint64_t base = p0 - (uint64_t)(ref_k - 1);  // first byte staged
+  uint64_t p0 = p_begin + (uint64_t)blockIdx.x * RP_TILE;
+  uint64_t p1 = p0 + RP_TILE < p_end ? p0 + RP_TILE : p_end;
+  uint64_t base = p0 - (uint64_t)(ref_k - 1);  // first contig byte staged
+  const uint8_t *src = chunk + (base - chunk_base);
   int nbytes = (int)(p1 - base);
-  for (int i = threadIdx.x; i < nbytes; i += RP_THREADS) sm[i] = seq[base + i];
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int n16 = nbytes >> 4;
+    for (int i = threadIdx.x; i < n16; i += RP_THREADS) rp_sm4[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+    for (int i = (n16 << 4) + threadIdx.x; i < nbytes; i += RP_THREADS) sm[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += RP_THREADS) sm[i] = src[i];
+  }
   __syncthreads();
   uint64_t q0 = p0 + (uint64_t)threadIdx.x * RP_RUN;
   if (q0 >= p1) return;
@@ -293,6 +372,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_refpass(const uint8_t *__restric
     //   odd, t == 0 (primed)  : ref[d .. d+k-1]                 (ends at p-d-1)
     //   odd, 1 <= t < k       : ref[d+t .. d+k-1] ++ ref[k+d+1 .. k+d+t]   (main.cpp:395-397 skips ref[d+k])
     //   odd, t >= k           : ref[p-d-k+1 .. p-d]
+    // (t < k only happens in the first chunk of a contig: chunk_base == 0 there, the quirk reads index `chunk`)
     uint64_t t = p - (uint64_t)(ref_k - 1);
     bool quirk = odd && t >= 1 && t < (uint64_t)k;
     int shift = d + ((odd && t == 0) ? 1 : 0);
@@ -306,8 +386,8 @@ __global__ void __launch_bounds__(RP_THREADS) k_refpass(const uint8_t *__restric
         for (int j = 0; j < k; ++j) s[j] = sm[sp - shift - k + 1 + j];
       } else {
         int n_old = k - (int)t;
-        for (int j = 0; j < n_old; ++j) s[j] = seq[(uint64_t)d + t + (uint64_t)j];
-        for (int j = 0; j < (int)t; ++j) s[n_old + j] = seq[(uint64_t)(k + d + 1) + (uint64_t)j];
+        for (int j = 0; j < n_old; ++j) s[j] = chunk[(uint64_t)d + t + (uint64_t)j];
+        for (int j = 0; j < (int)t; ++j) s[n_old + j] = chunk[(uint64_t)(k + d + 1) + (uint64_t)j];
       }
       h35 = hash_ascii(s, k);
     }
@@ -342,14 +422,25 @@ __global__ void k_refpass_short(const uint8_t *seq, uint64_t len, DevView v, uin
 // ---------------------------------------------------------------------------
 // K1: sample k-mer scan (main.cpp:487-500)
 //   ref_bf.increment(kmer, c);  if (!context_bf.test_key(context)) bf.increment(kmer, c);
-// A warp owns 32 k-mers (lane i hashes k-mer i: one coalesced 16-byte load, canonical form, XXH3).
-// The probe lines of the 32 k-mers are then copied into the warp's 4 KB shared-memory tile with
-// cp.async (LDGSTS, no register staging): in round r the four 8-lane groups of the warp copy the lines
-// of k-mers 4r..4r+3, lane j of a group moving uint4 j, so that one k-mer costs exactly one fully
-// coalesced 128-byte request, and all 32 lines are in flight together.  The tile is XOR-swizzled
-// (uint4 j of line L sits at column j ^ (L & 7)) so that every lane can then read ITS OWN line with
-// conflict-free 16-byte shared loads and do the filter-bit test and the six key compares locally.
-// The context filter, the rank directory and the counters are touched only on the ~1-4 % hit paths.
+//
+// A warp owns 32 k-mers per iteration: lane i hashes k-mer i (one coalesced 16-byte load, canonical form, XXH3) and
+// tests the L2-resident occupancy pre-filter.  Only about a third of the k-mers of a whole-genome workload need their
+// probe line at all, so probing lane by lane would leave two thirds of the lanes idle through the whole probe
+// sequence (the kernel is bound by instruction issue, profiles/round1_k1_v5.md).  The k-mers that need a line are
+// therefore COMPACTED: they go into a 64-entry ring in shared memory ({canonical k-mer | line, index, count, bit}),
+// and whenever the ring holds 32 entries the warp runs one FULL probe round:
+//   * the 32 probe lines are copied into the warp's 4 KB tile with cp.async (LDGSTS, no register staging): eight
+//     unrolled rounds, in each the four 8-lane groups move one line each, lane j of a group moving uint4 j -- a line
+//     costs exactly one fully coalesced 128-byte request and all 32 are in flight together.  The tile is XOR-swizzled
+//     (uint4 j of row L sits at column j ^ (L & 7)) so that every lane then reads ITS row with conflict-free 16-byte
+//     shared loads;
+//   * the lane tests its filter bit and compares the five key slots;
+//   * a key hit adds the count into the slot itself (the line was fetched a moment ago: the RED lands in L2);
+//   * a filter hit needs a second XXH3 (the 43-mer, for the context filter): the scan only records it --
+//     {context k-mer, address of the bit's counter, count} -- and k_scan_hits works all of them off afterwards.
+// (A bulk copy -- cp.async.bulk + mbarrier, one per line -- was considered for the line gather and rejected: UBLKCP
+// takes its addresses from uniform registers, so 32 different lines cost 32 serialised issues per round against the
+// 8 LDGSTS of this scheme; profiles/round2_k1.md.)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -384,10 +475,18 @@ __device__ __forceinline__ uint64_t canon_hash_lut(u128 x, u128 *canon, const ui
   *canon = c;
   return xxh3_64_words(w, K);
 }
+__device__ __forceinline__ u128 canon_only(u128 x, int k) {
+  u128 rc = revcomp(x, k);
+  return less128(x, rc) ? x : rc;
+}
 
 constexpr int SCAN_THREADS = 256;
-// per warp: a 4 KB tile + 32 row indices; per CTA: the 1 KB expansion table
-constexpr int SCAN_SMEM = (SCAN_THREADS / 32) * (32 * 128 + 32 * 4 + 4) + 256 * 4;  // (+ a hit counter per warp)
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_Q = 64;                        // ring entries per warp
+constexpr int SCAN_WARP_U4 = 256 + 2 * SCAN_Q;    // per warp: 4 KB tile + ring keys + ring meta (uint4 units)
+// + the 1 KB expansion table and a deferred-hit counter per warp
+constexpr int SCAN_SMEM = SCAN_WARPS * SCAN_WARP_U4 * 16 + 256 * 4 + SCAN_WARPS * 4;
+constexpr int SCAN_MIN_CTAS = 4;
 
 // Where the sample k-mers come from.  MODE 0: packed {lo,hi} words + u32 counts.  MODE 1: raw records of a
 // KMC database suffix file (.kmc_suf): (ref_k - p)/4 suffix bytes (2-bit codes, first base most significant)
@@ -404,11 +503,9 @@ struct ScanSrc {
   int prefix_len, suf_bytes, counter_size;
   uint32_t min_count;
   uint64_t max_count;
-  // Deferred filter hits.  A k-mer whose bf bit is set needs a second XXH3 (the 43-mer, for the context filter): rare
-  // per k-mer (~0.7 %) but not per warp (one iteration in five), and while one lane runs it 31 idle.  The scan
-  // therefore only records the hit -- {context k-mer, bf index, count}, 32 bytes, in the warp's own segment of
-  // hit_buf -- and k_scan_hits works all of them off afterwards with full warps.  A full segment falls back to the
-  // in-line path.  hit_buf == nullptr: always in line.
+  // Deferred filter hits: {context k-mer, counter address, count}, 32 bytes each, in the warp's own segment of
+  // hit_buf; k_scan_hits finishes them.  A full segment falls back to the in-line path.  hit_buf == nullptr:
+  // always in line.
   uint4 *hit_buf;
   uint32_t *hit_counts;  // per warp of the scan grid
   uint32_t seg_cap;      // entries per warp segment
@@ -427,16 +524,16 @@ __device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_l
 }
 
 template <int K, int REFK, int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t n, DevView v) {
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan(ScanSrc src, uint64_t n, DevView v) {
   extern __shared__ uint4 scan_sm[];
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
-  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-  uint4 *tile = scan_sm + (threadIdx.x >> 5) * 256;  // 32 lines x 8 uint4
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
+  uint4 *tile = scan_sm + wid * SCAN_WARP_U4;  // 32 rows x 8 uint4
+  uint4 *qkey = tile + 256, *qmeta = qkey + SCAN_Q;
   const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
-  uint32_t *rows = reinterpret_cast<uint32_t *>(scan_sm + (SCAN_THREADS / 32) * 256) + (threadIdx.x >> 5) * 32;
-  uint32_t *tab = reinterpret_cast<uint32_t *>(scan_sm + (SCAN_THREADS / 32) * 256) + (SCAN_THREADS / 32) * 32;
-  uint32_t *hitc = tab + 256 + (threadIdx.x >> 5);  // this warp's deferred-hit counter
+  uint32_t *tab = reinterpret_cast<uint32_t *>(scan_sm + SCAN_WARPS * SCAN_WARP_U4);
+  uint32_t *hitc = tab + 256 + wid;  // this warp's deferred-hit counter
   if (lane == 0) *hitc = 0;
   if constexpr (K > 0) {
     static_assert(SCAN_THREADS == 256, "one table entry per thread");
@@ -445,149 +542,179 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t 
   } else {
     __syncwarp();
   }
+  const bool inl = K > 0 ? (K <= INLINE_MAX_K) : (v.inline_counts != 0);
+  const uint32_t mz = inl ? 0x7FFFFFFFu : 0xFFFFFFFFu, mw = inl ? 0u : 0x3FFFFFFFu;  // key bits of slot words 2, 3
   const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  // 32-bit indices: the host never launches more than 2^31 k-mers at once
+  // 32-bit indices: the host never launches more than 2^30 k-mers at once
   const uint32_t n32 = (uint32_t)n;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t step = ((gridDim.x * blockDim.x) >> 5) * 32;
-  for (uint32_t base = warp * 32; base < n32; base += step) {
-    const uint32_t i = base + lane;
-    bool live = i < n32;
-    uint32_t cnt;
-    u128 x43, canon;
-    if constexpr (MODE == 0) {
-      uint4 q = live ? __ldg(src.kmers + i) : make_uint4(0, 0, 0, 0);
-      cnt = live ? __ldg(src.counts + i) : 0u;
-      x43.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
-      x43.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
-    } else {
-      // stage the warp's 32 records (contiguous bytes) in its shared-memory tile, then decode one per lane
-      const int rec = src.suf_bytes + src.counter_size;
-      const uint64_t byte0 = (uint64_t)base * (uint64_t)rec, start = byte0 & ~3ull;
-      const int n_words = (int)((byte0 - start) + 32u * (uint32_t)rec + 3u) >> 2;
-      __syncwarp();
-      uint32_t *stage = reinterpret_cast<uint32_t *>(tile);
-      for (int w = lane; w < n_words; w += 32) stage[w] = __ldg(reinterpret_cast<const uint32_t *>(src.recs + start) + w);
-      __syncwarp();
-      const uint8_t *rb = reinterpret_cast<const uint8_t *>(stage) + (byte0 - start) + (uint32_t)lane * (uint32_t)rec;
-      u128 suf = {0, 0};
-      for (int j = 0; j < src.suf_bytes; ++j) {
-        suf.hi = (suf.hi << 8) | (suf.lo >> 56);
-        suf.lo = (suf.lo << 8) | rb[j];
-      }
-      uint64_t c64 = src.counter_size ? 0 : 1;
-      for (int j = 0; j < src.counter_size; ++j) c64 |= (uint64_t)rb[src.suf_bytes + j] << (8 * j);
-      __syncwarp();  // the tile is reused for the probe lines below
-      // prefix of each record: one LUT search per warp in the common case (a prefix bucket spans many records)
-      const uint64_t g = src.first_rec + i;
-      const uint64_t g_first = src.first_rec + base;
-      const uint64_t g_last = src.first_rec + (base + 31 < n32 ? base + 31 : n32 - 1);
-      uint32_t pj = lut_bucket(src.lut, src.n_lut, g_first);
-      if (__ldg(src.lut + pj + 1) <= g_last) pj = lut_bucket(src.lut, src.n_lut, live ? g : g_first);
-      u128 pre = {(uint64_t)(pj & src.prefix_mask), 0};
-      const int sh = 8 * src.suf_bytes;  // the suffix holds 4 * suf_bytes symbols
-      if (sh >= 64) {
-        pre.hi = pre.lo << (sh - 64);
-        pre.lo = 0;
+  // destination of this lane's 16-byte piece within rows grp (even rounds) and grp + 4 (odd rounds) of a round
+  const uint32_t d_even = tile_addr + (uint32_t)(grp * 128 + ((sub ^ grp) * 16));
+  const uint32_t d_odd = tile_addr + (uint32_t)(grp * 128 + ((sub ^ (grp + 4)) * 16));
+  const char *line_src = reinterpret_cast<const char *>(v.lines) + sub * 16;
+  uint32_t qhead = 0, qn = 0;  // ring state (warp-uniform); qhead is 0 or 32
+  bool more = true;
+  for (uint32_t base = warp_id * 32;; base += step) {
+    more = more && base < n32;
+    if (more) {
+      const uint32_t i = base + lane;
+      bool live = i < n32;
+      uint32_t cnt;
+      u128 x43, canon;
+      if constexpr (MODE == 0) {
+        x43 = u128_of(live ? __ldg(src.kmers + i) : make_uint4(0, 0, 0, 0));
+        cnt = live ? __ldg(src.counts + i) : 0u;
+        // the warp's next batch (512 B of k-mers + 128 B of counts) into L2 while this one is hashed
+        if (lane < 5 && base + step < n32) {
+          const char *pf = lane < 4 ? reinterpret_cast<const char *>(src.kmers + base + step) + lane * 128
+                                    : reinterpret_cast<const char *>(src.counts + base + step);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
       } else {
-        pre.hi = sh ? (pre.lo >> (64 - sh)) : 0;
-        pre.lo <<= sh;
+        // stage the warp's 32 records (contiguous bytes) in its shared-memory tile, then decode one per lane
+        const int rec = src.suf_bytes + src.counter_size;
+        const uint64_t byte0 = (uint64_t)base * (uint64_t)rec, start = byte0 & ~3ull;
+        const int n_words = (int)((byte0 - start) + 32u * (uint32_t)rec + 3u) >> 2;
+        __syncwarp();  // the previous probe round's reads of the tile are done
+        uint32_t *stage = reinterpret_cast<uint32_t *>(tile);
+        for (int w = lane; w < n_words; w += 32) stage[w] = __ldg(reinterpret_cast<const uint32_t *>(src.recs + start) + w);
+        __syncwarp();
+        const uint8_t *rb = reinterpret_cast<const uint8_t *>(stage) + (byte0 - start) + (uint32_t)lane * (uint32_t)rec;
+        u128 suf = {0, 0};
+        for (int j = 0; j < src.suf_bytes; ++j) {
+          suf.hi = (suf.hi << 8) | (suf.lo >> 56);
+          suf.lo = (suf.lo << 8) | rb[j];
+        }
+        uint64_t c64 = src.counter_size ? 0 : 1;
+        for (int j = 0; j < src.counter_size; ++j) c64 |= (uint64_t)rb[src.suf_bytes + j] << (8 * j);
+        __syncwarp();  // the tile is reused for the probe lines below
+        // prefix of each record: one LUT search per warp in the common case (a prefix bucket spans many records)
+        const uint64_t g = src.first_rec + i;
+        const uint64_t g_first = src.first_rec + base;
+        const uint64_t g_last = src.first_rec + (base + 31 < n32 ? base + 31 : n32 - 1);
+        uint32_t pj = lut_bucket(src.lut, src.n_lut, g_first);
+        if (__ldg(src.lut + pj + 1) <= g_last) pj = lut_bucket(src.lut, src.n_lut, live ? g : g_first);
+        u128 pre = {(uint64_t)(pj & src.prefix_mask), 0};
+        const int sh = 8 * src.suf_bytes;  // the suffix holds 4 * suf_bytes symbols
+        if (sh >= 64) {
+          pre.hi = pre.lo << (sh - 64);
+          pre.lo = 0;
+        } else {
+          pre.hi = sh ? (pre.lo >> (64 - sh)) : 0;
+          pre.lo <<= sh;
+        }
+        x43.lo = pre.lo | suf.lo;
+        x43.hi = pre.hi | suf.hi;
+        // CKMCFile::ReadNextKmer skips records whose count is outside [min_count, max_count]
+        if (c64 < src.min_count || c64 > src.max_count) live = false;
+        cnt = (uint32_t)c64;
       }
-      x43.lo = pre.lo | suf.lo;
-      x43.hi = pre.hi | suf.hi;
-      // CKMCFile::ReadNextKmer skips records whose count is outside [min_count, max_count]
-      if (c64 < src.min_count || c64 > src.max_count) live = false;
-      cnt = (uint32_t)c64;
-    }
-    u128 x35 = mask128(shr128(x43, 2 * tail), 2 * k);
-    uint64_t h;
-    if constexpr (K > 0)
-      h = canon_hash_lut<K>(x35, &canon, tab);
-    else
-      h = canon_hash_rt(x35, k, &canon);
-    uint64_t idx = bf_index(v, h);
-    uint32_t line = (uint32_t)(idx >> 8);  // n_lines < 2^32 (bf_bits < 2^40)
-    uint32_t bit = (uint32_t)(idx & 255);
-    // occupancy pre-filter (L2): most probe lines hold nothing for a given k-mer; those are never fetched
-    const bool need = live && occ_test(v, idx);
-    const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
-    const int n_need = __popc(need_mask);
-    const int rank = __popc(need_mask & ((1u << lane) - 1u));  // row of this lane's line in the tile
-    __syncwarp();  // the previous iteration's reads of the tile and of the row list are done
-    if (need) rows[rank] = line;
-    __syncwarp();
-    {
-      // row L = grp, grp + 4, ...: uint4 `sub` of line rows[L] goes to column sub ^ (L & 7) of tile row L.  L & 7
-      // alternates between grp and grp + 4, i.e. the column toggles bit 2 from one round to the next.
-      uint32_t dst = tile_addr + (uint32_t)(grp * 128 + ((sub ^ grp) * 16));
-      int toggle = ((sub ^ grp) & 4) ? -64 : 64;
-      const uint32_t *rp = rows + grp;
-      const char *src0 = reinterpret_cast<const char *>(v.lines) + sub * 16;
-#pragma unroll 1
-      for (int L = grp; L < n_need; L += 4) {
-        cp_async16(dst, src0 + (uint64_t)(*rp) * 128);
-        rp += 4;
-        dst += 512 + toggle;
-        toggle = -toggle;
+      u128 x35 = mask128(shr128(x43, 2 * tail), 2 * k);
+      uint64_t h;
+      if constexpr (K > 0)
+        h = canon_hash_lut<K>(x35, &canon, tab);
+      else
+        h = canon_hash_rt(x35, k, &canon);
+      const uint64_t idx = bf_index(v, h);
+      // occupancy pre-filter (L2): most probe lines hold nothing for a given k-mer; those are never fetched
+      const bool need = live && occ_test(v, idx);
+      const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
+      if (need) {
+        const uint32_t e = (qhead + qn + (uint32_t)__popc(need_mask & ((1u << lane) - 1u))) & (SCAN_Q - 1);
+        qkey[e] = uint4_of(MODE == 0 ? canon : x43);
+        qmeta[e] = make_uint4((uint32_t)(idx >> 8), i, cnt, (uint32_t)(idx & 255));  // n_lines < 2^32 (bf_bits < 2^40)
       }
+      qn += (uint32_t)__popc(need_mask);
     }
-    if constexpr (MODE == 0) {
-      // while the lines are in flight: the warp's next batch (512 B of k-mers + 128 B of counts) into L2
-      if (lane < 5 && base + step < n32) {
-        const char *pf = lane < 4 ? reinterpret_cast<const char *>(src.kmers + base + step) + lane * 128
-                                  : reinterpret_cast<const char *>(src.counts + base + step);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-      }
-    }
-    cp_async_wait_all();
-    __syncwarp();
-    if (!need) continue;
-    // ---- every needing lane now owns row `rank` of the tile ----
-    const uint4 *mine = tile + rank * 8;
-    const int sw = rank & 7;
-    uint32_t wsel = bit >> 5;  // which of the 8 filter words
-    uint32_t fw = reinterpret_cast<const uint32_t *>(mine + ((wsel >> 2) ^ sw))[wsel & 3];
-    bool bf_hit = (fw >> (bit & 31u)) & 1u;
-    const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
-                   c3 = (uint32_t)(canon.hi >> 32);
-    // the low word of each key slot first (one 4-byte shared load per slot); the other three words only of the
-    // slots where it matches (a ref-key hit, ~3 % of the k-mers, or a 2^-32 coincidence)
-    uint32_t low_match = 0;  // bit s: the low word of slot s equals the k-mer's
+    if (qn >= 32 || (!more && qn)) {
+      // ---- one probe round over ring entries qhead .. qhead + n_probe - 1 ----
+      const uint32_t n_probe = qn < 32 ? qn : 32;
+      __syncwarp();  // the ring entries are visible; the previous round's reads of the tile are done
+      const uint4 kq = qkey[qhead + lane], mq = qmeta[qhead + lane];
+      {
+        const uint32_t *qline = reinterpret_cast<const uint32_t *>(qmeta + qhead + grp);  // .x of entry qhead + grp + 4r
+        uint32_t lid[8];
 #pragma unroll
-    for (int s = 0; s < LINE_KEYS; ++s)
-      low_match |= (uint32_t)(reinterpret_cast<const uint32_t *>(mine + ((2 + s) ^ sw))[0] == c0) << s;
-    int slot = -1;
-    while (low_match) {  // (some lane of the warp gets here in most iterations: keep it to the matching slot)
-      const int s = __ffs(low_match) - 1;
-      low_match &= low_match - 1;
-      uint4 p = mine[(2 + s) ^ sw];
-      if (((p.y ^ c1) | (p.z ^ c2) | ((p.w & (uint32_t)(KEY_HI_MASK >> 32)) ^ c3)) == 0) slot = s;
-    }
-    const uint32_t last_w = reinterpret_cast<const uint32_t *>(mine + ((2 + LINE_KEYS - 1) ^ sw))[3];
-    // ---- ref_bf.increment ----
-    if (slot >= 0) {
-      atomicAdd(v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot, cnt);
-    } else if (last_w & OVF_FLAG_W) {  // line overflowed at index time: the key may live in the overflow array
-      const int64_t os = ovf_find(v, h, canon);
-      if (os >= 0) atomicAdd(v.ovf_counts + os, cnt);
-    }
-    // ---- bf.increment unless the context filter vetoes it ----
-    if (bf_hit) {
-      const uint32_t pos = src.hit_buf ? atomicAdd(hitc, 1u) : 0xFFFFFFFFu;
-      if (pos < src.seg_cap) {  // recorded; k_scan_hits finishes it
-        uint4 *e = src.hit_buf + ((uint64_t)warp_id * src.seg_cap + pos) * 2;
-        e[0] = make_uint4((uint32_t)x43.lo, (uint32_t)(x43.lo >> 32), (uint32_t)x43.hi, (uint32_t)(x43.hi >> 32));
-        e[1] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), cnt, 0u);
-      } else {
-        u128 c43;
-        uint64_t h43;
-        if constexpr (REFK > 0)
-          h43 = canon_hash_lut<REFK>(x43, &c43, tab);
-        else
-          h43 = canon_hash_rt(x43, ref_k, &c43);
-        if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + bf_rank_of(v, idx), cnt);
+        for (int r = 0; r < 8; ++r) lid[r] = qline[r * 16];  // (stale entries past n_probe are read but never used)
+        if (n_probe == 32) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            cp_async16(((r & 1) ? d_odd : d_even) + (uint32_t)(r * 512), line_src + ((uint64_t)lid[r] << 7));
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if ((uint32_t)(4 * r + grp) < n_probe)
+              cp_async16(((r & 1) ? d_odd : d_even) + (uint32_t)(r * 512), line_src + ((uint64_t)lid[r] << 7));
+        }
       }
+      cp_async_wait_all();
+      __syncwarp();
+      if ((uint32_t)lane < n_probe) {
+        // ---- this lane owns row `lane` of the tile ----
+        const uint32_t line = mq.x, cnt = mq.z, bit = mq.w;
+        u128 canon, x43;
+        if constexpr (MODE == 0) {
+          canon = u128_of(kq);
+        } else {
+          x43 = u128_of(kq);
+          canon = canon_only(mask128(shr128(x43, 2 * tail), 2 * k), k);
+        }
+        const uint4 *mine = tile + lane * 8;
+        const int sw = lane & 7;
+        const uint32_t fw = reinterpret_cast<const uint32_t *>(mine + ((bit >> 7) ^ sw))[(bit >> 5) & 3];
+        const bool bf_hit = (fw >> (bit & 31u)) & 1u;
+        const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
+                       c3 = (uint32_t)(canon.hi >> 32);
+        int slot = -1;
+        uint32_t flag_w = 0;
+#pragma unroll
+        for (int s = 0; s < LINE_KEYS; ++s) {
+          const uint4 p = mine[(2 + s) ^ sw];
+          if (((p.x ^ c0) | (p.y ^ c1) | ((p.z ^ c2) & mz) | ((p.w ^ c3) & mw)) == 0) slot = s;
+          if (s == LINE_KEYS - 1) flag_w = inl ? p.z : p.w;
+        }
+        // ---- ref_bf.increment ----
+        if (slot >= 0) {
+          uint32_t *cp = inl ? line_words(v, line) + 8 + 4 * slot + 3 : v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot;
+          atomicAdd(cp, cnt);
+        } else if (flag_w >> 31) {  // line overflowed at index time: the key may live in the overflow table
+          const int64_t os = ovf_find(v, canon);
+          if (os >= 0) atomicAdd(v.ovf_counts + os, cnt);
+        }
+        // ---- bf.increment unless the context filter vetoes it ----
+        if (bf_hit) {
+          // counter of the bit: number j of the set bit inside the line, rank of the line
+          const uint32_t ws = bit >> 5, below = (1u << (bit & 31u)) - 1u;
+          const uint4 b0 = mine[0 ^ sw], b1 = mine[1 ^ sw];
+          const uint32_t wx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          int j = 0;
+#pragma unroll
+          for (uint32_t x = 0; x < 8; ++x) j += __popc(wx[x] & (x < ws ? 0xFFFFFFFFu : (x == ws ? below : 0u)));
+          const uint32_t rank = reinterpret_cast<const uint32_t *>(mine + (7 ^ sw))[0];
+          uint32_t *ap = j < LINE_INLINE_ALT ? line_words(v, line) + LINE_W_RANK + 1 + j
+                                             : v.bf_counts + (uint64_t)rank + (uint64_t)j;
+          if constexpr (MODE == 0) x43 = u128_of(__ldg(src.kmers + mq.y));
+          const uint32_t pos = src.hit_buf ? atomicAdd(hitc, 1u) : 0xFFFFFFFFu;
+          if (pos < src.seg_cap) {  // recorded; k_scan_hits finishes it
+            uint4 *e = src.hit_buf + ((uint64_t)warp_id * src.seg_cap + pos) * 2;
+            const uint64_t a64 = reinterpret_cast<uint64_t>(ap);
+            e[0] = uint4_of(x43);
+            e[1] = make_uint4((uint32_t)a64, (uint32_t)(a64 >> 32), cnt, 0u);
+          } else {
+            u128 c43;
+            uint64_t h43;
+            if constexpr (REFK > 0)
+              h43 = canon_hash_lut<REFK>(x43, &c43, tab);
+            else
+              h43 = canon_hash_rt(x43, ref_k, &c43);
+            if (!ctx_test(v, bf_index(v, h43))) atomicAdd(ap, cnt);
+          }
+        }
+      }
+      qhead = (qhead + 32) & (SCAN_Q - 1);
+      qn -= n_probe;
     }
+    if (!more && qn == 0) break;
   }
   if (src.hit_buf) {
     __syncwarp();
@@ -595,7 +722,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 5) k_scan(ScanSrc src, uint64_t 
   }
 }
 
-// second half of the scan for the recorded filter hits: 43-mer hash -> context filter -> rank -> counter
+// second half of the scan for the recorded filter hits: 43-mer hash -> context filter -> counter
 template <int REFK>
 __global__ void __launch_bounds__(256) k_scan_hits(const uint4 *__restrict__ hit_buf, const uint32_t *__restrict__ hit_counts,
                                                   uint32_t n_warps, uint32_t seg_cap, DevView v) {
@@ -606,20 +733,30 @@ __global__ void __launch_bounds__(256) k_scan_hits(const uint4 *__restrict__ hit
   const uint32_t w = (uint32_t)(t / seg_cap), slot = (uint32_t)(t % seg_cap);
   if (w >= n_warps || slot >= __ldg(hit_counts + w)) return;
   const uint4 a = __ldg(hit_buf + t * 2), b = __ldg(hit_buf + t * 2 + 1);
-  u128 x43 = {(uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32)}, c43;
-  const uint64_t idx = (uint64_t)b.x | ((uint64_t)b.y << 32);
-  const uint32_t r = bf_rank_of(v, idx);  // (independent of the hash: these loads overlap with it)
+  u128 x43 = u128_of(a), c43;
+  uint32_t *ap = reinterpret_cast<uint32_t *>((uint64_t)b.x | ((uint64_t)b.y << 32));
   uint64_t h43;
   if constexpr (REFK > 0)
     h43 = canon_hash_lut<REFK>(x43, &c43, tab);
   else
     h43 = canon_hash_rt(x43, v.ref_k, &c43);
-  if (!ctx_test(v, bf_index(v, h43))) atomicAdd(v.bf_counts + r, b.z);
+  if (!ctx_test(v, bf_index(v, h43))) atomicAdd(ap, b.z);
 }
 
 // ---------------------------------------------------------------------------
-// K4: signature look-ups (BF::get_count / KMAP::get_count) + coverage
+// K4: signature look-ups (BF::get_count / KMAP::get_count) + coverage.  One probe line per look-up: the count of a
+// ref key is in its slot, the counter of an alt bit in words 29..31 of the line (index.cuh).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ int32_t alt_get_count(const DevView &v, uint64_t idx) {  // BF::get_count (u16)
+  if (!v.bf_counts) return 0;  // write mode: no counters yet (bloom_filter.hpp:115-125)
+  const uint32_t *p = alt_counter_ptr(v, idx);
+  return p ? (int32_t)(*p & 0xFFFFu) : 0;
+}
+__device__ __forceinline__ int32_t ref_get_count(const DevView &v, uint64_t idx, u128 canon) {  // KMAP::get_count
+  const uint32_t *p = key_count_ptr(v, idx, canon);
+  return p ? (int32_t)*p : 0;
+}
+
 // flags the k-mers of allele slot 0 of every variant (they are looked up in ref_bf, main.cpp:167-170)
 __global__ void __launch_bounds__(256) k_mark_ref(const uint64_t *__restrict__ var_allele_off,
                                                  const uint64_t *__restrict__ allele_sig_off,
@@ -635,47 +772,50 @@ __global__ void __launch_bounds__(256) k_mark_ref(const uint64_t *__restrict__ v
 
 // mode 0: get_count  (is_ref selects KMAP/BF, out = int32 count)
 // mode 1: test_key on filter/table `which` (0 bf, 1 context_bf, 2 ref_bf; out = 0/1, -1 = irregular KMAP key)
+// out_pos != nullptr: k-mer i is written to out[out_pos[i]] and its is_ref flag is bit 62 of packed[out_pos[i]].hi
+// (the irregular k-mers of a packed batch)
 __global__ void __launch_bounds__(128) k_lookup(const uint8_t *__restrict__ pool, const uint64_t *__restrict__ off,
                                                const uint8_t *__restrict__ is_ref, uint64_t n, DevView v, int mode,
                                                int which, int32_t *__restrict__ out, unsigned long long *scalars,
-                                               const uint8_t *__restrict__ only_flagged) {
+                                               const uint8_t *__restrict__ only_flagged,
+                                               const uint32_t *__restrict__ out_pos, const uint4 *__restrict__ packed) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (only_flagged && !only_flagged[i]) return;  // second pass after k_lookup_fast: the k-mers it deferred
+  const uint64_t o = out_pos ? (uint64_t)out_pos[i] : i;
   uint64_t b = off[i], e = off[i + 1];
   int len = (int)(e - b);
   if (len > 128) {
     atomicExch(&scalars[3], 1ull);
-    out[i] = 0;
+    out[o] = 0;
     return;
   }
   uint8_t s[128];
   for (int j = 0; j < len; ++j) s[j] = pool[b + j];
-  bool use_table = mode == 0 ? (is_ref[i] != 0) : (which == 2);
+  const bool ref_flag = out_pos ? ((packed[o].w >> 30) & 1u) != 0 : (is_ref && is_ref[i] != 0);
+  bool use_table = mode == 0 ? ref_flag : (which == 2);
   u128 x, canon;
   if (use_table) {
     if (!pack_ascii(s, len, v.k, &x)) {
-      out[i] = (mode == 1) ? -1 : 0;  // irregular keys are resolved on the host (always count 0)
+      out[o] = (mode == 1) ? -1 : 0;  // irregular keys are resolved on the host (always count 0)
       return;
     }
     uint64_t h = canon_hash_rt(x, v.k, &canon);
-    int64_t loc = key_locate(v, h, bf_index(v, h), canon);
+    const uint32_t *cp = key_count_ptr(v, bf_index(v, h), canon);
     if (mode == 1)
-      out[i] = loc != -1;
+      out[o] = cp != nullptr;
     else
-      out[i] = loc != -1 ? (int32_t)*count_ptr(v, loc) : 0;
+      out[o] = cp ? (int32_t)*cp : 0;
     return;
   }
   // a Bloom filter: hash the canonical ASCII bytes of whatever length was given
   bool regular = len >= 1 && len <= 64 && pack_ascii(s, len, len, &x);
   uint64_t h = regular ? canon_hash_rt(x, len, &canon) : hash_ascii(s, len);
   uint64_t idx = bf_index(v, h);
-  bool set = (mode == 1 && which == 1) ? ctx_test(v, idx) : bf_test(v, idx);
-  if (mode == 1) {
-    out[i] = set;
-  } else {
-    out[i] = (set && v.rank) ? (int32_t)(v.bf_counts[bf_rank_of(v, idx)] & 0xFFFFu) : 0;
-  }
+  if (mode == 1)
+    out[o] = which == 1 ? ctx_test(v, idx) : bf_test(v, idx);
+  else
+    out[o] = alt_get_count(v, idx);
 }
 
 // Fast path of mode 0 for the compiled k: signature k-mers that are exactly K bytes long are read as aligned
@@ -712,18 +852,32 @@ __global__ void __launch_bounds__(128) k_lookup_fast(const uint8_t *__restrict__
   u128 canon;
   uint64_t h = canon_hash<K>(x, &canon);
   uint64_t idx = bf_index(v, h);
-  if (is_ref[i]) {
-    int64_t loc = key_locate(v, h, idx, canon);
-    out[i] = loc != -1 ? (int32_t)*count_ptr(v, loc) : 0;
-  } else {
-    out[i] = (bf_test(v, idx) && v.rank) ? (int32_t)(v.bf_counts[bf_rank_of(v, idx)] & 0xFFFFu) : 0;
-  }
+  out[i] = is_ref[i] ? ref_get_count(v, idx, canon) : alt_get_count(v, idx);
+}
+
+// Packed signature k-mers (exactly k symbols of ACGT, the form the host enumerator emits): {lo, hi} words;
+// hi bit 62 = k-mer of allele slot 0 (looked up in ref_bf), hi bit 63 = irregular (not k x ACGT: resolved by k_lookup
+// from the side pool).  16 bytes in, 4 bytes out, one probe line per k-mer.
+template <int K>
+__global__ void __launch_bounds__(128) k_lookup_packed(const uint4 *__restrict__ kmers, uint64_t n, DevView v,
+                                                      int32_t *__restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 q = __ldg(kmers + i);
+  if (q.w >> 31) return;  // irregular
+  const bool is_ref = (q.w >> 30) & 1u;
+  const int k = K > 0 ? K : v.k;
+  u128 x = mask128(u128_of(q), 2 * k), canon;
+  const uint64_t h = canon_hash_k<K>(x, k, &canon);
+  const uint64_t idx = bf_index(v, h);
+  out[i] = is_ref ? ref_get_count(v, idx, canon) : alt_get_count(v, idx);
 }
 
 // set_coverages (main.cpp:157-182): per allele slot, max over signatures of the order-dependent integer
 // running mean of the non-zero k-mer weights
-__global__ void __launch_bounds__(128) k_coverage(const int32_t *__restrict__ w, const uint64_t *__restrict__ sig_kmer_off,
-                                                 const uint64_t *__restrict__ allele_sig_off, uint64_t n_alleles,
+template <typename OFF>
+__global__ void __launch_bounds__(128) k_coverage(const int32_t *__restrict__ w, const OFF *__restrict__ sig_kmer_off,
+                                                 const OFF *__restrict__ allele_sig_off, uint64_t n_alleles,
                                                  uint32_t *__restrict__ cov) {
   uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_alleles) return;
@@ -799,18 +953,29 @@ MG_HD int genotype_one(const uint32_t *cov, const float *freq, int n, float err,
   return ng;
 }
 
+// lik_off != nullptr: the likelihoods of variant vi go to lik[lik_off[vi] ..] (the caller reads them back);
+// lik_off == nullptr: nobody reads them, the slots are bump-allocated from `cursor` (scratch)
+template <typename OFF>
 __global__ void __launch_bounds__(128) k_genotype(const uint32_t *__restrict__ cov, const float *__restrict__ freq,
-                                                 const uint64_t *__restrict__ var_allele_off,
-                                                 const uint64_t *__restrict__ lik_off, uint64_t n_variants, float err,
-                                                 int max_cov, int haploid, double *__restrict__ lik,
-                                                 int32_t *__restrict__ n_gts, int32_t *__restrict__ status,
-                                                 int32_t *__restrict__ best_gt, int32_t *__restrict__ gq) {
+                                                 const OFF *__restrict__ var_allele_off,
+                                                 const uint64_t *__restrict__ lik_off, unsigned long long *cursor,
+                                                 uint64_t n_variants, float err, int max_cov, int haploid,
+                                                 double *__restrict__ lik, int32_t *__restrict__ n_gts,
+                                                 int32_t *__restrict__ status, int32_t *__restrict__ best_gt,
+                                                 int32_t *__restrict__ gq) {
   uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (vi >= n_variants) return;
   uint64_t a0 = var_allele_off[vi];
   int n = (int)(var_allele_off[vi + 1] - a0);
+  uint64_t lo;
+  if (lik_off) {
+    lo = lik_off[vi];
+  } else {
+    const unsigned long long slots = (unsigned long long)(haploid ? n : n * (n + 1) / 2);
+    lo = atomicAdd(cursor, slots > (unsigned long long)n ? slots : (unsigned long long)n);
+  }
   int st, bg, q;
-  int ng = genotype_one(cov + a0, freq + a0, n, err, max_cov, haploid != 0, lik + lik_off[vi], &st, &bg, &q);
+  int ng = genotype_one(cov + a0, freq + a0, n, err, max_cov, haploid != 0, lik + lo, &st, &bg, &q);
   n_gts[vi] = ng;
   status[vi] = st;
   best_gt[vi] = bg;
@@ -848,36 +1013,23 @@ __global__ void __launch_bounds__(256) k_set_bits(const uint64_t *__restrict__ i
   uint32_t *w = as_lines ? words_rw + (b >> 8) * 32 + ((b & 255) >> 5) : words_rw + (b >> 5);
   atomicOr(w, 1u << (b & 31));
 }
-// every non-empty key slot of the probe lines (n_slots = 6 * n_lines) or of the overflow table
-__global__ void __launch_bounds__(256) k_emit_keys(const uint4 *__restrict__ lines, uint64_t n_lines,
-                                                  const u128 *__restrict__ ovf_keys, uint64_t ovf_cap,
-                                                  unsigned long long *counter, u128 *__restrict__ out, uint64_t cap) {
+// every non-empty key slot of the probe lines (n_slots = 5 * n_lines) or of the overflow table
+__global__ void __launch_bounds__(256) k_emit_keys(DevView v, uint64_t ovf_cap, unsigned long long *counter,
+                                                  u128 *__restrict__ out, uint64_t cap) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t n_slots = n_lines * LINE_KEYS;
+  uint64_t n_slots = v.n_lines * LINE_KEYS;
   u128 key;
   if (i < n_slots) {
-    key = key_of(lines[(i / LINE_KEYS) * LINE_U4 + 2 + (i % LINE_KEYS)]);
+    key = key_of(v, v.lines[(i / LINE_KEYS) * LINE_U4 + 2 + (i % LINE_KEYS)]);
   } else if (i < n_slots + ovf_cap) {
-    key = ovf_keys[i - n_slots];
-    key.hi &= KEY_HI_MASK;
+    key = v.ovf_keys[i - n_slots];
+    key.hi &= v.key_hi_mask;
   } else {
     return;
   }
-  if (key_empty(key)) return;
+  if (key_empty(v, key)) return;
   unsigned long long o = atomicAdd(counter, 1ull);
   if (o < cap) out[o] = key;
-}
-
-// dst[i] += src[i] (u32, wrap-around): the counter reduce of replicated contexts (mg_reduce_counts)
-__global__ void __launch_bounds__(256) k_add_u32(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint64_t n) {
-  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i + 3 < n) {
-    uint4 a = *reinterpret_cast<const uint4 *>(dst + i), b = *reinterpret_cast<const uint4 *>(src + i);
-    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
-    *reinterpret_cast<uint4 *>(dst + i) = a;
-  } else {
-    for (; i < n; ++i) dst[i] += src[i];
-  }
 }
 
 // ---------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 // libmalva_gpu.so -- the C ABI of include/malva_gpu.h over the hand-written sm_100a kernels of
-// kernels.cuh.  Device data layout: index.cuh (128-byte probe lines = filter bits + ref-key slots,
-// rank directory, u32 counters, overflow table, context filter).
+// kernels.cuh.  Device data layout: index.cuh (128-byte probe lines = filter bits + ref-key slots with their
+// counts + rank + alt counters, overflow table, context filter).
 // There is no CPU fallback anywhere: every entry point fails with MG_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -76,16 +77,23 @@ struct mg_ctx {
   uint32_t *occ = nullptr;         // occupancy pre-filter (index.cuh), one bit per 2^occ_shift bf indices
   uint64_t n_occ_words = 0;
   int occ_shift = 0;
-  uint32_t *rank = nullptr;        // n_lines + 1
-  uint32_t *bf_counts = nullptr;   // one per set bit of bf
-  uint32_t *key_counts = nullptr;  // n_lines x 6
+  uint32_t *bf_counts = nullptr;   // one per set bit of bf (dense image; live for set bits 3.. of a line)
+  uint32_t *key_counts = nullptr;  // n_lines x 5, wide layout (k >= 48) only
+  uint32_t *key_rank = nullptr;    // keys held by the lines before line L (built by the first mg_counters_gather)
+  uint32_t *key_dense = nullptr;   // dense image of the in-line key counts (n_keys - ovf_n entries)
   u128 *ovf_keys = nullptr;
   uint32_t *ovf_counts = nullptr;
   int ovf_log2 = 0;
   uint64_t ovf_n = 0;  // keys in the overflow table
-  bool ovf_sorted = false;  // after mg_finalize_alt: a sorted array instead of a hash table (index.cuh)
   uint64_t bf_ones = 0;
   uint64_t n_keys = 0;  // distinct packed ref keys (lines + overflow)
+  void *add_arena = nullptr;  // device staging of mg_add_signatures* batches (grow-only)
+  uint64_t add_arena_bytes = 0;
+  uint8_t *ref_pinned[2] = {nullptr, nullptr};  // pinned + device chunk buffers of mg_scan_reference
+  uint8_t *ref_dev[2] = {nullptr, nullptr};
+  cudaEvent_t ref_ev[2] = {nullptr, nullptr}, ref_kev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> rp_events;  // start/stop around the rolling-pass kernel of every chunk of the last contig
+  size_t rp_chunks = 0;
   bool alt_final = false, ctx_final = false;
   unsigned long long *d_scalars = nullptr;  // [0] new keys [1] irregular [2] popcount [3] error [4] spilled
   std::unordered_map<std::string, int> irregular_ref;  // ref keys that are not k symbols of ACGT (always count 0)
@@ -93,6 +101,7 @@ struct mg_ctx {
   void *d_stage_k[2] = {nullptr, nullptr};
   uint32_t *d_stage_c[2] = {nullptr, nullptr};
   int next_stage = 0;
+  uint64_t stage_unit = 0;  // bytes per k-mer the staging buffers were sized for
   uint4 *hit_buf[2] = {nullptr, nullptr};  // deferred filter hits of the scan, one set per stream (grow-only)
   uint32_t *hit_counts[2] = {nullptr, nullptr};
   uint64_t hit_entries[2] = {0, 0}, hit_warps[2] = {0, 0};
@@ -105,7 +114,6 @@ struct mg_ctx {
   uint64_t launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
   cudaEvent_t tj = nullptr;
   cudaEvent_t ge[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t rpe[2] = {nullptr, nullptr};  // around the last reference-pass kernel
   void *geno_scratch = nullptr;  // per-k-mer weights + ref flags of mg_genotype
   uint64_t geno_scratch_bytes = 0;
   void *geno_arena = nullptr;  // device image of the last mg_genotype batch (grow-only)
@@ -117,15 +125,15 @@ struct mg_ctx {
     v.lines = lines;
     v.n_lines = n_lines;
     v.ctx_words = ctx_words;
-    v.rank = rank;
     v.bf_counts = bf_counts;
     v.key_counts = key_counts;
     v.ovf_keys = ovf_keys;
     v.ovf_counts = ovf_counts;
     v.ovf_mask = (1ull << ovf_log2) - 1;
     v.ovf_shift = 64 - ovf_log2;
-    v.ovf_n = ovf_n;
-    v.ovf_sorted = ovf_sorted ? 1 : 0;
+    v.key_hi_mask = mg::key_hi_mask_for(k);
+    v.ovf_flag_hi = mg::ovf_flag_for(k);
+    v.inline_counts = k <= mg::INLINE_MAX_K ? 1 : 0;
     v.bf_bits = bf_bits;
     v.bf_mask = (bf_bits & (bf_bits - 1)) == 0 ? bf_bits - 1 : 0;
     v.k = k;
@@ -143,7 +151,7 @@ static int ovf_alloc(mg_ctx *c, int log2cap, u128 **keys, uint32_t **counts) {
   CU(cudaMalloc(keys, cap * sizeof(u128)));
   CU(cudaMalloc(counts, cap * sizeof(uint32_t)));
   c->launches++;
-  mg::k_fill_keys<<<grid_for(cap, 256), 256, 0, c->stream[0]>>>(*keys, cap);
+  mg::k_fill_keys<<<grid_for(cap, 256), 256, 0, c->stream[0]>>>(*keys, cap, mg::key_hi_mask_for(c->k));
   CU(cudaGetLastError());
   CU(cudaMemsetAsync(*counts, 0, cap * sizeof(uint32_t), c->stream[0]));
   return MG_OK;
@@ -167,7 +175,7 @@ static int ovf_reserve(mg_ctx *c, uint64_t extra) {
   c->ovf_log2 = nl;
   if (c->ovf_n) {
     c->launches++;
-    mg::k_rehash<<<grid_for(ocap, 256), 256, 0, c->stream[0]>>>(ok, oc, ocap, c->view(), nk);
+    mg::k_rehash<<<grid_for(ocap, 256), 256, 0, c->stream[0]>>>(ok, ocap, c->view(), nk);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(c->stream[0]));
@@ -218,12 +226,15 @@ static int ctx_init(mg_ctx *c) {
   for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
   CU(cudaMalloc(&c->lines, c->n_lines * 128));
   CU(cudaMalloc(&c->ctx_words, c->n_ctx_words * 4));
-  CU(cudaMalloc(&c->key_counts, c->n_lines * mg::LINE_KEYS * 4));
   c->launches++;
-  mg::k_init_lines<<<grid_for(c->n_lines * mg::LINE_U4, 256), 256, 0, c->stream[0]>>>(c->lines, c->n_lines);
+  mg::k_init_lines<<<grid_for(c->n_lines * mg::LINE_U4, 256), 256, 0, c->stream[0]>>>(c->lines, c->n_lines,
+                                                                                      mg::key_hi_mask_for(c->k));
   CU(cudaGetLastError());
   CU(cudaMemsetAsync(c->ctx_words, 0, c->n_ctx_words * 4, c->stream[0]));
-  CU(cudaMemsetAsync(c->key_counts, 0, c->n_lines * mg::LINE_KEYS * 4, c->stream[0]));
+  if (c->k > mg::INLINE_MAX_K) {  // wide keys leave no room for the count inside the slot
+    CU(cudaMalloc(&c->key_counts, c->n_lines * mg::LINE_KEYS * 4));
+    CU(cudaMemsetAsync(c->key_counts, 0, c->n_lines * mg::LINE_KEYS * 4, c->stream[0]));
+  }
   // occupancy pre-filter: at most 2^MG_OCC_LOG2_BITS bits (default 2^29 = 64 MB: half of the 126 MB L2, the measured optimum)
   {
     int cap_log2 = 29;
@@ -253,9 +264,18 @@ extern "C" void mg_destroy(mg_ctx *c) {
   cudaFree(c->lines);
   cudaFree(c->ctx_words);
   cudaFree(c->occ);
-  cudaFree(c->rank);
   cudaFree(c->bf_counts);
   cudaFree(c->key_counts);
+  cudaFree(c->key_rank);
+  cudaFree(c->key_dense);
+  cudaFree(c->add_arena);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ref_pinned[i]) cudaFreeHost(c->ref_pinned[i]);
+    cudaFree(c->ref_dev[i]);
+    if (c->ref_ev[i]) cudaEventDestroy(c->ref_ev[i]);
+    if (c->ref_kev[i]) cudaEventDestroy(c->ref_kev[i]);
+  }
+  for (auto e : c->rp_events) cudaEventDestroy(e);
   cudaFree(c->ovf_keys);
   cudaFree(c->ovf_counts);
   cudaFree(c->d_scalars);
@@ -272,8 +292,6 @@ extern "C" void mg_destroy(mg_ctx *c) {
   if (c->tj) cudaEventDestroy(c->tj);
   for (int i = 0; i < 4; ++i)
     if (c->ge[i]) cudaEventDestroy(c->ge[i]);
-  for (int i = 0; i < 2; ++i)
-    if (c->rpe[i]) cudaEventDestroy(c->rpe[i]);
   for (int i = 0; i < 64; ++i)
     if (c->evs[i]) cudaEventDestroy(c->evs[i]);
   delete c;
@@ -319,6 +337,22 @@ struct DevFree {
   ~DevFree() { cudaFree(p); }
 };
 
+// device staging of an insert batch: one grow-only arena per context instead of five cudaMalloc/cudaFree pairs per
+// call (each of which synchronises the device)
+static int add_arena(mg_ctx *c, uint64_t bytes, uint8_t **out) {
+  if (c->add_arena_bytes < bytes) {
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(c->add_arena);
+    c->add_arena = nullptr;
+    c->add_arena_bytes = 0;
+    CU(cudaMalloc(&c->add_arena, bytes + bytes / 4 + 4096));
+    c->add_arena_bytes = bytes + bytes / 4 + 4096;
+  }
+  *out = reinterpret_cast<uint8_t *>(c->add_arena);
+  return MG_OK;
+}
+static uint64_t al256(uint64_t x) { return (x + 255) & ~255ull; }
+
 // after an insert kernel: account for new keys, run the overflow pass for spilled keys
 static int finish_inserts(mg_ctx *c, const uint32_t *d_spill, const uint8_t *d_pool, const uint64_t *d_off,
                           const uint4 *d_packed, unsigned long long *n_irregular) {
@@ -351,25 +385,28 @@ extern "C" int mg_add_signatures(mg_ctx *c, const char *pool, const uint64_t *of
   if (n == 0) return MG_OK;
   if (n > 0xFFFFFFFFull) return set_err(MG_ERR_ARG, "batch too large (max 2^32-1 k-mers per call)");
   CU(cudaSetDevice(c->device));
-  uint64_t n_ref = 0;
-  for (uint64_t i = 0; i < n; ++i) n_ref += is_ref[i] != 0;
-  DevBatch b;
-  int rc = upload_batch(c, b, pool, off, is_ref, n);
+  const uint64_t bytes = off[n];
+  const uint64_t o_pool = 0, o_off = al256(bytes + 16), o_flags = o_off + al256((n + 1) * 8), o_irr = o_flags + al256(n),
+                 o_spill = o_irr + al256(n * 4), total = o_spill + al256(n * 4);
+  uint8_t *d = nullptr;
+  int rc = add_arena(c, total, &d);
   if (rc) return rc;
-  DevFree irr, spill;
-  CU(cudaMalloc(&irr.p, (n_ref ? n_ref : 1) * 4));
-  CU(cudaMalloc(&spill.p, (n_ref ? n_ref : 1) * 4));
-  CU(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), c->stream[0]));
+  cudaStream_t st = c->stream[0];
+  if (bytes) CU(cudaMemcpyAsync(d + o_pool, pool, bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_off, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_flags, is_ref, n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), st));
   c->launches++;
-  mg::k_add_signatures<<<grid_for(n, 128), 128, 0, c->stream[0]>>>(b.pool, b.off, b.flags, n, c->view(), c->lines, c->occ,
-                                                                   c->d_scalars, (uint32_t *)irr.p, (uint32_t *)spill.p);
+  mg::k_add_signatures<<<grid_for(n, 128), 128, 0, st>>>(d + o_pool, (const uint64_t *)(d + o_off), d + o_flags, n, c->view(),
+                                                         c->occ, c->d_scalars, (uint32_t *)(d + o_irr),
+                                                         (uint32_t *)(d + o_spill));
   CU(cudaGetLastError());
   unsigned long long n_irr = 0;
-  rc = finish_inserts(c, (const uint32_t *)spill.p, b.pool, b.off, nullptr, &n_irr);
+  rc = finish_inserts(c, (const uint32_t *)(d + o_spill), d + o_pool, (const uint64_t *)(d + o_off), nullptr, &n_irr);
   if (rc) return rc;
   if (n_irr) {  // ref keys that are not k x ACGT: keep them host-side (kmap.hpp:86-112 semantics)
     std::vector<uint32_t> idx(n_irr);
-    CU(cudaMemcpy(idx.data(), irr.p, n_irr * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(idx.data(), d + o_irr, n_irr * 4, cudaMemcpyDeviceToHost));
     for (uint32_t i : idx) {
       int len = (int)(off[i + 1] - off[i]);
       uint64_t w[18];
@@ -386,20 +423,19 @@ extern "C" int mg_add_signatures_packed(mg_ctx *c, const uint64_t *lohi, const u
   if (n == 0) return MG_OK;
   if (n > 0xFFFFFFFFull) return set_err(MG_ERR_ARG, "batch too large (max 2^32-1 k-mers per call)");
   CU(cudaSetDevice(c->device));
-  uint64_t n_ref = 0;
-  for (uint64_t i = 0; i < n; ++i) n_ref += is_ref[i] != 0;
-  DevFree dk, df, spill;
-  CU(cudaMalloc(&dk.p, n * 16));
-  CU(cudaMalloc(&df.p, n));
-  CU(cudaMalloc(&spill.p, (n_ref ? n_ref : 1) * 4));
-  CU(cudaMemcpyAsync(dk.p, lohi, n * 16, cudaMemcpyHostToDevice, c->stream[0]));
-  CU(cudaMemcpyAsync(df.p, is_ref, n, cudaMemcpyHostToDevice, c->stream[0]));
-  CU(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), c->stream[0]));
+  const uint64_t o_k = 0, o_f = al256(n * 16), o_spill = o_f + al256(n), total = o_spill + al256(n * 4);
+  uint8_t *d = nullptr;
+  int rc = add_arena(c, total, &d);
+  if (rc) return rc;
+  cudaStream_t st = c->stream[0];
+  CU(cudaMemcpyAsync(d + o_k, lohi, n * 16, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_f, is_ref, n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), st));
   c->launches++;
-  mg::k_add_packed<<<grid_for(n, 256), 256, 0, c->stream[0]>>>((const uint4 *)dk.p, (const uint8_t *)df.p, n, c->view(),
-                                                               c->lines, c->occ, c->d_scalars, (uint32_t *)spill.p);
+  mg::k_add_packed<<<grid_for(n, 256), 256, 0, st>>>((const uint4 *)(d + o_k), d + o_f, n, c->view(), c->occ, c->d_scalars,
+                                                     (uint32_t *)(d + o_spill));
   CU(cudaGetLastError());
-  return finish_inserts(c, (const uint32_t *)spill.p, nullptr, nullptr, (const uint4 *)dk.p, nullptr);
+  return finish_inserts(c, (const uint32_t *)(d + o_spill), nullptr, nullptr, (const uint4 *)(d + o_k), nullptr);
 }
 
 static int count_ones(mg_ctx *c, const uint32_t *words, uint64_t n_units, int stride, uint32_t *unit_count,
@@ -413,22 +449,37 @@ static int count_ones(mg_ctx *c, const uint32_t *words, uint64_t n_units, int st
   return MG_OK;
 }
 
+// exclusive prefix sum of per-line u32 values (n_lines + 1 entries in, n_lines + 1 out)
+static int line_scan(mg_ctx *c, uint32_t *d_in, uint32_t *d_out) {
+  DevFree tmp;
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_in, d_out, (int64_t)(c->n_lines + 1), c->stream[0]));
+  CU(cudaMalloc(&tmp.p, tmp_bytes ? tmp_bytes : 1));
+  CU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, d_in, d_out, (int64_t)(c->n_lines + 1), c->stream[0]));
+  c->launches++;
+  CU(cudaStreamSynchronize(c->stream[0]));
+  return MG_OK;
+}
+
 // The canonical index image (index.cuh): key slots sorted within every line; for the (rare) lines that took more
-// than six keys, the six smallest stay in the line and the rest go to a sorted overflow array.  The handful of
-// crowded lines is fixed up on the host.
+// than five keys, the five smallest stay in the line and the rest go to the overflow table, which is rebuilt with
+// the keys placed in ascending (home slot, key) order.  The handful of crowded lines is fixed up on the host.
 static int canonicalize_keys(mg_ctx *c) {
   c->launches++;
-  mg::k_sort_line_keys<<<grid_for(c->n_lines, 256), 256, 0, c->stream[0]>>>(c->lines, c->n_lines);
+  mg::k_sort_line_keys<<<grid_for(c->n_lines, 256), 256, 0, c->stream[0]>>>(c->view());
   CU(cudaGetLastError());
   const uint64_t cap = 1ull << c->ovf_log2;
+  const uint64_t hi_mask = mg::key_hi_mask_for(c->k), flag = mg::ovf_flag_for(c->k);
+  const u128 empty = {~0ull, hi_mask};
+  auto is_empty = [&](const u128 &k) { return k.lo == ~0ull && k.hi == hi_mask; };
   std::vector<u128> ovk;
   if (c->ovf_n) {
     std::vector<u128> raw(cap);
     CU(cudaMemcpyAsync(raw.data(), c->ovf_keys, cap * sizeof(u128), cudaMemcpyDeviceToHost, c->stream[0]));
     CU(cudaStreamSynchronize(c->stream[0]));
     for (auto &k : raw) {
-      k.hi &= mg::KEY_HI_MASK;
-      if (!(k.lo == ~0ull && k.hi == mg::KEY_HI_MASK)) ovk.push_back(k);
+      k.hi &= hi_mask;
+      if (!is_empty(k)) ovk.push_back(k);
     }
   }
   auto less = [](const u128 &a, const u128 &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); };
@@ -464,14 +515,13 @@ static int canonicalize_keys(mg_ctx *c) {
       std::vector<u128> all;
       for (int s = 0; s < mg::LINE_KEYS; ++s) {
         u128 k = slots[i * mg::LINE_KEYS + s];
-        k.hi &= mg::KEY_HI_MASK;
-        if (!(k.lo == ~0ull && k.hi == mg::KEY_HI_MASK)) all.push_back(k);
+        k.hi &= hi_mask;
+        if (!is_empty(k)) all.push_back(k);
       }
       for (; e < by_line.size() && by_line[e].first == ids[i]; ++e) all.push_back(by_line[e].second);
       std::sort(all.begin(), all.end(), less);
-      const u128 empty = {~0ull, mg::KEY_HI_MASK};
       for (size_t s = 0; s < (size_t)mg::LINE_KEYS; ++s) slots[i * mg::LINE_KEYS + s] = s < all.size() ? all[s] : empty;
-      slots[i * mg::LINE_KEYS + mg::LINE_KEYS - 1].hi |= 1ull << 63;  // the overflow flag stays
+      slots[i * mg::LINE_KEYS + mg::LINE_KEYS - 1].hi |= flag;  // the overflow flag stays
       if (all.size() > (size_t)mg::LINE_KEYS) ovk.insert(ovk.end(), all.begin() + mg::LINE_KEYS, all.end());
     }
     CU(cudaMemcpyAsync(d_keys.p, slots.data(), slots.size() * 16, cudaMemcpyHostToDevice, c->stream[0]));
@@ -480,16 +530,32 @@ static int canonicalize_keys(mg_ctx *c) {
         c->lines, (const uint64_t *)d_ids.p, ids.size(), (const uint4 *)d_keys.p);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream[0]));
-    std::sort(ovk.begin(), ovk.end(), less);
   }
-  // the overflow keys as a sorted array (padded with empty entries to a power of two), counts zeroed
-  int nl = 0;
-  while ((1ull << nl) < (ovk.size() ? ovk.size() : 1)) ++nl;
+  // the overflow table in canonical form: capacity from the key count alone, keys placed by linear probing in
+  // ascending (home slot, key) order -- the same image whatever the order of the inserts was
+  int nl = 10;
+  while ((1ull << nl) < 2 * ovk.size()) ++nl;
+  const uint64_t ncap = 1ull << nl;
+  std::vector<u128> table(ncap, empty);
+  {
+    std::vector<std::pair<uint64_t, u128>> by_home;
+    by_home.reserve(ovk.size());
+    for (const auto &k : ovk) by_home.push_back({mg::ovf_home(k, 64 - nl), k});
+    std::sort(by_home.begin(), by_home.end(), [&](const auto &a, const auto &b) {
+      return a.first < b.first || (a.first == b.first && less(a.second, b.second));
+    });
+    for (const auto &e : by_home) {
+      uint64_t slot = e.first;
+      while (!is_empty(table[slot])) slot = (slot + 1) & (ncap - 1);
+      table[slot] = e.second;
+    }
+  }
   u128 *nk = nullptr;
   uint32_t *nc = nullptr;
-  int rc = ovf_alloc(c, nl, &nk, &nc);
-  if (rc) return rc;
-  if (!ovk.empty()) CU(cudaMemcpyAsync(nk, ovk.data(), ovk.size() * sizeof(u128), cudaMemcpyHostToDevice, c->stream[0]));
+  CU(cudaMalloc(&nk, ncap * sizeof(u128)));
+  CU(cudaMalloc(&nc, ncap * sizeof(uint32_t)));
+  CU(cudaMemcpyAsync(nk, table.data(), ncap * sizeof(u128), cudaMemcpyHostToDevice, c->stream[0]));
+  CU(cudaMemsetAsync(nc, 0, ncap * sizeof(uint32_t), c->stream[0]));
   CU(cudaStreamSynchronize(c->stream[0]));
   CU(cudaFree(c->ovf_keys));
   CU(cudaFree(c->ovf_counts));
@@ -497,7 +563,6 @@ static int canonicalize_keys(mg_ctx *c) {
   c->ovf_counts = nc;
   c->ovf_log2 = nl;
   c->ovf_n = ovk.size();
-  c->ovf_sorted = true;
   return MG_OK;
 }
 
@@ -527,39 +592,110 @@ extern "C" int mg_finalize_alt(mg_ctx *c) {
   if (!c) return set_err(MG_ERR_ARG, "NULL ctx");
   if (c->alt_final) return MG_OK;
   CU(cudaSetDevice(c->device));
-  DevFree cnt, tmp;
-  CU(cudaMalloc(&cnt.p, (c->n_lines + 1) * 4));
-  CU(cudaMalloc(&c->rank, (c->n_lines + 1) * 4));
-  CU(cudaMemsetAsync((uint32_t *)cnt.p + c->n_lines, 0, 4, c->stream[0]));
-  unsigned long long ones = 0;
-  int rc = count_ones(c, reinterpret_cast<const uint32_t *>(c->lines), c->n_lines, 32, (uint32_t *)cnt.p, &ones);
-  if (rc) return rc;
-  if (ones > 0xFFFFFFFFull) return set_err(MG_ERR_ARG, "bf has %llu set bits; the rank directory is 32-bit", ones);
-  size_t tmp_bytes = 0;
-  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint32_t *)cnt.p, c->rank, (int64_t)(c->n_lines + 1),
-                                   c->stream[0]));
-  CU(cudaMalloc(&tmp.p, tmp_bytes ? tmp_bytes : 1));
-  CU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, (uint32_t *)cnt.p, c->rank, (int64_t)(c->n_lines + 1),
-                                   c->stream[0]));
-  c->launches++;
-  CU(cudaStreamSynchronize(c->stream[0]));
-  c->bf_ones = ones;
-  CU(cudaMalloc(&c->bf_counts, (ones ? ones : 1) * 4));
-  CU(cudaMemset(c->bf_counts, 0, (ones ? ones : 1) * 4));
-  rc = canonicalize_keys(c);
+  {
+    // switch_mode: ones per line -> exclusive scan -> the rank of every line goes into word 28 of the line itself
+    DevFree cnt, rank;
+    CU(cudaMalloc(&cnt.p, (c->n_lines + 1) * 4));
+    CU(cudaMalloc(&rank.p, (c->n_lines + 1) * 4));
+    CU(cudaMemsetAsync((uint32_t *)cnt.p + c->n_lines, 0, 4, c->stream[0]));
+    unsigned long long ones = 0;
+    int rc = count_ones(c, reinterpret_cast<const uint32_t *>(c->lines), c->n_lines, 32, (uint32_t *)cnt.p, &ones);
+    if (rc) return rc;
+    if (ones > 0xFFFFFFFFull) return set_err(MG_ERR_ARG, "bf has %llu set bits; the rank directory is 32-bit", ones);
+    rc = line_scan(c, (uint32_t *)cnt.p, (uint32_t *)rank.p);
+    if (rc) return rc;
+    c->launches++;
+    mg::k_write_rank<<<grid_for(c->n_lines, 256), 256, 0, c->stream[0]>>>(c->view(), (const uint32_t *)rank.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream[0]));
+    c->bf_ones = ones;
+  }
+  CU(cudaMalloc(&c->bf_counts, (c->bf_ones ? c->bf_ones : 1) * 4));
+  CU(cudaMemset(c->bf_counts, 0, (c->bf_ones ? c->bf_ones : 1) * 4));
+  int rc = canonicalize_keys(c);
   if (rc) return rc;
   c->alt_final = true;
   return pin_occ_in_l2(c);
 }
 
-template <int K, int REFK>
-static cudaError_t launch_refpass(mg_ctx *c, const uint8_t *d_seq, uint64_t len) {
-  uint64_t n_pos = len - (uint64_t)(c->ref_k - 1);
-  int grid = (int)((n_pos + mg::RP_TILE - 1) / mg::RP_TILE);
-  size_t smem = mg::RP_TILE + 64;
+// ---- dense counter image (index.cuh): gather before a reduce / download, scatter after a reduce ----
+static int counters_xfer(mg_ctx *c, bool scatter) {
+  const uint64_t n_line_keys = c->n_keys - c->ovf_n;
+  if (!c->key_rank) {  // keys held by the lines before each line: built once, on first use
+    DevFree cnt;
+    CU(cudaMalloc(&cnt.p, (c->n_lines + 1) * 4));
+    CU(cudaMalloc(&c->key_rank, (c->n_lines + 1) * 4));
+    CU(cudaMemsetAsync((uint32_t *)cnt.p + c->n_lines, 0, 4, c->stream[0]));
+    c->launches++;
+    mg::k_line_keycount<<<grid_for(c->n_lines, 256), 256, 0, c->stream[0]>>>(c->view(), (uint32_t *)cnt.p);
+    CU(cudaGetLastError());
+    int rc = line_scan(c, (uint32_t *)cnt.p, c->key_rank);
+    if (rc) return rc;
+    CU(cudaMalloc(&c->key_dense, (n_line_keys ? n_line_keys : 1) * 4));
+    CU(cudaMemsetAsync(c->key_dense, 0, (n_line_keys ? n_line_keys : 1) * 4, c->stream[0]));
+  }
   c->launches++;
-  mg::k_refpass<K, REFK><<<grid, mg::RP_THREADS, smem, c->stream[0]>>>(d_seq, len, c->view(), c->ctx_words);
+  const int grid = grid_for(c->n_lines * 8, 256);
+  if (scatter)
+    mg::k_counters_xfer<true><<<grid, 256, 0, c->stream[0]>>>(c->view(), c->key_rank, c->key_dense);
+  else
+    mg::k_counters_xfer<false><<<grid, 256, 0, c->stream[0]>>>(c->view(), c->key_rank, c->key_dense);
+  CU(cudaGetLastError());
+  return MG_OK;
+}
+extern "C" int mg_counters_gather(mg_ctx *c) {
+  if (!c) return set_err(MG_ERR_ARG, "NULL ctx");
+  if (!c->alt_final) return set_err(MG_ERR_STATE, "no counters before mg_finalize_alt");
+  CU(cudaSetDevice(c->device));
+  int rc = mg_sync(c);
+  if (rc) return rc;
+  rc = counters_xfer(c, false);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream[0]));
+  return MG_OK;
+}
+extern "C" int mg_counters_scatter(mg_ctx *c) {
+  if (!c) return set_err(MG_ERR_ARG, "NULL ctx");
+  if (!c->key_rank) return set_err(MG_ERR_STATE, "mg_counters_scatter before mg_counters_gather");
+  CU(cudaSetDevice(c->device));
+  int rc = counters_xfer(c, true);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream[0]));
+  return MG_OK;
+}
+
+template <int K, int REFK>
+static cudaError_t launch_refpass(mg_ctx *c, const uint8_t *d_chunk, uint64_t chunk_base, uint64_t p_begin, uint64_t p_end) {
+  int grid = (int)((p_end - p_begin + mg::RP_TILE - 1) / mg::RP_TILE);
+  size_t smem = mg::RP_TILE + 64 + 16;
+  c->launches++;
+  mg::k_refpass<K, REFK><<<grid, mg::RP_THREADS, smem, c->stream[0]>>>(d_chunk, chunk_base, p_begin, p_end, c->view(),
+                                                                        c->ctx_words);
   return cudaGetLastError();
+}
+
+// The contig goes to the device in chunks, each carrying the ref_k-1 bytes before its first window end (halo):
+// the H2D copy of chunk i+1 (stream 1) overlaps the kernel of chunk i (stream 0).  A caller buffer in pinned memory
+// (mg_host_alloc) is copied from directly; pageable memory goes through two pinned staging buffers, filled by
+// several host threads (one thread moves ~8 GB/s, the link takes ~50).
+constexpr uint64_t REF_CHUNK = 32ull << 20;  // window end positions per chunk (a multiple of RP_TILE)
+
+static void parallel_memcpy(void *dst, const void *src, size_t n) {
+  unsigned t = std::thread::hardware_concurrency();
+  t = t > 8 ? 8 : (t < 1 ? 1 : t);
+  if (n < (4u << 20) || t == 1) {
+    memcpy(dst, src, n);
+    return;
+  }
+  const size_t part = ((n + t - 1) / t + 4095) & ~(size_t)4095;
+  std::vector<std::thread> pool;
+  for (unsigned i = 1; i < t; ++i) {
+    const size_t o = (size_t)i * part;
+    if (o >= n) break;
+    pool.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, std::min(part, n - o)); });
+  }
+  memcpy(dst, src, std::min(part, n));
+  for (auto &th : pool) th.join();
 }
 
 extern "C" int mg_scan_reference(mg_ctx *c, const char *seq, uint64_t len) {
@@ -568,32 +704,72 @@ extern "C" int mg_scan_reference(mg_ctx *c, const char *seq, uint64_t len) {
   if (c->ctx_final) return set_err(MG_ERR_STATE, "mg_scan_reference after mg_finalize_context");
   CU(cudaSetDevice(c->device));
   int d = (c->ref_k - c->k) / 2;
-  DevFree ds;
+  cudaStream_t st = c->stream[0], cp = c->stream[1];
   if (len < (uint64_t)c->ref_k) {
     // the reference's substr(d, k) throws when d > size(); a shorter contig is hashed once, truncated
     if ((uint64_t)d > len || len == 0)
       return set_err(MG_ERR_ARG, "contig shorter than (ref_k-k)/2: the reference aborts here");
+    DevFree ds;
     CU(cudaMalloc(&ds.p, len));
-    CU(cudaMemcpyAsync(ds.p, seq, len, cudaMemcpyHostToDevice, c->stream[0]));
+    CU(cudaMemcpyAsync(ds.p, seq, len, cudaMemcpyHostToDevice, st));
     c->launches++;
-    mg::k_refpass_short<<<1, 32, 0, c->stream[0]>>>((const uint8_t *)ds.p, len, c->view(), c->ctx_words);
+    mg::k_refpass_short<<<1, 32, 0, st>>>((const uint8_t *)ds.p, len, c->view(), c->ctx_words);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream[0]));
+    CU(cudaStreamSynchronize(st));
     return MG_OK;
   }
-  CU(cudaMalloc(&ds.p, len));
-  CU(cudaMemcpyAsync(ds.p, seq, len, cudaMemcpyHostToDevice, c->stream[0]));
-  for (int i = 0; i < 2; ++i)
-    if (!c->rpe[i]) CU(cudaEventCreate(&c->rpe[i]));
-  CU(cudaEventRecord(c->rpe[0], c->stream[0]));
-  cudaError_t e;
-  if (c->k == 35 && c->ref_k == 43)
-    e = launch_refpass<35, 43>(c, (const uint8_t *)ds.p, len);
-  else
-    e = launch_refpass<0, 0>(c, (const uint8_t *)ds.p, len);
-  if (e != cudaSuccess) return set_err(MG_ERR_CUDA, "k_refpass launch -> %s", cudaGetErrorString(e));
-  CU(cudaEventRecord(c->rpe[1], c->stream[0]));
-  CU(cudaStreamSynchronize(c->stream[0]));
+  bool pinned_src = false;
+  {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, seq) == cudaSuccess)
+      pinned_src = at.type == cudaMemoryTypeHost;
+    else
+      cudaGetLastError();
+  }
+  const uint64_t halo = (uint64_t)(c->ref_k - 1), buf_bytes = REF_CHUNK + halo + 64;
+  for (int i = 0; i < 2; ++i) {
+    if (!c->ref_dev[i]) {
+      CU(cudaMalloc((void **)&c->ref_dev[i], buf_bytes));
+      CU(cudaEventCreateWithFlags(&c->ref_ev[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ref_kev[i], cudaEventDisableTiming));
+    }
+    if (!pinned_src && !c->ref_pinned[i]) CU(cudaHostAlloc((void **)&c->ref_pinned[i], buf_bytes, cudaHostAllocDefault));
+  }
+  // window end positions p in [ref_k-1, len); chunk j covers [ref_k-1 + j*REF_CHUNK, +REF_CHUNK) and needs the
+  // contig bytes [j*REF_CHUNK, (j+1)*REF_CHUNK + halo)
+  int slot = 0;
+  size_t n_chunks = 0;
+  for (uint64_t b0 = 0; b0 + halo < len; b0 += REF_CHUNK, slot ^= 1, ++n_chunks) {
+    const uint64_t nbytes = std::min<uint64_t>(REF_CHUNK + halo, len - b0);
+    const char *src = seq + b0;
+    if (!pinned_src) {
+      CU(cudaEventSynchronize(c->ref_ev[slot]));  // the H2D copy that last read this staging buffer is done
+      parallel_memcpy(c->ref_pinned[slot], seq + b0, nbytes);
+      src = reinterpret_cast<const char *>(c->ref_pinned[slot]);
+    }
+    CU(cudaStreamWaitEvent(cp, c->ref_kev[slot], 0));  // the kernel that last read this device buffer is done
+    CU(cudaMemcpyAsync(c->ref_dev[slot], src, nbytes, cudaMemcpyHostToDevice, cp));
+    CU(cudaEventRecord(c->ref_ev[slot], cp));
+    CU(cudaStreamWaitEvent(st, c->ref_ev[slot], 0));
+    while (c->rp_events.size() < 2 * (n_chunks + 1)) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      c->rp_events.push_back(e);
+    }
+    CU(cudaEventRecord(c->rp_events[2 * n_chunks], st));
+    const uint64_t p_begin = b0 + halo, p_end = b0 + nbytes;
+    cudaError_t e;
+    if (c->k == 35 && c->ref_k == 43)
+      e = launch_refpass<35, 43>(c, c->ref_dev[slot], b0, p_begin, p_end);
+    else
+      e = launch_refpass<0, 0>(c, c->ref_dev[slot], b0, p_begin, p_end);
+    if (e != cudaSuccess) return set_err(MG_ERR_CUDA, "k_refpass launch -> %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(c->rp_events[2 * n_chunks + 1], st));
+    CU(cudaEventRecord(c->ref_kev[slot], st));
+  }
+  c->rp_chunks = n_chunks;
+  CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(cp));
   return MG_OK;
 }
 
@@ -637,6 +813,10 @@ static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n,
     src.hit_counts = c->hit_counts[si];
     src.seg_cap = (uint32_t)seg;
   }
+  {  // more than 48 KB of dynamic shared memory needs the opt-in (per device; cheap enough to repeat)
+    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, mg::SCAN_SMEM);
+    if (e != cudaSuccess) return e;
+  }
   c->launches++;
   mg::k_scan<K, REFK, MODE><<<grid, mg::SCAN_THREADS, mg::SCAN_SMEM, st>>>(src, n, c->view());
   cudaError_t e = cudaGetLastError();
@@ -679,16 +859,29 @@ extern "C" int mg_scan_sample_kmers_device(mg_ctx *c, const void *d_lohi, const 
   return scan_device(c, d_lohi, d_counts, n, c->stream[0]);
 }
 
+// the two device staging buffers of the host-buffer scans, sized for `unit` bytes per k-mer (a packed word, or a
+// KMC record of any suffix + counter length)
+static int stage_reserve(mg_ctx *c, uint64_t unit) {
+  if (unit < 16) unit = 16;
+  if (c->stage_unit >= unit) return MG_OK;
+  int rc = mg_sync(c);
+  if (rc) return rc;
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(c->d_stage_k[i]);
+    c->d_stage_k[i] = nullptr;
+    if (!c->d_stage_c[i]) CU(cudaMalloc(&c->d_stage_c[i], STAGE_KMERS * 4));
+    CU(cudaMalloc(&c->d_stage_k[i], STAGE_KMERS * unit + 64));
+  }
+  c->stage_unit = unit;
+  return MG_OK;
+}
+
 extern "C" int mg_scan_sample_kmers(mg_ctx *c, const uint64_t *lohi, const uint32_t *counts, uint64_t n) {
   if (!c || ((!lohi || !counts) && n)) return set_err(MG_ERR_ARG, "NULL argument");
   if (!c->alt_final) return set_err(MG_ERR_STATE, "scan before mg_finalize_alt (BF::increment is a no-op in write mode)");
   CU(cudaSetDevice(c->device));
-  for (int i = 0; i < 2; ++i) {
-    if (!c->d_stage_k[i]) {
-      CU(cudaMalloc(&c->d_stage_k[i], STAGE_KMERS * 16 + 64));
-      CU(cudaMalloc(&c->d_stage_c[i], STAGE_KMERS * 4));
-    }
-  }
+  int rc0 = stage_reserve(c, 16);
+  if (rc0) return rc0;
   // chunks alternate between two (stream, device buffer) pairs: the H2D copy of chunk i+1 overlaps the
   // kernel of chunk i.
   for (uint64_t o = 0; o < n; o += STAGE_KMERS) {
@@ -737,13 +930,8 @@ extern "C" int mg_scan_kmc_records(mg_ctx *c, const uint8_t *records, uint64_t f
   if (!c->alt_final) return set_err(MG_ERR_STATE, "scan before mg_finalize_alt (BF::increment is a no-op in write mode)");
   CU(cudaSetDevice(c->device));
   const uint64_t rec = (uint64_t)(c->kmc_suf_bytes + c->kmc_counter_size);
-  if (rec > 16) return set_err(MG_ERR_ARG, "KMC record of %llu bytes does not fit the staging buffers", (unsigned long long)rec);
-  for (int i = 0; i < 2; ++i) {
-    if (!c->d_stage_k[i]) {
-      CU(cudaMalloc(&c->d_stage_k[i], STAGE_KMERS * 16 + 64));
-      CU(cudaMalloc(&c->d_stage_c[i], STAGE_KMERS * 4));
-    }
-  }
+  int rc0 = stage_reserve(c, rec);
+  if (rc0) return rc0;
   for (uint64_t o = 0; o < n; o += STAGE_KMERS) {
     uint64_t m = n - o < STAGE_KMERS ? n - o : STAGE_KMERS;
     int s = c->next_stage;
@@ -786,7 +974,7 @@ static int lookup_common(mg_ctx *c, const char *pool, const uint64_t *off, const
   CU(cudaMalloc(&d_out.p, (n ? n : 1) * 4));
   c->launches++;
   mg::k_lookup<<<grid_for(n, 128), 128, 0, c->stream[0]>>>(b.pool, b.off, b.flags, n, c->view(), mode, which,
-                                                           (int32_t *)d_out.p, c->d_scalars, nullptr);
+                                                           (int32_t *)d_out.p, c->d_scalars, nullptr, nullptr, nullptr);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out_host, d_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream[0]));
   CU(cudaStreamSynchronize(c->stream[0]));
@@ -819,19 +1007,35 @@ extern "C" int mg_get_counts(mg_ctx *c, const char *pool, const uint64_t *off, c
   return lookup_common(c, pool, off, is_ref, n, 0, 0, out);
 }
 
+// library-owned scratch of the genotyping calls: per-k-mer weights (+ flags), and the likelihood slots nobody reads
+static int geno_scratch(mg_ctx *c, uint64_t need) {
+  if (c->geno_scratch_bytes < need) {
+    CU(cudaStreamSynchronize(c->stream[0]));
+    cudaFree(c->geno_scratch);
+    c->geno_scratch = nullptr;
+    c->geno_scratch_bytes = 0;
+    CU(cudaMalloc(&c->geno_scratch, need + need / 4));
+    c->geno_scratch_bytes = need + need / 4;
+  }
+  return MG_OK;
+}
+// everything enqueued on the second stream (host-path scans) precedes what stream 0 does next
+static int join_streams(mg_ctx *c) {
+  if (!c->tj) CU(cudaEventCreateWithFlags(&c->tj, cudaEventDisableTiming));
+  CU(cudaEventRecord(c->tj, c->stream[1]));
+  CU(cudaStreamWaitEvent(c->stream[0], c->tj, 0));
+  return MG_OK;
+}
+
 // all pointers of in/out are DEVICE pointers here; scratch (k-mer flags + weights) is library-owned
 static int genotype_on_device(mg_ctx *c, const mg_variant_batch *in, const mg_genotype_out *out,
                               const mg_batch_dims *dm, float error_rate, int max_coverage, int haploid) {
   cudaStream_t st = c->stream[0];
   uint64_t nv = dm->n_variants, na = dm->n_alleles, nk = dm->n_kmers;
-  uint64_t need = (nk ? nk : 1) * 6;  // i32 weight + ref flag + deferred flag per k-mer
-  if (c->geno_scratch_bytes < need) {
-    cudaFree(c->geno_scratch);
-    c->geno_scratch = nullptr;
-    c->geno_scratch_bytes = 0;
-    CU(cudaMalloc(&c->geno_scratch, need));
-    c->geno_scratch_bytes = need;
-  }
+  int rc = geno_scratch(c, (nk ? nk : 1) * 6);  // i32 weight + ref flag + deferred flag per k-mer
+  if (rc) return rc;
+  rc = join_streams(c);
+  if (rc) return rc;
   int32_t *d_w = reinterpret_cast<int32_t *>(c->geno_scratch);
   uint8_t *d_flags = reinterpret_cast<uint8_t *>(c->geno_scratch) + (nk ? nk : 1) * 4;
   for (int i = 0; i < 4; ++i)
@@ -855,24 +1059,24 @@ static int genotype_on_device(mg_ctx *c, const mg_variant_batch *in, const mg_ge
       CU(cudaGetLastError());
       c->launches++;
       mg::k_lookup<<<grid_for(nk, 128), 128, 0, st>>>(d_pool, in->kmer_off, d_flags, nk, c->view(), 0, 0, d_w,
-                                                      c->d_scalars, d_slow);
+                                                      c->d_scalars, d_slow, nullptr, nullptr);
       CU(cudaGetLastError());
     } else {
       c->launches++;
       mg::k_lookup<<<grid_for(nk, 128), 128, 0, st>>>(d_pool, in->kmer_off, d_flags, nk, c->view(), 0, 0, d_w,
-                                                      c->d_scalars, nullptr);
+                                                      c->d_scalars, nullptr, nullptr, nullptr);
       CU(cudaGetLastError());
     }
   }
   CU(cudaEventRecord(c->ge[1], st));
   c->launches++;
-  mg::k_coverage<<<grid_for(na, 128), 128, 0, st>>>(d_w, in->sig_kmer_off, in->allele_sig_off, na, out->cov);
+  mg::k_coverage<uint64_t><<<grid_for(na, 128), 128, 0, st>>>(d_w, in->sig_kmer_off, in->allele_sig_off, na, out->cov);
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ge[2], st));
   c->launches++;
-  mg::k_genotype<<<grid_for(nv, 128), 128, 0, st>>>(out->cov, in->freq, in->var_allele_off, out->lik_off, nv,
-                                                    error_rate, max_coverage, haploid, out->lik, out->n_gts,
-                                                    out->status, out->best_gt, out->gq);
+  mg::k_genotype<uint64_t><<<grid_for(nv, 128), 128, 0, st>>>(out->cov, in->freq, in->var_allele_off, out->lik_off, nullptr,
+                                                              nv, error_rate, max_coverage, haploid, out->lik, out->n_gts,
+                                                              out->status, out->best_gt, out->gq);
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ge[3], st));
   return MG_OK;
@@ -961,6 +1165,155 @@ extern "C" int mg_genotype(mg_ctx *c, const mg_variant_batch *in, const mg_genot
   return check_too_long(c);
 }
 
+// ---- the same step for PACKED signature k-mers (2-bit words, u32 offsets): what the C++ host sends ----
+// all pointers of in/out are DEVICE pointers; out->lik == NULL: the likelihoods stay in library scratch
+static int genotype_packed_on_device(mg_ctx *c, const mg_packed_batch *in, const mg_genotype_out *out,
+                                     const mg_packed_dims *dm, float error_rate, int max_coverage, int haploid) {
+  cudaStream_t st = c->stream[0];
+  const uint64_t nv = dm->n_variants, na = dm->n_alleles, nk = dm->n_kmers;
+  const bool own_lik = out->lik == nullptr;
+  const uint64_t w_bytes = ((nk ? nk : 1) * 4 + 255) & ~255ull;
+  int rc = geno_scratch(c, w_bytes + (own_lik ? dm->lik_slots * 8 + 256 : 0));
+  if (rc) return rc;
+  rc = join_streams(c);
+  if (rc) return rc;
+  int32_t *d_w = reinterpret_cast<int32_t *>(c->geno_scratch);
+  double *d_lik = own_lik ? reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(c->geno_scratch) + w_bytes) : out->lik;
+  for (int i = 0; i < 4; ++i)
+    if (!c->ge[i]) CU(cudaEventCreate(&c->ge[i]));
+  CU(cudaEventRecord(c->ge[0], st));
+  if (nk) {
+    c->launches++;
+    if (c->k == 35)
+      mg::k_lookup_packed<35><<<grid_for(nk, 128), 128, 0, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
+    else
+      mg::k_lookup_packed<0><<<grid_for(nk, 128), 128, 0, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
+    CU(cudaGetLastError());
+    if (in->n_irregular) {  // not k symbols of ACGT: the byte-exact path, written to their places in the weight array
+      c->launches++;
+      mg::k_lookup<<<grid_for(in->n_irregular, 128), 128, 0, st>>>(
+          (const uint8_t *)in->irr_pool, in->irr_off, nullptr, in->n_irregular, c->view(), 0, 0, d_w, c->d_scalars, nullptr,
+          in->irr_kmer, (const uint4 *)in->kmers);
+      CU(cudaGetLastError());
+    }
+  }
+  CU(cudaEventRecord(c->ge[1], st));
+  c->launches++;
+  mg::k_coverage<uint32_t><<<grid_for(na, 128), 128, 0, st>>>(d_w, in->sig_kmer_off, in->allele_sig_off, na, out->cov);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ge[2], st));
+  if (own_lik) CU(cudaMemsetAsync(c->d_scalars + 5, 0, 8, st));
+  c->launches++;
+  mg::k_genotype<uint32_t><<<grid_for(nv, 128), 128, 0, st>>>(out->cov, in->freq, in->var_allele_off,
+                                                              own_lik ? nullptr : out->lik_off, c->d_scalars + 5, nv,
+                                                              error_rate, max_coverage, haploid, d_lik, out->n_gts,
+                                                              out->status, out->best_gt, out->gq);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ge[3], st));
+  return MG_OK;
+}
+
+static uint64_t lik_slots_of(const uint32_t *var_allele_off, uint64_t nv, int haploid) {
+  uint64_t t = 0;
+  for (uint64_t i = 0; i < nv; ++i) {
+    const uint64_t n = var_allele_off[i + 1] - var_allele_off[i];
+    t += std::max<uint64_t>(n, haploid ? n : n * (n + 1) / 2);
+  }
+  return t;
+}
+
+extern "C" int mg_genotype_packed_device(mg_ctx *c, const mg_packed_batch *in, const mg_genotype_out *out,
+                                         const mg_packed_dims *dims, float error_rate, int max_coverage, int haploid) {
+  if (!c || !in || !out || !dims) return set_err(MG_ERR_ARG, "NULL argument");
+  if (!c->alt_final) return set_err(MG_ERR_STATE, "mg_genotype_packed_device before mg_finalize_alt");
+  if (dims->n_variants == 0) return MG_OK;
+  if (!in->var_allele_off || !in->allele_sig_off || !in->sig_kmer_off || (!in->kmers && dims->n_kmers) || !in->freq ||
+      !out->cov || !out->n_gts || !out->status || !out->best_gt || !out->gq || (out->lik && !out->lik_off) ||
+      (in->n_irregular && (!in->irr_off || !in->irr_pool || !in->irr_kmer)))
+    return set_err(MG_ERR_ARG, "NULL array in batch");
+  CU(cudaSetDevice(c->device));
+  return genotype_packed_on_device(c, in, out, dims, error_rate, max_coverage, haploid);
+}
+
+extern "C" int mg_genotype_packed(mg_ctx *c, const mg_packed_batch *in, const mg_genotype_out *out, float error_rate,
+                                  int max_coverage, int haploid) {
+  if (!c || !in || !out) return set_err(MG_ERR_ARG, "NULL argument");
+  if (!c->alt_final) return set_err(MG_ERR_STATE, "mg_genotype_packed before mg_finalize_alt");
+  const uint64_t nv = in->n_variants;
+  if (nv == 0) return MG_OK;
+  if (!in->var_allele_off || !in->allele_sig_off || !in->sig_kmer_off || !in->freq || !out->cov || !out->n_gts ||
+      !out->status || !out->best_gt || !out->gq || (out->lik && !out->lik_off) ||
+      (in->n_irregular && (!in->irr_off || !in->irr_pool || !in->irr_kmer)))
+    return set_err(MG_ERR_ARG, "NULL array in batch");
+  CU(cudaSetDevice(c->device));
+  mg_packed_dims dm;
+  dm.n_variants = nv;
+  dm.n_alleles = in->var_allele_off[nv];
+  dm.n_sigs = in->allele_sig_off[dm.n_alleles];
+  dm.n_kmers = in->sig_kmer_off[dm.n_sigs];
+  dm.irr_pool_bytes = in->n_irregular ? in->irr_off[in->n_irregular] : 0;
+  dm.lik_slots = out->lik ? out->lik_off[nv] : lik_slots_of(in->var_allele_off, nv, haploid);
+  if (dm.n_kmers && !in->kmers) return set_err(MG_ERR_ARG, "NULL array in batch");
+  const uint64_t na = dm.n_alleles, ns = dm.n_sigs, nk = dm.n_kmers, ni = in->n_irregular, nl = out->lik ? dm.lik_slots : 0;
+  cudaStream_t st = c->stream[0];
+  auto al = [](uint64_t x) { return (x + 255) & ~255ull; };
+  const uint64_t o_vao = 0, o_aso = o_vao + al((nv + 1) * 4), o_sko = o_aso + al((na + 1) * 4),
+                 o_km = o_sko + al((ns + 1) * 4), o_freq = o_km + al(nk * 16), o_io = o_freq + al(na * 4),
+                 o_ip = o_io + al((ni + 1) * 8), o_ik = o_ip + al(dm.irr_pool_bytes), o_lo = o_ik + al(ni * 4),
+                 o_cov = o_lo + al(nl ? (nv + 1) * 8 : 0), o_i32 = o_cov + al(na * 4), o_lik = o_i32 + al(nv * 16),
+                 total = o_lik + al(nl * 8) + 256;
+  if (c->geno_arena_bytes < total) {  // grow-only device arena, reused across calls
+    CU(cudaStreamSynchronize(st));
+    cudaFree(c->geno_arena);
+    c->geno_arena = nullptr;
+    c->geno_arena_bytes = 0;
+    CU(cudaMalloc(&c->geno_arena, total + total / 4));
+    c->geno_arena_bytes = total + total / 4;
+  }
+  uint8_t *d = (uint8_t *)c->geno_arena;
+  CU(cudaMemcpyAsync(d + o_vao, in->var_allele_off, (nv + 1) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_aso, in->allele_sig_off, (na + 1) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_sko, in->sig_kmer_off, (ns + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (nk) CU(cudaMemcpyAsync(d + o_km, in->kmers, nk * 16, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_freq, in->freq, na * 4, cudaMemcpyHostToDevice, st));
+  if (ni) {
+    CU(cudaMemcpyAsync(d + o_io, in->irr_off, (ni + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (dm.irr_pool_bytes) CU(cudaMemcpyAsync(d + o_ip, in->irr_pool, dm.irr_pool_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_ik, in->irr_kmer, ni * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (nl) CU(cudaMemcpyAsync(d + o_lo, out->lik_off, (nv + 1) * 8, cudaMemcpyHostToDevice, st));
+  mg_packed_batch din = {};
+  din.n_variants = nv;
+  din.var_allele_off = reinterpret_cast<uint32_t *>(d + o_vao);
+  din.allele_sig_off = reinterpret_cast<uint32_t *>(d + o_aso);
+  din.sig_kmer_off = reinterpret_cast<uint32_t *>(d + o_sko);
+  din.kmers = reinterpret_cast<uint64_t *>(d + o_km);
+  din.freq = reinterpret_cast<float *>(d + o_freq);
+  din.n_irregular = ni;
+  din.irr_off = reinterpret_cast<uint64_t *>(d + o_io);
+  din.irr_pool = reinterpret_cast<const char *>(d + o_ip);
+  din.irr_kmer = reinterpret_cast<uint32_t *>(d + o_ik);
+  mg_genotype_out dout;
+  int32_t *i32 = reinterpret_cast<int32_t *>(d + o_i32);
+  dout.cov = reinterpret_cast<uint32_t *>(d + o_cov);
+  dout.n_gts = i32;
+  dout.status = i32 + nv;
+  dout.best_gt = i32 + 2 * nv;
+  dout.gq = i32 + 3 * nv;
+  dout.lik_off = nl ? reinterpret_cast<uint64_t *>(d + o_lo) : nullptr;
+  dout.lik = nl ? reinterpret_cast<double *>(d + o_lik) : nullptr;
+  int rc = genotype_packed_on_device(c, &din, &dout, &dm, error_rate, max_coverage, haploid);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out->cov, dout.cov, na * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->n_gts, dout.n_gts, nv * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->status, dout.status, nv * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->best_gt, dout.best_gt, nv * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out->gq, dout.gq, nv * 4, cudaMemcpyDeviceToHost, st));
+  if (nl) CU(cudaMemcpyAsync(out->lik, dout.lik, nl * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return check_too_long(c);
+}
+
 extern "C" int mg_bf_popcount(mg_ctx *c, int which, uint64_t *ones) {
   if (!c || !ones || which < 0 || which > 1) return set_err(MG_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
@@ -1001,7 +1354,7 @@ extern "C" int mg_bf_download_counts(mg_ctx *c, uint16_t *counts, uint64_t n) {
   if (!c->alt_final) return set_err(MG_ERR_STATE, "no counters before mg_finalize_alt");
   if (n > c->bf_ones) return set_err(MG_ERR_ARG, "n exceeds popcount");
   CU(cudaSetDevice(c->device));
-  int rc = mg_sync(c);
+  int rc = mg_counters_gather(c);  // the counters of the first three set bits of a line live inside the line
   if (rc) return rc;
   std::vector<uint32_t> tmp(n ? n : 1);
   CU(cudaMemcpy(tmp.data(), c->bf_counts, n * 4, cudaMemcpyDeviceToHost));
@@ -1029,21 +1382,24 @@ extern "C" int mg_index_stats(mg_ctx *c, uint64_t *stats, int n) {
 extern "C" int mg_counter_buffers(mg_ctx *c, void **d_ptr, uint64_t *n) {
   if (!c || !d_ptr || !n) return set_err(MG_ERR_ARG, "NULL argument");
   if (!c->alt_final) return set_err(MG_ERR_STATE, "no counters before mg_finalize_alt");
+  if (!c->key_rank) return set_err(MG_ERR_STATE, "mg_counter_buffers before mg_counters_gather");
   d_ptr[0] = c->bf_counts;
   n[0] = c->bf_ones;
-  d_ptr[1] = c->key_counts;
-  n[1] = c->n_lines * mg::LINE_KEYS;
+  d_ptr[1] = c->key_dense;
+  n[1] = c->n_keys - c->ovf_n;
   d_ptr[2] = c->ovf_counts;
   n[2] = 1ull << c->ovf_log2;
   return MG_OK;
 }
 
 // Replicate-and-reduce inside one process: ctx[0..n-1] hold the same index (any devices, the same
-// device included), each scanned its share of the sample stream; the three counter arrays of ctx[1..] are added
-// into ctx[0] -- peer copies over NVLink into a staging buffer on ctx[0]'s device, then an add kernel.  Exact
+// device included), each scanned its share of the sample stream.  Every context gathers its counters into the dense
+// image; one kernel per array on ctx[0]'s device then reads the peers' arrays in place over NVLink (peer access) and
+// adds them N-way into its own -- no staging copies; ctx[0] scatters the sums back into its probe lines.  Exact
 // because the index image is canonical (identical layouts) and the updates are modular adds.
 extern "C" int mg_reduce_counts(mg_ctx **ctx, int n) {
   if (!ctx || n < 1) return set_err(MG_ERR_ARG, "bad argument");
+  if (n > 16) return set_err(MG_ERR_ARG, "at most 16 contexts");
   for (int i = 0; i < n; ++i) {
     if (!ctx[i]) return set_err(MG_ERR_ARG, "NULL context");
     if (!ctx[i]->alt_final) return set_err(MG_ERR_STATE, "mg_reduce_counts before mg_finalize_alt");
@@ -1052,27 +1408,46 @@ extern "C" int mg_reduce_counts(mg_ctx **ctx, int n) {
       return set_err(MG_ERR_ARG, "context %d does not hold the same index as context 0", i);
     for (int j = 0; j < i; ++j)
       if (ctx[j] == ctx[i]) return set_err(MG_ERR_ARG, "context %d listed twice", i);
+  }
+  if (n == 1) return mg_sync(ctx[0]);
+  for (int i = 0; i < n; ++i) {  // (asynchronous on every device: the gathers run side by side)
+    CU(cudaSetDevice(ctx[i]->device));
     int rc = mg_sync(ctx[i]);
     if (rc) return rc;
+    rc = counters_xfer(ctx[i], false);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < n; ++i) {
+    CU(cudaSetDevice(ctx[i]->device));
+    CU(cudaStreamSynchronize(ctx[i]->stream[0]));
   }
   mg_ctx *c0 = ctx[0];
   CU(cudaSetDevice(c0->device));
-  const uint64_t CH = 1ull << 26;  // u32 elements per staging chunk (256 MB)
-  DevFree stage;
-  CU(cudaMalloc(&stage.p, CH * 4));
-  for (int i = 1; i < n; ++i) {
-    uint32_t *dst[3] = {c0->bf_counts, c0->key_counts, c0->ovf_counts};
-    uint32_t *src[3] = {ctx[i]->bf_counts, ctx[i]->key_counts, ctx[i]->ovf_counts};
-    uint64_t len[3] = {c0->bf_ones, c0->n_lines * mg::LINE_KEYS, 1ull << c0->ovf_log2};
-    for (int a = 0; a < 3; ++a)
-      for (uint64_t o = 0; o < len[a]; o += CH) {
-        uint64_t m = len[a] - o < CH ? len[a] - o : CH;
-        CU(cudaMemcpyPeerAsync(stage.p, c0->device, src[a] + o, ctx[i]->device, m * 4, c0->stream[0]));
-        c0->launches++;
-        mg::k_add_u32<<<grid_for((m + 3) / 4, 256), 256, 0, c0->stream[0]>>>(dst[a] + o, (const uint32_t *)stage.p, m);
-        CU(cudaGetLastError());
-      }
+  for (int i = 1; i < n; ++i)
+    if (ctx[i]->device != c0->device) {
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, c0->device, ctx[i]->device));
+      if (!can) return set_err(MG_ERR_CUDA, "device %d cannot read device %d's memory", c0->device, ctx[i]->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctx[i]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return set_err(MG_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) -> %s", ctx[i]->device, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  uint32_t *dst[3] = {c0->bf_counts, c0->key_dense, c0->ovf_counts};
+  const uint64_t len[3] = {c0->bf_ones, c0->n_keys - c0->ovf_n, 1ull << c0->ovf_log2};
+  for (int a = 0; a < 3; ++a) {
+    if (!len[a]) continue;
+    mg::PeerPtrs pp;
+    pp.n = n - 1;
+    for (int i = 1; i < n; ++i) pp.p[i - 1] = a == 0 ? ctx[i]->bf_counts : a == 1 ? ctx[i]->key_dense : ctx[i]->ovf_counts;
+    const uint64_t want = (len[a] / 4 + 255) / 256 + 1;
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)c0->sms * 16);
+    c0->launches++;
+    mg::k_sum_peers<<<grid, 256, 0, c0->stream[0]>>>(dst[a], pp, len[a]);
+    CU(cudaGetLastError());
   }
+  int rc = counters_xfer(c0, true);
+  if (rc) return rc;
   CU(cudaStreamSynchronize(c0->stream[0]));
   return MG_OK;
 }
@@ -1141,8 +1516,7 @@ extern "C" int mg_export_ref_keys(mg_ctx *c, uint64_t *lohi, uint64_t cap, uint6
   CU(cudaMemsetAsync(c->d_scalars, 0, 8, c->stream[0]));
   uint64_t ovf_cap = 1ull << c->ovf_log2, total = c->n_lines * mg::LINE_KEYS + ovf_cap;
   c->launches++;
-  mg::k_emit_keys<<<grid_for(total, 256), 256, 0, c->stream[0]>>>(c->lines, c->n_lines, c->ovf_keys, ovf_cap, c->d_scalars,
-                                                                  (u128 *)d.p, c->n_keys);
+  mg::k_emit_keys<<<grid_for(total, 256), 256, 0, c->stream[0]>>>(c->view(), ovf_cap, c->d_scalars, (u128 *)d.p, c->n_keys);
   CU(cudaGetLastError());
   unsigned long long got = 0;
   CU(cudaMemcpyAsync(&got, c->d_scalars, 8, cudaMemcpyDeviceToHost, c->stream[0]));
@@ -1435,10 +1809,16 @@ extern "C" int mg_genotype_kernel_ms(mg_ctx *c, float *ms3) {
   return MG_OK;
 }
 extern "C" int mg_refpass_kernel_ms(mg_ctx *c, float *ms) {
-  if (!c || !ms || !c->rpe[1]) return set_err(MG_ERR_ARG, "no mg_scan_reference call to report");
+  if (!c || !ms || !c->rp_chunks) return set_err(MG_ERR_ARG, "no mg_scan_reference call to report");
   CU(cudaSetDevice(c->device));
-  CU(cudaEventSynchronize(c->rpe[1]));
-  CU(cudaEventElapsedTime(ms, c->rpe[0], c->rpe[1]));
+  float total = 0;
+  for (size_t j = 0; j < c->rp_chunks; ++j) {  // the rolling-pass kernels of every chunk of the last contig
+    float t = 0;
+    CU(cudaEventSynchronize(c->rp_events[2 * j + 1]));
+    CU(cudaEventElapsedTime(&t, c->rp_events[2 * j], c->rp_events[2 * j + 1]));
+    total += t;
+  }
+  *ms = total;
   return MG_OK;
 }
 extern "C" int mg_launch_count(mg_ctx *c, uint64_t *n) {

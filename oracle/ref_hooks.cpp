@@ -52,15 +52,16 @@ uint64_t ref_kmap_size(void *m) { return ((KMAP *)m)->kmers.size(); }
 // ---- sample scan, one KMC record (main.cpp:490-499) -------------------------
 void ref_scan_kmer(void *bf, void *context_bf, void *ref_bf, const char *context_in, uint32_t counter,
                    int k, int ref_k) {
-  std::vector<char> context(context_in, context_in + ref_k);
-  context.push_back('\0');
-  std::transform(context.begin(), context.begin() + ref_k, context.begin(), ::toupper);
-  std::vector<char> kmer(k + 1);
-  strncpy(kmer.data(), context.data() + ((ref_k - k) / 2), k);
+  // stack arrays, as main.cpp:487-488 has them (char context[ref_k + 1]; char kmer[k + 1];)
+  char context[130], kmer[130];
+  memcpy(context, context_in, (size_t)ref_k);
+  context[ref_k] = '\0';
+  std::transform(context, context + ref_k, context, ::toupper);
+  strncpy(kmer, context + ((ref_k - k) / 2), k);
   kmer[k] = '\0';
-  ((KMAP *)ref_bf)->increment(kmer.data(), counter);
-  if (!((BF *)context_bf)->test_key(context.data())) {
-    ((BF *)bf)->increment(kmer.data(), counter);
+  ((KMAP *)ref_bf)->increment(kmer, counter);
+  if (!((BF *)context_bf)->test_key(context)) {
+    ((BF *)bf)->increment(kmer, counter);
   }
 }
 
@@ -92,6 +93,82 @@ void ref_scan_packed(void *bf, void *context_bf, void *ref_bf, const uint64_t *l
     unpack_kmer(lohi[2 * i], lohi[2 * i + 1], ref_k, context);  // kmer_obj.to_string(context), main.cpp:490
     ref_scan_kmer(bf, context_bf, ref_bf, context, counts[i], k, ref_k);
   }
+}
+
+// BF::get_count / KMAP::get_count over packed k-mers (bench.py's exact check of the device counters)
+void ref_get_counts_packed(void *bf, void *ref_bf, const uint64_t *lohi, const uint8_t *is_ref, uint64_t n, int k,
+                           int32_t *out) {
+  char kmer[130];
+  for (uint64_t i = 0; i < n; ++i) {
+    unpack_kmer(lohi[2 * i], lohi[2 * i + 1], k, kmer);
+    out[i] = is_ref[i] ? (int32_t)((KMAP *)ref_bf)->get_count(kmer) : (int32_t)((BF *)bf)->get_count(kmer);
+  }
+}
+
+// set_coverages + VB::genotype over a batch (main.cpp:151-184, 565-566; var_block.hpp:224-330): the CPU
+// counterpart of mg_genotype on the reference's own classes.  CSR as in mg_packed_batch (u32 offsets, packed
+// k-mers, ref allele = slot 0).  Returns a checksum of the best genotypes so that nothing is optimised away.
+uint64_t ref_genotype_batch(void *bf_, void *ref_bf_, uint64_t n_variants, const uint32_t *var_allele_off,
+                            const uint32_t *allele_sig_off, const uint32_t *sig_kmer_off, const uint64_t *lohi,
+                            const float *freq, int k, float error_rate, int max_cov, int haploid, uint32_t *cov_out,
+                            int32_t *best_out, int32_t *gq_out) {
+  BF &bf = *(BF *)bf_;
+  KMAP &ref_bf = *(KMAP *)ref_bf_;
+  uint64_t sum = 0;
+  char kmer[130];
+  for (uint64_t v = 0; v < n_variants; ++v) {
+    const uint32_t a0 = var_allele_off[v], a1 = var_allele_off[v + 1];
+    Variant var;
+    var.seq_name = "1";
+    var.ref_pos = 0;
+    var.idx = ".";
+    var.ref_sub = "A";
+    for (uint32_t i = a0 + 1; i < a1; ++i) var.alts.push_back("C");
+    var.quality = 0;
+    var.filter = "PASS";
+    var.info = ".";
+    var.coverages.assign(a1 - a0, 0);
+    var.frequencies.assign(freq + a0, freq + a1);
+    VB vb(k, error_rate);
+    vb.add_variant(var);
+    for (uint32_t a = a0; a < a1; ++a) {  // set_coverages, main.cpp:157-182
+      uint allele_cov = 0;
+      for (uint32_t s = allele_sig_off[a]; s < allele_sig_off[a + 1]; ++s) {
+        uint curr_cov = 0;
+        int n = 0;
+        for (uint32_t q = sig_kmer_off[s]; q < sig_kmer_off[s + 1]; ++q) {
+          unpack_kmer(lohi[2 * (uint64_t)q], lohi[2 * (uint64_t)q + 1] & 0x3FFFFFFFFFFFFFFFULL, k, kmer);
+          uint w = a == a0 ? (uint)ref_bf.get_count(kmer) : (uint)bf.get_count(kmer);
+          if (w > 0) {
+            curr_cov = (curr_cov * n + w) / (n + 1);
+            ++n;
+          }
+        }
+        if (curr_cov > allele_cov) allele_cov = curr_cov;
+      }
+      vb.set_variant_coverage(0, (int)(a - a0), allele_cov);
+      if (cov_out) cov_out[a] = allele_cov;
+    }
+    vb.genotype(max_cov, haploid != 0);
+    Variant r = vb.get_variant(0);
+    // arg-max of VB::output_variants (var_block.hpp:367-394)
+    double total = 0.0;
+    for (const auto &g : r.computed_gts) total += g.second;
+    double best = 0.0;
+    int bi = 0, i = 0;
+    for (const auto &g : r.computed_gts) {
+      double q = g.second / total;
+      if (q > best) {
+        best = q;
+        bi = i;
+      }
+      ++i;
+    }
+    if (best_out) best_out[v] = bi;
+    if (gq_out) gq_out[v] = (int)round(best * 100);
+    sum += (uint64_t)bi + (uint64_t)r.computed_gts.size();
+  }
+  return sum;
 }
 
 // ---- reference rolling pass over one contig (main.cpp:385-400) ---------------

@@ -69,6 +69,28 @@ def test_cli_haploid_example(cli, verbose, golden, tmp_path):
     assert got == expected, first_diff(got, expected)
 
 
+def test_cli_sars_cov2_example_config1(cli, tmp_path):
+    """BASELINE config 1 on its real input: example/sars_cov2.vcf.gz (15,154 records incl. multi-allelic x 27,934
+    haploid samples -- one var_block spanning the genome) + reference_sarsCov2.fasta + the bundled haploid reads,
+    `-1 -k 35 -r 43 -b 1`.  Expected: the verbose VCF the reference's own main.cpp printed on the same files
+    (tests/golden/sars/sars.expected.verbose.vcf.gz; 310 s index + 307 s call on one core of the build container,
+    GT histogram 13169 x 0:0, 1983 x 0:100, 1:94, 1:100 as in SURVEY 8c)."""
+    import time
+    src, hap = os.path.join(GOLD, "sars"), os.path.join(GOLD, "haploid")
+    for f in ("reference_sarsCov2.fasta", "sars_cov2.vcf.gz"):
+        os.symlink(os.path.join(src, f), tmp_path / f)
+    for f in ("haploid.kmc_pre", "haploid.kmc_suf"):
+        os.symlink(os.path.join(hap, f), tmp_path / f)
+    t0 = time.time()
+    got = run_ours(cli, ["-1", "-k", "35", "-r", "43", "-b", "1"], str(tmp_path / "reference_sarsCov2.fasta"),
+                   str(tmp_path / "sars_cov2.vcf.gz"), str(tmp_path / "haploid"), verbose=True)
+    print(f"sars_cov2 index + call: {time.time() - t0:.1f} s (reference: 310 s + 307 s)")
+    expected = gzip.open(os.path.join(src, "sars.expected.verbose.vcf.gz")).read()
+    assert got == expected, first_diff(got, expected)
+    gts = [l.split(b"\t")[-1] for l in got.split(b"\n") if l and not l.startswith(b"#")]
+    assert len(gts) == 15154 and gts.count(b"0:0") == 13169 and gts.count(b"0:100") == 1983
+
+
 def test_cli_threads_and_errors(cli, tmp_path):
     """one host thread gives the same bytes; a missing index / KMC database / INFO key fails like the reference"""
     case = synth.CASES[2]

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from malva_b200 import MalvaGpu, MalvaGpuError, SignatureBatch, kmc
+from malva_b200.api import PackedSignatureBatch, reduce_counts
 import parity_util as util
 
 pytestmark = pytest.mark.gpu
@@ -157,6 +158,18 @@ def test_coverage_and_genotype(oracle_lib, haploid, err):
             assert np.array_equal(got == 0, e["probs"] == 0)
             seen.add(e["status"])
         assert seen == {0, 1, 2}, seen
+        # the packed batch form (what the C++ host sends) is the same computation: identical bits out
+        pb = PackedSignatureBatch.from_batch(batch, 35)
+        assert len(pb.irr_kmer) > 0, "the synthetic signatures should include irregular k-mers"
+        rp = g.genotype_packed(pb, err, max_cov, haploid)
+        for name in ("cov", "status", "n_gts", "best_gt", "gq"):
+            assert np.array_equal(getattr(rp, name), getattr(r, name)), name
+        for v in range(batch.n_variants):
+            a, b = int(r.lik_off[v]), int(rp.lik_off[v])
+            assert np.array_equal(r.lik[a:a + r.n_gts[v]].view(np.uint64), rp.lik[b:b + rp.n_gts[v]].view(np.uint64)), v
+        rq = g.genotype_packed(pb, err, max_cov, haploid, want_lik=False)   # likelihoods stay on the device
+        for name in ("cov", "status", "n_gts", "best_gt", "gq"):
+            assert np.array_equal(getattr(rq, name), getattr(r, name)), name
     finally:
         g.close()
         o.close()
@@ -249,7 +262,7 @@ def _counter_arrays(g):
 
     g.sync()
     out = []
-    for ptr, n in g.counter_buffers():
+    for ptr, n in g.counter_buffers(gather=True):
         out.append(torch.as_tensor(_DevArray(ptr, n), device="cuda:0").cpu().numpy().copy() if n else np.zeros(0, np.uint32))
     return out
 
@@ -296,6 +309,15 @@ def test_replicas_built_in_any_order_have_one_image_and_their_counters_add_up(or
         # and the single-replica answers are the reference's
         assert np.array_equal(whole.get_counts(ks, fl), o.get_counts(ks, fl))
         assert np.array_equal(whole.bf_counts(), o.bf_counts())
+        # the in-process reduce (gather, N-way sum over peer memory, scatter back into the probe lines)
+        reduce_counts([a, b])
+        assert np.array_equal(a.get_counts(ks, fl), o.get_counts(ks, fl))
+        assert np.array_equal(a.bf_counts(), o.bf_counts())
+        # ... and the scan keeps working on the scattered counters
+        a.scan_sample_kmers(packed, counts)
+        whole.scan_sample_kmers(packed, counts)
+        assert np.array_equal(a.get_counts(ks, fl), whole.get_counts(ks, fl))
+        assert np.array_equal(a.bf_counts(), whole.bf_counts())
     finally:
         for x in (a, b, whole, o):
             x.close()
