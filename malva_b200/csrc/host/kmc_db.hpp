@@ -73,7 +73,8 @@ struct KmcDb {
     min_count = rd32(h + o), o += 4;
     max_count = rd32(h + o), o += 4;
     total_kmers = rd64(h + o), o += 8;
-    both_strands = !(h[o] & 1);
+    both_strands = !(h[o] & 1);  // (stored inverted)
+    if (o + 5 + 4 <= hoff) max_count |= (uint64_t)rd32(h + o + 1) << 32;  // KMC 3: high word of max_count
     if (lut_prefix_len > 15 || lut_prefix_len >= kmer_len || (kmer_len - lut_prefix_len) % 4 != 0 || counter_size > 8) {
       why = prefix + ".kmc_pre: unsupported layout";
       return false;

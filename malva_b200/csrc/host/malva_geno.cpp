@@ -10,8 +10,10 @@
 // without a usable CUDA device both sub-commands fail.
 //
 // What is organised differently from the reference's two loops:
-//   * VCF lines are decoded and var_blocks enumerated in parallel (blocks are independent), in batches, and a
-//     batch goes to the device in one call (mg_add_signatures / mg_genotype) instead of one k-mer at a time;
+//   * VCF lines are decoded and signatures enumerated in parallel (per variant, inside a block as well as across
+//     blocks), in batches; a batch goes to the device in one call (mg_add_signatures_packed / mg_genotype_packed:
+//     2-bit k-mer words) instead of one k-mer string at a time; the stages of consecutive batches overlap:
+//     read + decode | enumerate | device | format + write each run on their own thread;
 //   * the KMC database is not decoded on the host: raw suffix records stream through pinned buffers into
 //     mg_scan_kmc_records;
 //   * the index file holds sparse lists (index_file.hpp).
@@ -28,6 +30,9 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -171,7 +176,9 @@ double cpu_seconds() {
   return (double)u.ru_utime.tv_sec + (double)u.ru_utime.tv_usec * 1e-6;
 }
 double g_cpu_start = cpu_seconds();
+std::mutex g_pelapsed_mutex;  // (progress lines come from the reader thread as well)
 void pelapsed(const std::string &s, bool rollback = false) {
+  std::lock_guard<std::mutex> lock(g_pelapsed_mutex);
   auto now = Clock::now();
   char buf[512];
   rusage u;
@@ -259,7 +266,9 @@ class BlockStream {
     const bool more = reader_.next_lines(store_, lines_, max_lines, 12u << 20);
     t_read += sw.lap();
     std::vector<mh::Variant> vars(lines_.size());
-    const size_t grain = 256, n_tasks = (lines_.size() + grain - 1) / grain;
+    // (a line of a 27,934-sample panel is 84 KB: a 12 MB block holds ~150 of them, so the grain follows the count)
+    const size_t grain = std::max<size_t>(1, std::min<size_t>(256, lines_.size() / (4 * (size_t)o_.threads) + 1));
+    const size_t n_tasks = (lines_.size() + grain - 1) / grain;
     parallel_for(n_tasks, o_.threads, [&](size_t t) {
       for (size_t i = t * grain; i < std::min(lines_.size(), (t + 1) * grain); ++i)
         vars[i] = mh::parse_record(lines_[i].b, lines_[i].e, reader_.header, o_.freq_key, o_.uniform, freq_declared_);
@@ -338,20 +347,125 @@ class BatchPrefetcher {
   std::future<std::pair<bool, std::vector<mh::VarBlock>>> pending_;
 };
 
-// signatures of a batch of blocks, enumerated in parallel, concatenated in block order
+// signatures of a batch of blocks: tasks of ~64 consecutive variants (a block of thousands of variants is split,
+// small blocks are grouped) enumerated in parallel, their parts then copied side by side into one CSR
 void enumerate_batch(const std::vector<mh::VarBlock> &blocks, std::map<std::string, std::string> &refs, const Options &o,
                      mh::SignatureCsr &out) {
   for (const auto &b : blocks) refs[b.contig];  // (the reference's refs[name] creates missing contigs as empty)
-  // chunks of blocks per task keep the per-task CSR allocations coarse
-  const size_t chunk = 64, n_chunks = (blocks.size() + chunk - 1) / chunk;
-  std::vector<mh::SignatureCsr> parts(n_chunks);
-  parallel_for(n_chunks, o.threads, [&](size_t c) {
-    for (size_t b = c * chunk; b < std::min(blocks.size(), (c + 1) * chunk); ++b)
-      blocks[b].enumerate(refs.find(blocks[b].contig)->second, o.haploid, parts[c]);
+  struct Segment {
+    uint32_t block, begin, end;
+  };
+  constexpr size_t TASK_VARIANTS = 64;
+  std::vector<Segment> segs;
+  std::vector<size_t> task_first{0};  // tasks = runs of segments
+  size_t in_task = 0;
+  for (size_t b = 0; b < blocks.size(); ++b)
+    for (size_t v = 0; v < blocks[b].size();) {
+      const size_t take = std::min(blocks[b].size() - v, TASK_VARIANTS - in_task);
+      segs.push_back(Segment{(uint32_t)b, (uint32_t)v, (uint32_t)(v + take)});
+      v += take;
+      in_task += take;
+      if (in_task == TASK_VARIANTS) {
+        task_first.push_back(segs.size());
+        in_task = 0;
+      }
+    }
+  if (task_first.back() != segs.size()) task_first.push_back(segs.size());
+  const size_t n_tasks = task_first.size() - 1;
+  std::vector<mh::SignatureCsr> parts(n_tasks);
+  std::vector<const std::string *> ref_of(blocks.size());
+  for (size_t b = 0; b < blocks.size(); ++b) ref_of[b] = &refs.find(blocks[b].contig)->second;
+  parallel_for(n_tasks, o.threads, [&](size_t t) {
+    static thread_local mh::VarBlock::Scratch sc;
+    for (size_t i = task_first[t]; i < task_first[t + 1]; ++i)
+      blocks[segs[i].block].enumerate(*ref_of[segs[i].block], o.haploid, segs[i].begin, segs[i].end, sc, parts[t]);
   });
-  out.clear();
-  for (const auto &p : parts) out.append(p);
+  mh::SignatureCsr::concat(parts, out, [&](size_t n, const std::function<void(size_t)> &fn) { parallel_for(n, o.threads, fn); });
 }
+
+// A bounded hand-over between two stages of the batch pipeline.
+template <class T>
+class Channel {
+ public:
+  explicit Channel(size_t cap) : cap_(cap) {}
+  void push(T &&v) {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+    if (closed_) return;
+    q_.push_back(std::move(v));
+    cv_.notify_all();
+  }
+  bool pop(T &out) {  // false once the channel is closed and drained
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    out = std::move(q_.front());
+    q_.pop_front();
+    cv_.notify_all();
+    return true;
+  }
+  void close() {
+    std::lock_guard<std::mutex> l(m_);
+    closed_ = true;
+    cv_.notify_all();
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
+  size_t cap_;
+  bool closed_ = false;
+};
+
+// one batch on its way through the pipeline
+struct Batch {
+  std::vector<mh::VarBlock> blocks;
+  mh::SignatureCsr sigs;
+  double t_parse = 0, t_enum = 0, t_dev = 0;
+  // results of the device stage (call)
+  std::vector<uint64_t> lik_off;
+  std::vector<uint32_t> cov;
+  std::vector<int32_t> n_gts, status, best, gq;
+  std::vector<double> lik;
+};
+
+// stage 1 + 2 of both sub-commands: batches of decoded blocks (read ahead by the BatchPrefetcher's own thread) with
+// their signatures enumerated, handed over in order.  An exception ends the stream and is re-thrown by join().
+class EnumeratedBatches {
+ public:
+  EnumeratedBatches(BatchPrefetcher &src, std::map<std::string, std::string> &refs, const Options &o)
+      : out_(2), th_([this, &src, &refs, &o] {
+          try {
+            while (true) {
+              auto b = std::make_unique<Batch>();
+              Stopwatch sw;
+              if (!src.next(b->blocks)) break;
+              b->t_parse = sw.lap();
+              enumerate_batch(b->blocks, refs, o, b->sigs);
+              b->t_enum = sw.lap();
+              out_.push(std::move(b));
+            }
+          } catch (...) {
+            err_ = std::current_exception();
+          }
+          out_.close();
+        }) {}
+  ~EnumeratedBatches() {
+    out_.close();
+    if (th_.joinable()) th_.join();
+  }
+  bool next(std::unique_ptr<Batch> &b) { return out_.pop(b); }
+  void join() {
+    if (th_.joinable()) th_.join();
+    if (err_) std::rethrow_exception(err_);
+  }
+
+ private:
+  Channel<std::unique_ptr<Batch>> out_;
+  std::exception_ptr err_;
+  std::thread th_;
+};
 
 constexpr size_t LINES_PER_BATCH = 1 << 17;  // (a batch is ~12 MB of VCF text, at most this many records)
 
@@ -390,19 +504,36 @@ int index_main(int argc, char **argv) {
   Stopwatch sw;
   gpu(mg_create(&g.c, o.device, (int)o.k, (int)o.ref_k, o.bf_size), "mg_create");
   if (o.trace) fprintf(stderr, "[trace] mg_create (CUDA start-up + empty index) %.1f ms\n", sw.lap());
-  std::vector<mh::VarBlock> blocks;
-  mh::SignatureCsr sigs;
-  while (index_batches.next(blocks)) {
-    const double t_parse = sw.lap();
-    enumerate_batch(blocks, refs, o, sigs);
-    const double t_enum = sw.lap();
-    // add_kmers_to_bf (main.cpp:122-144): allele 0 -> ref_bf, others -> bf
-    gpu(mg_add_signatures(g.c, sigs.pool.data(), sigs.kmer_off.data(), sigs.kmer_is_ref.data(), sigs.n_kmers()),
-        "mg_add_signatures");
-    if (o.trace)
-      fprintf(stderr, "[trace] index batch: %zu blocks, %llu k-mers: wait for read+decode %.1f ms, enumerate %.1f ms, device %.1f ms\n",
-              blocks.size(), (unsigned long long)sigs.n_kmers(), t_parse, t_enum, sw.lap());
-    sw.lap();
+  {
+    EnumeratedBatches batches(index_batches, refs, o);  // enumerates batch i+1 while batch i is inserted
+    std::unique_ptr<Batch> b;
+    std::vector<uint64_t> reg;  // the regular k-mers of a batch, and the text of the irregular ones
+    std::vector<uint8_t> reg_is_ref, irr_is_ref;
+    while (batches.next(b)) {
+      sw.lap();
+      const mh::SignatureCsr &sg = b->sigs;
+      // add_kmers_to_bf (main.cpp:122-144): allele 0 -> ref_bf, others -> bf
+      reg.clear();
+      reg_is_ref.clear();
+      irr_is_ref.clear();
+      for (uint64_t i = 0; i < sg.n_kmers(); ++i) {
+        if (sg.is_irregular(i)) continue;
+        reg.push_back(sg.kmers[2 * i]);
+        reg.push_back(sg.kmers[2 * i + 1] & ~(mh::SIG_REF_ALLELE | mh::SIG_IRREGULAR));
+        reg_is_ref.push_back(sg.is_ref_kmer(i));
+      }
+      gpu(mg_add_signatures_packed(g.c, reg.data(), reg_is_ref.data(), reg_is_ref.size()), "mg_add_signatures_packed");
+      if (sg.n_irregular()) {  // shorter than k / non-ACGT symbols: as text, hashed byte-exactly on the device
+        for (uint64_t j = 0; j < sg.n_irregular(); ++j) irr_is_ref.push_back(sg.is_ref_kmer(sg.irr_kmer[j]));
+        gpu(mg_add_signatures(g.c, sg.irr_pool.data(), sg.irr_off.data(), irr_is_ref.data(), sg.n_irregular()),
+            "mg_add_signatures");
+      }
+      if (o.trace)
+        fprintf(stderr, "[trace] index batch: %zu blocks, %llu k-mers (%llu irregular): read+decode wait %.1f ms, enumerate %.1f ms, device %.1f ms\n",
+                b->blocks.size(), (unsigned long long)sg.n_kmers(), (unsigned long long)sg.n_irregular(), b->t_parse,
+                b->t_enum, sw.lap());
+    }
+    batches.join();
   }
   pelapsed("Processed " + std::to_string(stream.n_records) + " variants");
   gpu(mg_finalize_alt(g.c), "mg_finalize_alt");  // bf.switch_mode()
@@ -541,6 +672,8 @@ int call_main(int argc, char **argv) {
   pelapsed("Reference parsing");
   std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
   pelapsed("Reference processed");
+  // (host only: the first batches are decoded and enumerated while the KMC records stream through the device)
+  EnumeratedBatches batches(call_batches, refs, o);
 
   // STEP 2: the sample k-mer scan (main.cpp:482-500).  Raw suffix records go through rings of pinned buffers, one
   // ring per device, chunks dealt round-robin; the library copies and scans them asynchronously (double-buffered on
@@ -589,57 +722,85 @@ int call_main(int argc, char **argv) {
   // STEP 3: genotype (main.cpp:504-581)
   std::cout << stream.header().cleaned(o.verbose);
   pelapsed("VCF parsing and genotyping");
-  std::vector<mh::VarBlock> blocks;
-  mh::SignatureCsr sigs;
-  std::vector<uint64_t> lik_off;
-  std::vector<uint32_t> cov;
-  std::vector<int32_t> n_gts, status, best, gq;
-  std::vector<double> lik;
+  // three stages on three threads: enumerate (EnumeratedBatches) | device (below) | format + write (this thread)
+  Channel<std::unique_ptr<Batch>> done(2);
+  std::exception_ptr dev_err;
+  std::thread device([&] {
+    try {
+      std::unique_ptr<Batch> b;
+      while (batches.next(b)) {
+        Stopwatch sw;
+        const mh::SignatureCsr &sg = b->sigs;
+        const uint64_t nv = sg.n_variants();
+        if (nv) {
+          if (o.verbose) {
+            b->lik_off.assign(nv + 1, 0);
+            for (uint64_t i = 0; i < nv; ++i) {
+              uint64_t n = sg.var_allele_off[i + 1] - sg.var_allele_off[i];
+              b->lik_off[i + 1] = b->lik_off[i] + std::max<uint64_t>(n, o.haploid ? n : n * (n + 1) / 2);
+            }
+            b->lik.resize(b->lik_off[nv]);
+          }
+          b->cov.resize(sg.n_alleles());
+          b->n_gts.resize(nv), b->status.resize(nv), b->best.resize(nv), b->gq.resize(nv);
+          mg_packed_batch in = {nv,
+                                sg.var_allele_off.data(),
+                                sg.allele_sig_off.data(),
+                                sg.sig_kmer_off.data(),
+                                sg.kmers.data(),
+                                sg.freq.data(),
+                                sg.n_irregular(),
+                                sg.irr_off.data(),
+                                sg.irr_pool.data(),
+                                sg.irr_kmer.data()};
+          mg_genotype_out res = {b->cov.data(),  b->n_gts.data(), b->status.data(),
+                                 b->best.data(), b->gq.data(),    o.verbose ? b->lik_off.data() : nullptr,
+                                 o.verbose ? b->lik.data() : nullptr};
+          gpu(mg_genotype_packed(g.c, &in, &res, o.error_rate, (int)o.max_coverage, o.haploid ? 1 : 0), "mg_genotype_packed");
+        }
+        b->t_dev = sw.lap();
+        done.push(std::move(b));
+      }
+    } catch (...) {
+      dev_err = std::current_exception();
+    }
+    done.close();
+  });
+  struct Joiner {  // (an exception below must not leave the thread running)
+    std::thread &t;
+    Channel<std::unique_ptr<Batch>> &c;
+    ~Joiner() {
+      c.close();
+      if (t.joinable()) t.join();
+    }
+  } joiner{device, done};
   std::vector<const mh::Variant *> order;
   std::vector<std::string> text;
+  std::unique_ptr<Batch> b;
   Stopwatch sw;
-  while (call_batches.next(blocks)) {
-    const double t_parse = sw.lap();
-    enumerate_batch(blocks, refs, o, sigs);
-    const double t_enum = sw.lap();
-    const uint64_t nv = sigs.n_variants();
+  while (done.pop(b)) {
+    sw.lap();
+    const mh::SignatureCsr &sg = b->sigs;
+    const uint64_t nv = sg.n_variants();
     if (nv == 0) continue;
-    lik_off.assign(nv + 1, 0);
-    for (uint64_t i = 0; i < nv; ++i) {
-      uint64_t n = sigs.var_allele_off[i + 1] - sigs.var_allele_off[i];
-      lik_off[i + 1] = lik_off[i] + std::max<uint64_t>(n, o.haploid ? n : n * (n + 1) / 2);
-    }
-    cov.resize(sigs.n_alleles());
-    n_gts.resize(nv), status.resize(nv), best.resize(nv), gq.resize(nv);
-    lik.resize(o.verbose ? lik_off[nv] : 0);
-    mg_variant_batch in = {nv,
-                           sigs.var_allele_off.data(),
-                           sigs.allele_sig_off.data(),
-                           sigs.sig_kmer_off.data(),
-                           sigs.kmer_off.data(),
-                           sigs.pool.data(),
-                           sigs.freq.data()};
-    mg_genotype_out res = {cov.data(),  n_gts.data(),   status.data(),
-                           best.data(), gq.data(),      lik_off.data(),
-                           o.verbose ? lik.data() : nullptr};
-    gpu(mg_genotype(g.c, &in, &res, o.error_rate, (int)o.max_coverage, o.haploid ? 1 : 0), "mg_genotype");
-    const double t_dev = sw.lap();
     order.clear();
-    for (const auto &b : blocks)
-      for (size_t i = 0; i < b.size(); ++i) order.push_back(&b[i]);
+    for (const auto &blk : b->blocks)
+      for (size_t i = 0; i < blk.size(); ++i) order.push_back(&blk[i]);
     const size_t chunk = 4096, n_chunks = (nv + chunk - 1) / chunk;
     text.assign(n_chunks, std::string());
     parallel_for(n_chunks, o.threads, [&](size_t c) {
       for (size_t i = c * chunk; i < std::min<size_t>(nv, (c + 1) * chunk); ++i)
-        format_variant(*order[i], cov.data() + sigs.var_allele_off[i], n_gts[i], status[i], best[i], gq[i],
-                       o.verbose ? lik.data() + lik_off[i] : nullptr, o, text[c]);
+        format_variant(*order[i], b->cov.data() + sg.var_allele_off[i], b->n_gts[i], b->status[i], b->best[i], b->gq[i],
+                       o.verbose ? b->lik.data() + b->lik_off[i] : nullptr, o, text[c]);
     });
     for (const auto &t : text) fwrite(t.data(), 1, t.size(), stdout);
     if (o.trace)
-      fprintf(stderr, "[trace] call batch: %llu variants, %llu k-mers: wait for read+decode %.1f ms, enumerate %.1f ms, device %.1f ms, print %.1f ms\n",
-              (unsigned long long)nv, (unsigned long long)sigs.n_kmers(), t_parse, t_enum, t_dev, sw.lap());
-    sw.lap();
+      fprintf(stderr, "[trace] call batch: %llu variants, %llu k-mers: read+decode wait %.1f ms, enumerate %.1f ms, device %.1f ms, print %.1f ms\n",
+              (unsigned long long)nv, (unsigned long long)sg.n_kmers(), b->t_parse, b->t_enum, b->t_dev, sw.lap());
   }
+  device.join();
+  if (dev_err) std::rethrow_exception(dev_err);
+  batches.join();
   pelapsed("Processed " + std::to_string(stream.n_records) + " variants");
   fflush(stdout);
   pelapsed("Execution completed");
@@ -684,7 +845,7 @@ int signatures_main(int argc, char **argv) {
             std::cout << block_no << '\t' << b.contig << '\t' << b[i].ref_pos + 1 << '\t' << i << '\t' << (a - a0) << '\t';
             for (uint64_t q = sigs.sig_kmer_off[s]; q < sigs.sig_kmer_off[s + 1]; ++q) {
               if (q != sigs.sig_kmer_off[s]) std::cout << ',';
-              std::cout.write(sigs.pool.data() + sigs.kmer_off[q], (std::streamsize)(sigs.kmer_off[q + 1] - sigs.kmer_off[q]));
+              std::cout << sigs.text(q, (int)o.k);
             }
             std::cout << '\n';
           }

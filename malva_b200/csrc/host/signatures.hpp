@@ -1,8 +1,8 @@
 // Host-kept part of malva-geno (north star: "the C++ host keeps VCF parsing, FASTA reading and var_block
 // signature enumeration").  This file: the variant record and the var_block signature enumerator, written
-// from scratch to emit the batch (CSR) layout the C ABI consumes directly -- not the reference's
-// map<int, map<int, vector<vector<string>>>> -- and to be run on many blocks in parallel (blocks are
-// independent).
+// from scratch to emit the packed batch (mg_packed_batch: 2-bit k-mer words, u32 CSR offsets) the C ABI consumes
+// directly -- not the reference's map<int, map<int, vector<vector<string>>>> -- and to run in parallel over the
+// variants of a batch, inside a block as well as across blocks.
 //
 // Behaviour follows the reference decision by decision:
 //   block membership ("near")       var_block.hpp:417-423   (single-precision compare, see near())
@@ -11,11 +11,14 @@
 //   haplotype allele combinations   var_block.hpp:709-786
 //   signature construction          var_block.hpp:95-219
 // What differs is only how the work is organised:
-//   * haplotypes are tuples of small allele ids, not vectors of string_view; an allele id is the index of the
-//     first allele of the variant with the same TEXT, which is exactly the identity the reference's
-//     unordered_set<vector<string_view>> and Variant::get_allele_index (variant.hpp:228-240) use;
-//   * identical per-sample genotype patterns are collapsed before unphased patterns are expanded into their
-//     2^n haplotypes (2,504 samples mostly share a handful of patterns);
+//   * genotypes are kept SPARSE: per variant the samples whose genotype is not the default (reference allele on
+//     every haplotype, the variant's majority phasing flag); the haplotypes of a chain come from a merge of the
+//     chain members' sparse lists -- work proportional to the carriers, not to the panel size (27,934 samples in the
+//     SARS-CoV-2 example, a handful of carriers per record) -- plus one all-reference row for everybody else;
+//   * haplotypes are tuples of small allele ids; an allele id is the index of the first allele of the variant with
+//     the same TEXT, which is exactly the identity the reference's unordered_set<vector<string_view>> and
+//     Variant::get_allele_index (variant.hpp:228-240) use;
+//   * identical genotype patterns are collapsed before unphased patterns are expanded into their 2^n haplotypes;
 //   * duplicate signatures of an allele are dropped: the coverage of an allele is a max over its signatures
 //     (main.cpp:176-177) and filter/table inserts are idempotent, so results cannot change.
 // The order of the signatures of an allele is unspecified in the reference too (unordered_set iteration).
@@ -31,6 +34,12 @@
 
 namespace mh {
 
+struct GtEntry {  // genotype of one kept sample, as allele TEXT ids (see Variant::text_id)
+  uint32_t sample;
+  uint16_t h1, h2;
+  uint8_t phased;
+};
+
 struct Variant {
   std::string seq_name;
   int ref_pos = 0;  // 0-based
@@ -38,15 +47,17 @@ struct Variant {
   std::string ref_sub;
   std::vector<std::string> alts;  // symbolic (<..>) alleles removed, upper-cased
   float quality = 0;
-  std::vector<uint16_t> gt;     // two allele indices per kept sample (variant.hpp:158-211)
-  std::vector<uint8_t> phased;  // one flag per kept sample
+  // genotypes of the kept samples (variant.hpp:158-211): every sample without an entry is {0, 0, default_phased}
+  uint32_t n_samples_ = 0;
+  uint8_t default_phased = 1;
+  std::vector<GtEntry> gts;  // ascending sample index
   int ref_size = 0, min_size = 0, max_size = 0;
   bool has_alts = true, is_present = true;
   std::vector<float> frequencies;
   std::vector<uint16_t> text_id;  // allele index -> first allele index with the same text
 
   int n_alleles() const { return (int)alts.size() + 1; }
-  size_t n_samples() const { return phased.size(); }
+  size_t n_samples() const { return n_samples_; }
   const std::string &allele(int i) const { return i == 0 ? ref_sub : alts[(size_t)i - 1]; }
 
   void set_sizes() {  // variant.hpp:108-124
@@ -72,40 +83,116 @@ struct Variant {
     }
   }
   // a GT index past the kept ALTs is undefined behaviour in the reference (variant.hpp:221); clamp it
-  uint16_t gt_text_id(size_t sample, int which) const {
-    int a = gt[2 * sample + (size_t)which];
-    if (a >= n_alleles()) a = n_alleles() - 1;
-    return text_id[(size_t)a];
+  uint16_t text_id_of(int allele_index) const {
+    if (allele_index >= n_alleles()) allele_index = n_alleles() - 1;
+    return text_id[(size_t)allele_index];
   }
 };
 
-// Flattened signatures of a run of variants: variant -> allele slot -> signature -> k-mers.
+constexpr uint64_t SIG_IRREGULAR = 1ull << 63;  // mg_packed_batch: hi bit 63
+constexpr uint64_t SIG_REF_ALLELE = 1ull << 62;  // hi bit 62
+
+// Flattened signatures of a run of variants: variant -> allele slot -> signature -> k-mers (mg_packed_batch).
 struct SignatureCsr {
-  std::string pool;
-  std::vector<uint64_t> kmer_off{0}, sig_kmer_off{0}, allele_sig_off{0}, var_allele_off{0};
-  std::vector<uint8_t> kmer_is_ref;
+  std::vector<uint64_t> kmers;  // {lo, hi} per k-mer
+  std::vector<uint32_t> sig_kmer_off{0}, allele_sig_off{0}, var_allele_off{0};
   std::vector<float> freq;
+  // k-mers that are not exactly k symbols of ACGT (var_block.hpp:178-193 at contig ends; N / IUPAC in the reference)
+  std::string irr_pool;
+  std::vector<uint64_t> irr_off{0};
+  std::vector<uint32_t> irr_kmer;
   uint64_t n_variants() const { return var_allele_off.size() - 1; }
   uint64_t n_alleles() const { return allele_sig_off.size() - 1; }
-  uint64_t n_kmers() const { return kmer_off.size() - 1; }
+  uint64_t n_sigs() const { return sig_kmer_off.size() - 1; }
+  uint64_t n_kmers() const { return kmers.size() / 2; }
+  uint64_t n_irregular() const { return irr_kmer.size(); }
   void clear() {
-    pool.clear();
-    kmer_off.assign(1, 0);
+    kmers.clear();
     sig_kmer_off.assign(1, 0);
     allele_sig_off.assign(1, 0);
     var_allele_off.assign(1, 0);
-    kmer_is_ref.clear();
     freq.clear();
+    irr_pool.clear();
+    irr_off.assign(1, 0);
+    irr_kmer.clear();
   }
-  void append(const SignatureCsr &o) {
-    const uint64_t pb = pool.size(), kb = n_kmers(), sb = sig_kmer_off.size() - 1, ab = n_alleles();
-    pool += o.pool;
-    for (size_t i = 1; i < o.kmer_off.size(); ++i) kmer_off.push_back(pb + o.kmer_off[i]);
-    for (size_t i = 1; i < o.sig_kmer_off.size(); ++i) sig_kmer_off.push_back(kb + o.sig_kmer_off[i]);
-    for (size_t i = 1; i < o.allele_sig_off.size(); ++i) allele_sig_off.push_back(sb + o.allele_sig_off[i]);
-    for (size_t i = 1; i < o.var_allele_off.size(); ++i) var_allele_off.push_back(ab + o.var_allele_off[i]);
-    kmer_is_ref.insert(kmer_is_ref.end(), o.kmer_is_ref.begin(), o.kmer_is_ref.end());
-    freq.insert(freq.end(), o.freq.begin(), o.freq.end());
+  bool is_ref_kmer(uint64_t i) const { return (kmers[2 * i + 1] & SIG_REF_ALLELE) != 0; }
+  bool is_irregular(uint64_t i) const { return (kmers[2 * i + 1] & SIG_IRREGULAR) != 0; }
+  // text of k-mer i (the `signatures` sub-command, the irregular inserts)
+  std::string text(uint64_t i, int k) const {
+    const uint64_t lo = kmers[2 * i], hi = kmers[2 * i + 1];
+    if (hi & SIG_IRREGULAR) return irr_pool.substr(irr_off[lo], irr_off[lo + 1] - irr_off[lo]);
+    std::string s((size_t)k, 'A');
+    for (int j = 0; j < k; ++j) {
+      const int sh = 2 * (k - 1 - j);
+      const uint64_t code = sh >= 64 ? (hi >> (sh - 64)) : (lo >> sh);
+      s[(size_t)j] = "ACGT"[code & 3];
+    }
+    return s;
+  }
+  void add_kmer(const char *s, size_t len, int k, bool is_ref) {
+    uint64_t lo = 0, hi = 0;
+    bool regular = (int)len == k;
+    for (size_t j = 0; regular && j < len; ++j) {
+      uint64_t c;
+      switch (s[j]) {
+        case 'A': c = 0; break;
+        case 'C': c = 1; break;
+        case 'G': c = 2; break;
+        case 'T': c = 3; break;
+        default: regular = false; c = 0;
+      }
+      hi = (hi << 2) | (lo >> 62);
+      lo = (lo << 2) | c;
+    }
+    if (!regular) {
+      lo = irr_kmer.size();
+      hi = SIG_IRREGULAR;
+      irr_kmer.push_back((uint32_t)n_kmers());
+      irr_pool.append(s, len);
+      irr_off.push_back(irr_pool.size());
+    }
+    if (is_ref) hi |= SIG_REF_ALLELE;
+    kmers.push_back(lo);
+    kmers.push_back(hi);
+  }
+  // out = parts[0] ++ parts[1] ++ ... ; the copies (with their offset shifts) are independent and run through `par`
+  template <class ParallelFor>
+  static void concat(const std::vector<SignatureCsr> &parts, SignatureCsr &out, ParallelFor &&par) {
+    const size_t n = parts.size();
+    std::vector<uint64_t> v0(n + 1, 0), a0(n + 1, 0), s0(n + 1, 0), k0(n + 1, 0), i0(n + 1, 0), p0(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) {
+      v0[i + 1] = v0[i] + parts[i].n_variants();
+      a0[i + 1] = a0[i] + parts[i].n_alleles();
+      s0[i + 1] = s0[i] + parts[i].n_sigs();
+      k0[i + 1] = k0[i] + parts[i].n_kmers();
+      i0[i + 1] = i0[i] + parts[i].n_irregular();
+      p0[i + 1] = p0[i] + parts[i].irr_pool.size();
+    }
+    out.var_allele_off.resize(v0[n] + 1);
+    out.allele_sig_off.resize(a0[n] + 1);
+    out.sig_kmer_off.resize(s0[n] + 1);
+    out.kmers.resize(2 * k0[n]);
+    out.freq.resize(a0[n]);
+    out.irr_kmer.resize(i0[n]);
+    out.irr_off.resize(i0[n] + 1);
+    out.irr_pool.resize(p0[n]);
+    out.var_allele_off[0] = out.allele_sig_off[0] = out.sig_kmer_off[0] = 0;
+    out.irr_off[0] = 0;
+    par(n, [&](size_t i) {
+      const SignatureCsr &p = parts[i];
+      for (size_t j = 1; j < p.var_allele_off.size(); ++j) out.var_allele_off[v0[i] + j] = (uint32_t)(a0[i] + p.var_allele_off[j]);
+      for (size_t j = 1; j < p.allele_sig_off.size(); ++j) out.allele_sig_off[a0[i] + j] = (uint32_t)(s0[i] + p.allele_sig_off[j]);
+      for (size_t j = 1; j < p.sig_kmer_off.size(); ++j) out.sig_kmer_off[s0[i] + j] = (uint32_t)(k0[i] + p.sig_kmer_off[j]);
+      if (!p.kmers.empty()) memcpy(out.kmers.data() + 2 * k0[i], p.kmers.data(), p.kmers.size() * 8);
+      if (!p.freq.empty()) memcpy(out.freq.data() + a0[i], p.freq.data(), p.freq.size() * 4);
+      for (size_t j = 0; j < p.irr_kmer.size(); ++j) {
+        out.irr_kmer[i0[i] + j] = (uint32_t)(k0[i] + p.irr_kmer[j]);
+        out.kmers[2 * (k0[i] + p.irr_kmer[j])] = i0[i] + j;  // index of the k-mer's text in the merged side pool
+        out.irr_off[i0[i] + j + 1] = p0[i] + p.irr_off[j + 1];
+      }
+      if (!p.irr_pool.empty()) memcpy(&out.irr_pool[p0[i]], p.irr_pool.data(), p.irr_pool.size());
+    });
   }
 };
 
@@ -128,12 +215,24 @@ class VarBlock {
   bool is_near_to_last(const Variant &v) const { return variants_near(vars_.back(), v, k_, 0); }
   std::string contig;  // name of the contig the block lies on (last_seq_name at flush time)
 
-  // Signatures of every variant of the block, appended to `out`: one variant entry per block member, in order;
-  // allele slot a = allele index a (slots of duplicate-text alleles stay empty, like in the reference).
-  void enumerate(const std::string &reference, bool haploid, SignatureCsr &out) const {
-    Scratch sc;  // reused by every variant of the block
-    sample_classes(sc);
-    for (size_t vi = 0; vi < vars_.size(); ++vi) {
+  // Work arrays reused from variant to variant (one per enumerating thread): no allocation per sample or per chain.
+  struct SigRec {  // one signature of the current variant: its k-mers lie back to back in Scratch::text
+    uint32_t allele, text_off, text_len, n_kmers;
+  };
+  struct Scratch {
+    std::vector<uint16_t> pat, cand, haps;
+    std::vector<uint32_t> order, table;
+    std::vector<size_t> cursor;
+    size_t n_haps = 0;
+    std::string text, kmer;                // signature text of the current variant; the k-mer being built
+    std::vector<SigRec> sigs;              // its signatures
+    std::vector<std::string> between;      // reference text between the members of the current chain
+  };
+
+  // Signatures of the variants [begin, end) of the block, appended to `out`: one variant entry per block member, in
+  // order; allele slot a = allele index a (slots of duplicate-text alleles stay empty, like in the reference).
+  void enumerate(const std::string &reference, bool haploid, size_t begin, size_t end, Scratch &sc, SignatureCsr &out) const {
+    for (size_t vi = begin; vi < end && vi < vars_.size(); ++vi) {
       const Variant &v = vars_[vi];
       sc.text.clear();
       sc.sigs.clear();
@@ -143,11 +242,12 @@ class VarBlock {
       // by allele, duplicates dropped (equal text + equal k-mer count = equal k-mer list: every k-mer of a
       // multi-k-mer signature is k long)
       auto text_of = [&](const SigRec &r) { return std::string_view(sc.text.data() + r.text_off, r.text_len); };
-      std::sort(sc.sigs.begin(), sc.sigs.end(), [&](const SigRec &x, const SigRec &y) {
-        if (x.allele != y.allele) return x.allele < y.allele;
-        if (x.n_kmers != y.n_kmers) return x.n_kmers < y.n_kmers;
-        return text_of(x) < text_of(y);
-      });
+      if (sc.sigs.size() > 1)
+        std::sort(sc.sigs.begin(), sc.sigs.end(), [&](const SigRec &x, const SigRec &y) {
+          if (x.allele != y.allele) return x.allele < y.allele;
+          if (x.n_kmers != y.n_kmers) return x.n_kmers < y.n_kmers;
+          return text_of(x) < text_of(y);
+        });
       size_t si = 0;
       for (int a = 0; a < v.n_alleles(); ++a) {
         const SigRec *prev = nullptr;
@@ -156,36 +256,18 @@ class VarBlock {
           if (prev && prev->n_kmers == r.n_kmers && text_of(*prev) == text_of(r)) continue;
           prev = &r;
           const size_t klen = r.n_kmers > 1 ? (size_t)k_ : r.text_len;
-          for (uint32_t q = 0; q < r.n_kmers; ++q) {
-            out.pool.append(sc.text, r.text_off + q * klen, klen);
-            out.kmer_off.push_back(out.pool.size());
-            out.kmer_is_ref.push_back(a == 0);
-          }
-          out.sig_kmer_off.push_back(out.kmer_off.size() - 1);
+          for (uint32_t q = 0; q < r.n_kmers; ++q) out.add_kmer(sc.text.data() + r.text_off + q * klen, klen, k_, a == 0);
+          out.sig_kmer_off.push_back((uint32_t)out.n_kmers());
         }
-        out.allele_sig_off.push_back(out.sig_kmer_off.size() - 1);
+        out.allele_sig_off.push_back((uint32_t)out.n_sigs());
         out.freq.push_back((size_t)a < v.frequencies.size() ? v.frequencies[(size_t)a] : 0.0f);
       }
-      out.var_allele_off.push_back(out.allele_sig_off.size() - 1);
+      out.var_allele_off.push_back((uint32_t)out.n_alleles());
     }
   }
 
  private:
   using Chain = std::vector<int>;
-  // flat work arrays (rows of uint16 allele text-ids) kept across the variants of a block: no allocation per sample
-  struct SigRec {  // one signature of the current variant: its k-mers lie back to back in Scratch::text
-    uint32_t allele, text_off, text_len, n_kmers;
-  };
-  struct Scratch {
-    std::vector<uint16_t> pat, cand, haps;
-    std::vector<uint32_t> order, table;
-    std::vector<uint32_t> reps;  // one representative per class of panel samples with identical genotypes in the block
-    std::vector<uint16_t> block_rows;
-    size_t n_haps = 0;
-    std::string text, kmer;                // signature text of the current variant; the k-mer being built
-    std::vector<SigRec> sigs;              // its signatures
-    std::vector<std::string> between;      // reference text between the members of the current chain
-  };
   // one index per distinct row, in order of first occurrence.  Thousands of panel samples share a handful of
   // genotype patterns, so this is a small open-addressing hash set keyed by row content, not a sort.
   static void distinct_rows(const std::vector<uint16_t> &rows, size_t n_rows, size_t width, std::vector<uint32_t> &order,
@@ -291,6 +373,7 @@ class VarBlock {
 
   // var_block.hpp:631-677: left chains (reversed into genomic order) x right chains around the mid variant
   std::vector<Chain> full_chains(int i) const {
+    if (vars_.size() == 1) return std::vector<Chain>{Chain{i}};  // (a block of one: nothing to chain)
     std::vector<Chain> right = side_chains(i, +1), left = side_chains(i, -1), out;
     if (left.empty()) left.push_back(Chain{});
     if (right.empty()) right.push_back(Chain{});
@@ -304,55 +387,47 @@ class VarBlock {
     return out;
   }
 
-  // Panel samples whose genotypes agree at every variant of the block contribute the same haplotypes to every chain
-  // of the block: one pass over the block finds one representative per class (a few dozen for 2,504 samples), and
-  // the per-chain work below runs over the representatives only.
-  void sample_classes(Scratch &sc) const {
-    size_t ns = 0, nv = 0;
-    for (const Variant &v : vars_)
-      if (v.is_present) {
-        ns = std::max(ns, v.n_samples());
-        ++nv;
-      }
-    sc.reps.clear();
-    if (ns == 0) return;
-    const size_t W = 3 * nv;
-    sc.block_rows.assign(ns * W, 0);
-    size_t col = 0;
-    for (const Variant &v : vars_) {
-      if (!v.is_present) continue;
-      uint16_t *p = sc.block_rows.data() + 3 * col++;
-      const size_t have = std::min(ns, v.n_samples());
-      for (size_t smp = 0; smp < have; ++smp, p += W) {
-        p[0] = v.gt_text_id(smp, 0);
-        p[1] = v.gt_text_id(smp, 1);
-        p[2] = v.phased[smp] != 0;
-      }
-      for (size_t smp = have; smp < ns; ++smp, p += W) p[2] = 1;  // (fewer samples: reference, phased)
-    }
-    distinct_rows(sc.block_rows, ns, W, sc.reps, sc.table);
-  }
-
   // var_block.hpp:734-786: the distinct haplotypes (one allele per chain member) carried by the samples of the
   // central variant, as sc.n_haps rows of chain.size() text-ids in sc.haps.  Unphased patterns contribute every way
   // of picking one of the two alleles at each site (combine_haplotypes, var_block.hpp:709-728).
+  // The genotype patterns [h1 ids | h2 ids | phased] come from a merge of the members' sparse genotype lists: one
+  // row per sample that deviates from the default at some member, plus one all-reference row standing for every
+  // other sample (whatever its phasing flags: with no heterozygous site it yields that one haplotype).
   void haplotypes(const Chain &chain, int central, bool haploid, Scratch &sc) const {
-    const size_t n = chain.size(), central_samples = vars_[(size_t)central].n_samples(), W = 2 * n + 1;
-    // pattern of each sample class that the central variant carries: [h1 ids | h2 ids | phased]
+    const size_t n = chain.size(), W = 2 * n + 1;
+    const uint32_t central_samples = (uint32_t)vars_[(size_t)central].n_samples();
+    sc.cursor.assign(n, 0);
+    sc.pat.clear();
     size_t n_rows = 0;
-    sc.pat.resize(sc.reps.size() * W);
-    for (uint32_t smp : sc.reps) {
-      if (smp >= central_samples) continue;  // (the reference walks the samples of the central variant)
+    while (true) {
+      uint32_t s = 0xFFFFFFFFu;  // the next sample with an entry at some member
+      for (size_t m = 0; m < n; ++m) {
+        const Variant &v = vars_[(size_t)chain[m]];
+        if (sc.cursor[m] < v.gts.size()) s = std::min(s, v.gts[sc.cursor[m]].sample);
+      }
+      if (s >= central_samples) break;  // (the reference walks the samples of the central variant)
+      sc.pat.resize((n_rows + 1) * W);
       uint16_t *p = sc.pat.data() + n_rows++ * W;
       uint16_t ph = 1;
       for (size_t m = 0; m < n; ++m) {
         const Variant &v = vars_[(size_t)chain[m]];
-        const bool has = smp < v.n_samples();
-        p[m] = has ? v.gt_text_id(smp, 0) : 0;
-        p[n + m] = haploid ? p[m] : (has ? v.gt_text_id(smp, 1) : 0);
-        if (has && v.phased[smp] == 0) ph = 0;
+        if (sc.cursor[m] < v.gts.size() && v.gts[sc.cursor[m]].sample == s) {
+          const GtEntry &g = v.gts[sc.cursor[m]++];
+          p[m] = g.h1;
+          p[n + m] = haploid ? g.h1 : g.h2;
+          if (!g.phased) ph = 0;
+        } else {
+          p[m] = p[n + m] = 0;
+          if (s < v.n_samples() && !v.default_phased) ph = 0;  // (a variant with fewer samples: reference, phased)
+        }
       }
       p[2 * n] = haploid ? 1 : ph;
+    }
+    if (n_rows < central_samples) {  // samples at their default everywhere
+      sc.pat.resize((n_rows + 1) * W);
+      uint16_t *p = sc.pat.data() + n_rows++ * W;
+      std::fill(p, p + 2 * n, (uint16_t)0);
+      p[2 * n] = 1;
     }
     distinct_rows(sc.pat, n_rows, W, sc.order, sc.table);
     sc.cand.clear();

@@ -511,8 +511,14 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
     }
   }
   const int32_t VECTOR_END = INT32_MIN + 1;
-  v.gt.resize(2 * ns);
-  v.phased.resize(ns);
+  // genotypes as allele text ids, kept sparse (signatures.hpp): first the phasing flag most all-reference samples
+  // carry, then one entry per sample that differs from {0, 0, that flag}
+  static thread_local std::vector<uint16_t> h1s, h2s;
+  static thread_local std::vector<uint8_t> phs;
+  h1s.resize(ns);
+  h2s.resize(ns);
+  phs.resize(ns);
+  size_t ref_phased = 0, ref_unphased = 0;
   for (size_t i = 0; i < ns; ++i) {
     // the reference reads curr_gt[0] and curr_gt[1] of a row of max_ploidy entries; with ploidy 1 everywhere the
     // second read lands on the NEXT sample's first entry (variant.hpp:184) -- reproduced; the last sample sees
@@ -534,10 +540,17 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
     }
     if (a1 < 0) a1 = 0;
     if (a2 < 0) a2 = 0;
-    v.gt[2 * i] = (uint16_t)std::min(a1, 65535);
-    v.gt[2 * i + 1] = (uint16_t)std::min(a2, 65535);
-    v.phased[i] = ph ? 1 : 0;
+    h1s[i] = v.text_id_of(std::min(a1, 65535));
+    h2s[i] = v.text_id_of(std::min(a2, 65535));
+    phs[i] = ph ? 1 : 0;
+    if ((h1s[i] | h2s[i]) == 0) (ph ? ref_phased : ref_unphased)++;
   }
+  v.n_samples_ = (uint32_t)ns;
+  v.default_phased = ref_phased >= ref_unphased ? 1 : 0;
+  v.gts.reserve(ns - std::max(ref_phased, ref_unphased));
+  for (size_t i = 0; i < ns; ++i)
+    if ((h1s[i] | h2s[i]) != 0 || phs[i] != v.default_phased)
+      v.gts.push_back(GtEntry{(uint32_t)i, h1s[i], h2s[i], phs[i]});
   return v;
 }
 

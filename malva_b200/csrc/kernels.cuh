@@ -480,13 +480,12 @@ __device__ __forceinline__ u128 canon_only(u128 x, int k) {
   return less128(x, rc) ? x : rc;
 }
 
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int SCAN_Q = 64;                        // ring entries per warp
 constexpr int SCAN_WARP_U4 = 256 + 2 * SCAN_Q;    // per warp: 4 KB tile + ring keys + ring meta (uint4 units)
 // + the 1 KB expansion table and a deferred-hit counter per warp
-constexpr int SCAN_SMEM = SCAN_WARPS * SCAN_WARP_U4 * 16 + 256 * 4 + SCAN_WARPS * 4;
-constexpr int SCAN_MIN_CTAS = 4;
+constexpr int scan_smem(int threads) { return (threads / 32) * SCAN_WARP_U4 * 16 + 256 * 4 + (threads / 32) * 4; }
+// registers cap at 64 per thread either way (2048 resident threads per SM at most)
+constexpr int scan_min_ctas(int threads) { return 1024 / threads; }
 
 // Where the sample k-mers come from.  MODE 0: packed {lo,hi} words + u32 counts.  MODE 1: raw records of a
 // KMC database suffix file (.kmc_suf): (ref_k - p)/4 suffix bytes (2-bit codes, first base most significant)
@@ -523,9 +522,12 @@ __device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_l
   return lo;
 }
 
-template <int K, int REFK, int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan(ScanSrc src, uint64_t n, DevView v) {
+// THREADS: CTA size (the per-warp state is private, the CTA only shares the expansion table).  RING = false probes
+// after every batch of 32 k-mers, with whatever lanes need a line (the round-1 scheme), for comparison.
+template <int K, int REFK, int MODE, int THREADS, bool RING>
+__global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS)) k_scan(ScanSrc src, uint64_t n, DevView v) {
   extern __shared__ uint4 scan_sm[];
+  constexpr int SCAN_WARPS = THREADS / 32;
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
@@ -536,8 +538,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan(ScanSrc sr
   uint32_t *hitc = tab + 256 + wid;  // this warp's deferred-hit counter
   if (lane == 0) *hitc = 0;
   if constexpr (K > 0) {
-    static_assert(SCAN_THREADS == 256, "one table entry per thread");
-    tab[threadIdx.x] = expand4(threadIdx.x);
+    for (int t = threadIdx.x; t < 256; t += THREADS) tab[t] = expand4((uint32_t)t);
     __syncthreads();
   } else {
     __syncwarp();
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan(ScanSrc sr
       }
       qn += (uint32_t)__popc(need_mask);
     }
-    if (qn >= 32 || (!more && qn)) {
+    if (qn >= 32 || (!RING && qn) || (!more && qn)) {
       // ---- one probe round over ring entries qhead .. qhead + n_probe - 1 ----
       const uint32_t n_probe = qn < 32 ? qn : 32;
       __syncwarp();  // the ring entries are visible; the previous round's reads of the tile are done
@@ -964,16 +965,29 @@ __global__ void __launch_bounds__(128) k_genotype(const uint32_t *__restrict__ c
                                                  int32_t *__restrict__ status, int32_t *__restrict__ best_gt,
                                                  int32_t *__restrict__ gq) {
   uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (vi >= n_variants) return;
-  uint64_t a0 = var_allele_off[vi];
-  int n = (int)(var_allele_off[vi + 1] - a0);
+  const bool live = vi < n_variants;
+  uint64_t a0 = live ? (uint64_t)var_allele_off[vi] : 0;
+  int n = live ? (int)(var_allele_off[vi + 1] - a0) : 0;
   uint64_t lo;
   if (lik_off) {
-    lo = lik_off[vi];
+    lo = live ? lik_off[vi] : 0;
   } else {
-    const unsigned long long slots = (unsigned long long)(haploid ? n : n * (n + 1) / 2);
-    lo = atomicAdd(cursor, slots > (unsigned long long)n ? slots : (unsigned long long)n);
+    // one atomic per warp: an inclusive scan of the lanes' slot counts, the last lane reserves the total
+    const uint32_t g = (uint32_t)(haploid ? n : n * (n + 1) / 2);
+    const uint32_t slots = live ? (g > (uint32_t)n ? g : (uint32_t)n) : 0u;
+    const int lane = threadIdx.x & 31;
+    uint32_t incl = slots;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(cursor, (unsigned long long)incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    lo = base + (incl - slots);
   }
+  if (!live) return;
   int st, bg, q;
   int ng = genotype_one(cov + a0, freq + a0, n, err, max_cov, haploid != 0, lik + lo, &st, &bg, &q);
   n_gts[vi] = ng;

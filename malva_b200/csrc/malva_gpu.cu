@@ -779,15 +779,16 @@ extern "C" int mg_finalize_context(mg_ctx *c) {
   return MG_OK;
 }
 
-template <int K, int REFK, int MODE>
+template <int K, int REFK, int MODE, int THREADS, bool RING>
 static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n, cudaStream_t st) {
-  uint64_t want = (n + 255) / 256;  // one warp per 32 k-mers, 8 warps per CTA
-  uint64_t cap = (uint64_t)c->sms * (uint64_t)c->scan_ctas_per_sm;
+  constexpr int WARPS = THREADS / 32;
+  uint64_t want = (n + THREADS - 1) / THREADS;  // one warp per 32 k-mers
+  uint64_t cap = (uint64_t)c->sms * (uint64_t)c->scan_ctas_per_sm * (256 / THREADS);
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
   mg::ScanSrc src = src_in;
   const int si = st == c->stream[1] ? 1 : 0;
-  const uint64_t n_warps = (uint64_t)grid * (mg::SCAN_THREADS / 32);
+  const uint64_t n_warps = (uint64_t)grid * WARPS;
   if (c->defer_hits) {
     // a segment per warp of the grid, sized for one k-mer in 32 hitting the filter (expected: < 1 in 100; whatever
     // exceeds a segment is finished in line by the scan itself)
@@ -813,12 +814,13 @@ static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n,
     src.hit_counts = c->hit_counts[si];
     src.seg_cap = (uint32_t)seg;
   }
-  {  // more than 48 KB of dynamic shared memory needs the opt-in (per device; cheap enough to repeat)
-    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, mg::SCAN_SMEM);
+  constexpr int SMEM = mg::scan_smem(THREADS);
+  if (SMEM > 48 * 1024) {  // more than 48 KB of dynamic shared memory needs the opt-in (per device; cheap enough to repeat)
+    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE, THREADS, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
   }
   c->launches++;
-  mg::k_scan<K, REFK, MODE><<<grid, mg::SCAN_THREADS, mg::SCAN_SMEM, st>>>(src, n, c->view());
+  mg::k_scan<K, REFK, MODE, THREADS, RING><<<grid, THREADS, SMEM, st>>>(src, n, c->view());
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !src.hit_buf) return e;
   const uint64_t threads = n_warps * src.seg_cap;
@@ -831,10 +833,22 @@ static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n,
 template <int MODE>
 static int scan_src(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t st) {
   cudaError_t e;
-  if (c->k == 35 && c->ref_k == 43)
-    e = launch_scan<35, 43, MODE>(c, src, n, st);
-  else
-    e = launch_scan<0, 0, MODE>(c, src, n, st);
+  if (c->k == 35 && c->ref_k == 43) {
+    // MG_SCAN_VARIANT (tuning sweeps, profiles/sweep_k1_r2.py): CTA size and probe scheme of the packed-input scan
+    int variant = 0;
+    if (MODE == 0)
+      if (const char *ev = getenv("MG_SCAN_VARIANT")) variant = atoi(ev);
+    if (MODE == 0 && variant == 1)
+      e = launch_scan<35, 43, 0, 128, true>(c, src, n, st);
+    else if (MODE == 0 && variant == 2)
+      e = launch_scan<35, 43, 0, 256, false>(c, src, n, st);
+    else if (MODE == 0 && variant == 3)
+      e = launch_scan<35, 43, 0, 128, false>(c, src, n, st);
+    else
+      e = launch_scan<35, 43, MODE, 256, true>(c, src, n, st);
+  } else {
+    e = launch_scan<0, 0, MODE, 256, true>(c, src, n, st);
+  }
   if (e != cudaSuccess) return set_err(MG_ERR_CUDA, "k_scan launch -> %s", cudaGetErrorString(e));
   return MG_OK;
 }

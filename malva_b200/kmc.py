@@ -1,9 +1,7 @@
-"""Host-side k-mer utilities: 2-bit packing, a KMC-database reader/writer and a
-small k-mer counter that emulates the KMC defaults the MALVA pipeline relies on.
+"""Host-side k-mer utilities: 2-bit packing and a KMC-database reader/writer.
 
-Reference call sites served: the KMC listing loop ``main.cpp:482-490`` (reader)
-and the wrapper's ``kmc -m4 -k43 -t1 -fm`` invocation ``MALVA:107`` (counter:
-canonical k-mers, ``-ci2`` minimum count, ``-cs255`` counter cap).
+Reference call sites served: the KMC listing loop ``main.cpp:482-490`` (reader); the writer produces the
+databases the tests and goldens feed to both programs.
 
 The KMC API itself is third party (KMC >= 2.3, not vendored by the reference);
 the on-disk layout implemented here is restated from the published format
@@ -19,7 +17,6 @@ from __future__ import annotations
 
 import os
 import struct
-from collections import Counter
 from typing import Iterable, Tuple
 
 import numpy as np
@@ -73,61 +70,6 @@ def packed_to_strings(arr: np.ndarray, k: int) -> list:
     return [unpack_kmer(v, k) for v in packed_to_ints(arr)]
 
 
-def count_kmers(reads: Iterable[str], k: int, min_count: int = 2, counter_max: int = 255,
-                canonical: bool = True) -> Tuple[np.ndarray, np.ndarray]:
-    """Emulate ``kmc -k<k> -ci<min_count> -cs<counter_max>`` on an iterable of reads.
-
-    k-mers containing a non-ACGT symbol are skipped, as KMC does.  Returns the
-    sorted packed k-mers and their (capped) u32 counts.
-    """
-    cnt: Counter = Counter()
-    mask = (1 << (2 * k)) - 1
-    for r in reads:
-        r = r.strip().upper()
-        x = 0
-        valid = 0
-        for ch in r:
-            c = _CODE.get(ch)
-            if c is None:
-                valid = 0
-                x = 0
-                continue
-            x = ((x << 2) | c) & mask
-            valid += 1
-            if valid >= k:
-                cnt[canonical_int(x, k) if canonical else x] += 1
-    keys = sorted(v for v, c in cnt.items() if c >= min_count)
-    counts = np.array([min(cnt[v], counter_max) for v in keys], dtype=np.uint32)
-    return ints_to_packed(keys), counts
-
-
-def read_fastx(path: str) -> list:
-    """Minimal FASTA/FASTQ sequence reader (plain or gz)."""
-    import gzip
-
-    op = gzip.open if path.endswith(".gz") else open
-    seqs = []
-    with op(path, "rt") as fh:
-        lines = [l.rstrip("\n") for l in fh]
-    i = 0
-    while i < len(lines):
-        l = lines[i]
-        if l.startswith("@"):
-            seqs.append(lines[i + 1])
-            i += 4
-        elif l.startswith(">"):
-            j = i + 1
-            s = []
-            while j < len(lines) and not lines[j].startswith(">"):
-                s.append(lines[j])
-                j += 1
-            seqs.append("".join(s))
-            i = j
-        else:
-            i += 1
-    return seqs
-
-
 def _choose_lut_prefix_len(k: int, n: int) -> int:
     best = None
     for p in range(1, min(k, 13) + 1):   # (same rule as csrc/host/kmc_db.hpp: KmcWriter::choose_prefix_len)
@@ -170,11 +112,11 @@ def write_kmc_db(prefix: str, kmers: np.ndarray, counts: np.ndarray, k: int, *,
     pre += struct.pack(f"<{len(lut)}Q", *lut)
     if version == 0x200:
         pre += struct.pack(f"<{4 ** signature_len + 1}I", *([0] * (4 ** signature_len + 1)))
-        hdr = struct.pack("<7IQB", k, 0, counter_size, p, signature_len, min_count,
-                          max_count & 0xFFFFFFFF, n, 0 if both_strands else 1)
+        hdr = struct.pack("<7IQBI", k, 0, counter_size, p, signature_len, min_count,
+                          max_count & 0xFFFFFFFF, n, 0 if both_strands else 1, max_count >> 32)
     elif version == 0:
-        hdr = struct.pack("<6IQB", k, 0, counter_size, p, min_count, max_count & 0xFFFFFFFF, n,
-                          0 if both_strands else 1)
+        hdr = struct.pack("<6IQBI", k, 0, counter_size, p, min_count, max_count & 0xFFFFFFFF, n,
+                          0 if both_strands else 1, max_count >> 32)
     else:
         raise ValueError("version must be 0 or 0x200")
     hdr += b"\0" * (60 - len(hdr)) + struct.pack("<I", version)
@@ -224,6 +166,23 @@ def write_kmc_db_binned(prefix: str, kmers: np.ndarray, counts: np.ndarray, k: i
         fh.write(suf)
 
 
+def _parse_header(h: bytes, version: int):
+    """Header of a .kmc_pre file as the KMC API reads it (CKMCFile::ReadParamsFrom_prefix_file_buf): kmer_length, mode,
+    counter_size, lut_prefix_length, [signature_len: 0x200 only], min_count, max_count (low word), total_kmers,
+    both_strands (one byte, stored inverted), then -- KMC 3 -- the high word of max_count; the rest is reserved."""
+    if version == 0x200:
+        k, _mode, csz, p, sig, minc, maxc, total = struct.unpack("<7IQ", h[:36])
+        o = 36
+    else:
+        k, _mode, csz, p, minc, maxc, total = struct.unpack("<6IQ", h[:32])
+        sig, o = 0, 32
+    both = not (h[o] & 1)
+    if len(h) >= o + 5 + 4 + 4 + 4:          # (room before version / header_offset / marker)
+        maxc |= struct.unpack("<I", h[o + 1:o + 5])[0] << 32
+    sigmap = (4 ** sig + 1) * 4 if version == 0x200 else 0
+    return k, csz, p, sig, minc, maxc, total, both, sigmap
+
+
 def read_kmc_db(prefix: str) -> Tuple[np.ndarray, np.ndarray, int]:
     """List a KMC database: (packed k-mers, u32 counts, k); count filter applied."""
     pre = open(prefix + ".kmc_pre", "rb").read()
@@ -233,12 +192,7 @@ def read_kmc_db(prefix: str) -> Tuple[np.ndarray, np.ndarray, int]:
     if version not in (0, 0x200):
         raise ValueError(f"unsupported KMC version {version:#x}")
     h = pre[len(pre) - 8 - hoff:]
-    if version == 0x200:
-        k, _mode, csz, p, sig, minc, maxc, total = struct.unpack("<7IQ", h[:36])
-        sigmap = (4 ** sig + 1) * 4
-    else:
-        k, _mode, csz, p, minc, maxc, total = struct.unpack("<6IQ", h[:32])
-        sigmap = 0
+    k, csz, p, sig, minc, maxc, total, _both, sigmap = _parse_header(h, version)
     lut_bytes = len(pre) - 4 - 8 - hoff - sigmap
     lut = np.frombuffer(pre, dtype="<u8", count=lut_bytes // 8, offset=4)
     single = 4 ** p
@@ -272,12 +226,7 @@ def open_kmc_db(prefix: str) -> dict:
     if version not in (0, 0x200):
         raise ValueError(f"unsupported KMC version {version:#x}")
     h = pre[len(pre) - 8 - hoff:]
-    if version == 0x200:
-        k, _mode, csz, p, sig, minc, maxc, total = struct.unpack("<7IQ", h[:36])
-        sigmap = (4 ** sig + 1) * 4
-    else:
-        k, _mode, csz, p, minc, maxc, total = struct.unpack("<6IQ", h[:32])
-        sigmap = 0
+    k, csz, p, sig, minc, maxc, total, _both, sigmap = _parse_header(h, version)
     lut_bytes = len(pre) - 4 - 8 - hoff - sigmap
     lut = np.frombuffer(pre, dtype="<u8", count=lut_bytes // 8, offset=4)
     single = 4 ** p
@@ -288,4 +237,5 @@ def open_kmc_db(prefix: str) -> dict:
         raise ValueError("bad .kmc_suf marker")
     records = suf[4:4 + total * rec]
     return dict(k=k, lut=np.ascontiguousarray(lut[:n_lut]), lut_prefix_len=p, counter_size=csz, min_count=minc,
-                max_count=maxc, total=total, record_bytes=rec, records=records)
+                max_count=maxc, total=total, record_bytes=rec, records=records, both_strands=_both, version=version,
+                signature_len=sig)

@@ -8,7 +8,7 @@ Inputs  : /root/reference/example/haploid.tar.gz (haploid.fa, haploid.fq, haploi
           /root/reference/example/haploid.malva.vcf (the reference's shipped golden)
 Outputs : haploid.fa, haploid.vcf.gz, haploid.fq.gz -- inputs of the example, verbatim
           haploid.kmc_pre/.kmc_suf             -- reads counted as `kmc -k43 -ci2 -cs255` does
-                                                  (malva_b200.kmc.count_kmers)
+                                                  (oracle/kmc_count.py: count_kmers)
           haploid.malva.vcf                    -- shipped golden (GT:GQ only)
           haploid.malva.verbose.vcf            -- oracle/_ref `call -v` output: pins COVS + GTS
 The shim-built reference must reproduce haploid.malva.vcf byte for byte, else this aborts.
@@ -25,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from malva_b200 import kmc  # noqa: E402
+from oracle import kmc_count  # noqa: E402
 
 REF = "/root/reference/example"
 BIN = os.path.join(ROOT, "oracle", "_ref", "malva-geno-ref")
@@ -35,8 +36,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
         tarfile.open(os.path.join(REF, "haploid.tar.gz")).extractall(tmp, filter="data")
-        reads = kmc.read_fastx(os.path.join(tmp, "haploid.fq"))
-        km, ct = kmc.count_kmers(reads, 43, min_count=2, counter_max=255)
+        reads = kmc_count.read_fastx(os.path.join(tmp, "haploid.fq"))
+        km, ct = kmc_count.count_kmers(reads, 43, min_count=2, counter_max=255)
         kmc.write_kmc_db(os.path.join(tmp, "haploid"), km, ct, 43)
         flags = ["-k", "35", "-r", "43", "-b", "1", "-f", "AF", "-1"]
         args = ["haploid.fa", "haploid.vcf", "haploid"]

@@ -1,5 +1,5 @@
 """K6, canonical k-mer counting on the GPU (the `kmc` step in front of malva-geno), against the Python
-restatement of KMC's defaults (malva_b200.kmc.count_kmers: canonical k-mers, windows with non-ACGT skipped, -ci2,
+restatement of KMC's defaults (oracle/kmc_count.py: count_kmers: canonical k-mers, windows with non-ACGT skipped, -ci2,
 -cs255) that reproduces the reference's shipped golden, and end to end: reads -> `malva-geno count` -> `index` ->
 `call` must give the VCF the reference ships for its haploid example."""
 import gzip
@@ -12,6 +12,7 @@ import pytest
 
 from malva_b200 import KmerCounter, MalvaGpu, kmc
 from malva_b200 import build as mbuild
+from oracle import kmc_count
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "haploid")
@@ -41,7 +42,7 @@ def random_reads(rng, n_reads, genome_len=20000, read_len=(60, 260), n_rate=0.00
 def test_counts_match_the_kmc_restatement(k):
     rng = random.Random(100 + k)
     reads = random_reads(rng, 1500)
-    exp_k, exp_c = kmc.count_kmers(reads, k, min_count=2, counter_max=255)
+    exp_k, exp_c = kmc_count.count_kmers(reads, k, min_count=2, counter_max=255)
     c = KmerCounter(k)
     try:
         c.add(reads)
@@ -51,7 +52,7 @@ def test_counts_match_the_kmc_restatement(k):
         assert st["instances"] == sum(max(0, len(s) - k + 1) for r in reads for s in r.split("N"))
         # other thresholds on the same table: -ci1 with a counter cap of 3, -ci5
         for ci, cs in ((1, 3), (5, 255)):
-            e_k, e_c = kmc.count_kmers(reads, k, min_count=ci, counter_max=cs)
+            e_k, e_c = kmc_count.count_kmers(reads, k, min_count=ci, counter_max=cs)
             g_k, g_c = c.finish(ci, cs)
             assert np.array_equal(g_k, e_k) and np.array_equal(g_c, e_c)
     finally:
@@ -64,7 +65,7 @@ def test_many_calls_small_chunks_and_partitioned_passes(monkeypatch):
     k = 43
     rng = random.Random(7)
     reads = random_reads(rng, 600, read_len=(100, 3000))
-    exp_k, exp_c = kmc.count_kmers(reads, k, min_count=2, counter_max=255)
+    exp_k, exp_c = kmc_count.count_kmers(reads, k, min_count=2, counter_max=255)
     monkeypatch.setenv("MG_COUNT_CHUNK", "1024")
     c = KmerCounter(k)
     try:
@@ -202,7 +203,7 @@ def test_cli_count_reads_fasta_and_fastq_layouts(tmp_path):
     with gzip.open(fq, "wt") as fh:
         for i, s in enumerate(seqs + [""]):
             fh.write(f"@r{i}\n{s}\n+\n{'@' * len(s)}\n")
-    exp_k, exp_c = kmc.count_kmers(seqs, 43, min_count=2, counter_max=255)
+    exp_k, exp_c = kmc_count.count_kmers(seqs, 43, min_count=2, counter_max=255)
     exp = [f"{a}\t{b}" for a, b in zip(kmc.packed_to_strings(exp_k, 43), exp_c.tolist())]
     assert len(exp) > 1000
     for src in (fa, fq):
