@@ -110,26 +110,6 @@ __device__ __forceinline__ uint32_t line_word(const DevView &v, uint64_t line, i
 __device__ __forceinline__ bool bf_test(const DevView &v, uint64_t idx) {
   return (line_word(v, idx >> 8, (int)((idx & 255) >> 5)) >> (idx & 31)) & 1u;
 }
-// the u32 counter of SET bit idx of bf (BF::_counts[_brank(idx)], bloom_filter.hpp:108-110): inline in the
-// line for the first three set bits of the line, else the rank-indexed dense array
-// (nullptr when the bit is clear)
-__device__ __forceinline__ uint32_t *alt_counter_ptr(const DevView &v, uint64_t idx) {
-  const uint64_t line = idx >> 8;
-  const uint4 *p = v.lines + line * LINE_U4;
-  const uint4 a = __ldg(p), b = __ldg(p + 1);
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  const int ws = (int)((idx & 255) >> 5);
-  int j = 0;
-  uint32_t mine = 0;
-#pragma unroll
-  for (int x = 0; x < 8; ++x) mine = x == ws ? w[x] : mine;
-  if (!((mine >> (idx & 31)) & 1u)) return nullptr;
-#pragma unroll
-  for (int x = 0; x < 8; ++x) j += x < ws ? __popc(w[x]) : (x == ws ? __popc(w[x] & ((1u << (idx & 31)) - 1u)) : 0);
-  if (j < LINE_INLINE_ALT) return line_words(v, line) + LINE_W_RANK + 1 + j;
-  return v.bf_counts + (uint64_t)line_word(v, line, LINE_W_RANK) + (uint64_t)j;
-}
-
 __device__ __forceinline__ u128 key_of(const DevView &v, uint4 q) {
   u128 r;
   r.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);

@@ -445,9 +445,6 @@ __global__ void k_refpass_short(const uint8_t *seq, uint64_t len, DevView v, uin
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
 
 // canon_hash<K> (xxh3.cuh) with the 2-bit -> ASCII expansion done by a 256-entry shared-memory table (4 bases per
 // look-up) instead of shift/mask/PRMT sequences: the scan kernel is bound by the ALU pipe (LOP3/SHF/PRMT issue at
@@ -480,12 +477,20 @@ __device__ __forceinline__ u128 canon_only(u128 x, int k) {
   return less128(x, rc) ? x : rc;
 }
 
-constexpr int SCAN_Q = 64;                        // ring entries per warp
-constexpr int SCAN_WARP_U4 = 256 + 2 * SCAN_Q;    // per warp: 4 KB tile + ring keys + ring meta (uint4 units)
+// ring entries per warp: [a round in flight (32) +] the entries that pile up until the next turn (< 64)
+__host__ __device__ constexpr int scan_q(bool async) { return async ? 96 : 64; }
+// per warp: 4 KB tile + ring keys + ring meta (uint4 units)
+__host__ __device__ constexpr int scan_warp_u4(bool async, int ilp = 1) { return 256 + 2 * scan_q(async) + 0 * ilp; }
 // + the 1 KB expansion table and a deferred-hit counter per warp
-constexpr int scan_smem(int threads) { return (threads / 32) * SCAN_WARP_U4 * 16 + 256 * 4 + (threads / 32) * 4; }
-// registers cap at 64 per thread either way (2048 resident threads per SM at most)
-constexpr int scan_min_ctas(int threads) { return 1024 / threads; }
+__host__ __device__ constexpr int scan_smem(int threads, bool async, int ilp = 1) {
+  return (threads / 32) * scan_warp_u4(async, ilp) * 16 + 256 * 4 + (threads / 32) * 4;
+}
+// CTAs per SM that fit the shared memory (227 KB usable, 1 KB reserved per CTA), capped at 1024 threads (64 registers
+// each) -- 768 threads (85 registers) for the two-chain variant
+__host__ __device__ constexpr int scan_min_ctas(int threads, bool async, int ilp = 1) {
+  const int by_smem = (227 * 1024) / (scan_smem(threads, async, ilp) + 1024), by_threads = (ilp == 2 ? 768 : 1024) / threads;
+  return by_smem < by_threads ? by_smem : by_threads;
+}
 
 // Where the sample k-mers come from.  MODE 0: packed {lo,hi} words + u32 counts.  MODE 1: raw records of a
 // KMC database suffix file (.kmc_suf): (ref_k - p)/4 suffix bytes (2-bit codes, first base most significant)
@@ -522,12 +527,23 @@ __device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_l
   return lo;
 }
 
-// THREADS: CTA size (the per-warp state is private, the CTA only shares the expansion table).  RING = false probes
-// after every batch of 32 k-mers, with whatever lanes need a line (the round-1 scheme), for comparison.
-template <int K, int REFK, int MODE, int THREADS, bool RING>
-__global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS)) k_scan(ScanSrc src, uint64_t n, DevView v) {
+// THREADS: CTA size (the per-warp state is private, the CTA only shares the expansion table).
+// RING = false probes after every batch of 32 k-mers, with whatever lanes need a line (the round-1 scheme), for
+// comparison.  ASYNC: the k-mers of batch i+1 are loaded into registers while batch i is hashed, and the gather of a
+// round is only STARTED when the ring holds 32 entries: the warp goes on hashing and finishes the round (wait,
+// compare, count) at the next turn, a batch or more later.  (Also tried, profiles/round2_k1.md: parking a hashed
+// batch in shared memory until its pre-filter word arrives -- the extra shared-memory traffic cost more than the
+// hidden L2 latency.)  The raw-record mode stages records in the tile and stays synchronous.
+// ILP = 2 (synchronous rounds, packed input): every lane hashes TWO k-mers per iteration, written as straight-line
+// code over both so that the two dependent chains (canonical form -> table look-ups -> four 128-bit products)
+// interleave: with ~30 resident warps per SM the single chain left the issue slots half empty
+// (~11 cycles between two instructions of a warp, ncu).
+template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP = 1>
+__global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k_scan(ScanSrc src, uint64_t n, DevView v) {
+  static_assert(!ASYNC || (RING && MODE == 0), "the asynchronous round needs the ring and leaves the tile alone");
+  static_assert(ILP == 1 || (ILP == 2 && RING && MODE == 0), "two k-mers per lane: ring, packed input");
   extern __shared__ uint4 scan_sm[];
-  constexpr int SCAN_WARPS = THREADS / 32;
+  constexpr int SCAN_WARPS = THREADS / 32, SCAN_Q = scan_q(ASYNC), SCAN_WARP_U4 = scan_warp_u4(ASYNC, ILP);
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
@@ -545,6 +561,7 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS)) k_scan(ScanSr
   }
   const bool inl = K > 0 ? (K <= INLINE_MAX_K) : (v.inline_counts != 0);
   const uint32_t mz = inl ? 0x7FFFFFFFu : 0xFFFFFFFFu, mw = inl ? 0u : 0x3FFFFFFFu;  // key bits of slot words 2, 3
+  auto wrap = [](uint32_t x) { return x >= (uint32_t)SCAN_Q ? x - (uint32_t)SCAN_Q : x; };  // ring positions < 2 * SCAN_Q
   const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   // 32-bit indices: the host never launches more than 2^30 k-mers at once
   const uint32_t n32 = (uint32_t)n;
@@ -553,8 +570,253 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS)) k_scan(ScanSr
   const uint32_t d_even = tile_addr + (uint32_t)(grp * 128 + ((sub ^ grp) * 16));
   const uint32_t d_odd = tile_addr + (uint32_t)(grp * 128 + ((sub ^ (grp + 4)) * 16));
   const char *line_src = reinterpret_cast<const char *>(v.lines) + sub * 16;
-  uint32_t qhead = 0, qn = 0;  // ring state (warp-uniform); qhead is 0 or 32
+  // ring state (warp-uniform): fl_n entries from fl_pos on are the round in flight (ASYNC), the pd_n entries after
+  // them wait for the next round; fl_pos stays a multiple of 32 (only the very last round is partial)
+  uint32_t fl_pos = 0, fl_n = 0, pd_n = 0;
   bool more = true;
+  // START a round over the first min(pd_n, 32) pending entries: their 32 probe lines into the tile
+  auto start_round = [&]() {
+    const uint32_t n_new = pd_n < 32 ? pd_n : 32;
+    fl_pos = wrap(fl_pos + fl_n);
+    __syncwarp();  // the ring entries are visible; the previous round's reads of the tile are done
+    const uint32_t *qline = reinterpret_cast<const uint32_t *>(qmeta + fl_pos + grp);  // .x of entry fl_pos + grp + 4r
+    uint32_t lid[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) lid[r] = qline[r * 16];  // (stale entries past n_new are read but never used)
+    if (n_new == 32) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        cp_async16(((r & 1) ? d_odd : d_even) + (uint32_t)(r * 512), line_src + ((uint64_t)lid[r] << 7));
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if ((uint32_t)(4 * r + grp) < n_new)
+          cp_async16(((r & 1) ? d_odd : d_even) + (uint32_t)(r * 512), line_src + ((uint64_t)lid[r] << 7));
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    fl_n = n_new;
+    pd_n -= n_new;
+  };
+  // COMPLETE the round in flight: every lane < fl_n owns row `lane` of the tile
+  auto complete_round = [&]() {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    if ((uint32_t)lane < fl_n) {
+      const uint4 kq = qkey[fl_pos + lane], mq = qmeta[fl_pos + lane];
+      const uint32_t line = mq.x, cnt = mq.z, bit = mq.w;
+      u128 canon, x43;
+      if constexpr (MODE == 0) {
+        canon = u128_of(kq);
+      } else {
+        x43 = u128_of(kq);
+        canon = canon_only(mask128(shr128(x43, 2 * tail), 2 * k), k);
+      }
+      const uint4 *mine = tile + lane * 8;
+      const int sw = lane & 7;
+      const uint32_t fw = reinterpret_cast<const uint32_t *>(mine + ((bit >> 7) ^ sw))[(bit >> 5) & 3];
+      const bool bf_hit = (fw >> (bit & 31u)) & 1u;
+      const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
+                     c3 = (uint32_t)(canon.hi >> 32);
+      int slot = -1;
+      uint32_t flag_w = 0;
+#pragma unroll
+      for (int s = 0; s < LINE_KEYS; ++s) {
+        const uint4 p = mine[(2 + s) ^ sw];
+        if (((p.x ^ c0) | (p.y ^ c1) | ((p.z ^ c2) & mz) | ((p.w ^ c3) & mw)) == 0) slot = s;
+        if (s == LINE_KEYS - 1) flag_w = inl ? p.z : p.w;
+      }
+      // ---- ref_bf.increment ----
+      if (slot >= 0) {
+        uint32_t *cp = inl ? line_words(v, line) + 8 + 4 * slot + 3 : v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot;
+        atomicAdd(cp, cnt);
+      } else if (flag_w >> 31) {  // line overflowed at index time: the key may live in the overflow table
+        const int64_t os = ovf_find(v, canon);
+        if (os >= 0) atomicAdd(v.ovf_counts + os, cnt);
+      }
+      // ---- bf.increment unless the context filter vetoes it ----
+      if (bf_hit) {
+        // counter of the bit: number j of the set bit inside the line, rank of the line
+        const uint32_t ws = bit >> 5, below = (1u << (bit & 31u)) - 1u;
+        const uint4 b0 = mine[0 ^ sw], b1 = mine[1 ^ sw];
+        const uint32_t wx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        int j = 0;
+#pragma unroll
+        for (uint32_t x = 0; x < 8; ++x) j += __popc(wx[x] & (x < ws ? 0xFFFFFFFFu : (x == ws ? below : 0u)));
+        const uint32_t rank = reinterpret_cast<const uint32_t *>(mine + (7 ^ sw))[0];
+        uint32_t *ap = j < LINE_INLINE_ALT ? line_words(v, line) + LINE_W_RANK + 1 + j
+                                           : v.bf_counts + (uint64_t)rank + (uint64_t)j;
+        if constexpr (MODE == 0) x43 = u128_of(__ldg(src.kmers + mq.y));
+        const uint32_t pos = src.hit_buf ? atomicAdd(hitc, 1u) : 0xFFFFFFFFu;
+        if (pos < src.seg_cap) {  // recorded; k_scan_hits finishes it
+          uint4 *e = src.hit_buf + ((uint64_t)warp_id * src.seg_cap + pos) * 2;
+          const uint64_t a64 = reinterpret_cast<uint64_t>(ap);
+          e[0] = uint4_of(x43);
+          e[1] = make_uint4((uint32_t)a64, (uint32_t)(a64 >> 32), cnt, 0u);
+        } else {
+          u128 c43;
+          uint64_t h43;
+          if constexpr (REFK > 0)
+            h43 = canon_hash_lut<REFK>(x43, &c43, tab);
+          else
+            h43 = canon_hash_rt(x43, ref_k, &c43);
+          if (!ctx_test(v, bf_index(v, h43))) atomicAdd(ap, cnt);
+        }
+      }
+    }
+    fl_pos = wrap(fl_pos + fl_n);
+    fl_n = 0;
+  };
+  // A context k-mer of up to 48 bases never uses the top word of its 16 bytes: it is not loaded at all.  (Loaded
+  // and unused, its register gets recycled as a temporary while the 16-byte load is still in flight, and that
+  // write-after-write wait exposes the whole load latency -- ncu, profiles/round2_k1.md.)
+  constexpr bool SHORT_CTX = REFK > 0 && REFK <= 48;
+  auto load_kmer = [&](uint32_t i) {
+    if constexpr (SHORT_CTX) {
+      const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(src.kmers + i));
+      return make_uint4(lo.x, lo.y, __ldg(reinterpret_cast<const uint32_t *>(src.kmers + i) + 2), 0u);
+    } else {
+      return __ldg(src.kmers + i);
+    }
+  };
+  if constexpr (ASYNC) {
+    constexpr uint32_t W = 32u * ILP;  // k-mers per warp and iteration: ILP per lane
+    uint32_t base = warp_id * W;
+    uint4 q_cur[ILP];
+    uint32_t c_cur[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      const uint32_t i = base + 32u * u + lane;
+      q_cur[u] = i < n32 ? load_kmer(i) : make_uint4(0, 0, 0, 0);
+      c_cur[u] = i < n32 ? __ldg(src.counts + i) : 0u;
+    }
+    for (;; base += step * ILP) {
+      more = more && base < n32;
+      if (more) {
+        // the next batch's k-mers are requested before this one is hashed and used one iteration later
+        u128 x43[ILP], canon[ILP];
+        uint32_t cnt[ILP], idx_hi[ILP], bit[ILP];
+        bool need[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+          x43[u] = u128_of(q_cur[u]);
+          cnt[u] = c_cur[u];
+        }
+        const uint32_t nb = base + step * ILP;
+        if (nb < n32) {
+#pragma unroll
+          for (int u = 0; u < ILP; ++u) {
+            const uint32_t i = nb + 32u * u + lane;
+            q_cur[u] = i < n32 ? load_kmer(i) : make_uint4(0, 0, 0, 0);
+            c_cur[u] = i < n32 ? __ldg(src.counts + i) : 0u;
+          }
+          if (lane < 5 * ILP && nb + step * ILP < n32) {  // and the batch after that into L2 (k-mers, then counts)
+            const char *pf = lane < 4 * ILP
+                                 ? reinterpret_cast<const char *>(src.kmers + nb + step * ILP) + lane * 128
+                                 : reinterpret_cast<const char *>(src.counts + nb + step * ILP) + (lane - 4 * ILP) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+          }
+        }
+        uint64_t idx[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {  // (straight-line code over the ILP independent chains: they interleave)
+          const u128 x35 = mask128(shr128(x43[u], 2 * tail), 2 * k);
+          uint64_t h;
+          if constexpr (K > 0)
+            h = canon_hash_lut<K>(x35, &canon[u], tab);
+          else
+            h = canon_hash_rt(x35, k, &canon[u]);
+          idx[u] = bf_index(v, h);
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {  // occupancy pre-filter (L2), all words in flight together
+          need[u] = base + 32u * u + lane < n32 && occ_test(v, idx[u]);
+          idx_hi[u] = (uint32_t)(idx[u] >> 8);  // n_lines < 2^32 (bf_bits < 2^40)
+          bit[u] = (uint32_t)(idx[u] & 255);
+        }
+#pragma unroll 1
+        for (int u = 0; u < ILP; ++u) {
+          const bool hi = ILP == 2 && u == 1;
+          const bool nd = hi ? need[ILP - 1] : need[0];
+          const uint32_t need_mask = __ballot_sync(0xffffffffu, nd);
+          if (nd) {
+            const uint32_t e = wrap(fl_pos + fl_n + pd_n + (uint32_t)__popc(need_mask & ((1u << lane) - 1u)));
+            qkey[e] = uint4_of(hi ? canon[ILP - 1] : canon[0]);
+            qmeta[e] = make_uint4(hi ? idx_hi[ILP - 1] : idx_hi[0], base + 32u * u + lane, hi ? cnt[ILP - 1] : cnt[0],
+                                  hi ? bit[ILP - 1] : bit[0]);
+          }
+          pd_n += (uint32_t)__popc(need_mask);
+          // a full ring turns: the round in flight is finished (started a batch or more ago: its lines have landed),
+          // the next one started
+          if (pd_n >= 32) {
+            if (fl_n) complete_round();
+            start_round();
+          }
+        }
+      } else {  // the tail: nothing more to hash
+        if (fl_n) complete_round();
+        if (pd_n) start_round();
+        if (pd_n == 0 && fl_n == 0) break;
+      }
+    }
+  } else if constexpr (ILP == 2) {  // synchronous rounds, two k-mers per lane
+    for (uint32_t base = warp_id * 64;; base += 2 * step) {
+      more = more && base < n32;
+      if (more) {
+        uint4 q[2];
+        uint32_t cnt[2], idx_lo[2], bit[2];
+        bool need[2];
+        u128 canon[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t i = base + 32u * u + lane;
+          q[u] = i < n32 ? load_kmer(i) : make_uint4(0, 0, 0, 0);
+          cnt[u] = i < n32 ? __ldg(src.counts + i) : 0u;
+        }
+        // the warp's next 64 k-mers (1 KB + 256 B of counts) into L2 while these are hashed
+        if (lane < 10 && base + 2 * step < n32) {
+          const char *pf = lane < 8 ? reinterpret_cast<const char *>(src.kmers + base + 2 * step) + lane * 128
+                                    : reinterpret_cast<const char *>(src.counts + base + 2 * step) + (lane - 8) * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
+        uint64_t idx[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const u128 x35 = mask128(shr128(u128_of(q[u]), 2 * tail), 2 * k);
+          uint64_t h;
+          if constexpr (K > 0)
+            h = canon_hash_lut<K>(x35, &canon[u], tab);
+          else
+            h = canon_hash_rt(x35, k, &canon[u]);
+          idx[u] = bf_index(v, h);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {  // (both pre-filter words are in flight together)
+          need[u] = base + 32u * u + lane < n32 && occ_test(v, idx[u]);
+          idx_lo[u] = (uint32_t)(idx[u] >> 8);
+          bit[u] = (uint32_t)(idx[u] & 255);
+        }
+#pragma unroll 1
+        for (int u = 0; u < 2; ++u) {
+          const bool nd = u ? need[1] : need[0];
+          const uint32_t need_mask = __ballot_sync(0xffffffffu, nd);
+          if (nd) {
+            const uint32_t e = wrap(fl_pos + fl_n + pd_n + (uint32_t)__popc(need_mask & ((1u << lane) - 1u)));
+            qkey[e] = uint4_of(u ? canon[1] : canon[0]);
+            qmeta[e] = make_uint4(u ? idx_lo[1] : idx_lo[0], base + 32u * u + lane, u ? cnt[1] : cnt[0], u ? bit[1] : bit[0]);
+          }
+          pd_n += (uint32_t)__popc(need_mask);
+          if (pd_n >= 32) {
+            start_round();
+            complete_round();
+          }
+        }
+      } else if (pd_n) {
+        start_round();
+        complete_round();
+      }
+      if (!more && pd_n == 0) break;
+    }
+  } else {
   for (uint32_t base = warp_id * 32;; base += step) {
     more = more && base < n32;
     if (more) {
@@ -621,102 +883,19 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS)) k_scan(ScanSr
       const bool need = live && occ_test(v, idx);
       const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
       if (need) {
-        const uint32_t e = (qhead + qn + (uint32_t)__popc(need_mask & ((1u << lane) - 1u))) & (SCAN_Q - 1);
+        const uint32_t e = (fl_pos + fl_n + pd_n + (uint32_t)__popc(need_mask & ((1u << lane) - 1u))) & (SCAN_Q - 1);
         qkey[e] = uint4_of(MODE == 0 ? canon : x43);
         qmeta[e] = make_uint4((uint32_t)(idx >> 8), i, cnt, (uint32_t)(idx & 255));  // n_lines < 2^32 (bf_bits < 2^40)
       }
-      qn += (uint32_t)__popc(need_mask);
+      pd_n += (uint32_t)__popc(need_mask);
     }
-    if (qn >= 32 || (!RING && qn) || (!more && qn)) {
-      // ---- one probe round over ring entries qhead .. qhead + n_probe - 1 ----
-      const uint32_t n_probe = qn < 32 ? qn : 32;
-      __syncwarp();  // the ring entries are visible; the previous round's reads of the tile are done
-      const uint4 kq = qkey[qhead + lane], mq = qmeta[qhead + lane];
-      {
-        const uint32_t *qline = reinterpret_cast<const uint32_t *>(qmeta + qhead + grp);  // .x of entry qhead + grp + 4r
-        uint32_t lid[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) lid[r] = qline[r * 16];  // (stale entries past n_probe are read but never used)
-        if (n_probe == 32) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r)
-            cp_async16(((r & 1) ? d_odd : d_even) + (uint32_t)(r * 512), line_src + ((uint64_t)lid[r] << 7));
-        } else {
-#pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if ((uint32_t)(4 * r + grp) < n_probe)
-              cp_async16(((r & 1) ? d_odd : d_even) + (uint32_t)(r * 512), line_src + ((uint64_t)lid[r] << 7));
-        }
-      }
-      cp_async_wait_all();
-      __syncwarp();
-      if ((uint32_t)lane < n_probe) {
-        // ---- this lane owns row `lane` of the tile ----
-        const uint32_t line = mq.x, cnt = mq.z, bit = mq.w;
-        u128 canon, x43;
-        if constexpr (MODE == 0) {
-          canon = u128_of(kq);
-        } else {
-          x43 = u128_of(kq);
-          canon = canon_only(mask128(shr128(x43, 2 * tail), 2 * k), k);
-        }
-        const uint4 *mine = tile + lane * 8;
-        const int sw = lane & 7;
-        const uint32_t fw = reinterpret_cast<const uint32_t *>(mine + ((bit >> 7) ^ sw))[(bit >> 5) & 3];
-        const bool bf_hit = (fw >> (bit & 31u)) & 1u;
-        const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
-                       c3 = (uint32_t)(canon.hi >> 32);
-        int slot = -1;
-        uint32_t flag_w = 0;
-#pragma unroll
-        for (int s = 0; s < LINE_KEYS; ++s) {
-          const uint4 p = mine[(2 + s) ^ sw];
-          if (((p.x ^ c0) | (p.y ^ c1) | ((p.z ^ c2) & mz) | ((p.w ^ c3) & mw)) == 0) slot = s;
-          if (s == LINE_KEYS - 1) flag_w = inl ? p.z : p.w;
-        }
-        // ---- ref_bf.increment ----
-        if (slot >= 0) {
-          uint32_t *cp = inl ? line_words(v, line) + 8 + 4 * slot + 3 : v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot;
-          atomicAdd(cp, cnt);
-        } else if (flag_w >> 31) {  // line overflowed at index time: the key may live in the overflow table
-          const int64_t os = ovf_find(v, canon);
-          if (os >= 0) atomicAdd(v.ovf_counts + os, cnt);
-        }
-        // ---- bf.increment unless the context filter vetoes it ----
-        if (bf_hit) {
-          // counter of the bit: number j of the set bit inside the line, rank of the line
-          const uint32_t ws = bit >> 5, below = (1u << (bit & 31u)) - 1u;
-          const uint4 b0 = mine[0 ^ sw], b1 = mine[1 ^ sw];
-          const uint32_t wx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          int j = 0;
-#pragma unroll
-          for (uint32_t x = 0; x < 8; ++x) j += __popc(wx[x] & (x < ws ? 0xFFFFFFFFu : (x == ws ? below : 0u)));
-          const uint32_t rank = reinterpret_cast<const uint32_t *>(mine + (7 ^ sw))[0];
-          uint32_t *ap = j < LINE_INLINE_ALT ? line_words(v, line) + LINE_W_RANK + 1 + j
-                                             : v.bf_counts + (uint64_t)rank + (uint64_t)j;
-          if constexpr (MODE == 0) x43 = u128_of(__ldg(src.kmers + mq.y));
-          const uint32_t pos = src.hit_buf ? atomicAdd(hitc, 1u) : 0xFFFFFFFFu;
-          if (pos < src.seg_cap) {  // recorded; k_scan_hits finishes it
-            uint4 *e = src.hit_buf + ((uint64_t)warp_id * src.seg_cap + pos) * 2;
-            const uint64_t a64 = reinterpret_cast<uint64_t>(ap);
-            e[0] = uint4_of(x43);
-            e[1] = make_uint4((uint32_t)a64, (uint32_t)(a64 >> 32), cnt, 0u);
-          } else {
-            u128 c43;
-            uint64_t h43;
-            if constexpr (REFK > 0)
-              h43 = canon_hash_lut<REFK>(x43, &c43, tab);
-            else
-              h43 = canon_hash_rt(x43, ref_k, &c43);
-            if (!ctx_test(v, bf_index(v, h43))) atomicAdd(ap, cnt);
-          }
-        }
-      }
-      qhead = (qhead + 32) & (SCAN_Q - 1);
-      qn -= n_probe;
+    if (pd_n >= 32 || (!RING && pd_n) || (!more && pd_n)) {
+      start_round();
+      complete_round();
     }
-    if (!more && qn == 0) break;
+    if (!more && pd_n == 0) break;
   }
+  }  // !ASYNC
   if (src.hit_buf) {
     __syncwarp();
     if (lane == 0) src.hit_counts[warp_id] = *hitc < src.seg_cap ? *hitc : src.seg_cap;
@@ -748,14 +927,38 @@ __global__ void __launch_bounds__(256) k_scan_hits(const uint4 *__restrict__ hit
 // K4: signature look-ups (BF::get_count / KMAP::get_count) + coverage.  One probe line per look-up: the count of a
 // ref key is in its slot, the counter of an alt bit in words 29..31 of the line (index.cuh).
 // ---------------------------------------------------------------------------
+// Both read everything they may need from the probe line in ONE round of independent loads (the filter words, the
+// rank + inline counters; the five slots with their counts): a look-up is one memory round trip, not two.
 __device__ __forceinline__ int32_t alt_get_count(const DevView &v, uint64_t idx) {  // BF::get_count (u16)
   if (!v.bf_counts) return 0;  // write mode: no counters yet (bloom_filter.hpp:115-125)
-  const uint32_t *p = alt_counter_ptr(v, idx);
-  return p ? (int32_t)(*p & 0xFFFFu) : 0;
+  const uint4 *p = v.lines + (idx >> 8) * LINE_U4;
+  const uint4 a = __ldg(p), b = __ldg(p + 1), m = __ldg(p + 7);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const uint32_t ws = (uint32_t)((idx & 255) >> 5), below = (1u << (idx & 31)) - 1u;
+  uint32_t mine = 0;
+  int j = 0;
+#pragma unroll
+  for (uint32_t x = 0; x < 8; ++x) {
+    mine = x == ws ? w[x] : mine;
+    j += __popc(w[x] & (x < ws ? 0xFFFFFFFFu : (x == ws ? below : 0u)));
+  }
+  if (!((mine >> (idx & 31)) & 1u)) return 0;
+  const uint32_t c = j == 0 ? m.y : (j == 1 ? m.z : (j == 2 ? m.w : __ldg(v.bf_counts + (uint64_t)m.x + (uint64_t)j)));
+  return (int32_t)(c & 0xFFFFu);
 }
 __device__ __forceinline__ int32_t ref_get_count(const DevView &v, uint64_t idx, u128 canon) {  // KMAP::get_count
-  const uint32_t *p = key_count_ptr(v, idx, canon);
-  return p ? (int32_t)*p : 0;
+  const uint64_t line = idx >> 8;
+  const uint4 *p = v.lines + line * LINE_U4 + 2;
+  uint4 q[LINE_KEYS];
+#pragma unroll
+  for (int s = 0; s < LINE_KEYS; ++s) q[s] = __ldg(p + s);
+#pragma unroll
+  for (int s = 0; s < LINE_KEYS; ++s)
+    if (key_eq(key_of(v, q[s]), canon))
+      return v.inline_counts ? (int32_t)q[s].w : (int32_t)__ldg(v.key_counts + line * LINE_KEYS + (uint64_t)s);
+  if (!(u128_of(q[LINE_KEYS - 1]).hi & v.ovf_flag_hi)) return 0;
+  const int64_t slot = ovf_find(v, canon);
+  return slot < 0 ? 0 : (int32_t)__ldg(v.ovf_counts + slot);
 }
 
 // flags the k-mers of allele slot 0 of every variant (they are looked up in ref_bf, main.cpp:167-170)
@@ -859,19 +1062,89 @@ __global__ void __launch_bounds__(128) k_lookup_fast(const uint8_t *__restrict__
 // Packed signature k-mers (exactly k symbols of ACGT, the form the host enumerator emits): {lo, hi} words;
 // hi bit 62 = k-mer of allele slot 0 (looked up in ref_bf), hi bit 63 = irregular (not k x ACGT: resolved by k_lookup
 // from the side pool).  16 bytes in, 4 bytes out, one probe line per k-mer.
+// A warp takes 32 k-mers at a time: every lane hashes one, then the 32 probe lines are gathered into the warp's
+// 4 KB shared-memory tile exactly like a round of the sample scan (eight LDGSTS rounds, four whole lines each, the
+// line of row L announced by a shuffle), and every lane reads its own row.  One thread fetching its line by itself
+// -- five 16-byte loads for a ref key, three for an alt bit -- cost five (three) L1 tag look-ups per line and ran at
+// 45 % of the device's random-line rate with the load queues full (ncu, profiles/round2_k4.md).
+constexpr int LOOKUP_THREADS = 256;
+constexpr int LOOKUP_SMEM = (LOOKUP_THREADS / 32) * 4096;
+
 template <int K>
-__global__ void __launch_bounds__(128) k_lookup_packed(const uint4 *__restrict__ kmers, uint64_t n, DevView v,
-                                                      int32_t *__restrict__ out) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint4 q = __ldg(kmers + i);
-  if (q.w >> 31) return;  // irregular
-  const bool is_ref = (q.w >> 30) & 1u;
+__global__ void __launch_bounds__(LOOKUP_THREADS) k_lookup_packed(const uint4 *__restrict__ kmers, uint64_t n, DevView v,
+                                                                 int32_t *__restrict__ out) {
+  extern __shared__ uint4 lk_sm[];
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  uint4 *tile = lk_sm + (threadIdx.x >> 5) * 256;
+  const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
+  const uint32_t d_even = tile_addr + (uint32_t)(grp * 128 + ((sub ^ grp) * 16));
+  const uint32_t d_odd = tile_addr + (uint32_t)(grp * 128 + ((sub ^ (grp + 4)) * 16));
+  const char *line_src = reinterpret_cast<const char *>(v.lines) + sub * 16;
   const int k = K > 0 ? K : v.k;
-  u128 x = mask128(u128_of(q), 2 * k), canon;
-  const uint64_t h = canon_hash_k<K>(x, k, &canon);
-  const uint64_t idx = bf_index(v, h);
-  out[i] = is_ref ? ref_get_count(v, idx, canon) : alt_get_count(v, idx);
+  const bool inl = K > 0 ? (K <= INLINE_MAX_K) : (v.inline_counts != 0);
+  const uint32_t mz = inl ? 0x7FFFFFFFu : 0xFFFFFFFFu, mw = inl ? 0u : 0x3FFFFFFFu;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t base = warp0 * 32; base < n; base += n_warps * 32) {
+    const uint64_t i = base + (uint64_t)lane;
+    const uint4 q = i < n ? __ldg(kmers + i) : make_uint4(0, 0, 0, 0x80000000u);
+    const bool active = !(q.w >> 31);  // (past the end, or irregular: nothing to fetch)
+    const bool is_ref = (q.w >> 30) & 1u;
+    u128 canon;
+    const uint64_t h = canon_hash_k<K>(mask128(u128_of(q), 2 * k), k, &canon);
+    const uint64_t idx = bf_index(v, h);
+    const uint32_t line = (uint32_t)(idx >> 8), bit = (uint32_t)(idx & 255);
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    __syncwarp();  // the previous batch's reads of the tile are done
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t lid = __shfl_sync(0xffffffffu, line, 4 * r + grp);
+      if ((act >> (4 * r + grp)) & 1u)
+        cp_async16(((r & 1) ? d_odd : d_even) + (uint32_t)(r * 512), line_src + ((uint64_t)lid << 7));
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    if (!active) continue;
+    const uint4 *mine = tile + lane * 8;
+    const int sw = lane & 7;
+    int32_t res = 0;
+    if (is_ref) {  // KMAP::get_count: the count sits in the slot that holds the key
+      const uint32_t c0 = (uint32_t)canon.lo, c1 = (uint32_t)(canon.lo >> 32), c2 = (uint32_t)canon.hi,
+                     c3 = (uint32_t)(canon.hi >> 32);
+      int slot = -1;
+      uint32_t cnt_w = 0, flag_w = 0;
+#pragma unroll
+      for (int s = 0; s < LINE_KEYS; ++s) {
+        const uint4 p = mine[(2 + s) ^ sw];
+        if (((p.x ^ c0) | (p.y ^ c1) | ((p.z ^ c2) & mz) | ((p.w ^ c3) & mw)) == 0) {
+          slot = s;
+          cnt_w = p.w;
+        }
+        if (s == LINE_KEYS - 1) flag_w = inl ? p.z : p.w;
+      }
+      if (slot >= 0) {
+        res = inl ? (int32_t)cnt_w : (int32_t)__ldg(v.key_counts + (uint64_t)line * LINE_KEYS + (uint32_t)slot);
+      } else if (flag_w >> 31) {
+        const int64_t os = ovf_find(v, canon);
+        if (os >= 0) res = (int32_t)__ldg(v.ovf_counts + os);
+      }
+    } else if (v.bf_counts) {  // BF::get_count (u16); no counters before switch_mode
+      const uint32_t ws = bit >> 5, below = (1u << (bit & 31u)) - 1u;
+      const uint4 b0 = mine[0 ^ sw], b1 = mine[1 ^ sw], m = mine[7 ^ sw];
+      const uint32_t wx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t hit_w = 0;
+      int j = 0;
+#pragma unroll
+      for (uint32_t x = 0; x < 8; ++x) {
+        hit_w = x == ws ? wx[x] : hit_w;
+        j += __popc(wx[x] & (x < ws ? 0xFFFFFFFFu : (x == ws ? below : 0u)));
+      }
+      if ((hit_w >> (bit & 31u)) & 1u) {
+        const uint32_t c = j == 0 ? m.y : (j == 1 ? m.z : (j == 2 ? m.w : __ldg(v.bf_counts + (uint64_t)m.x + (uint64_t)j)));
+        res = (int32_t)(c & 0xFFFFu);
+      }
+    }
+    out[i] = res;
+  }
 }
 
 // set_coverages (main.cpp:157-182): per allele slot, max over signatures of the order-dependent integer

@@ -779,11 +779,13 @@ extern "C" int mg_finalize_context(mg_ctx *c) {
   return MG_OK;
 }
 
-template <int K, int REFK, int MODE, int THREADS, bool RING>
+template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP = 1>
 static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n, cudaStream_t st) {
   constexpr int WARPS = THREADS / 32;
-  uint64_t want = (n + THREADS - 1) / THREADS;  // one warp per 32 k-mers
-  uint64_t cap = (uint64_t)c->sms * (uint64_t)c->scan_ctas_per_sm * (256 / THREADS);
+  uint64_t want = (n + THREADS * ILP - 1) / (THREADS * ILP);  // one warp per 32 (64) k-mers
+  int per_sm = c->scan_ctas_per_sm;
+  if (const char *ev = getenv("MG_SCAN_CTAS_PER_SM")) per_sm = atoi(ev) > 0 ? atoi(ev) : per_sm;  // (sweeps: read per launch)
+  uint64_t cap = (uint64_t)c->sms * (uint64_t)per_sm * (256 / THREADS);
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
   mg::ScanSrc src = src_in;
@@ -814,13 +816,14 @@ static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n,
     src.hit_counts = c->hit_counts[si];
     src.seg_cap = (uint32_t)seg;
   }
-  constexpr int SMEM = mg::scan_smem(THREADS);
+  constexpr int SMEM = mg::scan_smem(THREADS, ASYNC, ILP);
   if (SMEM > 48 * 1024) {  // more than 48 KB of dynamic shared memory needs the opt-in (per device; cheap enough to repeat)
-    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE, THREADS, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
   }
   c->launches++;
-  mg::k_scan<K, REFK, MODE, THREADS, RING><<<grid, THREADS, SMEM, st>>>(src, n, c->view());
+  mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP><<<grid, THREADS, SMEM, st>>>(src, n, c->view());
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !src.hit_buf) return e;
   const uint64_t threads = n_warps * src.seg_cap;
@@ -834,20 +837,32 @@ template <int MODE>
 static int scan_src(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t st) {
   cudaError_t e;
   if (c->k == 35 && c->ref_k == 43) {
-    // MG_SCAN_VARIANT (tuning sweeps, profiles/sweep_k1_r2.py): CTA size and probe scheme of the packed-input scan
+    // MG_SCAN_VARIANT (tuning sweeps, profiles/sweep_k1_r2.py): the schemes tried for the packed-input scan.
+    // Default = 0: two k-mers per lane, asynchronous probe rounds, 256-thread CTAs (profiles/round2_k1.md).
     int variant = 0;
     if (MODE == 0)
       if (const char *ev = getenv("MG_SCAN_VARIANT")) variant = atoi(ev);
     if (MODE == 0 && variant == 1)
-      e = launch_scan<35, 43, 0, 128, true>(c, src, n, st);
+      e = launch_scan<35, 43, 0, 256, true, false>(c, src, n, st);     // one k-mer per lane, synchronous rounds
     else if (MODE == 0 && variant == 2)
-      e = launch_scan<35, 43, 0, 256, false>(c, src, n, st);
+      e = launch_scan<35, 43, 0, 256, false, false>(c, src, n, st);    // probe after every batch (the round-1 scheme)
     else if (MODE == 0 && variant == 3)
-      e = launch_scan<35, 43, 0, 128, false>(c, src, n, st);
+      e = launch_scan<35, 43, 0, 256, true, true>(c, src, n, st);      // one k-mer per lane, asynchronous rounds
+    else if (MODE == 0 && variant == 4)
+      e = launch_scan<35, 43, 0, 256, true, false, 2>(c, src, n, st);  // two k-mers per lane, synchronous rounds
+    else if (MODE == 0 && variant == 5)
+      e = launch_scan<35, 43, 0, 128, true, false, 2>(c, src, n, st);
+    else if (MODE == 0 && variant == 6)
+      e = launch_scan<35, 43, 0, 128, true, true, 2>(c, src, n, st);   // two k-mers per lane, asynchronous rounds, 128
+    else if (MODE == 0)
+      e = launch_scan<35, 43, 0, 256, true, true, 2>(c, src, n, st);
     else
-      e = launch_scan<35, 43, MODE, 256, true>(c, src, n, st);
+      e = launch_scan<35, 43, MODE, 256, true, false>(c, src, n, st);
   } else {
-    e = launch_scan<0, 0, MODE, 256, true>(c, src, n, st);
+    if (MODE == 0)
+      e = launch_scan<0, 0, 0, 256, true, true, 2>(c, src, n, st);
+    else
+      e = launch_scan<0, 0, MODE, 256, true, false>(c, src, n, st);
   }
   if (e != cudaSuccess) return set_err(MG_ERR_CUDA, "k_scan launch -> %s", cudaGetErrorString(e));
   return MG_OK;
@@ -1198,10 +1213,14 @@ static int genotype_packed_on_device(mg_ctx *c, const mg_packed_batch *in, const
   CU(cudaEventRecord(c->ge[0], st));
   if (nk) {
     c->launches++;
-    if (c->k == 35)
-      mg::k_lookup_packed<35><<<grid_for(nk, 128), 128, 0, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
-    else
-      mg::k_lookup_packed<0><<<grid_for(nk, 128), 128, 0, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
+    {
+      const uint64_t want = (nk + mg::LOOKUP_THREADS - 1) / mg::LOOKUP_THREADS, cap = (uint64_t)c->sms * 32;
+      const int grid = (int)(want < cap ? want : cap);
+      if (c->k == 35)
+        mg::k_lookup_packed<35><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
+      else
+        mg::k_lookup_packed<0><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
+    }
     CU(cudaGetLastError());
     if (in->n_irregular) {  // not k symbols of ACGT: the byte-exact path, written to their places in the weight array
       c->launches++;

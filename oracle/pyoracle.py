@@ -119,6 +119,8 @@ def ref() -> C.CDLL:
     L.ref_add_packed.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u8p, C.c_uint64, C.c_int]
     L.ref_scan_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u32p, C.c_uint64, C.c_int, C.c_int]
     L.ref_reference_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.ref_kmc_list.restype = C.c_long
+    L.ref_kmc_list.argtypes = [C.c_char_p, _u64p, C.c_char_p, C.c_long]
     L.ref_get_counts_packed.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u8p, C.c_uint64, C.c_int, C.POINTER(C.c_int32)]
     L.ref_genotype_batch.restype = C.c_uint64
     L.ref_genotype_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u32p, _u32p, _u32p, _u64p, _f32p, C.c_int,

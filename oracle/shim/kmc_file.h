@@ -73,6 +73,7 @@ class CKMCFile {
     max_count_ = rd32(h + o); o += 4;
     total_kmers_ = rd64(h + o); o += 8;
     both_strands_ = !(h[o] & 1);
+    if (o + 5 + 4 <= hoff) max_count_ |= (uint64)rd32(h + o + 1) << 32;  // KMC 3: high word of max_count
     size_t sigmap_bytes = version == 0x200 ? (((size_t)1 << (2 * signature_len_)) + 1) * 4 : 0;
     size_t lut_bytes = (size_t)fsz - 4 - 8 - hoff - sigmap_bytes;
     size_t n = lut_bytes / 8;
@@ -144,7 +145,8 @@ class CKMCFile {
 
   FILE *suf_ = nullptr;
   uint32 klen_ = 0, mode_ = 0, counter_size_ = 0, lut_prefix_len_ = 0, signature_len_ = 0;
-  uint32 min_count_ = 0, max_count_ = 0;
+  uint32 min_count_ = 0;
+  uint64 max_count_ = 0;
   uint64 total_kmers_ = 0, rec_ = 0;
   bool both_strands_ = true;
   std::vector<uint64> lut_;

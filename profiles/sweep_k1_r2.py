@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Round-2 sweep of the sample-scan kernel (K1) on the bench workload: CTA size x probe scheme (MG_SCAN_VARIANT:
-0 = 256 threads + ring, 1 = 128 + ring, 2 = 256 + probe after every batch, 3 = 128 + probe after every batch).
+"""Round-2 sweep of the sample-scan kernel (K1) on the bench workload: probe scheme x CTA size x grid cap
+(MG_SCAN_VARIANT: 0 = two k-mers per lane, asynchronous rounds, 256-thread CTAs (default); 1 = one k-mer per lane,
+synchronous rounds; 2 = probe after every batch of 32 k-mers as in round 1; 3 = one k-mer per lane, asynchronous rounds;
+4 / 5 = two k-mers per lane, synchronous rounds, 256 / 128 threads; 6 = as 0 with 128 threads; MG_SCAN_CTAS_PER_SM: grid cap).
 The index is built once; the variant is read at every launch.
     python profiles/sweep_k1_r2.py [--workload wg] [--variants 0,1,2,3] [--reps 10] > gpurun_out/r2_sweep_k1.txt"""
 import argparse
@@ -20,6 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="wg")
 ap.add_argument("--variants", default="0,1,2,3")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--ctas", default="128")
 args = ap.parse_args()
 wl = bench.WORKLOADS[args.workload]
 dev = torch.device("cuda", 0)
@@ -39,8 +42,9 @@ g.finalize_context()
 batches = [bench.make_sample_batch(torch, B, alt, ref, gen, dev)[:2] for _ in range(2)]
 del alt, ref
 torch.cuda.synchronize()
-for v in [int(x) for x in args.variants.split(",")]:
+for v, ctas in [(int(x), int(y)) for x in args.variants.split(",") for y in args.ctas.split(",")]:
     os.environ["MG_SCAN_VARIANT"] = str(v)
+    os.environ["MG_SCAN_CTAS_PER_SM"] = str(ctas)
     for i in range(3):
         g.scan_sample_kmers_ptr(batches[i & 1][0].data_ptr(), batches[i & 1][1].data_ptr(), B, device=True)
     g.sync()
@@ -49,6 +53,6 @@ for v in [int(x) for x in args.variants.split(",")]:
         g.scan_sample_kmers_ptr(batches[i & 1][0].data_ptr(), batches[i & 1][1].data_ptr(), B, device=True)
     g.event_record(1)
     ms = g.event_elapsed_ms(0, 1) / args.reps
-    print(f"variant={v}: {ms:.3f} ms/scan  {B / ms / 1e6:.2f} G k-mers/s  {B * 84 / ms / 1e6:.0f} GB/s algorithmic "
+    print(f"variant={v} ctas_per_sm={ctas}: {ms:.3f} ms/scan  {B / ms / 1e6:.2f} G k-mers/s  {B * 84 / ms / 1e6:.0f} GB/s algorithmic "
           f"(frac {B * 84 / ms / 1e6 / 6551.4:.3f})", flush=True)
 g.close()

@@ -176,8 +176,17 @@ def test_wrapper_script_runs_the_whole_pipeline(tmp_path):
     assert r.stdout == open(os.path.join(GOLD, "haploid.malva.vcf"), "rb").read()
     assert os.path.exists(tmp_path / "haploid.fq_malva43.kmercount.kmc_suf")
     assert os.path.exists(tmp_path / "haploid.vcf.c43.k35.malvax.zst")
-    r2 = subprocess.run(cmd, capture_output=True, cwd=tmp_path)   # second run reuses the database and the index
-    assert r2.returncode == 0 and r2.stdout == r.stdout and b"Index file exists already" in r2.stderr
+    # a second run reuses the k-mer database; the index is rebuilt (its file name does not carry -s / -1 / -u / -f / -p
+    # / -b or the reference, all of which its content depends on): other flags, other -- correct -- answer
+    r2 = subprocess.run(cmd, capture_output=True, cwd=tmp_path)
+    assert r2.returncode == 0 and r2.stdout == r.stdout and b"Found k-mer database" in r2.stderr
+    cmd_u = [wrapper, "-1", "-u", "-k", "35", "-r", "43", "-b", "1", "haploid.fa", "haploid.vcf", "haploid.fq"]
+    r3 = subprocess.run(cmd_u, capture_output=True, cwd=tmp_path)
+    r4 = subprocess.run([mbuild.CLI, "index", "-1", "-u", "-b", "1", "haploid.fa", "haploid.vcf",
+                         "haploid.fq_malva43.kmercount"], capture_output=True, cwd=tmp_path)
+    r5 = subprocess.run([mbuild.CLI, "call", "-1", "-u", "-b", "1", "haploid.fa", "haploid.vcf",
+                         "haploid.fq_malva43.kmercount"], capture_output=True, cwd=tmp_path)
+    assert r3.returncode == 0 and r4.returncode == 0 and r5.returncode == 0 and r3.stdout == r5.stdout
 
 
 def test_cli_count_reads_fasta_and_fastq_layouts(tmp_path):

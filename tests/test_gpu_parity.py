@@ -207,21 +207,35 @@ def test_scan_large_batch_properties(oracle_lib):
     assert once[0].sum() > 0 and once[1].sum() > 0
 
 
-@pytest.mark.parametrize("version,p,k,ref_k", [(0x200, 7, 35, 43), (0, 3, 35, 43), (0x200, 3, 31, 39), (0, 5, 36, 41)])
-def test_kmc_records_decoded_on_device(oracle_lib, tmp_path, version, p, k, ref_k):
+@pytest.mark.parametrize("version,p,k,ref_k,csz,minc,maxc", [
+    (0x200, 7, 35, 43, 1, 3, 200), (0, 3, 35, 43, 1, 3, 200), (0x200, 3, 31, 39, 1, 3, 200), (0, 5, 36, 41, 1, 3, 200),
+    (0x200, 7, 35, 43, 2, 3, 1000),            # -cs1000: two counter bytes
+    (0x200, 7, 35, 43, 3, 2, 70000),
+    (0x200, 3, 35, 43, 4, 3, (1 << 33) + 7),   # 64-bit max_count (high word of the KMC 3 header)
+    (0x200, 3, 60, 63, 2, 3, 60000),           # 15 suffix bytes + 2 counter bytes: records longer than a packed word
+    (0, 1, 21, 21, 4, 250, 250),               # a one-value [min, max] window; k == ref_k
+])
+def test_kmc_records_decoded_on_device(oracle_lib, tmp_path, version, p, k, ref_k, csz, minc, maxc):
     """mg_scan_kmc_records (raw .kmc_suf records + prefix LUT, decoded by the scan kernel) must leave the same
-    state as the oracle scanning the KMC listing -- including the [min_count, max_count] record filter."""
+    state as the oracle scanning the KMC listing -- including the [min_count, max_count] record filter -- over the
+    header variants of tests/test_kmc_format_cpu.py (counter sizes 1-4, KMC1 / 0x200, LUT prefix lengths)."""
     rng = random.Random(4000 + p + k)
     bits = 1 << 20
     genome = util.make_genome(rng, 20000)
     nested, freqs = util.synth_signatures(rng, genome, k, 300)
     ks, fl = util.flatten(nested)
-    words, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, 5000)
-    counts = np.minimum(counts, 255).astype(np.uint32)
-    counts[::7] = 2          # below min_count=3: skipped by ReadNextKmer
-    counts[::11] = 250       # above max_count=200: skipped too
+    words, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, 5000, big_counts=csz > 1)
+    counts = np.minimum(counts, min(256 ** csz - 1, 70000)).astype(np.uint32)
+    counts[::7] = 2          # below min_count: skipped by ReadNextKmer
+    counts[::11] = 250       # above max_count = 200 (one-byte cases): skipped too
+    counts[::13] = minc      # the edges themselves are kept
+    counts[::17] = min(maxc, 256 ** csz - 1)
+    if minc == maxc:
+        counts[::2] = minc
+    counts[::19] = minc - 1  # (below min_count whatever it is)
     prefix = str(tmp_path / "db")
-    kmc.write_kmc_db(prefix, packed, counts, ref_k, lut_prefix_len=p, version=version, min_count=3, max_count=200)
+    kmc.write_kmc_db(prefix, packed, counts, ref_k, lut_prefix_len=p, version=version, counter_size=csz, min_count=minc,
+                     max_count=maxc)
     listed, lcounts, kk = kmc.read_kmc_db(prefix)
     assert kk == ref_k and 0 < len(listed) < len(packed)
     db = kmc.open_kmc_db(prefix)
