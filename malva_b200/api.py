@@ -249,6 +249,7 @@ class MalvaGpu:
     def kmc_open(self, db: dict) -> None:
         """db = malva_b200.kmc.open_kmc_db(prefix): hand the prefix LUT + header of a KMC database to the device."""
         lut = np.ascontiguousarray(db["lut"], dtype=np.uint64)
+        self._kmc_record_bytes = (db["k"] - db["lut_prefix_len"]) // 4 + db["counter_size"]
         check(self._L.mg_kmc_open(self._h, _p(lut, _lib.u64p), len(lut), db["lut_prefix_len"], db["k"],
                                   db["counter_size"], db["min_count"], db["max_count"]))
 
@@ -257,8 +258,14 @@ class MalvaGpu:
         if isinstance(records, np.ndarray):
             records = np.ascontiguousarray(records, dtype=np.uint8)
             ptr = records.ctypes.data
+            if n is None:
+                if not getattr(self, "_kmc_record_bytes", 0):
+                    raise MalvaGpuError("scan_kmc_records before kmc_open")
+                n = len(records) // self._kmc_record_bytes
         else:
             ptr = int(records)
+            if n is None:
+                raise MalvaGpuError("scan_kmc_records: n is required with a raw address")
         check(self._L.mg_scan_kmc_records(self._h, ptr, first_record, n))
         if sync:
             self.sync()

@@ -244,9 +244,25 @@ void gpu(int rc, const char *what) {
 }
 
 // ---- the VCF loop of index_main / call_main (main.cpp:309-370, 522-579) as a stream of batches of blocks ----
+// A batch owns the records it was decoded into (`arena`, in file order, skipped records squeezed out) and the contig
+// names its blocks refer to; the blocks are views into the arena.
+struct BlockBatch {
+  std::vector<mh::Variant> arena;
+  std::vector<mh::VarBlock> blocks;
+  std::vector<std::unique_ptr<std::string>> contigs;
+  BlockBatch() = default;
+  BlockBatch(BlockBatch &&) = default;
+  BlockBatch &operator=(BlockBatch &&) = default;
+  void clear() {
+    arena.clear();
+    blocks.clear();
+    contigs.clear();
+  }
+};
+
 class BlockStream {
  public:
-  BlockStream(const Options &o, bool index_mode) : o_(o), index_mode_(index_mode), reader_(o.vcf_path), vb_((int)o.k) {
+  BlockStream(const Options &o, bool index_mode) : o_(o), index_mode_(index_mode), reader_(o.vcf_path) {
     is_file_ = o.samples != "-";
     samples_code = reader_.header.set_samples(o.samples);
     freq_declared_ = reader_.header.has_info(o.freq_key);
@@ -257,24 +273,37 @@ class BlockStream {
   uint64_t n_records = 0;
   const mh::VcfHeader &header() const { return reader_.header; }
 
-  // up to `max_lines` more records; blocks flushed by them are appended to `out`.  false when nothing is left.
-  bool next_batch(std::vector<mh::VarBlock> &out, size_t max_lines) {
+  // up to `max_lines` more records; the blocks they complete go to `out`.  false when nothing is left.
+  bool next_batch(BlockBatch &out, size_t max_lines) {
     out.clear();
     if (done_) return false;
-    // a block of whole lines (no per-line allocation), decoded in parallel
+    // a block of whole lines (no per-line allocation), decoded in parallel straight into the batch's arena, behind
+    // the records of the block that was still open when the previous batch ended
     Stopwatch sw;
     const bool more = reader_.next_lines(store_, lines_, max_lines, 12u << 20);
     t_read += sw.lap();
-    std::vector<mh::Variant> vars(lines_.size());
+    std::vector<mh::Variant> &vars = out.arena;
+    const size_t n_carry = carry_.size();
+    vars.resize(n_carry + lines_.size());
+    for (size_t i = 0; i < n_carry; ++i) vars[i] = std::move(carry_[i]);
+    carry_.clear();
     // (a line of a 27,934-sample panel is 84 KB: a 12 MB block holds ~150 of them, so the grain follows the count)
     const size_t grain = std::max<size_t>(1, std::min<size_t>(256, lines_.size() / (4 * (size_t)o_.threads) + 1));
     const size_t n_tasks = (lines_.size() + grain - 1) / grain;
     parallel_for(n_tasks, o_.threads, [&](size_t t) {
       for (size_t i = t * grain; i < std::min(lines_.size(), (t + 1) * grain); ++i)
-        vars[i] = mh::parse_record(lines_[i].b, lines_[i].e, reader_.header, o_.freq_key, o_.uniform, freq_declared_);
+        vars[n_carry + i] = mh::parse_record(lines_[i].b, lines_[i].e, reader_.header, o_.freq_key, o_.uniform, freq_declared_);
     });
     t_decode += sw.lap();
-    for (auto &v : vars) {
+    // grouping (main.cpp:330-362): `open` = first record of the block being built, `w` = where the next kept record goes
+    size_t w = n_carry, open = 0;
+    bool have_open = n_carry > 0;
+    auto flush = [&](size_t end) {
+      out.contigs.push_back(std::make_unique<std::string>(last_seq_name_));
+      out.blocks.emplace_back((int)o_.k, vars.data() + open, end - open, out.contigs.back().get());
+    };
+    for (size_t r = n_carry; r < vars.size(); ++r) {
+      mh::Variant &v = vars[r];
       ++n_records;
       if (n_records % 5000 == 0) pelapsed("Processed " + std::to_string(n_records) + " variants", true);
       if (last_seq_name_.empty()) {
@@ -284,37 +313,38 @@ class BlockStream {
       // index: variants with only symbolic ALTs or carried by no sample are skipped; call: the latter are kept
       // (they are genotyped 0/0, main.cpp:332 vs :538)
       if (!v.has_alts || (index_mode_ && !v.is_present)) continue;
-      if (vb_.empty()) {
-        vb_.add(std::move(v));
-        continue;
-      }
-      if (!vb_.is_near_to_last(v) || last_seq_name_ != v.seq_name) {
-        flush(out);
+      if (have_open && (!mh::variants_near(vars[w - 1], v, (int)o_.k, 0) || last_seq_name_ != v.seq_name)) {
+        flush(w);
+        have_open = false;
         if (last_seq_name_ != v.seq_name) {
           last_seq_name_ = v.seq_name;
           used_seq_names.push_back(last_seq_name_);
         }
       }
-      vb_.add(std::move(v));
+      if (!have_open) {
+        open = w;
+        have_open = true;
+      }
+      if (w != r) vars[w] = std::move(v);
+      ++w;
     }
     if (!more) {  // end of file
       done_ = true;
-      if (!vb_.empty()) flush(out);
+      if (have_open) flush(w);
+    } else if (have_open) {  // the open block continues in the next batch: its records travel on
+      for (size_t i = open; i < w; ++i) carry_.push_back(std::move(vars[i]));
+      w = open;
     }
+    vars.resize(w);  // (shrinks: the blocks' views stay valid)
     t_group += sw.lap();
-    return !out.empty() || !done_;
+    return !out.blocks.empty() || !done_;
   }
 
  private:
-  void flush(std::vector<mh::VarBlock> &out) {
-    vb_.contig = last_seq_name_;
-    out.push_back(std::move(vb_));
-    vb_ = mh::VarBlock((int)o_.k);
-  }
   const Options &o_;
   bool index_mode_, is_file_ = false, freq_declared_ = false, done_ = false;
   mh::VcfReader reader_;
-  mh::VarBlock vb_;
+  std::vector<mh::Variant> carry_;  // the records of the block that is still open between two batches
   std::string last_seq_name_;
   std::vector<char> store_;
   std::vector<mh::BlockLineReader::View> lines_;
@@ -325,7 +355,7 @@ class BatchPrefetcher {
  public:
   BatchPrefetcher(BlockStream &stream, size_t max_lines) : stream_(stream), max_lines_(max_lines) { launch(); }
   // false when the VCF is exhausted; otherwise `out` holds the next batch of flushed blocks (possibly empty)
-  bool next(std::vector<mh::VarBlock> &out) {
+  bool next(BlockBatch &out) {
     if (!pending_.valid()) return false;
     auto got = pending_.get();
     if (!got.first) return false;
@@ -337,21 +367,21 @@ class BatchPrefetcher {
  private:
   void launch() {
     pending_ = std::async(std::launch::async, [this] {
-      std::vector<mh::VarBlock> b;
+      BlockBatch b;
       bool ok = stream_.next_batch(b, max_lines_);
       return std::make_pair(ok, std::move(b));
     });
   }
   BlockStream &stream_;
   size_t max_lines_;
-  std::future<std::pair<bool, std::vector<mh::VarBlock>>> pending_;
+  std::future<std::pair<bool, BlockBatch>> pending_;
 };
 
 // signatures of a batch of blocks: tasks of ~64 consecutive variants (a block of thousands of variants is split,
 // small blocks are grouped) enumerated in parallel, their parts then copied side by side into one CSR
 void enumerate_batch(const std::vector<mh::VarBlock> &blocks, std::map<std::string, std::string> &refs, const Options &o,
                      mh::SignatureCsr &out) {
-  for (const auto &b : blocks) refs[b.contig];  // (the reference's refs[name] creates missing contigs as empty)
+  for (const auto &b : blocks) refs[*b.contig];  // (the reference's refs[name] creates missing contigs as empty)
   struct Segment {
     uint32_t block, begin, end;
   };
@@ -374,7 +404,7 @@ void enumerate_batch(const std::vector<mh::VarBlock> &blocks, std::map<std::stri
   const size_t n_tasks = task_first.size() - 1;
   std::vector<mh::SignatureCsr> parts(n_tasks);
   std::vector<const std::string *> ref_of(blocks.size());
-  for (size_t b = 0; b < blocks.size(); ++b) ref_of[b] = &refs.find(blocks[b].contig)->second;
+  for (size_t b = 0; b < blocks.size(); ++b) ref_of[b] = &refs.find(*blocks[b].contig)->second;
   parallel_for(n_tasks, o.threads, [&](size_t t) {
     static thread_local mh::VarBlock::Scratch sc;
     for (size_t i = task_first[t]; i < task_first[t + 1]; ++i)
@@ -420,7 +450,7 @@ class Channel {
 
 // one batch on its way through the pipeline
 struct Batch {
-  std::vector<mh::VarBlock> blocks;
+  BlockBatch vb;
   mh::SignatureCsr sigs;
   double t_parse = 0, t_enum = 0, t_dev = 0;
   // results of the device stage (call)
@@ -440,9 +470,9 @@ class EnumeratedBatches {
             while (true) {
               auto b = std::make_unique<Batch>();
               Stopwatch sw;
-              if (!src.next(b->blocks)) break;
+              if (!src.next(b->vb)) break;
               b->t_parse = sw.lap();
-              enumerate_batch(b->blocks, refs, o, b->sigs);
+              enumerate_batch(b->vb.blocks, refs, o, b->sigs);
               b->t_enum = sw.lap();
               out_.push(std::move(b));
             }
@@ -530,7 +560,7 @@ int index_main(int argc, char **argv) {
       }
       if (o.trace)
         fprintf(stderr, "[trace] index batch: %zu blocks, %llu k-mers (%llu irregular): read+decode wait %.1f ms, enumerate %.1f ms, device %.1f ms\n",
-                b->blocks.size(), (unsigned long long)sg.n_kmers(), (unsigned long long)sg.n_irregular(), b->t_parse,
+                b->vb.blocks.size(), (unsigned long long)sg.n_kmers(), (unsigned long long)sg.n_irregular(), b->t_parse,
                 b->t_enum, sw.lap());
     }
     batches.join();
@@ -784,7 +814,7 @@ int call_main(int argc, char **argv) {
     const uint64_t nv = sg.n_variants();
     if (nv == 0) continue;
     order.clear();
-    for (const auto &blk : b->blocks)
+    for (const auto &blk : b->vb.blocks)
       for (size_t i = 0; i < blk.size(); ++i) order.push_back(&blk[i]);
     const size_t chunk = 4096, n_chunks = (nv + chunk - 1) / chunk;
     text.assign(n_chunks, std::string());
@@ -819,7 +849,8 @@ int signatures_main(int argc, char **argv) {
     return 1;
   }
   std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
-  std::vector<mh::VarBlock> blocks;
+  BlockBatch batch;
+  std::vector<mh::VarBlock> &blocks = batch.blocks;
   mh::SignatureCsr sigs;
   uint64_t block_no = 0;
   const bool quiet = getenv("MALVA_SIGNATURES_QUIET") != nullptr;  // (timing runs: enumerate, print nothing)
@@ -827,7 +858,7 @@ int signatures_main(int argc, char **argv) {
   double t_batch = 0, t_enum = 0;
   while (true) {
     sw.lap();
-    const bool more = stream.next_batch(blocks, LINES_PER_BATCH);
+    const bool more = stream.next_batch(batch, LINES_PER_BATCH);
     t_batch += sw.lap();
     if (!more) break;
     enumerate_batch(blocks, refs, o, sigs);
@@ -842,7 +873,7 @@ int signatures_main(int argc, char **argv) {
         const uint64_t a0 = sigs.var_allele_off[vi], a1 = sigs.var_allele_off[vi + 1];
         for (uint64_t a = a0; a < a1; ++a)
           for (uint64_t s = sigs.allele_sig_off[a]; s < sigs.allele_sig_off[a + 1]; ++s) {
-            std::cout << block_no << '\t' << b.contig << '\t' << b[i].ref_pos + 1 << '\t' << i << '\t' << (a - a0) << '\t';
+            std::cout << block_no << '\t' << *b.contig << '\t' << b[i].ref_pos + 1 << '\t' << i << '\t' << (a - a0) << '\t';
             for (uint64_t q = sigs.sig_kmer_off[s]; q < sigs.sig_kmer_off[s + 1]; ++q) {
               if (q != sigs.sig_kmer_off[s]) std::cout << ',';
               std::cout << sigs.text(q, (int)o.k);

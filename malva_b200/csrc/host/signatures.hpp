@@ -203,17 +203,16 @@ inline bool variants_near(const Variant &a, const Variant &b, int k, int sum_to_
   return lhs >= (float)b.ref_pos;
 }
 
+// A var_block (var_block.hpp:40-90) as a VIEW: n consecutive variants of the batch they were decoded into.  Grouping
+// a batch into blocks moves no record and allocates nothing per block.
 class VarBlock {
  public:
   VarBlock() = default;
-  explicit VarBlock(int k) : k_(k) {}
-  bool empty() const { return vars_.empty(); }
-  void clear() { vars_.clear(); }
-  void add(Variant v) { vars_.push_back(std::move(v)); }
-  size_t size() const { return vars_.size(); }
+  VarBlock(int k, const Variant *first, size_t n, const std::string *contig_name) : contig(contig_name), k_(k), vars_(first), n_(n) {}
+  bool empty() const { return n_ == 0; }
+  size_t size() const { return n_; }
   const Variant &operator[](size_t i) const { return vars_[i]; }
-  bool is_near_to_last(const Variant &v) const { return variants_near(vars_.back(), v, k_, 0); }
-  std::string contig;  // name of the contig the block lies on (last_seq_name at flush time)
+  const std::string *contig = nullptr;  // name of the contig the block lies on (last_seq_name at flush time)
 
   // Work arrays reused from variant to variant (one per enumerating thread): no allocation per sample or per chain.
   struct SigRec {  // one signature of the current variant: its k-mers lie back to back in Scratch::text
@@ -232,7 +231,7 @@ class VarBlock {
   // Signatures of the variants [begin, end) of the block, appended to `out`: one variant entry per block member, in
   // order; allele slot a = allele index a (slots of duplicate-text alleles stay empty, like in the reference).
   void enumerate(const std::string &reference, bool haploid, size_t begin, size_t end, Scratch &sc, SignatureCsr &out) const {
-    for (size_t vi = begin; vi < end && vi < vars_.size(); ++vi) {
+    for (size_t vi = begin; vi < end && vi < n_; ++vi) {
       const Variant &v = vars_[vi];
       sc.text.clear();
       sc.sigs.clear();
@@ -327,7 +326,7 @@ class VarBlock {
     };
     auto gain = [&](int j) { return vars_[(size_t)j].ref_size - vars_[(size_t)j].min_size; };
     bool halt = false;
-    for (int j = i + dir; j >= 0 && j < (int)vars_.size() && !halt; j += dir) {
+    for (int j = i + dir; j >= 0 && j < (int)n_ && !halt; j += dir) {
       if (!vars_[(size_t)j].is_present || ovl(i, j)) continue;
       if (chains.empty()) {
         if (in_reach(j, 0)) {
@@ -373,7 +372,7 @@ class VarBlock {
 
   // var_block.hpp:631-677: left chains (reversed into genomic order) x right chains around the mid variant
   std::vector<Chain> full_chains(int i) const {
-    if (vars_.size() == 1) return std::vector<Chain>{Chain{i}};  // (a block of one: nothing to chain)
+    if (n_ == 1) return std::vector<Chain>{Chain{i}};  // (a block of one: nothing to chain)
     std::vector<Chain> right = side_chains(i, +1), left = side_chains(i, -1), out;
     if (left.empty()) left.push_back(Chain{});
     if (right.empty()) right.push_back(Chain{});
@@ -397,7 +396,9 @@ class VarBlock {
     const size_t n = chain.size(), W = 2 * n + 1;
     const uint32_t central_samples = (uint32_t)vars_[(size_t)central].n_samples();
     sc.cursor.assign(n, 0);
-    sc.pat.clear();
+    size_t max_rows = 1;  // one row per sample with an entry somewhere, + the all-reference row
+    for (size_t m = 0; m < n; ++m) max_rows += vars_[(size_t)chain[m]].gts.size();
+    if (sc.pat.size() < max_rows * W) sc.pat.resize(max_rows * W);
     size_t n_rows = 0;
     while (true) {
       uint32_t s = 0xFFFFFFFFu;  // the next sample with an entry at some member
@@ -406,7 +407,6 @@ class VarBlock {
         if (sc.cursor[m] < v.gts.size()) s = std::min(s, v.gts[sc.cursor[m]].sample);
       }
       if (s >= central_samples) break;  // (the reference walks the samples of the central variant)
-      sc.pat.resize((n_rows + 1) * W);
       uint16_t *p = sc.pat.data() + n_rows++ * W;
       uint16_t ph = 1;
       for (size_t m = 0; m < n; ++m) {
@@ -424,7 +424,6 @@ class VarBlock {
       p[2 * n] = haploid ? 1 : ph;
     }
     if (n_rows < central_samples) {  // samples at their default everywhere
-      sc.pat.resize((n_rows + 1) * W);
       uint16_t *p = sc.pat.data() + n_rows++ * W;
       std::fill(p, p + 2 * n, (uint16_t)0);
       p[2 * n] = 1;
@@ -461,10 +460,48 @@ class VarBlock {
     dst.append(s, (size_t)pos, (size_t)len);
   }
 
+  // A block of one variant (the common case away from dense regions): the chain is the variant itself and its
+  // haplotypes are simply the alleles somebody carries -- the reference allele if some sample has no entry, h1 (and
+  // h2 unless haploid) of every entry; phasing cannot matter with a single site.  Same set as haplotypes() gives.
+  bool single_site_haplotypes(const Variant &v, bool haploid, Scratch &sc) const {
+    if (v.n_alleles() > 64) return false;
+    uint64_t present = v.gts.size() < v.n_samples() ? 1ull : 0ull;
+    for (const GtEntry &g : v.gts) {
+      if (g.sample >= v.n_samples()) break;
+      present |= 1ull << g.h1;
+      if (!haploid) present |= 1ull << g.h2;
+    }
+    sc.haps.clear();
+    for (uint64_t m = present; m; m &= m - 1) sc.haps.push_back((uint16_t)__builtin_ctzll(m));
+    sc.n_haps = sc.haps.size();
+    return true;
+  }
+
   // var_block.hpp:114-216
   void signatures_of(int vi, const std::string &reference, bool haploid, Scratch &sc) const {
-    const Variant &v = vars_[(size_t)vi];
+    if (n_ == 1 && single_site_haplotypes(vars_[0], haploid, sc)) {
+      const int self = 0;
+      chain_signatures(&self, 1, vi, reference, sc);
+      return;
+    }
     for (const Chain &chain : full_chains(vi)) {
+      haplotypes(chain, vi, haploid, sc);
+      chain_signatures(chain.data(), chain.size(), vi, reference, sc);
+    }
+  }
+
+  // the signatures of variant vi within one chain, one per haplotype in sc.haps (var_block.hpp:120-216)
+  void chain_signatures(const int *chain_p, size_t chain_n, int vi, const std::string &reference, Scratch &sc) const {
+    const Variant &v = vars_[(size_t)vi];
+    struct ChainView {
+      const int *p;
+      size_t n;
+      size_t size() const { return n; }
+      int operator[](size_t i) const { return p[i]; }
+      int front() const { return p[0]; }
+      int back() const { return p[n - 1]; }
+    } chain{chain_p, chain_n};
+    {
       // reference text between consecutive members of the chain (var_block.hpp:682-702)
       if (sc.between.size() < chain.size()) sc.between.resize(chain.size());
       size_t mid_slot = 0, n_between = 0;
@@ -476,7 +513,6 @@ class VarBlock {
         gap.clear();
         append_clamped(gap, reference, (long)prev.ref_pos + prev.ref_size, (long)cur.ref_pos - (prev.ref_pos + prev.ref_size));
       }
-      haplotypes(chain, vi, haploid, sc);
       for (size_t hi = 0; hi < sc.n_haps; ++hi) {
         const uint16_t *h = sc.haps.data() + hi * chain.size();
         const int mid_id = h[mid_slot];
@@ -525,7 +561,8 @@ class VarBlock {
   }
 
   int k_ = 35;
-  std::vector<Variant> vars_;
+  const Variant *vars_ = nullptr;
+  size_t n_ = 0;
 };
 
 }  // namespace mh

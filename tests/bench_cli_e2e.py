@@ -3,7 +3,11 @@
 own main.cpp, CPU, single-threaded like the original) against this repository's `malva-geno` (C++ host + B200
 kernels) on the same synthetic chromosome-arm-sized inputs; outputs must be byte-identical.
 
-    python tests/bench_cli_e2e.py [Mbp=5] [samples=32] [bf_gb=1] > gpurun_out/cli_e2e.json
+    python tests/bench_cli_e2e.py [Mbp=5] [samples=32] [bf_gb=1] [fast] > gpurun_out/cli_e2e.json
+
+`fast`: inputs from tests/synth_fast.py (numpy, about a minute for the 250 Mbp of BASELINE's cfg3) instead of the seeded
+generator of the parity cases (tests/synth.py: Python `random`, 10 s per Mbp); the donor's 43-mers are then counted on
+the GPU by `malva-geno count -ci1` (K6) from the two donor haplotypes.
 
 (lives under tests/ because it executes the oracle build of the reference; not collected by pytest)
 """
@@ -69,17 +73,28 @@ def main():
     mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
     n_samples = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     bf_gb = sys.argv[3] if len(sys.argv) > 3 else "1"          # -b: filter size in GB (reference default: 4)
+    fast = len(sys.argv) > 4 and sys.argv[4] == "fast"
     mbuild.build()
     case = synth.Case("cli_e2e", 20261018 + 42, [("1", int(mbp * 1e6))], mean_gap=41, n_samples=n_samples)
     synth_write = kmc.write_kmc_db
     kmc.write_kmc_db = lambda prefix, uk, uc, k, **kw: fast_write_kmc(prefix, uk, uc, k)
     with tempfile.TemporaryDirectory() as d:
         t0 = time.time()
-        fa, vcf, prefix, n_kmers = synth.build_case(case, d)
+        if fast:
+            import synth_fast
+            fa, vcf, donor, _ = synth_fast.build(d, int(mbp * 1e6), n_samples)
+            prefix = os.path.join(d, "sample")
+            p = subprocess.run([mbuild.CLI, "count", "-k43", "-ci1", "-cs255", donor, prefix], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr[-2000:]
+            n_kmers = int(re.search(r"(\d+) written", p.stderr).group(1))
+            os.remove(donor)
+        else:
+            fa, vcf, prefix, n_kmers = synth.build_case(case, d)
         kmc.write_kmc_db = synth_write
         n_var = sum(1 for l in open(vcf) if not l.startswith("#"))
         res = {"reference_bases": int(mbp * 1e6), "variants": n_var, "panel_samples": n_samples, "sample_kmers": n_kmers,
-               "generate_s": round(time.time() - t0, 1), "host_cores": os.cpu_count(), "bf_gb": bf_gb}
+               "generate_s": round(time.time() - t0, 1), "host_cores": os.cpu_count(), "bf_gb": bf_gb,
+               "generator": "tests/synth_fast.py + malva-geno count" if fast else "tests/synth.py"}
         outs = {}
         for name, exe in (("reference_cpu", REF), ("malva_b200", mbuild.CLI)):
             r = {}
