@@ -17,9 +17,11 @@ the same filter size holding the CPU sample's keys scans the CPU sample, and eve
 GT and GQ is compared EXACTLY with the reference's own BF / KMAP / VB::genotype (oracle/_ref) fed the same input.
 `"verified": true` in the line means both held; a mismatch exits non-zero.
 
-N > 1 (torchrun, one process per GPU): replicate-and-reduce: every rank holds the full index,
-scans its own share of the sample stream, and the counters are sum-reduced to rank 0 with NCCL inside the
-timed region (dense gather on every rank, ncclReduce, scatter on rank 0).  Weak scaling: B k-mers per rank per step.
+N > 1 (torchrun, one process per GPU): replicate-and-reduce: every rank holds the full index and scans
+its own share of the sample stream; at genotyping time every rank looks the step's signature k-mers up in its own
+partial counters and the LOOK-UP RESULTS (4 bytes per signature k-mer) are sum-reduced to rank 0 with NCCL, inside
+the timed region and overlapped with the next scan; rank 0 genotypes from the sums (exact: get_count is linear in
+the counters).  Weak scaling: B k-mers per rank per step.
 """
 from __future__ import annotations
 
@@ -626,7 +628,8 @@ def run_ours(args, wl, rank, local_rank, world):
     counters = []
 
     def reduce_counters():
-        """gather (every rank) -> ncclReduce of the dense arrays -> scatter into rank 0's probe lines"""
+        """the other exact scheme (malva-geno call --devices, --verify): gather the counters (every rank) -> ncclReduce
+        of the dense arrays -> scatter into rank 0's probe lines"""
         nonlocal counters
         bufs = g.counter_buffers(gather=True)
         if not counters:
@@ -643,57 +646,82 @@ def run_ours(args, wl, rank, local_rank, world):
         if world > 1:
             dist.barrier()
 
+    # N > 1: the library works on torch's stream, so that its kernels and the NCCL reduces order without host syncs
+    w_bufs = [torch.zeros(max(nk, 1), dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
+    if world > 1:
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=dev)           # (torch's default stream is handle 0 = "restore" for mg_set_stream)
+        torch.cuda.set_stream(side)
+        g.set_stream(side.cuda_stream)
+
+    def finish(p):
+        """the reduce of a step's look-up results has landed: rank 0 genotypes from the sums"""
+        p[0].wait()                                    # (the stream waits, not the host)
+        if rank == 0:
+            g.genotype_weights_device(ptrs, pdims, p[1].data_ptr(), ERR, MAX_COV, False)
+
+    def run_steps(n_steps, timed):
+        pending = None
+        for i in range(n_steps):
+            if timed:
+                g.event_record(10 + 2 * (i % 8))
+            kk, cc = batches[i & 1]
+            g.scan_sample_kmers_ptr(kk.data_ptr(), cc.data_ptr(), B, device=True)
+            if timed:
+                g.event_record(11 + 2 * (i % 8))
+            if world == 1:
+                g.genotype_packed_device(ptrs, pdims, ERR, MAX_COV, False)
+                continue
+            w = w_bufs[i & 1]
+            g.lookup_packed_device(ptrs, pdims, w.data_ptr())
+            work = dist.reduce(w, dst=0, async_op=True)    # overlaps the next step's scan
+            if pending:
+                finish(pending)
+            pending = (work, w)
+        if pending:
+            finish(pending)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(args.warmup):
-        kk, cc = batches[i & 1]
-        g.scan_sample_kmers_ptr(kk.data_ptr(), cc.data_ptr(), B, device=True)
-        g.genotype_packed_device(ptrs, pdims, ERR, MAX_COV, False)
-    if world > 1:
-        # once per index, not per run: the key directory of the dense counter image (built by the first gather) and
-        # NCCL's channels for a transfer of this size
-        warm = [torch.as_tensor(DevArray(p, n), device=dev) for p, n in g.counter_buffers(gather=True) if n]
-        dist.reduce(torch.zeros_like(warm[0]), dst=0)
-        del warm
+    run_steps(args.warmup, False)
     barrier()
     launches0 = g.launch_count()
     sampler.mark()
     g.event_record(2)
-    for i in range(args.steps):
-        g.event_record(10 + 2 * (i % 8))
-        kk, cc = batches[i & 1]
-        g.scan_sample_kmers_ptr(kk.data_ptr(), cc.data_ptr(), B, device=True)
-        g.event_record(11 + 2 * (i % 8))
-        g.genotype_packed_device(ptrs, pdims, ERR, MAX_COV, False)
-    before = None
-    if world > 1:
-        g.sync()  # the library's streams -> torch's stream
-        t_red0 = time.perf_counter()
-        if args.verify:   # (the snapshot is not part of the reduce)
-            before = [t.clone() for t in [torch.as_tensor(DevArray(p, n), device=dev)
-                                          for p, n in g.counter_buffers(gather=True) if n]]
-            torch.cuda.synchronize()
-            t_red0 = time.perf_counter()
-        reduce_counters()
-        reduce_ms = (time.perf_counter() - t_red0) * 1e3
+    run_steps(args.steps, True)
     g.event_record(3)
     region_ms = g.event_elapsed_ms(2, 3)
     clocks = sampler.stop()
     launches = g.launch_count() - launches0
     barrier()
     scan_ms = [g.event_elapsed_ms(10 + 2 * j, 11 + 2 * j) for j in range(min(8, args.steps))]
-    geno_ms = g.genotype_kernel_ms()
+    geno_ms = g.genotype_kernel_ms() if rank == 0 else None
     tm = torch.tensor([region_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     region_ms = float(tm.item())
-    verified_reduce = None
-    if before is not None and rank == 0:
-        # identical replicas (canonical index image) that scanned identical batches: sum over ranks == world x mine
-        after = [torch.as_tensor(DevArray(p, n), device=dev) for p, n in g.counter_buffers(gather=True) if n]
-        verified_reduce = all(bool(torch.equal(t, b * world)) for t, b in zip(after, before)) and \
-            any(int(b.sum().item()) != 0 for b in before)
-        log(f"[verify] reduced counters == {world} x rank 0's own counters: {verified_reduce}")
+    verified_reduce = reduce_ms = None
+    if world > 1 and args.verify:
+        # identical replicas (canonical index image) that scanned identical batches:
+        #  (1) the summed look-up results of a step are exactly world x one rank's
+        w_own = torch.zeros(max(nk, 1), dtype=torch.int32, device=dev)
+        g.lookup_packed_device(ptrs, pdims, w_own.data_ptr())
+        w_sum = w_own.clone()
+        dist.reduce(w_sum, dst=0)
+        ok_w = bool(torch.equal(w_sum, w_own * world)) and int(w_own.abs().sum().item()) != 0
+        #  (2) the counter arrays themselves (gather -> ncclReduce -> scatter) are world x one rank's, element by element
+        before = [t.clone() for t in [torch.as_tensor(DevArray(p, n), device=dev)
+                                      for p, n in g.counter_buffers(gather=True) if n]]
+        torch.cuda.synchronize()
+        t_red0 = time.perf_counter()
+        reduce_counters()
+        reduce_ms = (time.perf_counter() - t_red0) * 1e3
+        if rank == 0:
+            after = [torch.as_tensor(DevArray(p, n), device=dev) for p, n in g.counter_buffers(gather=True) if n]
+            ok_c = all(bool(torch.equal(t, b * world)) for t, b in zip(after, before)) and \
+                any(int(b.sum().item()) != 0 for b in before)
+            verified_reduce = ok_w and ok_c
+            log(f"[verify] summed look-up results == {world} x rank 0's: {ok_w}; reduced counters == {world} x rank 0's: {ok_c}")
     ms_per_step = region_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -827,8 +855,12 @@ def run_ours(args, wl, rank, local_rank, world):
         "h2d_ceiling_GBps_at_N": h2d_ceiling,
         "numa_binding": numa,
         "gpu_launches": launches,
+        **({"multi_gpu": "every rank scans its own share of the sample stream into its replica's counters and looks the "
+                         "variant batch up in them (K4, raw); the 4-byte look-up results are summed onto rank 0 (ncclReduce, "
+                         f"{4 * nk} B per step, overlapped with the next step's scan) which computes coverage + "
+                         "likelihoods from the sums (get_count is linear in the counters)"} if world > 1 else {}),
         **({"verify_reduce_exact": verified_reduce} if verified_reduce is not None else {}),
-        **({"reduce_ms": reduce_ms} if world > 1 else {}),
+        **({"counter_reduce_ms": reduce_ms} if reduce_ms is not None else {}),
         **({"verified": True, "verify": verify} if verify else {}),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_scan<35,43>", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -849,6 +881,9 @@ def run_ours(args, wl, rank, local_rank, world):
         "roofline_k2": {"bound": "hbm", "kernel": "k_refpass<35,43>", "achieved": k2_bytes / (refpass_kernel_ms * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": k2_bytes / (refpass_kernel_ms * 1e-3) / 1e9 / peak,
                         "algorithmic_bytes": k2_bytes, "launches": n_chunks,
+                        "algorithmic_bytes_note": "33 B per reference base over the whole contig (one launch per 32 Mi-base "
+                                                  "chunk; `traffic` is the DRAM traffic of one full-chunk launch = 1.107e9 "
+                                                  "algorithmic bytes)",
                         "traffic": profile_json("k2_traffic.json").get("dram_bytes_per_launch")},
     }
     if cpu:

@@ -145,6 +145,22 @@ typedef struct {
 int mg_genotype_packed_device(mg_ctx *ctx, const mg_packed_batch *in, const mg_genotype_out *out,
                               const mg_packed_dims *dims, float error_rate, int max_coverage, int haploid);
 
+/* The two halves of the step on their own, for replicas that sum LOOK-UP RESULTS instead of counters: get_count is
+ * linear in the counters (bf: the u16 wrap of a sum of u32 parts; ref_bf: 32-bit wrap-around), so N replicas that each
+ * scanned a share of the sample stream look the batch up in their own partial counters (mg_lookup_packed_device:
+ * KMAP::get_count / BF::get_count per signature k-mer, bf counters UNMASKED), sum the weight vectors -- 4 bytes per
+ * signature k-mer, e.g. one ncclReduce per batch -- and the destination genotypes from the sum
+ * (mg_genotype_weights_device: applies BF::get_count's uint16_t to the bf weights in place, then set_coverages +
+ * VB::genotype).  No counter array travels.  All pointers DEVICE pointers; enqueued on the context's stream. */
+int mg_lookup_packed_device(mg_ctx *ctx, const mg_packed_batch *in, const mg_packed_dims *dims, uint32_t *d_weights);
+int mg_genotype_weights_device(mg_ctx *ctx, const mg_packed_batch *in, const mg_genotype_out *out,
+                               const mg_packed_dims *dims, uint32_t *d_weights, float error_rate, int max_coverage,
+                               int haploid);
+/* puts the caller's CUDA stream (a cudaStream_t, e.g. the one its collectives are ordered on) in the place of the
+ * context's own first stream: library work then orders with the caller's kernels without host synchronisation.
+ * NULL (also the handle of the legacy default stream, which therefore cannot be chosen) restores the private stream. */
+int mg_set_stream(mg_ctx *ctx, void *cuda_stream);
+
 /* -------------------- k-mer counting (the step before the path) ---------- */
 /* What the wrapper script obtains from `kmc -k<ref_k> -ci2 -cs255` (MALVA:107) and malva-geno lists through the KMC
  * API (main.cpp:482-490): canonical k-mers of the reads, windows with a non-ACGT symbol skipped, k-mers seen fewer

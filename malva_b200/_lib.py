@@ -101,6 +101,10 @@ SYMBOLS = {
                                      C.c_int]),
     "mg_genotype_packed_device": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.POINTER(GenotypeOut),
                                             C.POINTER(PackedDims), C.c_float, C.c_int, C.c_int]),
+    "mg_lookup_packed_device": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.POINTER(PackedDims), C.c_void_p]),
+    "mg_genotype_weights_device": (C.c_int, [C.c_void_p, C.POINTER(PackedBatch), C.POINTER(GenotypeOut),
+                                             C.POINTER(PackedDims), C.c_void_p, C.c_float, C.c_int, C.c_int]),
+    "mg_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_count_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "mg_count_destroy": (None, [C.c_void_p]),
     "mg_count_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]),

@@ -403,6 +403,35 @@ class MalvaGpu:
         check(self._L.mg_genotype_packed_device(self._h, C.byref(pb), C.byref(out), C.byref(dm), C.c_float(error_rate),
                                                 int(max_coverage), int(bool(haploid))))
 
+    def _packed_structs(self, ptrs: dict, dims: tuple):
+        c = lambda name, typ: C.cast(C.c_void_p(ptrs.get(name) or None), typ)
+        nv, na, ns, nk, ni, ipb, slots = dims
+        pb = _lib.PackedBatch(nv, c("var_allele_off", _lib.u32p), c("allele_sig_off", _lib.u32p),
+                              c("sig_kmer_off", _lib.u32p), C.c_void_p(ptrs["kmers"]), c("freq", _lib.f32p), ni,
+                              c("irr_off", _lib.u64p), C.c_void_p(ptrs.get("irr_pool") or None), c("irr_kmer", _lib.u32p))
+        out = _lib.GenotypeOut(c("cov", _lib.u32p), c("n_gts", _lib.i32p), c("status", _lib.i32p),
+                               c("best_gt", _lib.i32p), c("gq", _lib.i32p), c("lik_off", _lib.u64p), c("lik", _lib.f64p))
+        return pb, out, _lib.PackedDims(nv, na, ns, nk, ipb, slots)
+
+    def lookup_packed_device(self, ptrs: dict, dims: tuple, weights_ptr: int) -> None:
+        """K4 alone (mg_lookup_packed_device): raw u32 counts of the batch's signature k-mers into a device buffer;
+        replicas sum these vectors instead of their counters.  ptrs / dims as in genotype_packed_device."""
+        pb, _, dm = self._packed_structs(ptrs, dims)
+        check(self._L.mg_lookup_packed_device(self._h, C.byref(pb), C.byref(dm), C.c_void_p(weights_ptr)))
+
+    def genotype_weights_device(self, ptrs: dict, dims: tuple, weights_ptr: int, error_rate: float, max_coverage: int,
+                                haploid: bool) -> None:
+        """set_coverages + VB::genotype from (summed) weights (mg_genotype_weights_device); masks the bf weights to
+        uint16_t in place first."""
+        pb, out, dm = self._packed_structs(ptrs, dims)
+        check(self._L.mg_genotype_weights_device(self._h, C.byref(pb), C.byref(out), C.byref(dm), C.c_void_p(weights_ptr),
+                                                 C.c_float(error_rate), int(max_coverage), int(bool(haploid))))
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """library work goes to the caller's CUDA stream (a created stream, e.g. torch.cuda.Stream().cuda_stream);
+        None or 0 (which is also the handle of the legacy default stream) restores the context's own"""
+        check(self._L.mg_set_stream(self._h, C.c_void_p(cuda_stream or None)))
+
     def genotype_packed_host(self, ptrs: dict, n_variants: int, n_irregular: int, error_rate: float, max_coverage: int,
                              haploid: bool) -> None:
         """mg_genotype_packed on caller-owned HOST buffers given by address (e.g. pinned memory)."""

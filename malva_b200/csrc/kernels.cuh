@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(256) k_scan_hits(const uint4 *__restrict__ hit
 // ---------------------------------------------------------------------------
 // Both read everything they may need from the probe line in ONE round of independent loads (the filter words, the
 // rank + inline counters; the five slots with their counts): a look-up is one memory round trip, not two.
-__device__ __forceinline__ int32_t alt_get_count(const DevView &v, uint64_t idx) {  // BF::get_count (u16)
+__device__ __forceinline__ int32_t alt_get_count(const DevView &v, uint64_t idx, bool raw = false) {  // BF::get_count (u16)
   if (!v.bf_counts) return 0;  // write mode: no counters yet (bloom_filter.hpp:115-125)
   const uint4 *p = v.lines + (idx >> 8) * LINE_U4;
   const uint4 a = __ldg(p), b = __ldg(p + 1), m = __ldg(p + 7);
@@ -944,7 +944,7 @@ __device__ __forceinline__ int32_t alt_get_count(const DevView &v, uint64_t idx)
   }
   if (!((mine >> (idx & 31)) & 1u)) return 0;
   const uint32_t c = j == 0 ? m.y : (j == 1 ? m.z : (j == 2 ? m.w : __ldg(v.bf_counts + (uint64_t)m.x + (uint64_t)j)));
-  return (int32_t)(c & 0xFFFFu);
+  return raw ? (int32_t)c : (int32_t)(c & 0xFFFFu);
 }
 __device__ __forceinline__ int32_t ref_get_count(const DevView &v, uint64_t idx, u128 canon) {  // KMAP::get_count
   const uint64_t line = idx >> 8;
@@ -982,7 +982,8 @@ __global__ void __launch_bounds__(128) k_lookup(const uint8_t *__restrict__ pool
                                                const uint8_t *__restrict__ is_ref, uint64_t n, DevView v, int mode,
                                                int which, int32_t *__restrict__ out, unsigned long long *scalars,
                                                const uint8_t *__restrict__ only_flagged,
-                                               const uint32_t *__restrict__ out_pos, const uint4 *__restrict__ packed) {
+                                               const uint32_t *__restrict__ out_pos, const uint4 *__restrict__ packed,
+                                               bool raw = false) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (only_flagged && !only_flagged[i]) return;  // second pass after k_lookup_fast: the k-mers it deferred
@@ -1019,7 +1020,7 @@ __global__ void __launch_bounds__(128) k_lookup(const uint8_t *__restrict__ pool
   if (mode == 1)
     out[o] = which == 1 ? ctx_test(v, idx) : bf_test(v, idx);
   else
-    out[o] = alt_get_count(v, idx);
+    out[o] = alt_get_count(v, idx, raw);
 }
 
 // Fast path of mode 0 for the compiled k: signature k-mers that are exactly K bytes long are read as aligned
@@ -1070,7 +1071,9 @@ __global__ void __launch_bounds__(128) k_lookup_fast(const uint8_t *__restrict__
 constexpr int LOOKUP_THREADS = 256;
 constexpr int LOOKUP_SMEM = (LOOKUP_THREADS / 32) * 4096;
 
-template <int K>
+// RAW: bf counters are returned as the u32 accumulators they are (partial results of replicas are summed first, the
+// u16 wrap of int_vector<16> is applied to the sum: k_mask_alt)
+template <int K, bool RAW>
 __global__ void __launch_bounds__(LOOKUP_THREADS) k_lookup_packed(const uint4 *__restrict__ kmers, uint64_t n, DevView v,
                                                                  int32_t *__restrict__ out) {
   extern __shared__ uint4 lk_sm[];
@@ -1140,11 +1143,17 @@ __global__ void __launch_bounds__(LOOKUP_THREADS) k_lookup_packed(const uint4 *_
       }
       if ((hit_w >> (bit & 31u)) & 1u) {
         const uint32_t c = j == 0 ? m.y : (j == 1 ? m.z : (j == 2 ? m.w : __ldg(v.bf_counts + (uint64_t)m.x + (uint64_t)j)));
-        res = (int32_t)(c & 0xFFFFu);
+        res = RAW ? (int32_t)c : (int32_t)(c & 0xFFFFu);
       }
     }
     out[i] = res;
   }
+}
+// BF::get_count's uint16_t of summed raw bf counters (the k-mers that are not flagged as ref-allele k-mers)
+__global__ void __launch_bounds__(256) k_mask_alt(const uint4 *__restrict__ kmers, uint64_t n, int32_t *__restrict__ w) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!((__ldg(reinterpret_cast<const uint32_t *>(kmers + i) + 3) >> 30) & 1u)) w[i] &= 0xFFFF;
 }
 
 // set_coverages (main.cpp:157-182): per allele slot, max over signatures of the order-dependent integer

@@ -98,6 +98,7 @@ struct mg_ctx {
   unsigned long long *d_scalars = nullptr;  // [0] new keys [1] irregular [2] popcount [3] error [4] spilled
   std::unordered_map<std::string, int> irregular_ref;  // ref keys that are not k symbols of ACGT (always count 0)
   cudaStream_t stream[2] = {nullptr, nullptr};
+  cudaStream_t own_stream0 = nullptr;  // the context's own first stream while mg_set_stream has put the caller's there
   void *d_stage_k[2] = {nullptr, nullptr};
   uint32_t *d_stage_c[2] = {nullptr, nullptr};
   int next_stage = 0;
@@ -113,7 +114,7 @@ struct mg_ctx {
   int kmc_prefix_len = 0, kmc_suf_bytes = 0, kmc_counter_size = 0;
   uint64_t launches = 0;  // kernels launched by this context (bench.py's gpu_launches)
   cudaEvent_t tj = nullptr;
-  cudaEvent_t ge[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ge[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // look-up [0,1], coverage [4,2], genotype [2,3]
   void *geno_scratch = nullptr;  // per-k-mer weights + ref flags of mg_genotype
   uint64_t geno_scratch_bytes = 0;
   void *geno_arena = nullptr;  // device image of the last mg_genotype batch (grow-only)
@@ -287,10 +288,12 @@ extern "C" void mg_destroy(mg_ctx *c) {
     cudaFree(c->hit_counts[i]);
     cudaFree(c->d_stage_k[i]);
     cudaFree(c->d_stage_c[i]);
-    if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
   }
+  if (c->own_stream0) c->stream[0] = c->own_stream0;
+  for (int i = 0; i < 2; ++i)
+    if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
   if (c->tj) cudaEventDestroy(c->tj);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 5; ++i)
     if (c->ge[i]) cudaEventDestroy(c->ge[i]);
   for (int i = 0; i < 64; ++i)
     if (c->evs[i]) cudaEventDestroy(c->evs[i]);
@@ -1067,7 +1070,7 @@ static int genotype_on_device(mg_ctx *c, const mg_variant_batch *in, const mg_ge
   if (rc) return rc;
   int32_t *d_w = reinterpret_cast<int32_t *>(c->geno_scratch);
   uint8_t *d_flags = reinterpret_cast<uint8_t *>(c->geno_scratch) + (nk ? nk : 1) * 4;
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 5; ++i)
     if (!c->ge[i]) CU(cudaEventCreate(&c->ge[i]));
   CU(cudaEventRecord(c->ge[0], st));
   if (nk) {
@@ -1098,6 +1101,7 @@ static int genotype_on_device(mg_ctx *c, const mg_variant_batch *in, const mg_ge
     }
   }
   CU(cudaEventRecord(c->ge[1], st));
+  CU(cudaEventRecord(c->ge[4], st));
   c->launches++;
   mg::k_coverage<uint64_t><<<grid_for(na, 128), 128, 0, st>>>(d_w, in->sig_kmer_off, in->allele_sig_off, na, out->cov);
   CU(cudaGetLastError());
@@ -1195,42 +1199,42 @@ extern "C" int mg_genotype(mg_ctx *c, const mg_variant_batch *in, const mg_genot
 }
 
 // ---- the same step for PACKED signature k-mers (2-bit words, u32 offsets): what the C++ host sends ----
-// all pointers of in/out are DEVICE pointers; out->lik == NULL: the likelihoods stay in library scratch
-static int genotype_packed_on_device(mg_ctx *c, const mg_packed_batch *in, const mg_genotype_out *out,
-                                     const mg_packed_dims *dm, float error_rate, int max_coverage, int haploid) {
+// all pointers of in/out are DEVICE pointers
+// K4 alone: the count of every signature k-mer of the batch into d_w (raw: bf counters unmasked)
+static int lookup_packed_on_device(mg_ctx *c, const mg_packed_batch *in, const mg_packed_dims *dm, int32_t *d_w, bool raw) {
   cudaStream_t st = c->stream[0];
-  const uint64_t nv = dm->n_variants, na = dm->n_alleles, nk = dm->n_kmers;
-  const bool own_lik = out->lik == nullptr;
-  const uint64_t w_bytes = ((nk ? nk : 1) * 4 + 255) & ~255ull;
-  int rc = geno_scratch(c, w_bytes + (own_lik ? dm->lik_slots * 8 + 256 : 0));
-  if (rc) return rc;
-  rc = join_streams(c);
-  if (rc) return rc;
-  int32_t *d_w = reinterpret_cast<int32_t *>(c->geno_scratch);
-  double *d_lik = own_lik ? reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(c->geno_scratch) + w_bytes) : out->lik;
-  for (int i = 0; i < 4; ++i)
-    if (!c->ge[i]) CU(cudaEventCreate(&c->ge[i]));
-  CU(cudaEventRecord(c->ge[0], st));
-  if (nk) {
-    c->launches++;
-    {
-      const uint64_t want = (nk + mg::LOOKUP_THREADS - 1) / mg::LOOKUP_THREADS, cap = (uint64_t)c->sms * 32;
-      const int grid = (int)(want < cap ? want : cap);
-      if (c->k == 35)
-        mg::k_lookup_packed<35><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
-      else
-        mg::k_lookup_packed<0><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>((const uint4 *)in->kmers, nk, c->view(), d_w);
-    }
-    CU(cudaGetLastError());
-    if (in->n_irregular) {  // not k symbols of ACGT: the byte-exact path, written to their places in the weight array
-      c->launches++;
-      mg::k_lookup<<<grid_for(in->n_irregular, 128), 128, 0, st>>>(
-          (const uint8_t *)in->irr_pool, in->irr_off, nullptr, in->n_irregular, c->view(), 0, 0, d_w, c->d_scalars, nullptr,
-          in->irr_kmer, (const uint4 *)in->kmers);
-      CU(cudaGetLastError());
-    }
+  const uint64_t nk = dm->n_kmers;
+  if (!nk) return MG_OK;
+  c->launches++;
+  {
+    const uint64_t want = (nk + mg::LOOKUP_THREADS - 1) / mg::LOOKUP_THREADS, cap = (uint64_t)c->sms * 32;
+    const int grid = (int)(want < cap ? want : cap);
+    const uint4 *km = (const uint4 *)in->kmers;
+    if (c->k == 35 && !raw)
+      mg::k_lookup_packed<35, false><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>(km, nk, c->view(), d_w);
+    else if (c->k == 35)
+      mg::k_lookup_packed<35, true><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>(km, nk, c->view(), d_w);
+    else if (!raw)
+      mg::k_lookup_packed<0, false><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>(km, nk, c->view(), d_w);
+    else
+      mg::k_lookup_packed<0, true><<<grid, mg::LOOKUP_THREADS, mg::LOOKUP_SMEM, st>>>(km, nk, c->view(), d_w);
   }
-  CU(cudaEventRecord(c->ge[1], st));
+  CU(cudaGetLastError());
+  if (in->n_irregular) {  // not k symbols of ACGT: the byte-exact path, written to their places in the weight array
+    c->launches++;
+    mg::k_lookup<<<grid_for(in->n_irregular, 128), 128, 0, st>>>(
+        (const uint8_t *)in->irr_pool, in->irr_off, nullptr, in->n_irregular, c->view(), 0, 0, d_w, c->d_scalars, nullptr,
+        in->irr_kmer, (const uint4 *)in->kmers, raw);
+    CU(cudaGetLastError());
+  }
+  return MG_OK;
+}
+// set_coverages + VB::genotype from the weights in d_w; out->lik == NULL: the likelihoods stay in library scratch
+static int genotype_from_weights(mg_ctx *c, const mg_packed_batch *in, const mg_genotype_out *out, const mg_packed_dims *dm,
+                                 const int32_t *d_w, double *d_lik, float error_rate, int max_coverage, int haploid) {
+  cudaStream_t st = c->stream[0];
+  const uint64_t nv = dm->n_variants, na = dm->n_alleles;
+  const bool own_lik = out->lik == nullptr;
   c->launches++;
   mg::k_coverage<uint32_t><<<grid_for(na, 128), 128, 0, st>>>(d_w, in->sig_kmer_off, in->allele_sig_off, na, out->cov);
   CU(cudaGetLastError());
@@ -1244,6 +1248,86 @@ static int genotype_packed_on_device(mg_ctx *c, const mg_packed_batch *in, const
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ge[3], st));
   return MG_OK;
+}
+static int genotype_packed_on_device(mg_ctx *c, const mg_packed_batch *in, const mg_genotype_out *out,
+                                     const mg_packed_dims *dm, float error_rate, int max_coverage, int haploid) {
+  cudaStream_t st = c->stream[0];
+  const uint64_t nk = dm->n_kmers;
+  const bool own_lik = out->lik == nullptr;
+  const uint64_t w_bytes = ((nk ? nk : 1) * 4 + 255) & ~255ull;
+  int rc = geno_scratch(c, w_bytes + (own_lik ? dm->lik_slots * 8 + 256 : 0));
+  if (rc) return rc;
+  rc = join_streams(c);
+  if (rc) return rc;
+  int32_t *d_w = reinterpret_cast<int32_t *>(c->geno_scratch);
+  double *d_lik = own_lik ? reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(c->geno_scratch) + w_bytes) : out->lik;
+  for (int i = 0; i < 5; ++i)
+    if (!c->ge[i]) CU(cudaEventCreate(&c->ge[i]));
+  CU(cudaEventRecord(c->ge[0], st));
+  rc = lookup_packed_on_device(c, in, dm, d_w, false);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ge[1], st));
+  CU(cudaEventRecord(c->ge[4], st));
+  return genotype_from_weights(c, in, out, dm, d_w, d_lik, error_rate, max_coverage, haploid);
+}
+
+// ---- the two halves on their own: replicas sum the LOOK-UP RESULTS of a batch instead of their counters ----
+// get_count is linear in the counters (bf: the u16 wrap of a sum is the wrap of the sum of the parts; ref_bf: 32-bit
+// wrap-around), so N replicas that each scanned a share of the sample stream can each look the batch up in their own
+// partial counters, sum the weight vectors (4 bytes per signature k-mer: NCCL, a few tens of MB per batch) and
+// genotype from the sum -- no counter array ever travels, and no layout has to agree between the replicas.
+extern "C" int mg_lookup_packed_device(mg_ctx *c, const mg_packed_batch *in, const mg_packed_dims *dims, uint32_t *d_weights) {
+  if (!c || !in || !dims || (!d_weights && dims->n_kmers)) return set_err(MG_ERR_ARG, "NULL argument");
+  if (!c->alt_final) return set_err(MG_ERR_STATE, "mg_lookup_packed_device before mg_finalize_alt");
+  if ((!in->kmers && dims->n_kmers) || (in->n_irregular && (!in->irr_off || !in->irr_pool || !in->irr_kmer)))
+    return set_err(MG_ERR_ARG, "NULL array in batch");
+  CU(cudaSetDevice(c->device));
+  int rc = join_streams(c);
+  if (rc) return rc;
+  for (int i = 0; i < 5; ++i)
+    if (!c->ge[i]) CU(cudaEventCreate(&c->ge[i]));
+  CU(cudaEventRecord(c->ge[0], c->stream[0]));
+  rc = lookup_packed_on_device(c, in, dims, reinterpret_cast<int32_t *>(d_weights), true);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ge[1], c->stream[0]));
+  return MG_OK;
+}
+extern "C" int mg_genotype_weights_device(mg_ctx *c, const mg_packed_batch *in, const mg_genotype_out *out,
+                                          const mg_packed_dims *dims, uint32_t *d_weights, float error_rate,
+                                          int max_coverage, int haploid) {
+  if (!c || !in || !out || !dims || (!d_weights && dims->n_kmers)) return set_err(MG_ERR_ARG, "NULL argument");
+  if (dims->n_variants == 0) return MG_OK;
+  if (!in->var_allele_off || !in->allele_sig_off || !in->sig_kmer_off || (!in->kmers && dims->n_kmers) || !in->freq ||
+      !out->cov || !out->n_gts || !out->status || !out->best_gt || !out->gq || (out->lik && !out->lik_off))
+    return set_err(MG_ERR_ARG, "NULL array in batch");
+  CU(cudaSetDevice(c->device));
+  const bool own_lik = out->lik == nullptr;
+  int rc = geno_scratch(c, own_lik ? dims->lik_slots * 8 + 256 : 256);
+  if (rc) return rc;
+  for (int i = 0; i < 5; ++i)
+    if (!c->ge[i]) CU(cudaEventCreate(&c->ge[i]));
+  CU(cudaEventRecord(c->ge[4], c->stream[0]));
+  if (dims->n_kmers) {  // BF::get_count returns uint16_t: the wrap-around of the summed bf counters
+    c->launches++;
+    mg::k_mask_alt<<<grid_for(dims->n_kmers, 256), 256, 0, c->stream[0]>>>((const uint4 *)in->kmers, dims->n_kmers,
+                                                                            reinterpret_cast<int32_t *>(d_weights));
+    CU(cudaGetLastError());
+  }
+  return genotype_from_weights(c, in, out, dims, reinterpret_cast<const int32_t *>(d_weights),
+                               own_lik ? reinterpret_cast<double *>(c->geno_scratch) : out->lik, error_rate, max_coverage,
+                               haploid);
+}
+
+// The caller's stream (e.g. torch's current stream) in the place of the context's own first stream: library work
+// then orders with the caller's kernels and collectives without host synchronisation.  NULL restores the private one.
+extern "C" int mg_set_stream(mg_ctx *c, void *cuda_stream) {
+  if (!c) return set_err(MG_ERR_ARG, "NULL ctx");
+  CU(cudaSetDevice(c->device));
+  int rc = mg_sync(c);
+  if (rc) return rc;
+  if (!c->own_stream0) c->own_stream0 = c->stream[0];
+  c->stream[0] = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream0;
+  return c->alt_final ? pin_occ_in_l2(c) : MG_OK;  // (the L2 access-policy window is a stream attribute)
 }
 
 static uint64_t lik_slots_of(const uint32_t *var_allele_off, uint64_t nv, int haploid) {
@@ -1838,7 +1922,13 @@ extern "C" int mg_genotype_kernel_ms(mg_ctx *c, float *ms3) {
   if (!c || !ms3 || !c->ge[3]) return set_err(MG_ERR_ARG, "no mg_genotype call to report");
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->ge[3]));
-  for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms3[i], c->ge[i], c->ge[i + 1]));
+  ms3[0] = 0;  // (mg_genotype_weights_device alone: no look-up of this context to report)
+  if (cudaEventQuery(c->ge[1]) == cudaSuccess && cudaEventElapsedTime(&ms3[0], c->ge[0], c->ge[1]) != cudaSuccess) {
+    cudaGetLastError();
+    ms3[0] = 0;
+  }
+  CU(cudaEventElapsedTime(&ms3[1], c->ge[4], c->ge[2]));
+  CU(cudaEventElapsedTime(&ms3[2], c->ge[2], c->ge[3]));
   return MG_OK;
 }
 extern "C" int mg_refpass_kernel_ms(mg_ctx *c, float *ms) {

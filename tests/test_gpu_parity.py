@@ -337,6 +337,78 @@ def test_replicas_built_in_any_order_have_one_image_and_their_counters_add_up(or
             x.close()
 
 
+def test_replicas_sum_lookup_results_instead_of_counters(oracle_lib):
+    """the other multi-GPU scheme (include/malva_gpu.h: mg_lookup_packed_device / mg_genotype_weights_device): every
+    replica looks the batch up in its own partial counters (bf counters raw), the weight vectors are summed (what
+    bench.py does with ncclReduce), and the genotypes computed from the sum equal a single context's -- incl. the
+    uint16 wrap-around of bf counters that only the SUM exceeds.  The library's work is put on torch's stream."""
+    import torch
+
+    k, ref_k, bits = 35, 43, 1 << 22
+    rng = random.Random(2024)
+    genome = util.make_genome(rng, 30000)
+    nested, freqs = util.synth_signatures(rng, genome, k, 500)
+    ks, fl = util.flatten(nested)
+    words, packed, counts = util.synth_sample(rng, genome, nested, k, ref_k, 30000, big_counts=True)
+    a, b, whole = (MalvaGpu(k=k, ref_k=ref_k, bf_bits=bits) for _ in range(3))
+    try:
+        for x in (a, b, whole):
+            x.add_signatures(ks, fl)
+            x.finalize_alt()
+            x.scan_reference(genome)
+            x.finalize_context()
+        side = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        for x in (a, b, whole):
+            x.set_stream(side.cuda_stream)
+        half = len(packed) // 2
+        # each half is scanned several times so that bf counters pass 2^16 in the sum but not in either part
+        for _ in range(3):
+            a.scan_sample_kmers(packed[:half], counts[:half])
+            b.scan_sample_kmers(packed[half:], counts[half:])
+            whole.scan_sample_kmers(packed, counts)
+        batch = SignatureBatch.from_nested(nested, freqs)
+        pb = PackedSignatureBatch.from_batch(batch, k)
+        exp = whole.genotype_packed(pb, 0.001, 10 ** 9, False)
+        dev = torch.device("cuda", 0)
+        nv, na = pb.n_variants, int(pb.var_allele_off[-1])
+        nk = len(pb.kmers)
+        t = {"var_allele_off": torch.from_numpy(pb.var_allele_off.astype(np.int32)).to(dev),
+             "allele_sig_off": torch.from_numpy(pb.allele_sig_off.astype(np.int32)).to(dev),
+             "sig_kmer_off": torch.from_numpy(pb.sig_kmer_off.astype(np.int32)).to(dev),
+             "kmers": torch.from_numpy(pb.kmers.view(np.int64).reshape(-1, 2).copy()).to(dev),
+             "freq": torch.from_numpy(pb.freq).to(dev),
+             "irr_off": torch.from_numpy(pb.irr_off.astype(np.int64)).to(dev),
+             "irr_pool": torch.from_numpy(np.frombuffer(pb.irr_pool, np.uint8).copy()).to(dev),
+             "irr_kmer": torch.from_numpy(pb.irr_kmer.astype(np.int32)).to(dev),
+             "cov": torch.zeros(na, dtype=torch.int32, device=dev)}
+        for nme in ("n_gts", "status", "best_gt", "gq"):
+            t[nme] = torch.zeros(nv, dtype=torch.int32, device=dev)
+        ptrs = {n: x.data_ptr() for n, x in t.items()}
+        nall = np.diff(pb.var_allele_off.astype(np.int64))
+        dims = (nv, na, len(pb.sig_kmer_off) - 1, nk, len(pb.irr_kmer), len(pb.irr_pool),
+                int(np.maximum(nall * (nall + 1) // 2, nall).sum()))
+        wa = torch.zeros(nk, dtype=torch.int32, device=dev)
+        wb = torch.zeros(nk, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):                          # no host synchronisation between the five calls
+            a.lookup_packed_device(ptrs, dims, wa.data_ptr())
+            b.lookup_packed_device(ptrs, dims, wb.data_ptr())
+            total = wa + wb                                    # (stream-ordered with the library's kernels)
+            a.genotype_weights_device(ptrs, dims, total.data_ptr(), 0.001, 10 ** 9, False)
+        torch.cuda.synchronize()
+        assert int((total.to(torch.int64) & 0xFFFFFFFF).max()) > 65535, "the wrap-around is not exercised"
+        for x in (a, b, whole):
+            x.set_stream(0)
+        assert np.array_equal(t["cov"].cpu().numpy().view(np.uint32), exp.cov)
+        for nme, e in (("n_gts", exp.n_gts), ("status", exp.status), ("best_gt", exp.best_gt), ("gq", exp.gq)):
+            assert np.array_equal(t[nme].cpu().numpy(), e), nme
+        assert (exp.cov > 0).sum() > 100
+    finally:
+        for x in (a, b, whole):
+            x.close()
+
+
 def test_kmc_database_with_several_bins(oracle_lib, tmp_path):
     """the layout real KMC2 files have: one prefix LUT per bin, records sorted within a bin only.  The device finds
     the prefix of a record from its global index through the concatenated LUT."""
