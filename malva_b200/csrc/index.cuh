@@ -86,10 +86,23 @@ MG_HD uint64_t ovf_home(u128 key, int shift) { return ((key.lo ^ (key.hi * 0xC2B
 __device__ __forceinline__ uint64_t bf_index(const DevView &v, uint64_t h) {
   return v.bf_mask ? (h & v.bf_mask) : (h % v.bf_bits);
 }
+// read-only loads that do not allocate a line in L1 (data with no reuse inside an SM)
+__device__ __forceinline__ uint32_t ldg_na(const uint32_t *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_na(const uint2 *p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+template <bool NA = false>
 __device__ __forceinline__ bool occ_test(const DevView &v, uint64_t idx) {
   if (!v.occ) return true;
   uint64_t o = idx >> v.occ_shift;
-  return (__ldg(v.occ + (o >> 5)) >> (o & 31)) & 1u;
+  const uint32_t w = NA ? ldg_na(v.occ + (o >> 5)) : __ldg(v.occ + (o >> 5));
+  return (w >> (o & 31)) & 1u;
 }
 __device__ __forceinline__ void occ_set(const DevView &v, uint32_t *occ_rw, uint64_t idx) {
   if (!occ_rw) return;

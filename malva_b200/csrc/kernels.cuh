@@ -480,15 +480,23 @@ __device__ __forceinline__ u128 canon_only(u128 x, int k) {
 // ring entries per warp: [a round in flight (32) +] the entries that pile up until the next turn (< 64)
 __host__ __device__ constexpr int scan_q(bool async) { return async ? 96 : 64; }
 // per warp: 4 KB tile + ring keys + ring meta (uint4 units)
-__host__ __device__ constexpr int scan_warp_u4(bool async, int ilp = 1) { return 256 + 2 * scan_q(async) + 0 * ilp; }
+// LD == 2 needs one 16-byte landing slot per k-mer of a batch for the pre-filter pieces: its own, except with
+// synchronous rounds and two k-mers per lane, where the (then idle) tile takes them
+__host__ __device__ constexpr bool scan_occs(int ld, bool async, int ilp) { return ld == 2 && (async || ilp == 1); }
+__host__ __device__ constexpr bool scan_dense(int ld, bool async, int ilp) { return ld == 2 && !async && ilp == 2; }
+// (+ with `occs`, those slots)
+__host__ __device__ constexpr int scan_warp_u4(bool async, int ilp = 1, bool occs = false) {
+  return 256 + 2 * scan_q(async) + (occs ? 32 * ilp : 0);
+}
 // + the 1 KB expansion table and a deferred-hit counter per warp
-__host__ __device__ constexpr int scan_smem(int threads, bool async, int ilp = 1) {
-  return (threads / 32) * scan_warp_u4(async, ilp) * 16 + 256 * 4 + (threads / 32) * 4;
+__host__ __device__ constexpr int scan_smem(int threads, bool async, int ilp = 1, bool occs = false) {
+  return (threads / 32) * scan_warp_u4(async, ilp, occs) * 16 + 256 * 4 + (threads / 32) * 4;
 }
 // CTAs per SM that fit the shared memory (227 KB usable, 1 KB reserved per CTA), capped at 1024 threads (64 registers
 // each) -- 768 threads (85 registers) for the two-chain variant
-__host__ __device__ constexpr int scan_min_ctas(int threads, bool async, int ilp = 1) {
-  const int by_smem = (227 * 1024) / (scan_smem(threads, async, ilp) + 1024), by_threads = (ilp == 2 ? 768 : 1024) / threads;
+__host__ __device__ constexpr int scan_min_ctas(int threads, bool async, int ilp = 1, bool occs = false, bool dense = false) {
+  const int by_smem = (227 * 1024) / (scan_smem(threads, async, ilp, occs) + 1024),
+            by_threads = (ilp == 2 && !dense ? 768 : 1024) / threads;
   return by_smem < by_threads ? by_smem : by_threads;
 }
 
@@ -538,17 +546,24 @@ __device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_l
 // code over both so that the two dependent chains (canonical form -> table look-ups -> four 128-bit products)
 // interleave: with ~30 resident warps per SM the single chain left the issue slots half empty
 // (~11 cycles between two instructions of a warp, ncu).
-template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP = 1>
-__global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k_scan(ScanSrc src, uint64_t n, DevView v) {
+// LD != 0: the k-mer and count loads do not allocate in L1 (ld.global.nc.L1::no_allocate); the pre-filter word is
+// read as occ_test<NA> says; LD == 2: the 16-byte piece of the pre-filter that holds a k-mer's bit is copied to a
+// shared-memory slot with cp.async.cg (LDGSTS.BYPASS: nothing of it passes through L1) and read from there.
+template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP = 1, int LD = 0>
+__global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP, scan_occs(LD, ASYNC, ILP), scan_dense(LD, ASYNC, ILP)))
+    k_scan(ScanSrc src, uint64_t n, DevView v) {
   static_assert(!ASYNC || (RING && MODE == 0), "the asynchronous round needs the ring and leaves the tile alone");
   static_assert(ILP == 1 || (ILP == 2 && RING && MODE == 0), "two k-mers per lane: ring, packed input");
   extern __shared__ uint4 scan_sm[];
-  constexpr int SCAN_WARPS = THREADS / 32, SCAN_Q = scan_q(ASYNC), SCAN_WARP_U4 = scan_warp_u4(ASYNC, ILP);
+  constexpr int SCAN_WARPS = THREADS / 32, SCAN_Q = scan_q(ASYNC), SCAN_WARP_U4 = scan_warp_u4(ASYNC, ILP, scan_occs(LD, ASYNC, ILP));
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
   uint4 *tile = scan_sm + wid * SCAN_WARP_U4;  // 32 rows x 8 uint4
   uint4 *qkey = tile + 256, *qmeta = qkey + SCAN_Q;
+  // LD == 2: this lane's landing slots (one per k-mer of a batch, 32 apart)
+  const uint4 *oslot = (scan_dense(LD, ASYNC, ILP) ? tile : qmeta + SCAN_Q) + lane;
+  const uint32_t oslot_addr = (uint32_t)__cvta_generic_to_shared(oslot);
   const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
   uint32_t *tab = reinterpret_cast<uint32_t *>(scan_sm + SCAN_WARPS * SCAN_WARP_U4);
   uint32_t *hitc = tab + 256 + wid;  // this warp's deferred-hit counter
@@ -671,7 +686,10 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
   // write-after-write wait exposes the whole load latency -- ncu, profiles/round2_k1.md.)
   constexpr bool SHORT_CTX = REFK > 0 && REFK <= 48;
   auto load_kmer = [&](uint32_t i) {
-    if constexpr (SHORT_CTX) {
+    if constexpr (SHORT_CTX && LD != 0) {
+      const uint2 lo = ldg_na(reinterpret_cast<const uint2 *>(src.kmers + i));
+      return make_uint4(lo.x, lo.y, ldg_na(reinterpret_cast<const uint32_t *>(src.kmers + i) + 2), 0u);
+    } else if constexpr (SHORT_CTX) {
       const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(src.kmers + i));
       return make_uint4(lo.x, lo.y, __ldg(reinterpret_cast<const uint32_t *>(src.kmers + i) + 2), 0u);
     } else {
@@ -687,7 +705,7 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
     for (int u = 0; u < ILP; ++u) {
       const uint32_t i = base + 32u * u + lane;
       q_cur[u] = i < n32 ? load_kmer(i) : make_uint4(0, 0, 0, 0);
-      c_cur[u] = i < n32 ? __ldg(src.counts + i) : 0u;
+      c_cur[u] = i < n32 ? (LD ? ldg_na(src.counts + i) : __ldg(src.counts + i)) : 0u;
     }
     for (;; base += step * ILP) {
       more = more && base < n32;
@@ -707,7 +725,7 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
           for (int u = 0; u < ILP; ++u) {
             const uint32_t i = nb + 32u * u + lane;
             q_cur[u] = i < n32 ? load_kmer(i) : make_uint4(0, 0, 0, 0);
-            c_cur[u] = i < n32 ? __ldg(src.counts + i) : 0u;
+            c_cur[u] = i < n32 ? (LD ? ldg_na(src.counts + i) : __ldg(src.counts + i)) : 0u;
           }
           if (lane < 5 * ILP && nb + step * ILP < n32) {  // and the batch after that into L2 (k-mers, then counts)
             const char *pf = lane < 4 * ILP
@@ -727,11 +745,33 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
             h = canon_hash_rt(x35, k, &canon[u]);
           idx[u] = bf_index(v, h);
         }
+        if constexpr (LD == 2) {
+          uint32_t ob[ILP];  // bit inside the 16-byte piece
+          if (v.occ) {
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+              const uint64_t o = idx[u] >> v.occ_shift;
+              ob[u] = (uint32_t)o & 127u;
+              cp_async16(oslot_addr + (uint32_t)(u * 512), reinterpret_cast<const char *>(v.occ) + ((o >> 7) << 4));
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+          }
+#pragma unroll
+          for (int u = 0; u < ILP; ++u) {
+            bool hit = true;
+            if (v.occ) hit = (reinterpret_cast<const uint32_t *>(oslot + u * 32)[ob[u] >> 5] >> (ob[u] & 31u)) & 1u;
+            need[u] = base + 32u * u + lane < n32 && hit;
+            idx_hi[u] = (uint32_t)(idx[u] >> 8);
+            bit[u] = (uint32_t)(idx[u] & 255);
+          }
+        } else {
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {  // occupancy pre-filter (L2), all words in flight together
-          need[u] = base + 32u * u + lane < n32 && occ_test(v, idx[u]);
+          need[u] = base + 32u * u + lane < n32 && occ_test<LD != 0>(v, idx[u]);
           idx_hi[u] = (uint32_t)(idx[u] >> 8);  // n_lines < 2^32 (bf_bits < 2^40)
           bit[u] = (uint32_t)(idx[u] & 255);
+        }
         }
 #pragma unroll 1
         for (int u = 0; u < ILP; ++u) {
@@ -770,7 +810,7 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
         for (int u = 0; u < 2; ++u) {
           const uint32_t i = base + 32u * u + lane;
           q[u] = i < n32 ? load_kmer(i) : make_uint4(0, 0, 0, 0);
-          cnt[u] = i < n32 ? __ldg(src.counts + i) : 0u;
+          cnt[u] = i < n32 ? (LD ? ldg_na(src.counts + i) : __ldg(src.counts + i)) : 0u;
         }
         // the warp's next 64 k-mers (1 KB + 256 B of counts) into L2 while these are hashed
         if (lane < 10 && base + 2 * step < n32) {
@@ -789,11 +829,33 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
             h = canon_hash_rt(x35, k, &canon[u]);
           idx[u] = bf_index(v, h);
         }
+        if constexpr (LD == 2) {  // the pieces land in the tile: no round is in flight here
+          uint32_t ob[2];
+          if (v.occ) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint64_t o = idx[u] >> v.occ_shift;
+              ob[u] = (uint32_t)o & 127u;
+              cp_async16(oslot_addr + (uint32_t)(u * 512), reinterpret_cast<const char *>(v.occ) + ((o >> 7) << 4));
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            bool hit = true;
+            if (v.occ) hit = (reinterpret_cast<const uint32_t *>(oslot + u * 32)[ob[u] >> 5] >> (ob[u] & 31u)) & 1u;
+            need[u] = base + 32u * u + lane < n32 && hit;
+            idx_lo[u] = (uint32_t)(idx[u] >> 8);
+            bit[u] = (uint32_t)(idx[u] & 255);
+          }
+        } else {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {  // (both pre-filter words are in flight together)
-          need[u] = base + 32u * u + lane < n32 && occ_test(v, idx[u]);
+          need[u] = base + 32u * u + lane < n32 && occ_test<LD != 0>(v, idx[u]);
           idx_lo[u] = (uint32_t)(idx[u] >> 8);
           bit[u] = (uint32_t)(idx[u] & 255);
+        }
         }
 #pragma unroll 1
         for (int u = 0; u < 2; ++u) {
@@ -825,8 +887,8 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
       uint32_t cnt;
       u128 x43, canon;
       if constexpr (MODE == 0) {
-        x43 = u128_of(live ? __ldg(src.kmers + i) : make_uint4(0, 0, 0, 0));
-        cnt = live ? __ldg(src.counts + i) : 0u;
+        x43 = u128_of(live ? load_kmer(i) : make_uint4(0, 0, 0, 0));
+        cnt = live ? (LD ? ldg_na(src.counts + i) : __ldg(src.counts + i)) : 0u;
         // the warp's next batch (512 B of k-mers + 128 B of counts) into L2 while this one is hashed
         if (lane < 5 && base + step < n32) {
           const char *pf = lane < 4 ? reinterpret_cast<const char *>(src.kmers + base + step) + lane * 128
@@ -880,7 +942,18 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP)) k
         h = canon_hash_rt(x35, k, &canon);
       const uint64_t idx = bf_index(v, h);
       // occupancy pre-filter (L2): most probe lines hold nothing for a given k-mer; those are never fetched
-      const bool need = live && occ_test(v, idx);
+      bool need = live;
+      if constexpr (LD == 2) {
+        if (v.occ) {
+          const uint64_t o = idx >> v.occ_shift;
+          cp_async16(oslot_addr, reinterpret_cast<const char *>(v.occ) + ((o >> 7) << 4));
+          asm volatile("cp.async.commit_group;\n" ::: "memory");
+          asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+          need = live && ((reinterpret_cast<const uint32_t *>(oslot)[((uint32_t)o & 127u) >> 5] >> ((uint32_t)o & 31u)) & 1u);
+        }
+      } else {
+        need = live && occ_test<LD != 0>(v, idx);
+      }
       const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
       if (need) {
         const uint32_t e = (fl_pos + fl_n + pd_n + (uint32_t)__popc(need_mask & ((1u << lane) - 1u))) & (SCAN_Q - 1);

@@ -107,7 +107,7 @@ struct mg_ctx {
   uint32_t *hit_counts[2] = {nullptr, nullptr};
   uint64_t hit_entries[2] = {0, 0}, hit_warps[2] = {0, 0};
   bool defer_hits = true;
-  int scan_ctas_per_sm = 128;  // grid cap of the scan kernel, in CTAs per SM (measured optimum 64..256, profiles/)
+  int scan_ctas_per_sm = 64;  // grid cap of the scan kernel, in 256-thread CTAs per SM (measured optimum 32..128, profiles/)
   uint64_t *kmc_lut = nullptr;  // device copy of the KMC prefix LUT (+ guard)
   uint32_t kmc_n_lut = 0, kmc_min = 0;
   uint64_t kmc_max = 0;
@@ -222,7 +222,7 @@ static int ctx_init(mg_ctx *c) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sms = prop.multiProcessorCount;
-  if (const char *e = getenv("MG_SCAN_CTAS_PER_SM")) c->scan_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 128;
+  if (const char *e = getenv("MG_SCAN_CTAS_PER_SM")) c->scan_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 64;
   if (const char *e = getenv("MG_SCAN_DEFER_HITS")) c->defer_hits = atoi(e) != 0;
   for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
   CU(cudaMalloc(&c->lines, c->n_lines * 128));
@@ -245,6 +245,7 @@ static int ctx_init(mg_ctx *c) {
       if (cap_log2 > 34) cap_log2 = 34;
       while (((bf_bits - 1) >> c->occ_shift) + 1 > (1ull << cap_log2)) ++c->occ_shift;
       c->n_occ_words = ((((bf_bits - 1) >> c->occ_shift) + 1) + 31) / 32;
+      c->n_occ_words = (c->n_occ_words + 3) & ~3ull;  // whole 16-byte pieces (the scan copies them with cp.async)
       CU(cudaMalloc(&c->occ, c->n_occ_words * 4));
       CU(cudaMemsetAsync(c->occ, 0, c->n_occ_words * 4, c->stream[0]));
     }
@@ -782,7 +783,7 @@ extern "C" int mg_finalize_context(mg_ctx *c) {
   return MG_OK;
 }
 
-template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP = 1>
+template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP = 1, int LD = 0>
 static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n, cudaStream_t st) {
   constexpr int WARPS = THREADS / 32;
   uint64_t want = (n + THREADS * ILP - 1) / (THREADS * ILP);  // one warp per 32 (64) k-mers
@@ -819,14 +820,31 @@ static cudaError_t launch_scan(mg_ctx *c, const mg::ScanSrc &src_in, uint64_t n,
     src.hit_counts = c->hit_counts[si];
     src.seg_cap = (uint32_t)seg;
   }
-  constexpr int SMEM = mg::scan_smem(THREADS, ASYNC, ILP);
+  constexpr int SMEM = mg::scan_smem(THREADS, ASYNC, ILP, mg::scan_occs(LD, ASYNC, ILP));
   if (SMEM > 48 * 1024) {  // more than 48 KB of dynamic shared memory needs the opt-in (per device; cheap enough to repeat)
-    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP>,
+    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP, LD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
   }
+  if (LD == 2 && !getenv("MG_SCAN_CARVEOUT")) {  // nothing of this build's traffic needs L1: all of it to shared memory
+    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP, LD>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+  }
+  if (const char *ev = getenv("MG_SCAN_CARVEOUT")) {  // (sweeps) shared-memory share of the unified L1, percent
+    cudaError_t e = cudaFuncSetAttribute(mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP, LD>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, atoi(ev));
+    if (e != cudaSuccess) return e;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP, LD>, THREADS, SMEM);
+    static int said = -1;
+    if (said != atoi(ev) * 1000 + THREADS) {
+      said = atoi(ev) * 1000 + THREADS;
+      fprintf(stderr, "[k_scan] carveout %d %%: %d CTAs of %d threads per SM, %d B of shared memory each\n", atoi(ev), nb, THREADS, SMEM);
+    }
+  }
   c->launches++;
-  mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP><<<grid, THREADS, SMEM, st>>>(src, n, c->view());
+  mg::k_scan<K, REFK, MODE, THREADS, RING, ASYNC, ILP, LD><<<grid, THREADS, SMEM, st>>>(src, n, c->view());
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !src.hit_buf) return e;
   const uint64_t threads = n_warps * src.seg_cap;
@@ -841,7 +859,8 @@ static int scan_src(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t 
   cudaError_t e;
   if (c->k == 35 && c->ref_k == 43) {
     // MG_SCAN_VARIANT (tuning sweeps, profiles/sweep_k1_r2.py): the schemes tried for the packed-input scan.
-    // Default = 0: two k-mers per lane, asynchronous probe rounds, 256-thread CTAs (profiles/round2_k1.md).
+    // Default = 0: two k-mers per lane, asynchronous probe rounds, 256-thread CTAs, pre-filter pieces through
+    // cp.async (profiles/round2_k1.md).
     int variant = 0;
     if (MODE == 0)
       if (const char *ev = getenv("MG_SCAN_VARIANT")) variant = atoi(ev);
@@ -857,15 +876,25 @@ static int scan_src(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t 
       e = launch_scan<35, 43, 0, 128, true, false, 2>(c, src, n, st);
     else if (MODE == 0 && variant == 6)
       e = launch_scan<35, 43, 0, 128, true, true, 2>(c, src, n, st);   // two k-mers per lane, asynchronous rounds, 128
+    else if (MODE == 0 && variant == 7)
+      e = launch_scan<35, 43, 0, 256, true, true, 2>(c, src, n, st);     // the default, all loads through L1
+    else if (MODE == 0 && variant == 8)
+      e = launch_scan<35, 43, 0, 256, true, true, 2, 1>(c, src, n, st);  // the default, loads that do not allocate in L1
+    else if (MODE == 0 && variant == 9)
+      e = launch_scan<35, 43, 0, 128, true, true, 2, 2>(c, src, n, st);  // the default with 128-thread CTAs
+    else if (MODE == 0 && variant == 10)
+      e = launch_scan<35, 43, 0, 256, true, false, 1, 2>(c, src, n, st);  // one k-mer per lane, 4 CTAs (32 warps) per SM
+    else if (MODE == 0 && variant == 11)
+      e = launch_scan<35, 43, 0, 256, true, false, 2, 2>(c, src, n, st);  // two per lane, synchronous, 4 CTAs per SM
     else if (MODE == 0)
-      e = launch_scan<35, 43, 0, 256, true, true, 2>(c, src, n, st);
+      e = launch_scan<35, 43, 0, 256, true, true, 2, 2>(c, src, n, st);
     else
-      e = launch_scan<35, 43, MODE, 256, true, false>(c, src, n, st);
+      e = launch_scan<35, 43, MODE, 256, true, false, 1, 2>(c, src, n, st);
   } else {
     if (MODE == 0)
-      e = launch_scan<0, 0, 0, 256, true, true, 2>(c, src, n, st);
+      e = launch_scan<0, 0, 0, 256, true, true, 2, 2>(c, src, n, st);
     else
-      e = launch_scan<0, 0, MODE, 256, true, false>(c, src, n, st);
+      e = launch_scan<0, 0, MODE, 256, true, false, 1, 2>(c, src, n, st);
   }
   if (e != cudaSuccess) return set_err(MG_ERR_CUDA, "k_scan launch -> %s", cudaGetErrorString(e));
   return MG_OK;

@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """Round-2 sweep of the sample-scan kernel (K1) on the bench workload: probe scheme x CTA size x grid cap
-(MG_SCAN_VARIANT: 0 = two k-mers per lane, asynchronous rounds, 256-thread CTAs (default); 1 = one k-mer per lane,
-synchronous rounds; 2 = probe after every batch of 32 k-mers as in round 1; 3 = one k-mer per lane, asynchronous rounds;
-4 / 5 = two k-mers per lane, synchronous rounds, 256 / 128 threads; 6 = as 0 with 128 threads; MG_SCAN_CTAS_PER_SM: grid cap).
+(MG_SCAN_VARIANT: 0 = two k-mers per lane, asynchronous rounds, 256-thread CTAs, pre-filter pieces through cp.async
+(default); 1 = one k-mer per lane, synchronous rounds; 2 = probe after every batch of 32 k-mers as in round 1; 3 = one
+k-mer per lane, asynchronous rounds; 4 / 5 = two k-mers per lane, synchronous rounds, 256 / 128 threads; 6 = as 7 with
+128 threads; 7 = as 0 with every load through L1; 8 = as 7 with loads that do not allocate in L1; 9 = as 0 with
+128 threads; 10 / 11 = one / two k-mers per lane, synchronous rounds, cp.async pre-filter, 4 CTAs per SM;
+MG_SCAN_CTAS_PER_SM: grid cap in 256-thread units; MG_SCAN_CARVEOUT: shared-memory carve-out in percent).
 The index is built once; the variant is read at every launch.
     python profiles/sweep_k1_r2.py [--workload wg] [--variants 0,1,2,3] [--reps 10] > gpurun_out/r2_sweep_k1.txt"""
 import argparse
