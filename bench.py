@@ -53,6 +53,10 @@ WORKLOADS = {
     "wg3": dict(bf_bits=1 << 35, n_alt=300_000_000, n_ref=300_000_000, ref_bases=250_000_000, batch=1 << 27,
                 variants=2_850_000, name="synthetic whole-genome 30x, dense end: 2^35-bit filters, 3e8 alt + 3e8 ref "
                                          "signature k-mers; step = 2^27 sample 43-mers + 2.85e6 variants"),
+    # the whole-genome load factors on probe lines that fit L2 (64 MB; run with MG_OCC_LOG2_BITS=21): the scan with
+    # its random DRAM traffic taken away = the arithmetic floor of K1 (profiles/round2_k1.md; not a bench line)
+    "l2": dict(bf_bits=1 << 27, n_alt=390_625, n_ref=390_625, ref_bases=1_000_000, batch=1 << 27, variants=90_000,
+               name="whole-genome load factors, L2-resident probe lines (not a bench line)"),
     # small twin for quick checks (not a bench line)
     "small": dict(bf_bits=1 << 30, n_alt=2_000_000, n_ref=2_000_000, ref_bases=5_000_000, batch=1 << 22,
                   variants=90_000, name="small twin (not a bench line)"),
@@ -773,6 +777,9 @@ def run_ours(args, wl, rank, local_rank, world):
             steps = max(3, min(args.steps, 6))
             scan()
             g.genotype_packed_host(h_ptrs, nv, 0, ERR, MAX_COV, False)
+            if world > 1:
+                g.sync()
+                reduce_counters()                                        # (first call builds the key ranks: not timed)
             barrier()
             t0 = time.perf_counter()
             g.event_record(4)
