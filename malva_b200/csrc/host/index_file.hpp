@@ -14,8 +14,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 extern "C" {
@@ -28,7 +31,28 @@ unsigned ZSTD_isError(size_t code);
 namespace mh {
 
 constexpr char INDEX_MAGIC[16] = {'M', 'A', 'L', 'V', 'A', 'G', 'P', 'U', 'I', 'D', 'X', '1', 0, 0, 0, 0};
-constexpr size_t INDEX_CHUNK = 64u << 20;
+constexpr size_t INDEX_CHUNK = 8u << 20;  // chunks are compressed and decompressed independently, several at a time
+
+inline int index_threads() {
+  unsigned n = std::thread::hardware_concurrency();
+  return (int)(n < 1 ? 1 : n > 16 ? 16 : n);
+}
+// fn(i) for i in [0, n) on up to index_threads() threads
+template <typename F>
+inline void index_parallel(size_t n, F &&fn) {
+  const int t = (int)std::min<size_t>((size_t)index_threads(), n);
+  if (t <= 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (int w = 0; w < t; ++w)
+    pool.emplace_back([&] {
+      for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+    });
+  for (auto &th : pool) th.join();
+}
 
 class IndexWriter {
  public:
@@ -68,18 +92,27 @@ class IndexWriter {
   void write_section(const void *data, uint64_t n_items, size_t item) {
     put(&n_items, 8);
     const uint8_t *p = (const uint8_t *)data;
-    uint64_t left = n_items * item;
-    std::vector<uint8_t> out(ZSTD_compressBound(INDEX_CHUNK));
-    while (left) {
-      uint64_t raw = left < INDEX_CHUNK ? left : INDEX_CHUNK;
-      size_t z = ZSTD_compress(out.data(), out.size(), p, (size_t)raw, 3);
-      if (ZSTD_isError(z)) throw std::runtime_error("zstd compression failed");
-      uint64_t z64 = z;
-      put(&raw, 8);
-      put(&z64, 8);
-      put(out.data(), z);
-      p += raw;
-      left -= raw;
+    const uint64_t total = n_items * item, n_chunks = (total + INDEX_CHUNK - 1) / INDEX_CHUNK;
+    // a wave of chunks is compressed in parallel (level 1: the file is read back once, by `call`), then written in order
+    const size_t wave = (size_t)index_threads() * 2, bound = ZSTD_compressBound(INDEX_CHUNK);
+    std::vector<std::vector<uint8_t>> out(std::min<uint64_t>(wave, n_chunks));
+    std::vector<size_t> zs(out.size());
+    for (uint64_t c0 = 0; c0 < n_chunks; c0 += wave) {
+      const size_t m = (size_t)std::min<uint64_t>(wave, n_chunks - c0);
+      bool failed = false;
+      index_parallel(m, [&](size_t j) {
+        const uint64_t off = (c0 + j) * INDEX_CHUNK, raw = std::min<uint64_t>(INDEX_CHUNK, total - off);
+        if (out[j].size() < bound) out[j].resize(bound);
+        zs[j] = ZSTD_compress(out[j].data(), out[j].size(), p + off, (size_t)raw, 1);
+        if (ZSTD_isError(zs[j])) failed = true;
+      });
+      if (failed) throw std::runtime_error("zstd compression failed");
+      for (size_t j = 0; j < m; ++j) {
+        const uint64_t off = (c0 + j) * INDEX_CHUNK, raw = std::min<uint64_t>(INDEX_CHUNK, total - off), z64 = zs[j];
+        put(&raw, 8);
+        put(&z64, 8);
+        put(out[j].data(), zs[j]);
+      }
     }
     uint64_t zero = 0;
     put(&zero, 8);
@@ -125,22 +158,32 @@ class IndexReader {
     get(&n_items, 8);
     std::vector<uint64_t> data(n_items * item / 8);
     uint8_t *p = (uint8_t *)data.data();
-    uint64_t left = n_items * item;
-    std::vector<uint8_t> in;
+    const uint64_t total = n_items * item;
+    // the compressed chunks are read in file order, then decompressed in parallel into their places
+    struct Chunk {
+      uint64_t raw, off;
+      std::vector<uint8_t> z;
+    };
+    std::vector<Chunk> chunks;
+    uint64_t off = 0;
     while (true) {
       uint64_t raw = 0, z = 0;
       get(&raw, 8);
       if (raw == 0) break;
       get(&z, 8);
-      if (raw > left) throw std::runtime_error("index file corrupt (section overflow)");
-      in.resize(z);
-      get(in.data(), z);
-      size_t r = ZSTD_decompress(p, (size_t)raw, in.data(), (size_t)z);
-      if (ZSTD_isError(r) || r != raw) throw std::runtime_error("index file corrupt (zstd)");
-      p += raw;
-      left -= raw;
+      if (raw > total - off) throw std::runtime_error("index file corrupt (section overflow)");
+      chunks.push_back(Chunk{raw, off, std::vector<uint8_t>(z)});
+      get(chunks.back().z.data(), z);
+      off += raw;
     }
-    if (left) throw std::runtime_error("index file corrupt (section short)");
+    if (off != total) throw std::runtime_error("index file corrupt (section short)");
+    bool failed = false;
+    index_parallel(chunks.size(), [&](size_t i) {
+      const Chunk &c = chunks[i];
+      size_t r = ZSTD_decompress(p + c.off, (size_t)c.raw, c.z.data(), c.z.size());
+      if (ZSTD_isError(r) || r != c.raw) failed = true;
+    });
+    if (failed) throw std::runtime_error("index file corrupt (zstd)");
     return data;
   }
   FILE *fp_;

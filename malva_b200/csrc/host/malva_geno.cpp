@@ -508,7 +508,13 @@ struct Ctx {
 int index_main(int argc, char **argv) {
   Options o;
   if (!parse_arguments(argc, argv, o, 3)) return EXIT_FAILURE;
-  auto cuda_up = std::async(std::launch::async, [&] { return mg_warmup(o.device); });  // overlaps with the file reading
+  // CUDA start-up and the empty index (allocation + clearing of the filters) overlap with the file reading
+  Ctx g;
+  Stopwatch sw;
+  auto ctx_up = std::async(std::launch::async, [&]() -> std::string {
+    if (mg_warmup(o.device) != MG_OK || mg_create(&g.c, o.device, (int)o.k, (int)o.ref_k, o.bf_size) != MG_OK) return mg_last_error();
+    return std::string();
+  });
   BlockStream stream(o, true);
   if (stream.samples_code != 0) {
     std::cerr << "ERROR: VCF samples subset (code: " << stream.samples_code << ")" << std::endl;
@@ -530,10 +536,14 @@ int index_main(int argc, char **argv) {
   pelapsed("Reference processed");
 
   pelapsed("VCF parsing (Bloom Filter construction)");
-  Ctx g;
-  Stopwatch sw;
-  gpu(mg_create(&g.c, o.device, (int)o.k, (int)o.ref_k, o.bf_size), "mg_create");
-  if (o.trace) fprintf(stderr, "[trace] mg_create (CUDA start-up + empty index) %.1f ms\n", sw.lap());
+  {
+    const double before = sw.lap();
+    const std::string err = ctx_up.get();
+    if (!err.empty()) throw GpuError("mg_create: " + err);
+    if (o.trace)
+      fprintf(stderr, "[trace] files read %.1f ms; then waited %.1f ms more for mg_create (CUDA start-up + empty index)\n", before,
+              sw.lap());
+  }
   {
     EnumeratedBatches batches(index_batches, refs, o);  // enumerates batch i+1 while batch i is inserted
     std::unique_ptr<Batch> b;
@@ -578,6 +588,7 @@ int index_main(int argc, char **argv) {
   gpu(mg_finalize_context(g.c), "mg_finalize_context");  // context_bf.switch_mode()
 
   {
+    sw.lap();
     mh::IndexWriter w(o.vcf_path + ".c" + std::to_string(o.ref_k) + ".k" + std::to_string(o.k) + ".malvax.zst", o.k,
                       o.ref_k, o.bf_size);
     for (int which : {1, 0}) {  // context_bf, then bf, then ref_bf (main.cpp:409-411)
@@ -593,6 +604,7 @@ int index_main(int argc, char **argv) {
     if (n) gpu(mg_export_ref_keys(g.c, keys.data(), n, &n), "mg_export_ref_keys");
     w.write_keys(keys);
     w.close();
+    if (o.trace) fprintf(stderr, "[trace] index file (export from the device, compress, write) %.1f ms\n", sw.lap());
   }
   finish(0);
 }
@@ -679,6 +691,9 @@ int call_main(int argc, char **argv) {
     }
   }
   BatchPrefetcher call_batches(stream, LINES_PER_BATCH);  // first VCF batch decoded while the index loads and the scan runs
+  // the reference FASTA is read while CUDA starts and the index loads (host-only work, 1.4 s for 250 Mbp)
+  std::future<std::map<std::string, std::string>> refs_ready =
+      std::async(std::launch::async, [&o] { return mh::read_fasta(o.fasta_path, o.strip_chr); });
   const int n_dev = (int)o.devices.size();
   std::vector<Ctx> gs((size_t)n_dev);
   Ctx &g = gs[0];  // the context that answers after the reduce
@@ -700,7 +715,7 @@ int call_main(int argc, char **argv) {
     }
   }
   pelapsed("Reference parsing");
-  std::map<std::string, std::string> refs = mh::read_fasta(o.fasta_path, o.strip_chr);
+  std::map<std::string, std::string> refs = refs_ready.get();
   pelapsed("Reference processed");
   // (host only: the first batches are decoded and enumerated while the KMC records stream through the device)
   EnumeratedBatches batches(call_batches, refs, o);
@@ -715,6 +730,7 @@ int call_main(int argc, char **argv) {
     constexpr uint64_t CHUNK = 1ull << 22;  // records per buffer
     std::vector<uint8_t *> buf((size_t)(n_dev * RING), nullptr);
     std::vector<char> used((size_t)(n_dev * RING), 0);
+    Stopwatch sw;
     for (int d = 0; d < n_dev; ++d) {
       gpu(mg_kmc_open(gs[(size_t)d].c, db.lut.data(), db.lut.size(), db.lut_prefix_len, db.kmer_len, db.counter_size,
                       db.min_count, db.max_count),
@@ -722,19 +738,28 @@ int call_main(int argc, char **argv) {
       for (int s = 0; s < RING; ++s) gpu(mg_host_alloc((void **)&buf[(size_t)(d * RING + s)], CHUNK * db.record_bytes + 64), "mg_host_alloc");
     }
     uint64_t first = 0;
+    double t_alloc = sw.lap(), t_wait = 0, t_read = 0, t_submit = 0;
     for (uint64_t chunk = 0;; ++chunk) {
       const int d = (int)(chunk % (uint64_t)n_dev), slot = d * RING + (int)((chunk / (uint64_t)n_dev) % RING);
       mg_ctx *c = gs[(size_t)d].c;
       if (used[(size_t)slot]) gpu(mg_event_sync(c, 32 + slot % RING), "mg_event_sync");
+      t_wait += sw.lap();
       uint64_t n = db.read_records(buf[(size_t)slot], first, CHUNK);
+      t_read += sw.lap();
       if (n == 0) break;
       gpu(mg_scan_kmc_records(c, buf[(size_t)slot], first, n), "mg_scan_kmc_records");
       gpu(mg_event_record(c, 32 + slot % RING), "mg_event_record");
+      t_submit += sw.lap();
       used[(size_t)slot] = 1;
       first += n;
     }
     for (auto &x : gs) gpu(mg_sync(x.c), "mg_sync");
+    const double t_drain = sw.lap();
     for (auto &b : buf) mg_host_free(b);
+    if (o.trace)
+      fprintf(stderr, "[trace] KMC scan: %llu records; pinned buffers %.1f ms, file reads %.1f ms, waiting for a free buffer "
+                      "%.1f ms, submitting %.1f ms, draining %.1f ms, freeing %.1f ms\n",
+              (unsigned long long)first, t_alloc, t_read, t_wait, t_submit, t_drain, sw.lap());
     if (first != db.total_kmers)
       throw std::runtime_error(o.kmc_path + ".kmc_suf is shorter than its header says");
     if (n_dev > 1) {

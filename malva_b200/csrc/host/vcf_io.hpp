@@ -9,7 +9,11 @@
 //     (variant.hpp:158-211)
 // Record decoding is a pure function of one text line, so that batches of lines are decoded in parallel.
 #pragma once
+#include <sys/stat.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <cmath>
 #include <cstdint>
@@ -73,6 +77,8 @@ class BlockLineReader {
   }
   BlockLineReader(const BlockLineReader &) = delete;
   BlockLineReader &operator=(const BlockLineReader &) = delete;
+  // true when the file is not compressed (its size then bounds what is left to read)
+  bool plain() { return gzdirect(fp_) != 0; }
 
   // one line (header parsing); false at end of file
   bool next(std::string &line) {
@@ -143,34 +149,87 @@ class BlockLineReader {
   bool eof_ = false;
 };
 
+namespace detail {
+// dst[i] = toupper(src[i]) (C locale) for i < n; returns whether any src[i] is white space (isspace, C locale)
+inline bool upper_copy(char *dst, const char *src, size_t n) {
+  size_t i = 0;
+  bool space = false;
+#if defined(__SSE2__)
+  __m128i any = _mm_setzero_si128();
+  const __m128i a_m1 = _mm_set1_epi8('a' - 1), z_p1 = _mm_set1_epi8('z' + 1), bit = _mm_set1_epi8(0x20),
+                sp = _mm_set1_epi8(' '), t_m1 = _mm_set1_epi8(8), r_p1 = _mm_set1_epi8(14);
+  for (; i + 16 <= n; i += 16) {
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+    // (signed compares: bytes >= 0x80 are negative and fall outside both ranges, as they should)
+    const __m128i lower = _mm_and_si128(_mm_cmpgt_epi8(c, a_m1), _mm_cmpgt_epi8(z_p1, c));
+    const __m128i ws = _mm_or_si128(_mm_cmpeq_epi8(c, sp), _mm_and_si128(_mm_cmpgt_epi8(c, t_m1), _mm_cmpgt_epi8(r_p1, c)));
+    any = _mm_or_si128(any, ws);
+    _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + i), _mm_sub_epi8(c, _mm_and_si128(lower, bit)));
+  }
+  space = _mm_movemask_epi8(any) != 0;
+#endif
+  for (; i < n; ++i) {
+    const unsigned char c = (unsigned char)src[i];
+    space |= (c == ' ') | ((unsigned)(c - 9u) < 5u);
+    dst[i] = (char)((unsigned)(c - 'a') < 26u ? c - 32 : c);
+  }
+  return space;
+}
+}  // namespace detail
+
 // whole reference, upper-cased, name = first word of the header line, optional "chr" strip (main.cpp:283-295).
 // FASTA and FASTQ-style records are both accepted, like kseq does.
 inline std::map<std::string, std::string> read_fasta(const std::string &path, bool strip_chr) {
   std::map<std::string, std::string> refs;
-  LineReader in(path);
-  std::string line;
+  BlockLineReader in(path);
+  std::vector<char> store;
+  std::vector<BlockLineReader::View> lines;
   std::string *cur = nullptr;
   bool in_qual = false;
   size_t qual_left = 0;
-  while (in.next(line)) {
-    if (in_qual) {  // FASTQ quality lines: as many symbols as the sequence had
-      qual_left = line.size() >= qual_left ? 0 : qual_left - line.size();
-      if (qual_left == 0) in_qual = false;
-      continue;
+  size_t left = 0;  // bytes of an uncompressed file not yet seen (0: unknown)
+  {
+    struct stat st;
+    if (in.plain() && stat(path.c_str(), &st) == 0) left = (size_t)st.st_size;
+  }
+  // lines are views into 16 MB blocks of the file: one copy from the file, one into the sequence
+  while (in.next_block(store, lines, (size_t)1 << 22, (size_t)16 << 20, true)) {
+    for (const BlockLineReader::View &ln : lines) {
+      const size_t n = (size_t)(ln.e - ln.b);
+      left = left > n + 1 ? left - n - 1 : 0;
+      if (in_qual) {  // FASTQ quality lines: as many symbols as the sequence had
+        qual_left = n >= qual_left ? 0 : qual_left - n;
+        if (qual_left == 0) in_qual = false;
+        continue;
+      }
+      if (n && (ln.b[0] == '>' || ln.b[0] == '@')) {
+        const char *e = ln.b + 1;
+        while (e < ln.e && *e != ' ' && *e != '\t') ++e;
+        std::string name(ln.b + 1, e);
+        if (strip_chr && name.compare(0, 3, "chr") == 0) name = name.substr(3);
+        cur = &refs[name];
+        cur->clear();
+      } else if (n && ln.b[0] == '+' && cur) {
+        in_qual = !cur->empty();
+        qual_left = cur->size();
+      } else if (cur && n) {  // sequence text: upper-cased, white space dropped (rare: noticed on the way, removed afterwards)
+        const size_t old_size = cur->size();
+        // growing a sequence copies it and touches fresh pages (several microseconds per page fault in a container):
+        // an uncompressed file says how much can still come, so a contig is usually allocated once
+        if (cur->capacity() < old_size + n)
+          cur->reserve(std::max({old_size + n, 2 * cur->capacity(), std::min<size_t>(left, (size_t)1 << 29)}));
+        cur->resize(old_size + n);
+        char *q = &(*cur)[old_size];
+        const bool space = detail::upper_copy(q, ln.b, n);
+        if (space) {
+          size_t w = 0;
+          for (size_t i = 0; i < n; ++i)
+            if (!isspace((unsigned char)q[i])) q[w++] = q[i];
+          cur->resize(old_size + w);
+        }
+      }
     }
-    if (!line.empty() && (line[0] == '>' || line[0] == '@')) {
-      size_t e = line.find_first_of(" \t");
-      std::string name = line.substr(1, e == std::string::npos ? std::string::npos : e - 1);
-      if (strip_chr && name.compare(0, 3, "chr") == 0) name = name.substr(3);
-      cur = &refs[name];
-      cur->clear();
-    } else if (!line.empty() && line[0] == '+' && cur) {
-      in_qual = !cur->empty();
-      qual_left = cur->size();
-    } else if (cur) {
-      for (char c : line)
-        if (!isspace((unsigned char)c)) cur->push_back((char)toupper((unsigned char)c));
-    }
+    if (lines.empty() && store.empty()) break;
   }
   return refs;
 }

@@ -3,7 +3,9 @@
 own main.cpp, CPU, single-threaded like the original) against this repository's `malva-geno` (C++ host + B200
 kernels) on the same synthetic chromosome-arm-sized inputs; outputs must be byte-identical.
 
-    python tests/bench_cli_e2e.py [Mbp=5] [samples=32] [bf_gb=1] [fast] > gpurun_out/cli_e2e.json
+    python tests/bench_cli_e2e.py [Mbp=5] [samples=32] [bf_gb=1] [fast] [ours] > gpurun_out/cli_e2e.json
+
+`ours`: only this repository's binary is run (profiling runs: the reference takes 8 minutes at 250 Mbp).
 
 `fast`: inputs from tests/synth_fast.py (numpy, about a minute for the 250 Mbp of BASELINE's cfg3) instead of the seeded
 generator of the parity cases (tests/synth.py: Python `random`, 10 s per Mbp); the donor's 43-mers are then counted on
@@ -63,9 +65,31 @@ def fast_write_kmc(prefix, keys, counts, k, p=7):
 
 
 def phases(stderr):
-    out = {}
+    """the reference's own progress lines; the one-per-5000-variants lines are summed into one entry"""
+    out, acc, n, worst = {}, 0.0, 0, 0.0
     for m in re.finditer(r"\[malva-geno/([^\]]+)\] Execution Time ([0-9.e+-]+)s", stderr):
-        out[m.group(1)] = float(m.group(2))
+        if m.group(1).startswith("Processed "):
+            acc, n, worst = acc + float(m.group(2)), n + 1, max(worst, float(m.group(2)))
+        else:
+            out[m.group(1)] = float(m.group(2))
+    if n:
+        out["Processed N variants (sum of %d progress lines)" % n] = round(acc, 4)
+        out["Processed N variants (longest single line)"] = worst
+    return out
+
+
+def traces(stderr):
+    """--trace lines of this repository's binary; the per-batch lines are summed per stage"""
+    lines = [l for l in stderr.split("\n") if l.startswith("[trace]")]
+    batch = [l for l in lines if " batch: " in l]
+    out = [l for l in lines if " batch: " not in l]
+    if batch:
+        tot = {}
+        for l in batch:
+            for name, ms in re.findall(r"([a-z+ ]+?) ([0-9.]+) ms", l.split(": ", 1)[1]):
+                tot[name.strip(", ")] = round(tot.get(name.strip(", "), 0.0) + float(ms), 1)
+        out.append("[%d per-batch trace lines, ms summed per stage] %s" % (len(batch), json.dumps(tot)))
+        out += batch[:2]
     return out
 
 
@@ -74,6 +98,7 @@ def main():
     n_samples = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     bf_gb = sys.argv[3] if len(sys.argv) > 3 else "1"          # -b: filter size in GB (reference default: 4)
     fast = len(sys.argv) > 4 and sys.argv[4] == "fast"
+    ours_only = "ours" in sys.argv[4:]
     mbuild.build()
     case = synth.Case("cli_e2e", 20261018 + 42, [("1", int(mbp * 1e6))], mean_gap=41, n_samples=n_samples)
     synth_write = kmc.write_kmc_db
@@ -97,13 +122,15 @@ def main():
                "generator": "tests/synth_fast.py + malva-geno count" if fast else "tests/synth.py"}
         outs = {}
         for name, exe in (("reference_cpu", REF), ("malva_b200", mbuild.CLI)):
+            if ours_only and name == "reference_cpu":
+                continue
             r = {}
             for sub in ("index", "call"):
                 t = time.time()
                 extra = ["--trace"] if name == "malva_b200" else []
                 p = subprocess.run([exe, sub, "-k", "35", "-r", "43", "-b", bf_gb] + extra + [fa, vcf, prefix], capture_output=True, text=True)
                 if extra:
-                    r[sub + "_trace"] = [l for l in p.stderr.split("\n") if l.startswith("[trace]")]
+                    r[sub + "_trace"] = traces(p.stderr)
                 r[sub + "_wall_s"] = round(time.time() - t, 3)
                 assert p.returncode == 0, p.stderr[-2000:]
                 r[sub + "_phases_s"] = phases(p.stderr)
@@ -111,6 +138,9 @@ def main():
                     outs[name] = p.stdout
             os.remove(vcf + ".c43.k35.malvax.zst")
             res[name] = r
+        if ours_only:
+            print(json.dumps(res, indent=1))
+            return
         res["outputs_identical"] = outs["reference_cpu"] == outs["malva_b200"]
         a, b = res["reference_cpu"], res["malva_b200"]
         scan_ref = a["call_phases_s"].get("BF weights created")

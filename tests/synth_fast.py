@@ -1,5 +1,5 @@
 """Vectorised generator of chromosome-scale inputs for the whole-program comparison (tests/bench_cli_e2e.py --fast):
-SURVEY 8d's cfg3 shape -- one contig of uniform ACGT with a 10 kb N run every 50 Mb, sorted SNV / indel records with
+SURVEY 8d's cfg3 shape -- one contig of uniform ACGT (60-column lines) with a 10 kb N run every 50 Mb, sorted SNV / indel records with
 exponential gaps (mean 41 bp), 88 % SNVs and 12 % indels (geometric length, mean 3, at most 50), AF ~ min(0.5,
 1 / (2 N u)), 32 phased samples drawn from AF, and a donor whose two haplotypes carry the SNVs of a genotype drawn from
 AF (indel records are genotyped too; the donor carries their reference allele).  tests/synth.py stays the generator of
@@ -24,8 +24,11 @@ def build(outdir: str, n_bases: int, n_samples: int = 32, mean_gap: int = 41, se
     fa = os.path.join(outdir, "ref.fa")
     with open(fa, "wb") as fh:
         fh.write(b">1\n")
-        fh.write(ref.tobytes())
-        fh.write(b"\n")
+        whole = (n_bases // 60) * 60            # 60-column lines, like the reference genomes in circulation
+        fh.write(np.hstack([ref[:whole].reshape(-1, 60), np.full((whole // 60, 1), 10, np.uint8)]).tobytes())
+        if whole < n_bases:
+            fh.write(ref[whole:].tobytes())
+            fh.write(b"\n")
     # ---- records ----
     n_guess = int(n_bases / mean_gap * 1.05) + 16
     pos = np.cumsum(g.exponential(mean_gap, n_guess).astype(np.int64) + 1) + 100
