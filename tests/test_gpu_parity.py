@@ -77,6 +77,25 @@ def test_index_scan_state_bit_exact(oracle_lib, k, ref_k, bf_bits):
         o.close()
 
 
+@pytest.mark.parametrize("variant", list(range(1, 12)))
+def test_every_scan_build_is_bit_exact(oracle_lib, monkeypatch, variant):
+    """the other builds of the (35, 43) scan kernel that the sweeps select with MG_SCAN_VARIANT (csrc/malva_gpu.cu:
+    probe after every batch, ring with synchronous / asynchronous rounds, one or two k-mers per lane, 128-thread CTAs,
+    loads through L1, four CTAs per SM) leave exactly the oracle's counters -- dense filter, counts past 2^16"""
+    monkeypatch.setenv("MG_SCAN_VARIANT", str(variant))       # (read at every launch)
+    g, o, genome, nested, freqs, ks, fl, words = _run_pair(oracle_lib, 35, 43, 3 * (1 << 18) + 5, seed=4242, n_var=400,
+                                                           n_sample=9000, big_counts=True)
+    try:
+        assert np.array_equal(g.bf_counts(), o.bf_counts()), "rank-indexed bf counters"
+        for flag in (0, 1):
+            fl_q = [flag] * len(ks)
+            assert np.array_equal(g.get_counts(ks, fl_q), o.get_counts(ks, fl_q)), f"get_count is_ref={flag}"
+        assert int(o.bf_counts().astype(np.int64).sum()) > 0 and (o.get_counts(ks, [1] * len(ks)) > 0).sum() > 20
+    finally:
+        g.close()
+        o.close()
+
+
 def test_u16_wraparound_and_int_counts(oracle_lib):
     # counts up to 70000 per record: bf counters wrap mod 2^16, ref_bf counts do not
     g, o, genome, nested, freqs, ks, fl, words = _run_pair(oracle_lib, 35, 43, 1 << 18, seed=5, n_sample=20000,
