@@ -477,8 +477,12 @@ __device__ __forceinline__ u128 canon_only(u128 x, int k) {
   return less128(x, rc) ? x : rc;
 }
 
-// ring entries per warp: [a round in flight (32) +] the entries that pile up until the next turn (< 64)
-__host__ __device__ constexpr int scan_q(bool async) { return async ? 96 : 64; }
+// ring entries per warp: [a round in flight (32) +] the entries that pile up until the next turn (< 64; < 96 when
+// both k-mers of a lane are pushed in one go: the cp.async build, which has the shared memory to spare)
+__host__ __device__ constexpr bool scan_push2(bool async, int ilp, int ld) { return async && ilp == 2 && ld == 2; }
+__host__ __device__ constexpr int scan_q(bool async, int ilp = 1, int ld = 0) {
+  return async ? (scan_push2(async, ilp, ld) ? 128 : 96) : 64;
+}
 // per warp: 4 KB tile + ring keys + ring meta (uint4 units)
 // LD == 2 needs one 16-byte landing slot per k-mer of a batch for the pre-filter pieces: its own, except with
 // synchronous rounds and two k-mers per lane, where the (then idle) tile takes them
@@ -486,7 +490,7 @@ __host__ __device__ constexpr bool scan_occs(int ld, bool async, int ilp) { retu
 __host__ __device__ constexpr bool scan_dense(int ld, bool async, int ilp) { return ld == 2 && !async && ilp == 2; }
 // (+ with `occs`, those slots)
 __host__ __device__ constexpr int scan_warp_u4(bool async, int ilp = 1, bool occs = false) {
-  return 256 + 2 * scan_q(async) + (occs ? 32 * ilp : 0);
+  return 256 + 2 * scan_q(async, ilp, occs ? 2 : 0) + (occs ? 32 * ilp : 0);
 }
 // + the 1 KB expansion table and a deferred-hit counter per warp
 __host__ __device__ constexpr int scan_smem(int threads, bool async, int ilp = 1, bool occs = false) {
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP, sc
   static_assert(!ASYNC || (RING && MODE == 0), "the asynchronous round needs the ring and leaves the tile alone");
   static_assert(ILP == 1 || (ILP == 2 && RING && MODE == 0), "two k-mers per lane: ring, packed input");
   extern __shared__ uint4 scan_sm[];
-  constexpr int SCAN_WARPS = THREADS / 32, SCAN_Q = scan_q(ASYNC), SCAN_WARP_U4 = scan_warp_u4(ASYNC, ILP, scan_occs(LD, ASYNC, ILP));
+  constexpr int SCAN_WARPS = THREADS / 32, SCAN_Q = scan_q(ASYNC, ILP, LD), SCAN_WARP_U4 = scan_warp_u4(ASYNC, ILP, scan_occs(LD, ASYNC, ILP));
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
   const int tail = ref_k - k - (ref_k - k) / 2;  // bases of the context after the k-mer (main.cpp:493)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
@@ -773,23 +777,46 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP, sc
           bit[u] = (uint32_t)(idx[u] & 255);
         }
         }
-#pragma unroll 1
-        for (int u = 0; u < ILP; ++u) {
-          const bool hi = ILP == 2 && u == 1;
-          const bool nd = hi ? need[ILP - 1] : need[0];
-          const uint32_t need_mask = __ballot_sync(0xffffffffu, nd);
-          if (nd) {
-            const uint32_t e = wrap(fl_pos + fl_n + pd_n + (uint32_t)__popc(need_mask & ((1u << lane) - 1u)));
-            qkey[e] = uint4_of(hi ? canon[ILP - 1] : canon[0]);
-            qmeta[e] = make_uint4(hi ? idx_hi[ILP - 1] : idx_hi[0], base + 32u * u + lane, hi ? cnt[ILP - 1] : cnt[0],
-                                  hi ? bit[ILP - 1] : bit[0]);
+        if constexpr (scan_push2(ASYNC, ILP, LD)) {  // both k-mers of the lane go into the ring in one go
+          const uint32_t m0 = __ballot_sync(0xffffffffu, need[0]), m1 = __ballot_sync(0xffffffffu, need[1]);
+          const uint32_t lt = (1u << lane) - 1u, c0 = (uint32_t)__popc(m0), at = fl_pos + fl_n + pd_n;
+          if (need[0]) {
+            const uint32_t e = wrap(at + (uint32_t)__popc(m0 & lt));
+            qkey[e] = uint4_of(canon[0]);
+            qmeta[e] = make_uint4(idx_hi[0], base + lane, cnt[0], bit[0]);
           }
-          pd_n += (uint32_t)__popc(need_mask);
+          if (need[1]) {
+            const uint32_t e = wrap(at + c0 + (uint32_t)__popc(m1 & lt));
+            qkey[e] = uint4_of(canon[1]);
+            qmeta[e] = make_uint4(idx_hi[1], base + 32u + lane, cnt[1], bit[1]);
+          }
+          pd_n += c0 + (uint32_t)__popc(m1);
           // a full ring turns: the round in flight is finished (started a batch or more ago: its lines have landed),
-          // the next one started
-          if (pd_n >= 32) {
+          // the next one started (twice in a row when both batches passed the pre-filter almost whole)
+#pragma unroll 1
+          while (pd_n >= 32) {
             if (fl_n) complete_round();
             start_round();
+          }
+        } else {
+#pragma unroll 1
+          for (int u = 0; u < ILP; ++u) {
+            const bool hi = ILP == 2 && u == 1;
+            const bool nd = hi ? need[ILP - 1] : need[0];
+            const uint32_t need_mask = __ballot_sync(0xffffffffu, nd);
+            if (nd) {
+              const uint32_t e = wrap(fl_pos + fl_n + pd_n + (uint32_t)__popc(need_mask & ((1u << lane) - 1u)));
+              qkey[e] = uint4_of(hi ? canon[ILP - 1] : canon[0]);
+              qmeta[e] = make_uint4(hi ? idx_hi[ILP - 1] : idx_hi[0], base + 32u * u + lane, hi ? cnt[ILP - 1] : cnt[0],
+                                    hi ? bit[ILP - 1] : bit[0]);
+            }
+            pd_n += (uint32_t)__popc(need_mask);
+            // a full ring turns: the round in flight is finished (started a batch or more ago: its lines have landed),
+            // the next one started
+            if (pd_n >= 32) {
+              if (fl_n) complete_round();
+              start_round();
+            }
           }
         }
       } else {  // the tail: nothing more to hash
