@@ -398,25 +398,89 @@ inline std::string upper(const char *b, const char *e) {
 inline float missing_float() {  // bcf_float_missing: a NaN
   return std::nanf("");
 }
-inline bool info_floats(const Field &info, const std::string &key, std::vector<float> &out) {
+// strtod for the plain decimals VCF INFO fields hold ("0.000312", "1.5e-05", "1"): at most 19 significant digits that fit
+// 2^53 and a decimal exponent within +-22 -- both the digits and the power of ten are then exact doubles and ONE IEEE
+// multiplication or division gives the correctly rounded value, i.e. what strtod returns (Clinger's fast path).
+// Anything else (more digits, larger exponents, inf/nan, hex, trailing text) is left to strtod itself.
+inline bool fast_decimal(const char *b, const char *e, double *out) {
+  static const double P10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const char *p = b;
+  bool neg = false;
+  if (p < e && (*p == '-' || *p == '+')) neg = *p++ == '-';
+  uint64_t m = 0;
+  int digits = 0, exp10 = 0;
+  bool any = false;
+  while (p < e && *p >= '0' && *p <= '9') {
+    if (m || *p != '0') {
+      if (++digits > 19) return false;
+      m = m * 10 + (uint64_t)(*p - '0');
+    }
+    any = true;
+    ++p;
+  }
+  if (p < e && *p == '.') {
+    ++p;
+    while (p < e && *p >= '0' && *p <= '9') {
+      if (m || *p != '0') {
+        if (++digits > 19) return false;
+        m = m * 10 + (uint64_t)(*p - '0');
+      }
+      --exp10;
+      any = true;
+      ++p;
+    }
+  }
+  if (!any) return false;
+  if (p < e && (*p == 'e' || *p == 'E')) {
+    ++p;
+    bool eneg = false;
+    if (p < e && (*p == '-' || *p == '+')) eneg = *p++ == '-';
+    if (p >= e || *p < '0' || *p > '9') return false;
+    int x = 0;
+    while (p < e && *p >= '0' && *p <= '9') {
+      x = x * 10 + (*p++ - '0');
+      if (x > 9999) return false;
+    }
+    exp10 += eneg ? -x : x;
+  }
+  if (p != e || m > (1ull << 53) || exp10 < -22 || exp10 > 22) return false;
+  double v = (double)m;
+  v = exp10 < 0 ? v / P10[-exp10] : v * P10[exp10];
+  *out = neg ? -v : v;
+  return true;
+}
+// one float token the way htslib reads it: strtod, narrowed; "." or nothing = missing
+inline float float_token(const char *q, const char *t) {
+  double d;
+  if (t == q || (t - q == 1 && *q == '.')) return missing_float();
+  if (fast_decimal(q, t, &d)) return (float)d;
+  return (float)strtod(std::string(q, t).c_str(), nullptr);
+}
+
+// the float values of INFO key `key`: returns how many there are (up to `cap` of them are stored), or -1 when the key
+// is absent
+inline int info_floats(const Field &info, const std::string &key, float *out, int cap) {
   const char *p = info.b;
   while (p < info.e) {
     const char *e = (const char *)memchr(p, ';', (size_t)(info.e - p));
     if (!e) e = info.e;
     if ((size_t)(e - p) > key.size() && memcmp(p, key.data(), key.size()) == 0 && p[key.size()] == '=') {
       const char *q = p + key.size() + 1;
+      int n = 0;
       while (q <= e) {
         const char *t = (const char *)memchr(q, ',', (size_t)(e - q));
         if (!t) t = e;
-        std::string tok(q, t);
-        out.push_back((tok == "." || tok.empty()) ? missing_float() : (float)strtod(tok.c_str(), nullptr));
+        const float f = float_token(q, t);
+        if (n < cap) out[n] = f;
+        ++n;
         q = t + 1;
       }
-      return true;
+      return n;
     }
     p = e + 1;
   }
-  return false;
+  return -1;
 }
 }  // namespace detail
 
@@ -458,17 +522,17 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
       a = t + 1;
     }
   }
-  v.quality = c[5].is(".") ? detail::missing_float() : (float)strtod(c[5].str().c_str(), nullptr);
+  v.quality = c[5].is(".") ? detail::missing_float() : (c[5].b == c[5].e ? 0.0f : detail::float_token(c[5].b, c[5].e));
   v.set_sizes();
   if (!v.has_alts) return v;
   // ---- extract_frequencies (variant.hpp:126-156) ----
   if (!uniform) {
-    std::vector<float> af;
-    if (!freq_key_declared || !detail::info_floats(c[7], freq_key, af))
+    const size_t na = v.alts.size();
+    v.frequencies.assign(na + 1, 0.0f);  // (values the record does not list stay 0)
+    const int n_af = freq_key_declared ? detail::info_floats(c[7], freq_key, v.frequencies.data() + 1, (int)na) : -1;
+    if (n_af < 0)
       throw std::runtime_error("INFO key " + freq_key + " missing at " + v.seq_name + ":" + std::to_string(v.ref_pos + 1) +
                                " (the reference dereferences NULL here; use -u or -f)");
-    v.frequencies.push_back(0.0f);
-    for (size_t i = 0; i < v.alts.size(); ++i) v.frequencies.push_back(i < af.size() ? af[i] : 0.0f);
     double sum = 0.0;
     for (float f : v.frequencies) sum += f;
     v.frequencies[0] = (float)(1.0 - sum);
@@ -501,11 +565,14 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
   }
   // raw codes per kept sample, htslib style: ((allele + 1) << 1) | phased; `first`/`second`/ploidy per sample
   const size_t ns = header.keep.size();
-  static thread_local std::vector<int32_t> g0, g1;  // scratch, one set per decoding thread
-  static thread_local std::vector<uint8_t> ploidy;
-  g0.assign(ns, 0);
-  g1.assign(ns, 0);
-  ploidy.assign(ns, 1);
+  static thread_local std::vector<int32_t> g0_tl, g1_tl;  // scratch, one set per decoding thread
+  static thread_local std::vector<uint8_t> ploidy_tl;
+  g0_tl.assign(ns, 0);
+  g1_tl.assign(ns, 0);
+  ploidy_tl.assign(ns, 1);
+  int32_t *const g0 = g0_tl.data(), *const g1 = g1_tl.data();
+  uint8_t *const ploidy = ploidy_tl.data();
+  const int *const keep = header.keep.data();
   size_t max_ploidy = 1;
   {
     size_t ki = 0;  // next kept sample to fill
@@ -515,7 +582,7 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
       // (sample columns are a few bytes long: plain loops beat memchr here)
       if (gt_field == 0 && end - s >= 4 && (s[3] == '\t' || s[3] == ':') && s[0] >= '0' && s[0] <= '9' && s[2] >= '0' &&
           s[2] <= '9' && (s[1] == '|' || s[1] == '/')) {  // "a|b" / "a/b" with one-digit alleles, GT first
-        if (col == header.keep[ki]) {
+        if (col == keep[ki]) {
           g0[ki] = ((s[0] - '0') + 1) << 1;
           g1[ki] = (((s[2] - '0') + 1) << 1) | (s[1] == '|');
           ploidy[ki] = 2;
@@ -530,7 +597,7 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
       }
       const char *t = s;
       while (t < end && *t != '\t') ++t;
-      if (col == header.keep[ki]) {
+      if (col == keep[ki]) {
         const char *q = s;
         for (int f = 0; f < gt_field && q; ++f) {
           q = (const char *)memchr(q, ':', (size_t)(t - q));
@@ -572,11 +639,14 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
   const int32_t VECTOR_END = INT32_MIN + 1;
   // genotypes as allele text ids, kept sparse (signatures.hpp): first the phasing flag most all-reference samples
   // carry, then one entry per sample that differs from {0, 0, that flag}
-  static thread_local std::vector<uint16_t> h1s, h2s;
-  static thread_local std::vector<uint8_t> phs;
-  h1s.resize(ns);
-  h2s.resize(ns);
-  phs.resize(ns);
+  static thread_local std::vector<uint16_t> h1_tl, h2_tl;
+  static thread_local std::vector<uint8_t> ph_tl;
+  h1_tl.resize(ns);
+  h2_tl.resize(ns);
+  ph_tl.resize(ns);
+  // (plain pointers: every use of a function-local thread_local goes through its TLS wrapper)
+  uint16_t *const h1s = h1_tl.data(), *const h2s = h2_tl.data();
+  uint8_t *const phs = ph_tl.data();
   size_t ref_phased = 0, ref_unphased = 0;
   for (size_t i = 0; i < ns; ++i) {
     // the reference reads curr_gt[0] and curr_gt[1] of a row of max_ploidy entries; with ploidy 1 everywhere the

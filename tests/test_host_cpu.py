@@ -234,6 +234,58 @@ int main(int argc, char **argv) {
     assert os.path.getsize(tmp_path / "idx.zst") < 30_000_000   # 72 MB of indices -> deltas -> zstd
 
 
+def test_fast_decimal_equals_strtod(tmp_path):
+    """csrc/host/vcf_io.hpp: the INFO / QUAL float parser takes an exact short cut for plain decimals (<= 19 digits below
+    2^53, decimal exponent within +-22: one correctly rounded IEEE operation) and leaves the rest to strtod; htslib
+    parses these fields with strtod, so every token must come out bit-identical to strtod's value narrowed to float"""
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "vcf_io.hpp"
+#include <cstdio>
+#include <random>
+static int check(const std::string &t, long &fast) {
+  double d = 0;
+  if (mh::detail::fast_decimal(t.data(), t.data() + t.size(), &d)) {
+    ++fast;
+    double e = strtod(t.c_str(), nullptr);
+    if (memcmp(&d, &e, 8) != 0) { printf("MISMATCH %s: %.17g vs %.17g\n", t.c_str(), d, e); return 1; }
+  }
+  float f = mh::detail::float_token(t.data(), t.data() + t.size());
+  float g = (t.empty() || t == ".") ? mh::detail::missing_float() : (float)strtod(t.c_str(), nullptr);
+  if (memcmp(&f, &g, 4) != 0) { printf("TOKEN MISMATCH %s\n", t.c_str()); return 1; }
+  return 0;
+}
+int main() {
+  std::mt19937_64 g(11);
+  long fast = 0, n = 0; int bad = 0;
+  const char *fixed[] = {"0", "-0", "1", "0.5", ".5", "5.", "1e22", "1e-22", "1e23", "1e-23", "9007199254740992", "9007199254740993",
+                         "0.000312", "1.5e-05", "3.0E+2", "00012.500", "0.0000000000000000000001", "123456789012345678901",
+                         "1.7976931348623157e308", "4.9e-324", "nan", "inf", "-inf", "0x10", "1.5abc", "", ".", "+", "-", "e5", "1e", "1e+",
+                         "0.1", "0.2", "0.3", "0.7", "2.2250738585072014e-308", "17.17e1", "1234567890123456789", "9999999999999999999"};
+  for (const char *f : fixed) { bad += check(f, fast); ++n; }
+  for (int i = 0; i < 2000000; ++i) {
+    std::string t;
+    if (g() % 8 == 0) t += (g() & 1) ? "-" : "+";
+    int ni = (int)(g() % 4), nf = (int)(g() % 21);
+    for (int j = 0; j < ni; ++j) t += (char)('0' + g() % 10);
+    if (nf || g() % 3 == 0) { t += '.'; for (int j = 0; j < nf; ++j) t += (char)('0' + (g() % 4 ? g() % 10 : 0)); }
+    if (g() % 4 == 0) { t += (g() & 1) ? 'e' : 'E'; if (g() % 2) t += (g() & 1) ? '-' : '+'; t += std::to_string(g() % 30); }
+    bad += check(t, fast); ++n;
+  }
+  printf("%ld tokens, %ld through the short cut, %d mismatches\n", n, fast, bad);
+  return bad ? 1 : 0;
+}
+''')
+    exe = tmp_path / "t"
+    host = os.path.join(os.path.dirname(mbuild.CLI), "csrc", "host")
+    stdcxx = next(p for p in ("/usr/lib/x86_64-linux-gnu/libstdc++.so.6", "/lib/x86_64-linux-gnu/libstdc++.so.6") if os.path.exists(p))
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", host, "-o", str(exe), str(src), "-lz", "-nostdlib++", stdcxx, "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    n_fast = int(r.stdout.split(" tokens, ")[1].split(" ")[0])
+    assert n_fast > 1_000_000, r.stdout                      # (the short cut is what runs on ordinary AF values)
+
+
 def test_sample_list_errors_and_subset(cli, tmp_path):
     """-s: an unknown name stops the run with the reference's message and htslib's code (index of the name + 1,
     main.cpp:266-271); a valid list keeps the listed samples in HEADER order whatever the order in the file"""
