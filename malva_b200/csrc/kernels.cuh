@@ -479,9 +479,9 @@ __device__ __forceinline__ u128 canon_only(u128 x, int k) {
 
 // ring entries per warp: [a round in flight (32) +] the entries that pile up until the next turn (< 64; < 96 when
 // both k-mers of a lane are pushed in one go: the cp.async build, which has the shared memory to spare)
-__host__ __device__ constexpr bool scan_push2(bool async, int ilp, int ld) { return async && ilp == 2 && ld == 2; }
+__host__ __device__ constexpr bool scan_push2(bool async, int ilp, int ld) { return async && ilp >= 2 && ld == 2; }
 __host__ __device__ constexpr int scan_q(bool async, int ilp = 1, int ld = 0) {
-  return async ? (scan_push2(async, ilp, ld) ? 128 : 96) : 64;
+  return async ? (scan_push2(async, ilp, ld) ? 64 + 32 * ilp : 96) : 64;
 }
 // per warp: 4 KB tile + ring keys + ring meta (uint4 units)
 // LD == 2 needs one 16-byte landing slot per k-mer of a batch for the pre-filter pieces: its own, except with
@@ -500,7 +500,7 @@ __host__ __device__ constexpr int scan_smem(int threads, bool async, int ilp = 1
 // each) -- 768 threads (85 registers) for the two-chain variant
 __host__ __device__ constexpr int scan_min_ctas(int threads, bool async, int ilp = 1, bool occs = false, bool dense = false) {
   const int by_smem = (227 * 1024) / (scan_smem(threads, async, ilp, occs) + 1024),
-            by_threads = (ilp == 2 && !dense ? 768 : 1024) / threads;
+            by_threads = (ilp >= 4 ? 512 : ilp == 3 ? 640 : ilp == 2 && !dense ? 768 : 1024) / threads;
   return by_smem < by_threads ? by_smem : by_threads;
 }
 
@@ -557,7 +557,8 @@ template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP
 __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP, scan_occs(LD, ASYNC, ILP), scan_dense(LD, ASYNC, ILP)))
     k_scan(ScanSrc src, uint64_t n, DevView v) {
   static_assert(!ASYNC || (RING && MODE == 0), "the asynchronous round needs the ring and leaves the tile alone");
-  static_assert(ILP == 1 || (ILP == 2 && RING && MODE == 0), "two k-mers per lane: ring, packed input");
+  static_assert(ILP == 1 || (ILP >= 2 && ILP <= 4 && RING && MODE == 0), "several k-mers per lane: ring, packed input");
+  static_assert(ILP <= 2 || scan_push2(ASYNC, ILP, LD), "more than two k-mers per lane: the cp.async build only");
   extern __shared__ uint4 scan_sm[];
   constexpr int SCAN_WARPS = THREADS / 32, SCAN_Q = scan_q(ASYNC, ILP, LD), SCAN_WARP_U4 = scan_warp_u4(ASYNC, ILP, scan_occs(LD, ASYNC, ILP));
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
@@ -777,22 +778,23 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP, sc
           bit[u] = (uint32_t)(idx[u] & 255);
         }
         }
-        if constexpr (scan_push2(ASYNC, ILP, LD)) {  // both k-mers of the lane go into the ring in one go
-          const uint32_t m0 = __ballot_sync(0xffffffffu, need[0]), m1 = __ballot_sync(0xffffffffu, need[1]);
-          const uint32_t lt = (1u << lane) - 1u, c0 = (uint32_t)__popc(m0), at = fl_pos + fl_n + pd_n;
-          if (need[0]) {
-            const uint32_t e = wrap(at + (uint32_t)__popc(m0 & lt));
-            qkey[e] = uint4_of(canon[0]);
-            qmeta[e] = make_uint4(idx_hi[0], base + lane, cnt[0], bit[0]);
+        if constexpr (scan_push2(ASYNC, ILP, LD)) {  // all k-mers of the lane go into the ring in one go
+          const uint32_t lt = (1u << lane) - 1u, at = fl_pos + fl_n + pd_n;
+          uint32_t m[ILP], off = 0;
+#pragma unroll
+          for (int u = 0; u < ILP; ++u) m[u] = __ballot_sync(0xffffffffu, need[u]);
+#pragma unroll
+          for (int u = 0; u < ILP; ++u) {
+            if (need[u]) {
+              const uint32_t e = wrap(at + off + (uint32_t)__popc(m[u] & lt));
+              qkey[e] = uint4_of(canon[u]);
+              qmeta[e] = make_uint4(idx_hi[u], base + 32u * u + lane, cnt[u], bit[u]);
+            }
+            off += (uint32_t)__popc(m[u]);
           }
-          if (need[1]) {
-            const uint32_t e = wrap(at + c0 + (uint32_t)__popc(m1 & lt));
-            qkey[e] = uint4_of(canon[1]);
-            qmeta[e] = make_uint4(idx_hi[1], base + 32u + lane, cnt[1], bit[1]);
-          }
-          pd_n += c0 + (uint32_t)__popc(m1);
+          pd_n += off;
           // a full ring turns: the round in flight is finished (started a batch or more ago: its lines have landed),
-          // the next one started (twice in a row when both batches passed the pre-filter almost whole)
+          // the next one started (again when the batches passed the pre-filter almost whole)
 #pragma unroll 1
           while (pd_n >= 32) {
             if (fl_n) complete_round();

@@ -886,6 +886,12 @@ static int scan_src(mg_ctx *c, const mg::ScanSrc &src, uint64_t n, cudaStream_t 
       e = launch_scan<35, 43, 0, 256, true, false, 1, 2>(c, src, n, st);  // one k-mer per lane, 4 CTAs (32 warps) per SM
     else if (MODE == 0 && variant == 11)
       e = launch_scan<35, 43, 0, 256, true, false, 2, 2>(c, src, n, st);  // two per lane, synchronous, 4 CTAs per SM
+    else if (MODE == 0 && variant == 12)
+      e = launch_scan<35, 43, 0, 128, true, true, 3, 2>(c, src, n, st);   // three k-mers per lane, 5 CTAs of 128
+    else if (MODE == 0 && variant == 13)
+      e = launch_scan<35, 43, 0, 128, true, true, 4, 2>(c, src, n, st);   // four k-mers per lane, 4 CTAs of 128
+    else if (MODE == 0 && variant == 14)
+      e = launch_scan<35, 43, 0, 256, true, true, 3, 2>(c, src, n, st);   // three k-mers per lane, 2 CTAs of 256
     else if (MODE == 0)
       e = launch_scan<35, 43, 0, 256, true, true, 2, 2>(c, src, n, st);
     else

@@ -4,7 +4,8 @@
 (default); 1 = one k-mer per lane, synchronous rounds; 2 = probe after every batch of 32 k-mers as in round 1; 3 = one
 k-mer per lane, asynchronous rounds; 4 / 5 = two k-mers per lane, synchronous rounds, 256 / 128 threads; 6 = as 7 with
 128 threads; 7 = as 0 with every load through L1; 8 = as 7 with loads that do not allocate in L1; 9 = as 0 with
-128 threads; 10 / 11 = one / two k-mers per lane, synchronous rounds, cp.async pre-filter, 4 CTAs per SM;
+128 threads; 10 / 11 = one / two k-mers per lane, synchronous rounds, cp.async pre-filter, 4 CTAs per SM; 12 / 13 = three /
+four k-mers per lane in 128-thread CTAs; 14 = three per lane in 256-thread CTAs;
 MG_SCAN_CTAS_PER_SM: grid cap in 256-thread units; MG_SCAN_CARVEOUT: shared-memory carve-out in percent).
 The index is built once; the variant is read at every launch.
     python profiles/sweep_k1_r2.py [--workload wg] [--variants 0,1,2,3] [--reps 10] > gpurun_out/r2_sweep_k1.txt"""
