@@ -96,6 +96,28 @@ def test_every_scan_build_is_bit_exact(oracle_lib, monkeypatch, variant):
         o.close()
 
 
+@pytest.mark.parametrize("occ_log2,defer", [(0, 1), (10, 1), (10, 0), (16, 0), (29, 0)])
+@pytest.mark.parametrize("k,ref_k", [(35, 43), (31, 39)])
+def test_prefilter_granularity_and_hit_path(oracle_lib, monkeypatch, occ_log2, defer, k, ref_k):
+    """the small filters of this file get one pre-filter bit per filter bit; the whole-genome shape has one per 64.
+    MG_OCC_LOG2_BITS caps the pre-filter (0 = none at all; 10 and 16 = one bit per 4096 / 64 filter bits here) and
+    MG_SCAN_DEFER_HITS picks whether filter hits are finished in line or by k_scan_hits: same counters either way"""
+    monkeypatch.setenv("MG_OCC_LOG2_BITS", str(occ_log2))     # (both read when the context is created)
+    monkeypatch.setenv("MG_SCAN_DEFER_HITS", str(defer))
+    g, o, genome, nested, freqs, ks, fl, words = _run_pair(oracle_lib, k, ref_k, 1 << 22, seed=900 + occ_log2 + defer,
+                                                           n_var=400, n_sample=9000, big_counts=True)
+    try:
+        assert np.array_equal(g.bits(1), o.bits(1)), "context_bf bits (the reference pass goes through the pre-filter too)"
+        assert np.array_equal(g.bf_counts(), o.bf_counts()), "rank-indexed bf counters"
+        for flag in (0, 1):
+            fl_q = [flag] * len(ks)
+            assert np.array_equal(g.get_counts(ks, fl_q), o.get_counts(ks, fl_q)), f"get_count is_ref={flag}"
+        assert int(o.bf_counts().astype(np.int64).sum()) > 0
+    finally:
+        g.close()
+        o.close()
+
+
 def test_u16_wraparound_and_int_counts(oracle_lib):
     # counts up to 70000 per record: bf counters wrap mod 2^16, ref_bf counts do not
     g, o, genome, nested, freqs, ks, fl, words = _run_pair(oracle_lib, 35, 43, 1 << 18, seed=5, n_sample=20000,
