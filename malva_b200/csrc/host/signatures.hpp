@@ -393,6 +393,7 @@ class VarBlock {
   // row per sample that deviates from the default at some member, plus one all-reference row standing for every
   // other sample (whatever its phasing flags: with no heterozygous site it yields that one haplotype).
   void haplotypes(const Chain &chain, int central, bool haploid, Scratch &sc) const {
+    if (chain.size() <= 8 && haplotypes_small(chain, central, haploid, sc)) return;
     const size_t n = chain.size(), W = 2 * n + 1;
     const uint32_t central_samples = (uint32_t)vars_[(size_t)central].n_samples();
     sc.cursor.assign(n, 0);
@@ -453,6 +454,72 @@ class VarBlock {
     for (size_t i = 0; i < sc.order.size(); ++i)
       memcpy(sc.haps.data() + i * n, sc.cand.data() + (size_t)sc.order[i] * n, n * sizeof(uint16_t));
     sc.n_haps = sc.order.size();
+  }
+
+  // The same set of haplotypes for the common case -- a chain of at most 8 members whose allele ids all fit a byte:
+  // a haplotype is then one u64 (member m in byte m), the candidates of all samples are collected in a small array and
+  // made distinct by sort + unique.  (The ORDER of sc.haps does not matter: VarBlock::enumerate sorts the signatures
+  // they produce.)  Returns false -- nothing written -- when an id or the number of candidates does not fit.
+  bool haplotypes_small(const Chain &chain, int central, bool haploid, Scratch &sc) const {
+    const size_t n = chain.size();
+    constexpr size_t MAX_KEYS = 512;
+    uint64_t keys[MAX_KEYS];
+    size_t n_keys = 0, cursor[8] = {0, 0, 0, 0, 0, 0, 0, 0}, n_rows = 0;
+    const Variant *member[8];
+    for (size_t m = 0; m < n; ++m) member[m] = &vars_[(size_t)chain[m]];
+    const uint32_t central_samples = (uint32_t)vars_[(size_t)central].n_samples();
+    while (true) {
+      uint32_t s = 0xFFFFFFFFu;  // the next sample with an entry at some member
+      for (size_t m = 0; m < n; ++m)
+        if (cursor[m] < member[m]->gts.size()) s = std::min(s, member[m]->gts[cursor[m]].sample);
+      if (s >= central_samples) break;
+      ++n_rows;
+      uint64_t k1 = 0, k2 = 0;
+      bool ph = true;
+      for (size_t m = 0; m < n; ++m) {
+        const Variant &v = *member[m];
+        if (cursor[m] < v.gts.size() && v.gts[cursor[m]].sample == s) {
+          const GtEntry &g = v.gts[cursor[m]++];
+          if ((g.h1 | g.h2) > 255) return false;
+          k1 |= (uint64_t)g.h1 << (8 * m);
+          k2 |= (uint64_t)(haploid ? g.h1 : g.h2) << (8 * m);
+          if (!g.phased) ph = false;
+        } else if (s < v.n_samples() && !v.default_phased) {
+          ph = false;
+        }
+      }
+      if (haploid) {
+        if (n_keys + 1 > MAX_KEYS) return false;
+        keys[n_keys++] = k1;
+      } else if (ph) {
+        if (n_keys + 2 > MAX_KEYS) return false;
+        keys[n_keys++] = k1;
+        keys[n_keys++] = k2;
+      } else {  // unphased: every way of picking one of the two alleles at each heterozygous site
+        uint64_t diff = k1 ^ k2, het_mask[8];
+        size_t n_het = 0;
+        for (size_t m = 0; m < n; ++m)
+          if ((diff >> (8 * m)) & 0xFF) het_mask[n_het++] = 0xFFull << (8 * m);
+        if (n_keys + ((size_t)1 << n_het) > MAX_KEYS) return false;
+        for (uint64_t mask = 0; mask < (1ull << n_het); ++mask) {
+          uint64_t key = k1;
+          for (size_t b = 0; b < n_het; ++b)
+            if ((mask >> b) & 1) key = (key & ~het_mask[b]) | (k2 & het_mask[b]);
+          keys[n_keys++] = key;
+        }
+      }
+    }
+    if (n_rows < central_samples) {  // samples at their default everywhere: the all-reference haplotype
+      if (n_keys + 1 > MAX_KEYS) return false;
+      keys[n_keys++] = 0;
+    }
+    std::sort(keys, keys + n_keys);
+    n_keys = (size_t)(std::unique(keys, keys + n_keys) - keys);
+    sc.haps.resize(n_keys * n);
+    for (size_t i = 0; i < n_keys; ++i)
+      for (size_t m = 0; m < n; ++m) sc.haps[i * n + m] = (uint16_t)((keys[i] >> (8 * m)) & 0xFF);
+    sc.n_haps = n_keys;
+    return true;
   }
 
   static void append_clamped(std::string &dst, const std::string &s, long pos, long len) {
