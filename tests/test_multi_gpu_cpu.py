@@ -1,4 +1,4 @@
-"""N > 1 on CPU (gloo, world size 2): the replicate-and-reduce scheme of bench.py / DESIGN.md section 7.
+"""N > 1 on CPU (gloo, world size 2): the two replicate-and-reduce schemes of DESIGN.md section 7.
 
 Every rank holds a full replica of the index (here: the CPU oracle's), scans its own share of the sample
 stream, and the counter arrays are sum-reduced to rank 0.  The reduced state must equal a single-process
@@ -71,4 +71,43 @@ def test_replicate_and_reduce_world2(oracle_lib, tmp_path):
     assert np.array_equal(got["bf"], o.bf_counts())
     assert np.array_equal(got["ref"], o.get_counts(ks, [1] * len(ks)).astype(np.int64) & 0xFFFFFFFF)
     assert o.bf_counts().sum() > 0
+    o.close()
+
+
+def _worker_lookup(rank, world, port, out_path):
+    """the per-batch scheme of bench.py at N > 1: every rank looks the variant batch up in its OWN partial counters
+    (BF::get_count for alt k-mers, KMAP::get_count for ref k-mers), the results are summed onto rank 0, which masks
+    them the way the counters wrap (u16 / u32) before computing coverages"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pyoracle
+
+    L = pyoracle.oracle()
+    o, ks, packed, counts = _build(L, 78)
+    lo, hi = rank * len(packed) // world, (rank + 1) * len(packed) // world
+    for _ in range(3):                                                   # (several passes: sums pass 2^16)
+        o.scan_sample_kmers(packed[lo:hi].copy(), counts[lo:hi].copy())
+    w_alt = torch.from_numpy(o.get_counts(ks, [0] * len(ks)).astype(np.int64))
+    w_ref = torch.from_numpy(o.get_counts(ks, [1] * len(ks)).astype(np.int64))
+    dist.reduce(w_alt, dst=0)
+    dist.reduce(w_ref, dst=0)
+    if rank == 0:
+        np.savez(out_path, alt=w_alt.numpy() & 0xFFFF, ref=w_ref.numpy() & 0xFFFFFFFF, alt_raw_max=int(w_alt.max()))
+    o.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_replicas_sum_lookup_results_world2(oracle_lib, tmp_path):
+    out = str(tmp_path / "weights.npz")
+    mp.spawn(_worker_lookup, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    o, ks, packed, counts = _build(oracle_lib, 78)
+    for _ in range(3):
+        o.scan_sample_kmers(packed, counts)
+    assert np.array_equal(got["alt"], o.get_counts(ks, [0] * len(ks)).astype(np.int64) & 0xFFFF)
+    assert np.array_equal(got["ref"], o.get_counts(ks, [1] * len(ks)).astype(np.int64) & 0xFFFFFFFF)
+    assert int(got["alt_raw_max"]) > 0
     o.close()
