@@ -477,11 +477,11 @@ __device__ __forceinline__ u128 canon_only(u128 x, int k) {
   return less128(x, rc) ? x : rc;
 }
 
-// ring entries per warp: [a round in flight (32) +] the entries that pile up until the next turn (< 64; < 96 when
-// both k-mers of a lane are pushed in one go: the cp.async build, which has the shared memory to spare)
-__host__ __device__ constexpr bool scan_push2(bool async, int ilp, int ld) { return async && ilp >= 2 && ld == 2; }
+// ring entries per warp: [a round in flight (32) +] the entries that pile up until the next turn (< 64; < 32 + 32 ILP
+// when all ILP k-mers of a lane are pushed in one go: the cp.async build, which has the shared memory to spare)
+__host__ __device__ constexpr bool scan_push_all(bool async, int ilp, int ld) { return async && ilp >= 2 && ld == 2; }
 __host__ __device__ constexpr int scan_q(bool async, int ilp = 1, int ld = 0) {
-  return async ? (scan_push2(async, ilp, ld) ? 64 + 32 * ilp : 96) : 64;
+  return async ? (scan_push_all(async, ilp, ld) ? 64 + 32 * ilp : 96) : 64;
 }
 // per warp: 4 KB tile + ring keys + ring meta (uint4 units)
 // LD == 2 needs one 16-byte landing slot per k-mer of a batch for the pre-filter pieces: its own, except with
@@ -546,19 +546,24 @@ __device__ __forceinline__ uint32_t lut_bucket(const uint64_t *lut, uint32_t n_l
 // compare, count) at the next turn, a batch or more later.  (Also tried, profiles/round2_k1.md: parking a hashed
 // batch in shared memory until its pre-filter word arrives -- the extra shared-memory traffic cost more than the
 // hidden L2 latency.)  The raw-record mode stages records in the tile and stays synchronous.
-// ILP = 2 (synchronous rounds, packed input): every lane hashes TWO k-mers per iteration, written as straight-line
-// code over both so that the two dependent chains (canonical form -> table look-ups -> four 128-bit products)
-// interleave: with ~30 resident warps per SM the single chain left the issue slots half empty
-// (~11 cycles between two instructions of a warp, ncu).
-// LD != 0: the k-mer and count loads do not allocate in L1 (ld.global.nc.L1::no_allocate); the pre-filter word is
-// read as occ_test<NA> says; LD == 2: the 16-byte piece of the pre-filter that holds a k-mer's bit is copied to a
-// shared-memory slot with cp.async.cg (LDGSTS.BYPASS: nothing of it passes through L1) and read from there.
+// ILP = 2..4 (packed input): every lane hashes ILP k-mers per iteration, written as straight-line code over all of
+// them so that the dependent chains (canonical form -> table look-ups -> four 128-bit products) interleave: with ~30
+// resident warps per SM the single chain left the issue slots half empty (~11 cycles between two instructions of a
+// warp, ncu).  Two is the default; three and four (sweep builds) cost warps for registers and are no faster.
+// LD: how the scan reads global memory.  0: ld.global.nc through L1.  1: the k-mer, count and pre-filter loads do
+// not allocate in L1 (ld.global.nc.L1::no_allocate).  2 (the default build): as 1, and the 16-byte piece of the
+// pre-filter that holds a k-mer's bit is copied to a shared-memory slot with cp.async.cg (LDGSTS.BYPASS: nothing of
+// it passes through L1) and read from there.  Why: the 32 random pre-filter words of a warp each hold an L1 line
+// while in flight; with shared memory carved out for three CTAs the remaining L1 (28-60 KB) capped the loads in
+// flight per SM, and the kernel ran 25 % slower at the 228 KB carve-out than at 196 KB (profiles/round2_k1_final.md).
+// Through cp.async the kernel no longer cares, takes the whole carve-out, and has room for a ring deep enough to
+// push all k-mers of a lane at once (one ballot / prefix / turn check per batch instead of one per k-mer).
 template <int K, int REFK, int MODE, int THREADS, bool RING, bool ASYNC, int ILP = 1, int LD = 0>
 __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP, scan_occs(LD, ASYNC, ILP), scan_dense(LD, ASYNC, ILP)))
     k_scan(ScanSrc src, uint64_t n, DevView v) {
   static_assert(!ASYNC || (RING && MODE == 0), "the asynchronous round needs the ring and leaves the tile alone");
   static_assert(ILP == 1 || (ILP >= 2 && ILP <= 4 && RING && MODE == 0), "several k-mers per lane: ring, packed input");
-  static_assert(ILP <= 2 || scan_push2(ASYNC, ILP, LD), "more than two k-mers per lane: the cp.async build only");
+  static_assert(ILP <= 2 || scan_push_all(ASYNC, ILP, LD), "more than two k-mers per lane: the cp.async build only");
   extern __shared__ uint4 scan_sm[];
   constexpr int SCAN_WARPS = THREADS / 32, SCAN_Q = scan_q(ASYNC, ILP, LD), SCAN_WARP_U4 = scan_warp_u4(ASYNC, ILP, scan_occs(LD, ASYNC, ILP));
   const int k = K > 0 ? K : v.k, ref_k = REFK > 0 ? REFK : v.ref_k;
@@ -778,7 +783,7 @@ __global__ void __launch_bounds__(THREADS, scan_min_ctas(THREADS, ASYNC, ILP, sc
           bit[u] = (uint32_t)(idx[u] & 255);
         }
         }
-        if constexpr (scan_push2(ASYNC, ILP, LD)) {  // all k-mers of the lane go into the ring in one go
+        if constexpr (scan_push_all(ASYNC, ILP, LD)) {  // all k-mers of the lane go into the ring in one go
           const uint32_t lt = (1u << lane) - 1u, at = fl_pos + fl_n + pd_n;
           uint32_t m[ILP], off = 0;
 #pragma unroll
