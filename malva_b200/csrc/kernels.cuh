@@ -423,11 +423,11 @@ __global__ void k_refpass_short(const uint8_t *seq, uint64_t len, DevView v, uin
 // K1: sample k-mer scan (main.cpp:487-500)
 //   ref_bf.increment(kmer, c);  if (!context_bf.test_key(context)) bf.increment(kmer, c);
 //
-// A warp owns 32 k-mers per iteration: lane i hashes k-mer i (one coalesced 16-byte load, canonical form, XXH3) and
-// tests the L2-resident occupancy pre-filter.  Only about a third of the k-mers of a whole-genome workload need their
+// A warp owns 32 (x ILP) k-mers per iteration: lane i hashes k-mer i (coalesced loads, canonical form, XXH3) and
+// tests the L2-resident occupancy pre-filter (default build: its 16-byte piece arrives in shared memory by cp.async).  Only about a third of the k-mers of a whole-genome workload need their
 // probe line at all, so probing lane by lane would leave two thirds of the lanes idle through the whole probe
 // sequence (the kernel is bound by instruction issue, profiles/round1_k1_v5.md).  The k-mers that need a line are
-// therefore COMPACTED: they go into a 64-entry ring in shared memory ({canonical k-mer | line, index, count, bit}),
+// therefore COMPACTED: they go into a ring in shared memory ({canonical k-mer | line, index, count, bit}; 64-128 entries),
 // and whenever the ring holds 32 entries the warp runs one FULL probe round:
 //   * the 32 probe lines are copied into the warp's 4 KB tile with cp.async (LDGSTS, no register staging): eight
 //     unrolled rounds, in each the four 8-lane groups move one line each, lane j of a group moving uint4 j -- a line
