@@ -163,6 +163,7 @@ bool parse_arguments(int argc, char **argv, Options &o, int n_positional) {
   o.vcf_path = argv[optind++];
   if (n_positional > 2) o.kmc_path = argv[optind++];
   if (o.threads <= 0) o.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  mh::io_threads() = o.threads;
   if (o.devices.empty()) o.devices.push_back(o.device);
   o.device = o.devices[0];
   return true;
@@ -873,6 +874,7 @@ int call_main(int argc, char **argv) {
 int signatures_main(int argc, char **argv) {
   Options o;
   if (!parse_arguments(argc, argv, o, 2)) return EXIT_FAILURE;
+  mh::count_rows() = o.trace;
   BlockStream stream(o, o.index_blocks);
   if (stream.samples_code != 0) {
     std::cerr << "ERROR: VCF samples subset (code: " << stream.samples_code << ")" << std::endl;
@@ -890,7 +892,12 @@ int signatures_main(int argc, char **argv) {
     sw.lap();
     const bool more = stream.next_batch(batch, LINES_PER_BATCH);
     t_batch += sw.lap();
-    if (!more) break;
+    if (!more) {
+      if (o.trace)
+        fprintf(stderr, "[trace] fixed-stride GT decode: %llu of %llu rows with samples\n",
+                (unsigned long long)mh::fast_gt_rows().load(), (unsigned long long)mh::sample_rows().load());
+      break;
+    }
     enumerate_batch(blocks, refs, o, sigs);
     t_enum += sw.lap();
     if (o.trace)

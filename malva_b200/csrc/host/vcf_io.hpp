@@ -15,13 +15,17 @@
 #include <emmintrin.h>
 #endif
 
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "signatures.hpp"
@@ -61,6 +65,183 @@ class LineReader {
   std::vector<char> buf_;
 };
 
+// MALVA_GENERAL_DECODE=1 in the environment switches the short cuts of this file off (block-parallel BGZF inflate,
+// fixed-stride GT columns): the tests run both ways and compare.
+inline bool general_decode_only() {
+  static const bool on = getenv("MALVA_GENERAL_DECODE") != nullptr;
+  return on;
+}
+
+// rows decoded by the fixed-stride GT short cut / rows with samples in all (reported by `signatures --trace`)
+inline std::atomic<uint64_t> &fast_gt_rows() {
+  static std::atomic<uint64_t> n{0};
+  return n;
+}
+inline std::atomic<uint64_t> &sample_rows() {
+  static std::atomic<uint64_t> n{0};
+  return n;
+}
+inline bool &count_rows() {  // off unless tracing: the counters are shared by all decoding threads
+  static bool on = false;
+  return on;
+}
+
+// host threads the readers may use for block-parallel work (set once by the command-line driver; default: all)
+inline int &io_threads() {
+  static int n = (int)std::max(1u, std::thread::hardware_concurrency());
+  return n;
+}
+
+// BGZF (bgzip / htslib: what .vcf.gz files in circulation are): a series of gzip members of at most 64 KB, each
+// carrying its own compressed size in a "BC" extra field and its uncompressed size in its trailer -- so the members
+// of a stretch of the file can be located without inflating anything and inflated side by side, each straight to its
+// place in the caller's buffer.  (The reference reads through htslib, one member after the other on one thread.)
+// CRC-32 and size of every member are checked, as zlib's gzread does for plain gzip.
+class BgzfSource {
+ public:
+  // true if the file starts with a BGZF member header
+  static bool is_bgzf(const std::string &path) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    unsigned char h[18];
+    const size_t n = fread(h, 1, sizeof h, f);
+    fclose(f);
+    return n == sizeof h && header_ok(h);
+  }
+  explicit BgzfSource(const std::string &path) : f_(fopen(path.c_str(), "rb")) {
+    if (!f_) throw std::runtime_error("cannot open " + path);
+  }
+  ~BgzfSource() {
+    if (f_) fclose(f_);
+  }
+  BgzfSource(const BgzfSource &) = delete;
+  BgzfSource &operator=(const BgzfSource &) = delete;
+
+  // up to `want` bytes of the uncompressed stream; less only at the end of the file
+  size_t read(char *dst, size_t want) {
+    size_t done = 0;
+    while (done < want) {
+      if (spill_pos_ < spill_.size()) {  // what was left of a member that did not fit the previous request
+        const size_t n = std::min(want - done, spill_.size() - spill_pos_);
+        memcpy(dst + done, spill_.data() + spill_pos_, n);
+        spill_pos_ += n;
+        done += n;
+        continue;
+      }
+      // the members of the next stretch that fit what is still wanted, whole
+      struct Member {
+        size_t in_off, in_len, out_off, out_len;
+      };
+      std::vector<Member> ms;
+      size_t out = 0;
+      bool full = false;
+      while (!full && ms.size() < 8192) {
+        // (refilling may move the buffer: only between stretches, never under members already picked)
+        if (cend_ - cpos_ < 18) {
+          if (!ms.empty()) break;
+          if (!have(18)) break;
+        }
+        const unsigned char *h = cbuf_.data() + cpos_;
+        if (!header_ok(h)) throw std::runtime_error("BGZF: bad member header");
+        const size_t bsize = (size_t)(h[16] | (h[17] << 8)) + 1;
+        if (bsize < 26) throw std::runtime_error("BGZF: bad member size");
+        if (cend_ - cpos_ < bsize) {
+          if (!ms.empty()) break;
+          if (!have(bsize)) throw std::runtime_error("BGZF: truncated member");
+          h = cbuf_.data() + cpos_;
+        }
+        const size_t isize = (size_t)h[bsize - 4] | ((size_t)h[bsize - 3] << 8) | ((size_t)h[bsize - 2] << 16) | ((size_t)h[bsize - 1] << 24);
+        if (isize > want - done - out) {
+          if (!ms.empty()) break;  // goes with the next stretch
+          // a single member larger than the room left: inflate it aside, hand out its head
+          spill_.resize(isize);
+          spill_pos_ = 0;
+          inflate_member(h, bsize, spill_.data(), isize);
+          cpos_ += bsize;
+          full = true;
+          break;
+        }
+        ms.push_back(Member{cpos_, bsize, done + out, isize});
+        out += isize;
+        cpos_ += bsize;
+      }
+      if (full) continue;
+      if (ms.empty()) break;  // end of the file
+      const int t = (int)std::min<size_t>((size_t)io_threads(), (ms.size() + 15) / 16);
+      if (t <= 1) {
+        for (const Member &m : ms) inflate_member(cbuf_.data() + m.in_off, m.in_len, dst + m.out_off, m.out_len);
+      } else {
+        std::atomic<size_t> next{0};
+        std::vector<std::exception_ptr> errs((size_t)t);
+        std::vector<std::thread> pool;
+        for (int w = 0; w < t; ++w)
+          pool.emplace_back([&, w] {
+            try {
+              for (size_t i; (i = next.fetch_add(16)) < ms.size();)
+                for (size_t j = i; j < std::min(ms.size(), i + 16); ++j)
+                  inflate_member(cbuf_.data() + ms[j].in_off, ms[j].in_len, dst + ms[j].out_off, ms[j].out_len);
+            } catch (...) {
+              errs[(size_t)w] = std::current_exception();
+              next.store(ms.size());
+            }
+          });
+        for (auto &th : pool) th.join();
+        for (auto &e : errs)
+          if (e) std::rethrow_exception(e);
+      }
+      done += out;
+    }
+    return done;
+  }
+
+ private:
+  static bool header_ok(const unsigned char *h) {
+    return h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && h[3] == 4 && h[10] == 6 && h[11] == 0 && h[12] == 'B' && h[13] == 'C' &&
+           h[14] == 2 && h[15] == 0;
+  }
+  // makes sure `n` bytes from cpos_ on are in cbuf_ (reading more of the file if need be); false at the end of the file
+  bool have(size_t n) {
+    if (cend_ - cpos_ >= n) return true;
+    if (!eof_) {
+      if (cpos_ > 0) {
+        memmove(cbuf_.data(), cbuf_.data() + cpos_, cend_ - cpos_);
+        cend_ -= cpos_;
+        cpos_ = 0;
+      }
+      const size_t chunk = std::max<size_t>(n, (size_t)8 << 20);
+      if (cbuf_.size() < cend_ + chunk) cbuf_.resize(cend_ + chunk);
+      const size_t got = fread(cbuf_.data() + cend_, 1, chunk, f_);
+      cend_ += got;
+      if (got < chunk) eof_ = true;
+    }
+    if (cend_ - cpos_ >= n) return true;
+    if (cend_ != cpos_) throw std::runtime_error("BGZF: truncated file");
+    return false;
+  }
+  static void inflate_member(const unsigned char *h, size_t bsize, char *dst, size_t isize) {
+    z_stream z;
+    memset(&z, 0, sizeof z);
+    if (inflateInit2(&z, -15) != Z_OK) throw std::runtime_error("BGZF: inflateInit2 failed");
+    z.next_in = const_cast<unsigned char *>(h + 18);
+    z.avail_in = (unsigned)(bsize - 18 - 8);
+    z.next_out = reinterpret_cast<unsigned char *>(dst);
+    z.avail_out = (unsigned)isize;
+    const int rc = inflate(&z, Z_FINISH);
+    const bool ok = rc == Z_STREAM_END && z.avail_out == 0;
+    inflateEnd(&z);
+    const unsigned long want_crc = (unsigned long)h[bsize - 8] | ((unsigned long)h[bsize - 7] << 8) |
+                                   ((unsigned long)h[bsize - 6] << 16) | ((unsigned long)h[bsize - 5] << 24);
+    if (!ok || crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const unsigned char *>(dst), (unsigned)isize) != want_crc)
+      throw std::runtime_error("BGZF: corrupt member");
+  }
+  FILE *f_;
+  std::vector<unsigned char> cbuf_;
+  size_t cpos_ = 0, cend_ = 0;
+  bool eof_ = false;
+  std::vector<char> spill_;
+  size_t spill_pos_ = 0;
+};
+
 // Block-wise reader: whole lines of a plain or gz file, many at a time, as views into one buffer (no per-line
 // allocation; the VCF decode that follows runs on the views in parallel).
 class BlockLineReader {
@@ -68,7 +249,12 @@ class BlockLineReader {
   struct View {
     const char *b, *e;
   };
-  explicit BlockLineReader(const std::string &path) : fp_(gzopen(path.c_str(), "r")) {
+  explicit BlockLineReader(const std::string &path) {
+    if (!general_decode_only() && BgzfSource::is_bgzf(path)) {
+      bgzf_.reset(new BgzfSource(path));
+      return;
+    }
+    fp_ = gzopen(path.c_str(), "r");
     if (!fp_) throw std::runtime_error("cannot open " + path);
     gzbuffer(fp_, 1 << 20);
   }
@@ -78,7 +264,7 @@ class BlockLineReader {
   BlockLineReader(const BlockLineReader &) = delete;
   BlockLineReader &operator=(const BlockLineReader &) = delete;
   // true when the file is not compressed (its size then bounds what is left to read)
-  bool plain() { return gzdirect(fp_) != 0; }
+  bool plain() { return fp_ && gzdirect(fp_) != 0; }
 
   // one line (header parsing); false at end of file
   bool next(std::string &line) {
@@ -108,10 +294,9 @@ class BlockLineReader {
       while (!eof_ && store.size() < target) {
         const size_t old = store.size(), want = target - old + (1 << 16);
         store.resize(old + want);
-        int got = gzread(fp_, store.data() + old, (unsigned)want);
-        if (got < 0) throw std::runtime_error("read error");
-        store.resize(old + (size_t)got);
-        if ((size_t)got < want) eof_ = true;
+        const size_t got = read_some(store.data() + old, want);
+        store.resize(old + got);
+        if (got < want) eof_ = true;
       }
       if (eof_ || memchr(store.data(), '\n', store.size())) break;
       target *= 2;  // one line longer than the target: keep reading
@@ -138,12 +323,18 @@ class BlockLineReader {
   void fill(size_t want) {
     size_t old = buf_.size();
     buf_.resize(old + want);
-    int got = gzread(fp_, buf_.data() + old, (unsigned)want);
-    if (got < 0) throw std::runtime_error("read error");
-    buf_.resize(old + (size_t)got);
-    if ((size_t)got < want) eof_ = true;
+    const size_t got = read_some(buf_.data() + old, want);
+    buf_.resize(old + got);
+    if (got < want) eof_ = true;
   }
-  gzFile fp_;
+  size_t read_some(char *dst, size_t want) {
+    if (bgzf_) return bgzf_->read(dst, want);
+    const int got = gzread(fp_, dst, (unsigned)want);
+    if (got < 0) throw std::runtime_error("read error");
+    return (size_t)got;
+  }
+  gzFile fp_ = nullptr;
+  std::unique_ptr<BgzfSource> bgzf_;
   std::vector<char> buf_;
   size_t pos_ = 0;
   bool eof_ = false;
@@ -482,6 +673,120 @@ inline int info_floats(const Field &info, const std::string &key, float *out, in
   }
   return -1;
 }
+
+// ---- extract_genotypes for the layout panels come in: FORMAT is "GT" alone, every sample kept, every column the same
+// width -- "a|b" / "a/b" with one-symbol alleles (3 bytes + tab) or one symbol alone (haploid panels, 1 byte + tab).
+// Columns then sit at a fixed stride, the run of the mill ("0|0", "0/0", "0") is recognised 16 bytes at a time, and only
+// the columns that differ are decoded; the result is the sparse genotype list parse_record() would build (same
+// decisions, variant.hpp:158-211, including the one-allele rows whose second read lands on the NEXT sample's first
+// entry).  Returns false -- nothing written -- for any other layout: the caller then takes the general path.
+inline int gt_symbol(char c) {  // allele index of a one-symbol GT entry; '.' (missing) counts as the reference allele
+  if (c >= '0' && c <= '9') return c - '0';
+  return c == '.' ? 0 : -1;
+}
+inline bool fast_gt_columns(const char *s, const char *end, size_t ns, Variant &v) {
+  if (ns == 0 || !s) return false;
+  const size_t len = (size_t)(end - s);
+  static thread_local std::vector<uint32_t> exc_tl;  // samples whose column is not the run-of-the-mill one
+  std::vector<uint32_t> &exc = exc_tl;
+  exc.clear();
+  v.gts.clear();
+  size_t ref_phased = 0, ref_unphased = 0;
+  if (len == 4 * ns - 1) {  // ---- "a|b" columns ----
+    if (s[1] != '|' && s[1] != '/') return false;
+    const char sep = s[1];
+    const int guess = sep == '|';  // phasing of the reference-reference columns, to be confirmed by the counts
+    const char def4[4] = {'0', sep, '0', '\t'};
+    uint32_t def;
+    memcpy(&def, def4, 4);
+    size_t i = 0;
+    const size_t whole = ns - 1;  // (the last column has no tab behind it)
+#if defined(__SSE2__)
+    const __m128i d16 = _mm_set1_epi32((int)def);
+    for (; i + 4 <= whole; i += 4) {
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 4 * i));
+      const int eq = _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpeq_epi32(c, d16)));
+      if (eq == 0xF) continue;
+      for (int j = 0; j < 4; ++j)
+        if (!((eq >> j) & 1)) exc.push_back((uint32_t)(i + (size_t)j));
+    }
+#endif
+    for (; i < whole; ++i) {
+      uint32_t w;
+      memcpy(&w, s + 4 * i, 4);
+      if (w != def) exc.push_back((uint32_t)i);
+    }
+    exc.push_back((uint32_t)(ns - 1));
+    for (uint32_t e : exc) {
+      const char *q = s + 4 * (size_t)e;
+      const int a1 = gt_symbol(q[0]), a2 = gt_symbol(q[2]);
+      if (a1 < 0 || a2 < 0 || (q[1] != '|' && q[1] != '/') || (e + 1 < ns && q[3] != '\t')) return false;
+      const uint16_t h1 = v.text_id_of(a1), h2 = v.text_id_of(a2);
+      const uint8_t ph = q[1] == '|';
+      if ((h1 | h2) == 0) {
+        (ph ? ref_phased : ref_unphased)++;
+        if (ph == guess) continue;
+      }
+      v.gts.push_back(GtEntry{e, h1, h2, ph});
+    }
+    (guess ? ref_phased : ref_unphased) += ns - exc.size();
+    if ((ref_phased >= ref_unphased ? 1 : 0) != guess) return false;  // (mixed files: the general path sorts it out)
+    v.default_phased = (uint8_t)guess;
+  } else if (len == 2 * ns - 1) {  // ---- one-symbol columns: sample i reads {own symbol, NEXT sample's symbol}, unphased;
+    //                                  the last one {own, own}, phased (see parse_record) ----
+    const char def2[2] = {'0', '\t'};
+    uint16_t def;
+    memcpy(&def, def2, 2);
+    size_t i = 0;
+    const size_t whole = ns - 1;
+#if defined(__SSE2__)
+    const __m128i d16 = _mm_set1_epi16((short)def);
+    for (; i + 8 <= whole; i += 8) {
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 2 * i));
+      const int eq = _mm_movemask_epi8(_mm_cmpeq_epi16(c, d16));
+      if (eq == 0xFFFF) continue;
+      for (int j = 0; j < 8; ++j)
+        if (((eq >> (2 * j)) & 3) != 3) exc.push_back((uint32_t)(i + (size_t)j));
+    }
+#endif
+    for (; i < whole; ++i) {
+      uint16_t w;
+      memcpy(&w, s + 2 * i, 2);
+      if (w != def) exc.push_back((uint32_t)i);
+    }
+    if (exc.empty() || exc.back() != (uint32_t)(ns - 1)) exc.push_back((uint32_t)(ns - 1));
+    // a column that differs makes its own sample and the one before it differ
+    size_t n_touched = 0;
+    uint32_t last_done = 0xFFFFFFFFu;
+    for (uint32_t e : exc) {
+      const char *q = s + 2 * (size_t)e;
+      if (gt_symbol(q[0]) < 0 || (e + 1 < ns && q[1] != '\t')) return false;
+      for (uint32_t t = e == 0 ? 0 : e - 1; t <= e; ++t) {
+        if (last_done != 0xFFFFFFFFu && t <= last_done) continue;
+        last_done = t;
+        ++n_touched;
+        const int a1 = gt_symbol(s[2 * (size_t)t]);
+        const bool last = t + 1 == ns;
+        const int a2 = last ? a1 : gt_symbol(s[2 * (size_t)t + 2]);
+        if (a1 < 0 || a2 < 0) return false;
+        const uint16_t h1 = v.text_id_of(a1), h2 = v.text_id_of(a2);
+        const uint8_t ph = last ? 1 : 0;
+        if ((h1 | h2) == 0) {
+          (ph ? ref_phased : ref_unphased)++;
+          if (!ph) continue;
+        }
+        v.gts.push_back(GtEntry{t, h1, h2, ph});
+      }
+    }
+    ref_unphased += ns - n_touched;
+    if (ref_phased >= ref_unphased) return false;  // (a panel of one or two samples: the general path)
+    v.default_phased = 0;
+  } else {
+    return false;
+  }
+  v.n_samples_ = (uint32_t)ns;
+  return true;
+}
 }  // namespace detail
 
 // Variant(hdr, rec, freq_key, uniform), variant.hpp:66-103, from one VCF data line.
@@ -565,6 +870,13 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
   }
   // raw codes per kept sample, htslib style: ((allele + 1) << 1) | phased; `first`/`second`/ploidy per sample
   const size_t ns = header.keep.size();
+  if (count_rows()) sample_rows().fetch_add(1, std::memory_order_relaxed);
+  if (gt_field == 0 && c[8].size() == 2 && ns == header.samples.size() && !general_decode_only() &&
+      detail::fast_gt_columns(samples_begin, end, ns, v)) {
+    if (count_rows()) fast_gt_rows().fetch_add(1, std::memory_order_relaxed);
+    return v;
+  }
+  v.gts.clear();
   static thread_local std::vector<int32_t> g0_tl, g1_tl;  // scratch, one set per decoding thread
   static thread_local std::vector<uint8_t> ploidy_tl;
   g0_tl.assign(ns, 0);

@@ -2,6 +2,7 @@
 VB::extract_kmers (oracle/_ref hook) and block grouping rules: `malva-geno signatures` prints what the CLI would
 send to the device for every var_block.  No GPU involved (the signatures sub-command never touches CUDA)."""
 import os
+import re
 import subprocess
 
 import pytest
@@ -347,3 +348,131 @@ def test_signatures_many_samples(cli, ref_lib, tmp_path, haploid):
         exp, exp_used = expected_signatures(ref_lib, fa, vcf, 35, haploid, "AF", False, index_mode)
         assert got == exp and used == exp_used
         assert sum(len(v) for b in exp.values() for v in b.values()) > 2000
+
+
+# ---- short cuts of the VCF reader (block-parallel BGZF inflate, fixed-stride GT columns) against its general paths --------
+
+def _bgzf_bytes(data: bytes, rng, max_member=6000) -> bytes:
+    """BGZF as bgzip writes it: gzip members with a 'BC' extra field holding their own size, cut at arbitrary byte
+    positions (lines straddle members), a few empty members in between, the 28-byte EOF marker at the end."""
+    import struct
+    import zlib
+
+    def member(chunk: bytes) -> bytes:
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(chunk) + c.flush()
+        bsize = 18 + len(body) + 8
+        assert bsize <= 65536
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1) + body +
+                struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+    out, pos = [], 0
+    while pos < len(data):
+        n = rng.randrange(1, max_member)
+        out.append(member(data[pos:pos + n]))
+        pos += n
+        if rng.random() < 0.05:
+            out.append(member(b""))
+    out.append(member(b""))
+    return b"".join(out)
+
+
+def _signatures_text(cli, fa, vcf, flags, general, threads=None):
+    env = dict(os.environ)
+    env.pop("MALVA_GENERAL_DECODE", None)
+    if general:
+        env["MALVA_GENERAL_DECODE"] = "1"
+    cmd = [cli, "signatures"] + list(flags) + (["--threads", str(threads)] if threads else []) + [fa, vcf]
+    return subprocess.run(cmd, capture_output=True, text=True, env=env)
+
+
+def test_bgzf_reader_equals_gzip_reader(cli, tmp_path):
+    """the block-parallel BGZF source hands out the same bytes as zlib's gzread (the general path, which also reads
+    BGZF as concatenated gzip members) and as the plain file; a damaged member is an error, not silent garbage"""
+    import random
+
+    rng = random.Random(4242)
+    refs = synth.make_reference(rng, [("1", 20_000), ("2", 9_000)], n_run_every=5000)
+    recs = synth.make_variants(rng, refs, 12, 60, False, multi_frac=0.15, sym_frac=0.02, long_frac=0.01, k=35)
+    fa, vcf = str(tmp_path / "r.fa"), str(tmp_path / "v.vcf")
+    synth.write_fasta(fa, refs)
+    synth.write_vcf(vcf, refs, recs, 60, False, 0.02, rng)
+    plain = open(vcf, "rb").read()
+    want = _signatures_text(cli, fa, vcf, [], general=True)
+    assert want.returncode == 0 and want.stdout.count("\n") > 500
+    for trial, max_member in enumerate((300, 6000, 60000)):
+        bg = str(tmp_path / f"v{trial}.vcf.gz")
+        blob = _bgzf_bytes(plain, rng, max_member)
+        open(bg, "wb").write(blob)
+        for general in (False, True):
+            for threads in (1, 4):
+                got = _signatures_text(cli, fa, bg, [], general, threads)
+                assert got.returncode == 0, got.stderr
+                assert got.stdout == want.stdout, (trial, general, threads)
+    # one flipped byte inside a member's deflate stream / a truncated file
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x55
+    open(str(tmp_path / "bad.vcf.gz"), "wb").write(bytes(bad))
+    r = _signatures_text(cli, fa, str(tmp_path / "bad.vcf.gz"), [], general=False)
+    assert r.returncode != 0 and "BGZF" in r.stderr
+    open(str(tmp_path / "cut.vcf.gz"), "wb").write(blob[: len(blob) // 2])
+    r = _signatures_text(cli, fa, str(tmp_path / "cut.vcf.gz"), [], general=False)
+    assert r.returncode != 0 and "BGZF" in r.stderr
+
+
+@pytest.mark.parametrize("haploid", [False, True])
+@pytest.mark.parametrize("n_samples", [1, 2, 3, 5, 17, 64, 131])
+def test_fixed_stride_gt_columns_equal_general_decode(cli, ref_lib, tmp_path, haploid, n_samples):
+    """FORMAT = GT with one-symbol alleles takes the fixed-stride decode (vcf_io.hpp fast_gt_columns); the result is
+    what the general decode gives and what the reference's Variant / VB::extract_kmers give (variant.hpp:158-211),
+    for every mix the short cut has to get right or hand back: phased / unphased / mostly-unphased rows, missing
+    entries, single-entry diploid columns, ten or more alleles (two-symbol indices), a FORMAT with a second field"""
+    import random
+
+    rng = random.Random(977 * n_samples + haploid)
+    refs = synth.make_reference(rng, [("1", 9_000)], n_run_every=5000)
+    recs = synth.make_variants(rng, refs, 10, n_samples, haploid, multi_frac=0.3, sym_frac=0.02, long_frac=0.01, k=35)
+    for i, r in enumerate(recs):
+        n_real = len([a for a in r.alts if not a.startswith("<")])
+        mode = i % 6
+        gts = []
+        for s in range(n_samples):
+            a, b = (rng.randrange(0, n_real + 1) if rng.random() < 0.3 else 0 for _ in range(2))
+            if haploid:
+                gts.append("." if rng.random() < 0.05 else str(a))
+                continue
+            sep = {0: "|", 1: "/", 2: "|" if rng.random() < 0.8 else "/", 3: "/" if rng.random() < 0.8 else "|",
+                   4: "|", 5: "|"}[mode]
+            g = f"{a}{sep}{b}"
+            if mode == 4 and rng.random() < 0.1:
+                g = "." + sep + (str(b) if rng.random() < 0.5 else ".")
+            if mode == 5 and s == n_samples // 2:
+                g = str(a)                 # one column of another width: the whole row goes the general way
+            gts.append(g)
+        r.gts = gts
+    fa, vcf = str(tmp_path / "r.fa"), str(tmp_path / "v.vcf")
+    synth.write_fasta(fa, refs)
+    synth.write_vcf(vcf, refs, recs, n_samples, haploid, 0.02, rng)
+    flags = ["-1"] if haploid else []
+    fast = _signatures_text(cli, fa, vcf, flags, general=False)
+    slow = _signatures_text(cli, fa, vcf, flags, general=True)
+    assert fast.returncode == 0 and slow.returncode == 0, fast.stderr + slow.stderr
+    assert fast.stdout == slow.stdout
+    tr = subprocess.run([cli, "signatures", "--trace"] + flags + [fa, vcf], capture_output=True, text=True, check=True).stderr
+    took, rows = map(int, re.search(r"fixed-stride GT decode: (\d+) of (\d+) rows", tr).groups())
+    assert 0.8 * len(recs) <= rows <= len(recs) and took < rows
+    assert n_samples < 5 or took >= rows // 3             # both ways are exercised by the file
+    got, used = cli_signatures(cli, fa, vcf, flags, False)
+    exp, exp_used = expected_signatures(ref_lib, fa, vcf, 35, haploid, "AF", False, False)
+    assert got == exp and used == exp_used
+
+
+def test_sars_cov2_panel_fast_and_general_decode_agree(cli):
+    """BASELINE config 1's real VCF (BGZF, 15,154 records x 27,934 one-symbol haploid columns): both decodes give the
+    same signatures, byte for byte"""
+    src = os.path.join(os.path.dirname(GOLD), "sars")
+    fa, vcf = os.path.join(src, "reference_sarsCov2.fasta"), os.path.join(src, "sars_cov2.vcf.gz")
+    fast = _signatures_text(cli, fa, vcf, ["-1"], general=False)
+    slow = _signatures_text(cli, fa, vcf, ["-1"], general=True)
+    assert fast.returncode == 0 and slow.returncode == 0
+    assert fast.stdout == slow.stdout and fast.stdout.count("\n") > 10_000
