@@ -24,6 +24,7 @@
 //        database that `index` / `call` (and the reference) read
 //   malva-geno kmc-dump <kmc_output_prefix>                 lists a database as text (no GPU involved)
 //   malva-geno signatures [--index-blocks] [flags] <reference.fa> <variants.vcf>     (no GPU involved; CPU tests)
+//   malva-geno format-selftest                              the output stage's number formatting against libc (CPU tests)
 #include <getopt.h>
 #include <sys/resource.h>
 #include <unistd.h>
@@ -616,12 +617,23 @@ int index_main(int argc, char **argv) {
 
 // ------------------------------------------------------------------------------------------------
 // one VCF line per variant of the batch, VB::output_variants (var_block.hpp:337-396)
+inline void append_int(std::string &out, long long x) {  // what std::to_string(int) appends, without the temporary
+  char tmp[24];
+  char *e = tmp + sizeof(tmp), *p = e;
+  unsigned long long u = x < 0 ? 0ull - (unsigned long long)x : (unsigned long long)x;
+  do {
+    *--p = (char)('0' + u % 10);
+    u /= 10;
+  } while (u);
+  if (x < 0) *--p = '-';
+  out.append(p, (size_t)(e - p));
+}
+
 void format_variant(const mh::Variant &v, const uint32_t *cov, int n_gts, int status, int best, int gq, const double *lik,
                     const Options &o, std::string &out) {
-  char num[64];
   out += v.seq_name;
   out += '\t';
-  out += std::to_string(v.ref_pos + 1);
+  append_int(out, (long long)v.ref_pos + 1);
   out += '\t';
   out += v.idx;
   out += '\t';
@@ -634,47 +646,103 @@ void format_variant(const mh::Variant &v, const uint32_t *cov, int n_gts, int st
   out += '\t';
   if (std::isnan(v.quality)) {
     out += '.';
+  } else if (v.quality >= 0.0f && v.quality < 1000000.0f && (float)(int)v.quality == v.quality && !std::signbit(v.quality)) {
+    append_int(out, (int)v.quality);  // what %g prints for a whole number below 1e6
   } else {
+    char num[64];
     snprintf(num, sizeof(num), "%g", (double)v.quality);  // ostream << float
     out += num;
   }
   const int n = v.n_alleles();
   // name of the i-th computed genotype: "g" / "g1/g2" in emission order, or the default for vetoed variants
-  auto gt_name = [&](int i) -> std::string {
-    if (status != 0) return o.haploid ? "0" : "0/0";
-    if (o.haploid) return std::to_string(i);
+  auto append_gt_name = [&](int i) {
+    if (status != 0) {
+      out += o.haploid ? "0" : "0/0";
+      return;
+    }
+    if (o.haploid) {
+      append_int(out, i);
+      return;
+    }
     int g1 = 0, left = i;
     while (left >= n - g1) {
       left -= n - g1;
       ++g1;
     }
-    return std::to_string(g1) + "/" + std::to_string(g1 + left);
+    append_int(out, g1);
+    out += '/';
+    append_int(out, g1 + left);
   };
-  std::string info = ".";
+  out += "\tPASS\t";
   if (o.verbose) {
-    info = "COVS=";
+    out += "COVS=";
     for (int a = 0; a < n; ++a) {
-      if (a) info += ',';
-      info += std::to_string((int)cov[a]);
+      if (a) out += ',';
+      append_int(out, (int)cov[a]);
     }
-    info += ";GTS=";
+    out += ";GTS=";
     double total = 0.0;
     for (int i = 0; i < n_gts; ++i) total += lik[i];
     for (int i = 0; i < n_gts; ++i) {
-      if (i) info += ',';
-      info += gt_name(i);
-      info += ':';
+      if (i) out += ',';
+      append_gt_name(i);
+      out += ':';
       volatile double q = lik[i] / total;  // 0/0 -> the machine's default NaN, printed "-nan" like the reference
-      info += std::to_string((double)q);
+      out += std::to_string((double)q);
     }
+  } else {
+    out += '.';
   }
-  out += "\tPASS\t";
-  out += info;
   out += "\tGT:GQ\t";
-  out += gt_name(best);
+  append_gt_name(best);
   out += ':';
-  out += std::to_string(gq);
+  append_int(out, gq);
   out += '\n';
+}
+
+// CPU-only check of the formatting short cuts of format_variant against the library calls they stand in for
+// (`malva-geno format-selftest`, run by tests/test_host_cpu.py): std::to_string for integers, "%g" for QUAL.
+int format_selftest_main() {
+  Options o;
+  uint64_t bad = 0, n = 0;
+  auto check_int = [&](long long x) {
+    std::string a;
+    append_int(a, x);
+    ++n;
+    if (a != std::to_string(x)) ++bad;
+  };
+  for (long long x = -70000; x <= 70000; ++x) check_int(x);
+  for (int sh = 0; sh < 63; ++sh)
+    for (long long d = -2; d <= 2; ++d) check_int((1ll << sh) + d), check_int(-((1ll << sh) + d));
+  check_int(INT32_MAX), check_int(INT32_MIN), check_int(INT64_MAX), check_int(INT64_MIN + 1);
+  auto check_qual = [&](float q) {
+    mh::Variant v;
+    v.seq_name = "1", v.idx = ".", v.ref_sub = "A", v.alts = {"C"}, v.quality = q;
+    std::string line, want = "1\t1\t.\tA\tC\t";
+    const uint32_t cov[2] = {0, 0};
+    format_variant(v, cov, 0, 1, 0, 0, nullptr, o, line);
+    char num[64];
+    snprintf(num, sizeof(num), "%g", (double)q);
+    want += std::isnan(q) ? "." : num;
+    want += "\tPASS\t.\tGT:GQ\t0/0:0\n";
+    ++n;
+    if (line != want) {
+      if (++bad <= 5) fprintf(stderr, "QUAL %a: got %s", (double)q, line.c_str());
+    }
+  };
+  for (int i = -2000; i <= 2000000; ++i) check_qual((float)i);
+  for (int i = 0; i <= 200000; ++i) check_qual((float)i * 0.25f), check_qual((float)i * 0.01f), check_qual(-(float)i * 0.5f);
+  for (float q : {0.0f, -0.0f, 999999.0f, 999999.5f, 1e6f, 1e7f, 1e-5f, 3.4e38f, -3.4e38f, INFINITY, -INFINITY, NAN, 16777216.0f, 1e-40f})
+    check_qual(q);
+  uint32_t r = 12345;
+  for (int i = 0; i < 2000000; ++i) {  // arbitrary bit patterns
+    r = r * 1664525u + 1013904223u;
+    float q;
+    memcpy(&q, &r, 4);
+    check_qual(q);
+  }
+  printf("format-selftest: %llu cases, %llu differ\n", (unsigned long long)n, (unsigned long long)bad);
+  return bad ? 1 : 0;
 }
 
 int call_main(int argc, char **argv) {
@@ -1122,6 +1190,7 @@ int main(int argc, char **argv) {
     if (strcmp(argv[1], "signatures") == 0) return signatures_main(argc - 1, argv + 1);
     if (strcmp(argv[1], "count") == 0) return count_main(argc - 1, argv + 1);
     if (strcmp(argv[1], "kmc-dump") == 0) return kmc_dump_main(argc - 1, argv + 1);
+    if (strcmp(argv[1], "format-selftest") == 0) return format_selftest_main();
   } catch (const GpuError &e) {
     std::cerr << "malva-geno: GPU error: " << e.what() << " (there is no CPU fallback)" << std::endl;
     return 2;

@@ -476,3 +476,10 @@ def test_sars_cov2_panel_fast_and_general_decode_agree(cli):
     slow = _signatures_text(cli, fa, vcf, ["-1"], general=True)
     assert fast.returncode == 0 and slow.returncode == 0
     assert fast.stdout == slow.stdout and fast.stdout.count("\n") > 10_000
+
+
+def test_format_short_cuts_equal_the_library_calls(cli):
+    """the integer and QUAL formatting of the output stage (malva_geno.cpp format_variant) against std::to_string and
+    "%g" over 4.7e6 values (whole numbers, fractions, -0, inf, nan, denormals, random bit patterns)"""
+    r = subprocess.run([cli, "format-selftest"], capture_output=True, text=True)
+    assert r.returncode == 0 and " 0 differ" in r.stdout, r.stdout + r.stderr
