@@ -131,19 +131,27 @@ struct SignatureCsr {
     return s;
   }
   void add_kmer(const char *s, size_t len, int k, bool is_ref) {
+    // A/C/G/T -> 0..3, anything else -> 0x80; no branch per symbol (the bases are as good as random)
+    static const struct Codes {
+      uint8_t of[256];
+      Codes() {
+        memset(of, 0x80, sizeof of);
+        of[(unsigned char)'A'] = 0, of[(unsigned char)'C'] = 1, of[(unsigned char)'G'] = 2, of[(unsigned char)'T'] = 3;
+      }
+    } codes;
     uint64_t lo = 0, hi = 0;
     bool regular = (int)len == k;
-    for (size_t j = 0; regular && j < len; ++j) {
-      uint64_t c;
-      switch (s[j]) {
-        case 'A': c = 0; break;
-        case 'C': c = 1; break;
-        case 'G': c = 2; break;
-        case 'T': c = 3; break;
-        default: regular = false; c = 0;
+    if (regular) {
+      unsigned __int128 acc = 0;
+      unsigned bad = 0;
+      for (size_t j = 0; j < len; ++j) {
+        const unsigned c = codes.of[(unsigned char)s[j]];
+        bad |= c;
+        acc = (acc << 2) | (c & 3u);
       }
-      hi = (hi << 2) | (lo >> 62);
-      lo = (lo << 2) | c;
+      regular = (bad & 0x80u) == 0;
+      lo = regular ? (uint64_t)acc : 0;
+      hi = regular ? (uint64_t)(acc >> 64) : 0;
     }
     if (!regular) {
       lo = irr_kmer.size();
@@ -203,6 +211,85 @@ inline bool variants_near(const Variant &a, const Variant &b, int k, int sum_to_
   return lhs >= (float)b.ref_pos;
 }
 
+// A chain of variant indices (block-local).  Chains are built and thrown away by the million; up to 14 members live
+// inside the object, longer ones (dense panels) move to the heap.
+class Chain {
+ public:
+  Chain() = default;
+  explicit Chain(int first) { push_back(first); }
+  Chain(const Chain &o) { assign(o.p_, o.n_); }
+  Chain(Chain &&o) noexcept { take(o); }
+  Chain &operator=(const Chain &o) {
+    if (this != &o) assign(o.p_, o.n_);
+    return *this;
+  }
+  Chain &operator=(Chain &&o) noexcept {
+    if (this != &o) {
+      release();
+      take(o);
+    }
+    return *this;
+  }
+  ~Chain() { release(); }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  int operator[](size_t i) const { return p_[i]; }
+  int back() const { return p_[n_ - 1]; }
+  const int *data() const { return p_; }
+  const int *begin() const { return p_; }
+  const int *end() const { return p_ + n_; }
+  void clear() { n_ = 0; }
+  void pop_back() { --n_; }
+  void push_back(int v) {
+    if (n_ == cap_) grow(2 * cap_);
+    p_[n_++] = v;
+  }
+  void append(const int *first, size_t n) {
+    if (n_ + n > cap_) grow(std::max<size_t>(2 * cap_, n_ + n));
+    memcpy(p_ + n_, first, n * sizeof(int));
+    n_ += (uint32_t)n;
+  }
+  void append_reversed(const Chain &o) {
+    for (size_t i = o.n_; i > 0; --i) push_back(o.p_[i - 1]);
+  }
+
+ private:
+  static constexpr uint32_t INLINE = 14;
+  void assign(const int *src, uint32_t n) {
+    n_ = 0;
+    append(src, n);
+  }
+  void take(Chain &o) {
+    if (o.p_ == o.inl_) {
+      p_ = inl_;
+      cap_ = INLINE;
+      memcpy(inl_, o.inl_, o.n_ * sizeof(int));
+    } else {
+      p_ = o.p_;
+      cap_ = o.cap_;
+      o.p_ = o.inl_;
+      o.cap_ = INLINE;
+    }
+    n_ = o.n_;
+    o.n_ = 0;
+  }
+  void release() {
+    if (p_ != inl_) delete[] p_;
+    p_ = inl_;
+    cap_ = INLINE;
+  }
+  void grow(size_t cap) {
+    int *q = new int[cap];
+    memcpy(q, p_, n_ * sizeof(int));
+    if (p_ != inl_) delete[] p_;
+    p_ = q;
+    cap_ = (uint32_t)cap;
+  }
+  int inl_[INLINE];
+  int *p_ = inl_;
+  uint32_t n_ = 0, cap_ = INLINE;
+};
+
 // A var_block (var_block.hpp:40-90) as a VIEW: n consecutive variants of the batch they were decoded into.  Grouping
 // a batch into blocks moves no record and allocates nothing per block.
 class VarBlock {
@@ -226,6 +313,8 @@ class VarBlock {
     std::string text, kmer;                // signature text of the current variant; the k-mer being built
     std::vector<SigRec> sigs;              // its signatures
     std::vector<std::string> between;      // reference text between the members of the current chain
+    std::vector<Chain> left, right, forks, full;  // the chains around the current variant
+    std::vector<int> reach_l, reach_r, fork_reach;
   };
 
   // Signatures of the variants [begin, end) of the block, appended to `out`: one variant entry per block member, in
@@ -266,7 +355,6 @@ class VarBlock {
   }
 
  private:
-  using Chain = std::vector<int>;
   // one index per distinct row, in order of first occurrence.  Thousands of panel samples share a handful of
   // genotype patterns, so this is a small open-addressing hash set keyed by row content, not a sort.
   static void distinct_rows(const std::vector<uint16_t> &rows, size_t n_rows, size_t width, std::vector<uint32_t> &order,
@@ -313,10 +401,10 @@ class VarBlock {
 
   // var_block.hpp:436-525 (dir = +1) and 534-624 (dir = -1): every chain of mutually compatible neighbours that
   // stays within reach of the mid variant.  Pairs are always tested in genomic order.
-  std::vector<Chain> side_chains(int i, int dir) const {
+  void side_chains(int i, int dir, std::vector<Chain> &chains, std::vector<int> &reach, Scratch &sc) const {
     const Variant &mid = vars_[(size_t)i];
-    std::vector<Chain> chains;
-    std::vector<int> reach;  // bases the chain's deletions add to the reach of the mid variant
+    chains.clear();
+    reach.clear();  // bases the chain's deletions add to the reach of the mid variant
     auto ovl = [&](int near_mid, int far) {
       return dir > 0 ? overlapping(vars_[(size_t)near_mid], vars_[(size_t)far])
                      : overlapping(vars_[(size_t)far], vars_[(size_t)near_mid]);
@@ -330,7 +418,7 @@ class VarBlock {
       if (!vars_[(size_t)j].is_present || ovl(i, j)) continue;
       if (chains.empty()) {
         if (in_reach(j, 0)) {
-          chains.push_back(Chain{j});
+          chains.emplace_back(j);
           reach.push_back(gain(j));
         }
         continue;
@@ -346,8 +434,10 @@ class VarBlock {
       }
       if (compatible) continue;
       // it clashes with every tail: fork each chain, cut back to the part it is compatible with
-      std::vector<Chain> forks;
-      std::vector<int> fork_reach;
+      std::vector<Chain> &forks = sc.forks;
+      std::vector<int> &fork_reach = sc.fork_reach;
+      forks.clear();
+      fork_reach.clear();
       for (size_t c = 0; c < chains.size(); ++c) {
         Chain f = chains[c];
         int r = reach[c];
@@ -367,21 +457,27 @@ class VarBlock {
         reach.push_back(fork_reach[c]);
       }
     }
-    return chains;
   }
 
-  // var_block.hpp:631-677: left chains (reversed into genomic order) x right chains around the mid variant
-  std::vector<Chain> full_chains(int i) const {
-    if (n_ == 1) return std::vector<Chain>{Chain{i}};  // (a block of one: nothing to chain)
-    std::vector<Chain> right = side_chains(i, +1), left = side_chains(i, -1), out;
-    if (left.empty()) left.push_back(Chain{});
-    if (right.empty()) right.push_back(Chain{});
-    for (const Chain &l : left)
-      for (const Chain &r : right) {
-        Chain c(l.rbegin(), l.rend());
+  // var_block.hpp:631-677: left chains (reversed into genomic order) x right chains around the mid variant, in sc.full
+  const std::vector<Chain> &full_chains(int i, Scratch &sc) const {
+    std::vector<Chain> &out = sc.full;
+    out.clear();
+    if (n_ == 1) {  // (a block of one: nothing to chain)
+      out.emplace_back(i);
+      return out;
+    }
+    side_chains(i, +1, sc.right, sc.reach_r, sc);
+    side_chains(i, -1, sc.left, sc.reach_l, sc);
+    if (sc.left.empty()) sc.left.emplace_back();
+    if (sc.right.empty()) sc.right.emplace_back();
+    for (const Chain &l : sc.left)
+      for (const Chain &r : sc.right) {
+        out.emplace_back();
+        Chain &c = out.back();
+        c.append_reversed(l);
         c.push_back(i);
-        c.insert(c.end(), r.begin(), r.end());
-        out.push_back(std::move(c));
+        c.append(r.data(), r.size());
       }
     return out;
   }
@@ -551,7 +647,7 @@ class VarBlock {
       chain_signatures(&self, 1, vi, reference, sc);
       return;
     }
-    for (const Chain &chain : full_chains(vi)) {
+    for (const Chain &chain : full_chains(vi, sc)) {
       haplotypes(chain, vi, haploid, sc);
       chain_signatures(chain.data(), chain.size(), vi, reference, sc);
     }
