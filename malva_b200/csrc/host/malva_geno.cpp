@@ -717,7 +717,8 @@ int format_selftest_main() {
   check_int(INT32_MAX), check_int(INT32_MIN), check_int(INT64_MAX), check_int(INT64_MIN + 1);
   auto check_qual = [&](float q) {
     mh::Variant v;
-    v.seq_name = "1", v.idx = ".", v.ref_sub = "A", v.alts = {"C"}, v.quality = q;
+    v.seq_name = "1", v.idx = ".", v.ref_sub = "A", v.quality = q;
+    v.alts.push_back("C");
     std::string line, want = "1\t1\t.\tA\tC\t";
     const uint32_t cov[2] = {0, 0};
     format_variant(v, cov, 0, 1, 0, 0, nullptr, o, line);
