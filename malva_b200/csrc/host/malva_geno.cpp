@@ -304,8 +304,9 @@ class BlockStream {
     // grouping (main.cpp:330-362): `open` = first record of the block being built, `w` = where the next kept record goes
     size_t w = n_carry, open = 0;
     bool have_open = n_carry > 0;
-    auto flush = [&](size_t end) {
-      out.contigs.push_back(std::make_unique<std::string>(last_seq_name_));
+    auto flush = [&](size_t end) {  // (one name object per run of blocks on the same contig, not one per block)
+      if (out.contigs.empty() || *out.contigs.back() != last_seq_name_)
+        out.contigs.push_back(std::make_unique<std::string>(last_seq_name_));
       out.blocks.emplace_back((int)o_.k, vars.data() + open, end - open, out.contigs.back().get());
     };
     for (size_t r = n_carry; r < vars.size(); ++r) {
