@@ -239,26 +239,40 @@ struct SignatureCsr {
     }
     return s;
   }
+  // 8 symbols (first one in the low byte of `w`) -> their 2-bit codes, first symbol most significant, in 16 bits;
+  // false if one of them is not A, C, G or T.  All eight at once: the code of a symbol is ((c >> 1) ^ (c >> 2)) & 3
+  // (A 0, C 1, G 2, T 3), the symbol a code stands for is rebuilt bit by bit and compared with what was read.
+  static bool pack8(uint64_t w, uint64_t &codes16) {
+    constexpr uint64_t ONES = 0x0101010101010101ull;
+    const uint64_t x = ((w >> 1) ^ (w >> 2)) & (3 * ONES);
+    const uint64_t c0 = x & ONES, c1 = (x >> 1) & ONES, both = c0 & c1;
+    const uint64_t expect = (0x40 * ONES) | (both ^ ONES) | ((c0 ^ c1) << 1) | (c1 << 2) | (both << 4);
+    uint64_t r = __builtin_bswap64(x);  // first symbol in the high byte
+    r = (r | (r >> 6)) & 0x000F000F000F000Full;
+    r = (r | (r >> 12)) & 0x000000FF000000FFull;
+    r = (r | (r >> 24)) & 0xFFFFull;
+    codes16 = r;
+    return expect == w;
+  }
   void add_kmer(const char *s, size_t len, int k, bool is_ref) {
-    // A/C/G/T -> 0..3, anything else -> 0x80; no branch per symbol (the bases are as good as random)
-    static const struct Codes {
-      uint8_t of[256];
-      Codes() {
-        memset(of, 0x80, sizeof of);
-        of[(unsigned char)'A'] = 0, of[(unsigned char)'C'] = 1, of[(unsigned char)'G'] = 2, of[(unsigned char)'T'] = 3;
-      }
-    } codes;
     uint64_t lo = 0, hi = 0;
-    bool regular = (int)len == k;
+    bool regular = (int)len == k && len <= 64;
     if (regular) {
       unsigned __int128 acc = 0;
-      unsigned bad = 0;
-      for (size_t j = 0; j < len; ++j) {
-        const unsigned c = codes.of[(unsigned char)s[j]];
-        bad |= c;
-        acc = (acc << 2) | (c & 3u);
+      size_t j = 0;
+      uint64_t w, c;
+      for (; j + 8 <= len; j += 8) {
+        memcpy(&w, s + j, 8);
+        regular &= pack8(w, c);
+        acc = (acc << 16) | c;
       }
-      regular = (bad & 0x80u) == 0;
+      if (j < len) {  // the last 1..7 symbols, padded with 'A's that are shifted out again
+        const size_t rest = len - j;
+        w = 0x4141414141414141ull;
+        memcpy(&w, s + j, rest);
+        regular &= pack8(w, c);
+        acc = (acc << (2 * rest)) | (c >> (16 - 2 * rest));
+      }
       lo = regular ? (uint64_t)acc : 0;
       hi = regular ? (uint64_t)(acc >> 64) : 0;
     }
