@@ -249,6 +249,56 @@ void gpu(int rc, const char *what) {
   if (rc != MG_OK) throw GpuError(std::string(what) + ": " + mg_last_error());
 }
 
+// A bounded hand-over between two stages of the batch pipeline.
+template <class T>
+class Channel {
+ public:
+  explicit Channel(size_t cap) : cap_(cap) {}
+  void push(T &&v) {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+    if (closed_) return;
+    q_.push_back(std::move(v));
+    cv_.notify_all();
+  }
+  bool pop(T &out) {  // false once the channel is closed and drained
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    out = std::move(q_.front());
+    q_.pop_front();
+    cv_.notify_all();
+    return true;
+  }
+  bool try_pop(T &out) {  // what is there right now, without waiting
+    std::lock_guard<std::mutex> l(m_);
+    if (q_.empty()) return false;
+    out = std::move(q_.front());
+    q_.pop_front();
+    cv_.notify_all();
+    return true;
+  }
+  bool try_push(T &&v) {  // dropped (false) if the channel is full or closed
+    std::lock_guard<std::mutex> l(m_);
+    if (closed_ || q_.size() >= cap_) return false;
+    q_.push_back(std::move(v));
+    cv_.notify_all();
+    return true;
+  }
+  void close() {
+    std::lock_guard<std::mutex> l(m_);
+    closed_ = true;
+    cv_.notify_all();
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
+  size_t cap_;
+  bool closed_ = false;
+};
+
 // ---- the VCF loop of index_main / call_main (main.cpp:309-370, 522-579) as a stream of batches of blocks ----
 // A batch owns the records it was decoded into (`arena`, in file order, skipped records squeezed out) and the contig
 // names its blocks refer to; the blocks are views into the arena.
@@ -273,6 +323,13 @@ class BlockStream {
     samples_code = reader_.header.set_samples(o.samples);
     freq_declared_ = reader_.header.has_info(o.freq_key);
   }
+  ~BlockStream() {
+    text_.close();
+    spare_.close();
+    if (reader_thread_.joinable()) reader_thread_.join();
+  }
+  BlockStream(const BlockStream &) = delete;
+  BlockStream &operator=(const BlockStream &) = delete;
   int samples_code = 0;
   double t_read = 0, t_decode = 0, t_group = 0;  // ms spent reading lines / decoding records / grouping blocks
   std::vector<std::string> used_seq_names;  // main.cpp:304-306, 323-328, 352-356
@@ -283,11 +340,16 @@ class BlockStream {
   bool next_batch(BlockBatch &out, size_t max_lines) {
     out.clear();
     if (done_) return false;
-    // a block of whole lines (no per-line allocation), decoded in parallel straight into the batch's arena, behind
-    // the records of the block that was still open when the previous batch ended
+    // a block of whole lines (no per-line allocation; read ahead by the reader thread), decoded in parallel straight
+    // into the batch's arena, behind the records of the block that was still open when the previous batch ended
+    if (!reader_thread_.joinable()) start_reader(max_lines);
+    std::unique_ptr<TextBlock> tb;
+    if (!text_.pop(tb)) throw std::runtime_error("VCF reader thread ended early");
+    if (tb->err) std::rethrow_exception(tb->err);
+    const bool more = tb->more;
+    const std::vector<mh::BlockLineReader::View> &lines_ = tb->lines;
+    t_read += tb->read_ms;
     Stopwatch sw;
-    const bool more = reader_.next_lines(store_, lines_, max_lines, 12u << 20);
-    t_read += sw.lap();
     std::vector<mh::Variant> &vars = out.arena;
     const size_t n_carry = carry_.size();
     vars.resize(n_carry + lines_.size());
@@ -301,6 +363,8 @@ class BlockStream {
         vars[n_carry + i] = mh::parse_record(lines_[i].b, lines_[i].e, reader_.header, o_.freq_key, o_.uniform, freq_declared_);
     });
     t_decode += sw.lap();
+    tb->lines.clear();
+    spare_.try_push(std::move(tb));  // the text is not needed any more: its buffers go back to the reader
     // grouping (main.cpp:330-362): `open` = first record of the block being built, `w` = where the next kept record goes
     size_t w = n_carry, open = 0;
     bool have_open = n_carry > 0;
@@ -353,8 +417,37 @@ class BlockStream {
   mh::VcfReader reader_;
   std::vector<mh::Variant> carry_;  // the records of the block that is still open between two batches
   std::string last_seq_name_;
-  std::vector<char> store_;
-  std::vector<mh::BlockLineReader::View> lines_;
+
+  // The file is read (and inflated, and cut into lines) by a thread of its own, one block of text ahead of the
+  // decode: reading a block is serial work of the same order as decoding it on all threads.
+  struct TextBlock {
+    std::vector<char> store;
+    std::vector<mh::BlockLineReader::View> lines;
+    bool more = false;
+    double read_ms = 0;
+    std::exception_ptr err;
+  };
+  void start_reader(size_t max_lines) {
+    reader_thread_ = std::thread([this, max_lines] {
+      while (true) {
+        std::unique_ptr<TextBlock> tb;
+        if (!spare_.try_pop(tb)) tb = std::make_unique<TextBlock>();
+        Stopwatch sw;
+        try {
+          tb->more = reader_.next_lines(tb->store, tb->lines, max_lines, 12u << 20);
+        } catch (...) {
+          tb->err = std::current_exception();
+          tb->more = false;
+        }
+        tb->read_ms = sw.lap();
+        const bool last = !tb->more;
+        text_.push(std::move(tb));
+        if (last) break;
+      }
+    });
+  }
+  Channel<std::unique_ptr<TextBlock>> text_{1}, spare_{4};
+  std::thread reader_thread_;
 };
 
 // Reads and decodes batch i+1 on a background thread while batch i is enumerated, sent to the device and printed.
@@ -419,41 +512,6 @@ void enumerate_batch(const std::vector<mh::VarBlock> &blocks, std::map<std::stri
   });
   mh::SignatureCsr::concat(parts, out, [&](size_t n, const std::function<void(size_t)> &fn) { parallel_for(n, o.threads, fn); });
 }
-
-// A bounded hand-over between two stages of the batch pipeline.
-template <class T>
-class Channel {
- public:
-  explicit Channel(size_t cap) : cap_(cap) {}
-  void push(T &&v) {
-    std::unique_lock<std::mutex> l(m_);
-    cv_.wait(l, [&] { return q_.size() < cap_ || closed_; });
-    if (closed_) return;
-    q_.push_back(std::move(v));
-    cv_.notify_all();
-  }
-  bool pop(T &out) {  // false once the channel is closed and drained
-    std::unique_lock<std::mutex> l(m_);
-    cv_.wait(l, [&] { return !q_.empty() || closed_; });
-    if (q_.empty()) return false;
-    out = std::move(q_.front());
-    q_.pop_front();
-    cv_.notify_all();
-    return true;
-  }
-  void close() {
-    std::lock_guard<std::mutex> l(m_);
-    closed_ = true;
-    cv_.notify_all();
-  }
-
- private:
-  std::mutex m_;
-  std::condition_variable cv_;
-  std::deque<T> q_;
-  size_t cap_;
-  bool closed_ = false;
-};
 
 // one batch on its way through the pipeline
 struct Batch {
@@ -958,9 +1016,10 @@ int signatures_main(int argc, char **argv) {
   const bool quiet = getenv("MALVA_SIGNATURES_QUIET") != nullptr;  // (timing runs: enumerate, print nothing)
   Stopwatch sw;
   double t_batch = 0, t_enum = 0;
+  BatchPrefetcher ahead(stream, LINES_PER_BATCH);
   while (true) {
     sw.lap();
-    const bool more = stream.next_batch(batch, LINES_PER_BATCH);
+    const bool more = ahead.next(batch);  // (decoded one batch ahead, like in index / call)
     t_batch += sw.lap();
     if (!more) {
       if (o.trace)
