@@ -435,7 +435,6 @@ class VarBlock {
     size_t n_haps = 0;
     std::string text, kmer;                // signature text of the current variant; the k-mer being built
     std::vector<SigRec> sigs;              // its signatures
-    std::vector<std::string> between;      // reference text between the members of the current chain
     std::vector<Chain> left, right, forks, full;  // the chains around the current variant
     std::vector<int> reach_l, reach_r, fork_reach;
   };
@@ -741,11 +740,6 @@ class VarBlock {
     return true;
   }
 
-  static void append_clamped(std::string &dst, const std::string &s, long pos, long len) {
-    if (len <= 0 || pos < 0 || pos >= (long)s.size()) return;  // (the reference would throw on pos > size)
-    dst.append(s, (size_t)pos, (size_t)len);
-  }
-
   // A block of one variant (the common case away from dense regions): the chain is the variant itself and its
   // haplotypes are simply the alleles somebody carries -- the reference allele if some sample has no entry, h1 (and
   // h2 unless haploid) of every entry; phasing cannot matter with a single site.  Same set as haplotypes() gives.
@@ -776,73 +770,88 @@ class VarBlock {
     }
   }
 
-  // the signatures of variant vi within one chain, one per haplotype in sc.haps (var_block.hpp:120-216)
-  void chain_signatures(const int *chain_p, size_t chain_n, int vi, const std::string &reference, Scratch &sc) const {
+  // the signatures of variant vi within one chain, one per haplotype in sc.haps (var_block.hpp:120-216).  The text of
+  // a haplotype -- alleles of the members with the reference between them -- is put together with plain copies in
+  // sc.kmer, then extended with reference text or cut on either side straight into sc.text.
+  void chain_signatures(const int *chain, size_t chain_n, int vi, const std::string &reference, Scratch &sc) const {
     const Variant &v = vars_[(size_t)vi];
-    struct ChainView {
-      const int *p;
+    struct Piece {  // a stretch of the reference, clamped like std::string::append(str, pos, len)
+      const char *p;
       size_t n;
-      size_t size() const { return n; }
-      int operator[](size_t i) const { return p[i]; }
-      int front() const { return p[0]; }
-      int back() const { return p[n - 1]; }
-    } chain{chain_p, chain_n};
-    {
-      // reference text between consecutive members of the chain (var_block.hpp:682-702)
-      if (sc.between.size() < chain.size()) sc.between.resize(chain.size());
-      size_t mid_slot = 0, n_between = 0;
-      for (size_t m = 0; m < chain.size(); ++m) {
-        if (chain[m] == vi) mid_slot = m;
-        if (m == 0) continue;
-        const Variant &prev = vars_[(size_t)chain[m - 1]], &cur = vars_[(size_t)chain[m]];
-        std::string &gap = sc.between[n_between++];
-        gap.clear();
-        append_clamped(gap, reference, (long)prev.ref_pos + prev.ref_size, (long)cur.ref_pos - (prev.ref_pos + prev.ref_size));
-      }
-      for (size_t hi = 0; hi < sc.n_haps; ++hi) {
-        const uint16_t *h = sc.haps.data() + hi * chain.size();
-        const int mid_id = h[mid_slot];
-        const std::string &mid_allele = v.allele(mid_id);
-        SigRec rec{(uint32_t)mid_id, (uint32_t)sc.text.size(), 0, 0};
-        if (chain.size() == 1 && (int)mid_allele.size() >= k_) {
-          // an allele at least k long: every k-mer inside the allele itself (var_block.hpp:130-144)
-          for (size_t p = 0; p + (size_t)k_ <= mid_allele.size(); ++p) {
-            sc.text.append(mid_allele, p, (size_t)k_);
-            ++rec.n_kmers;
-          }
-        } else {
-          std::string &kmer = sc.kmer;
-          kmer.clear();
-          int mid_pos = 0;
-          for (size_t m = 0; m < chain.size(); ++m) {
-            if (m == mid_slot) mid_pos = (int)kmer.size();
-            kmer += vars_[(size_t)chain[m]].allele(h[m]);
-            if (m < n_between) kmer += sc.between[m];
-          }
-          const int first_part = mid_pos + (int)mid_allele.size() / 2;
-          const int second_part = (int)kmer.size() - first_part;
-          const int missing_prefix = k_ / 2 - first_part;
-          const int missing_suffix = (int)std::ceil((float)k_ / 2) - second_part;
-          // extend with reference text / cut, left then right; the result goes straight into sc.text
-          if (missing_prefix >= 0) {
-            const Variant &first = vars_[(size_t)chain.front()];
-            append_clamped(sc.text, reference, (long)first.ref_pos - missing_prefix, missing_prefix);
-          } else {
-            kmer.erase(0, std::min<size_t>(kmer.size(), (size_t)(-missing_prefix)));
-          }
-          if (missing_suffix >= 0) {
-            sc.text += kmer;
-            const Variant &last = vars_[(size_t)chain.back()];
-            append_clamped(sc.text, reference, (long)last.ref_pos + last.ref_size, missing_suffix);
-          } else {
-            const size_t cut = std::min<size_t>(kmer.size(), (size_t)(-missing_suffix));
-            sc.text.append(kmer, 0, kmer.size() - cut);
-          }
-          rec.n_kmers = 1;
+    };
+    auto ref_piece = [&](long pos, long len) -> Piece {
+      if (len <= 0 || pos < 0 || pos >= (long)reference.size()) return Piece{nullptr, 0};  // (the reference would throw on pos > size)
+      return Piece{reference.data() + pos, std::min<size_t>((size_t)len, reference.size() - (size_t)pos)};
+    };
+    // reference text between consecutive members of the chain (var_block.hpp:682-702)
+    Piece between_inl[16];
+    std::vector<Piece> between_heap;
+    Piece *between = between_inl;
+    if (chain_n > 16) {
+      between_heap.resize(chain_n);
+      between = between_heap.data();
+    }
+    size_t mid_slot = 0, room = 0;
+    for (size_t m = 0; m < chain_n; ++m) {
+      const Variant &cur = vars_[(size_t)chain[m]];
+      if (chain[m] == vi) mid_slot = m;
+      room += (size_t)std::max(cur.max_size, cur.ref_size);
+      if (m == 0) continue;
+      const Variant &prev = vars_[(size_t)chain[m - 1]];
+      between[m - 1] = ref_piece((long)prev.ref_pos + prev.ref_size, (long)cur.ref_pos - (prev.ref_pos + prev.ref_size));
+      room += between[m - 1].n;
+    }
+    if (sc.kmer.size() < room) sc.kmer.resize(room);
+    char *const hap = &sc.kmer[0];
+    const Variant &first = vars_[(size_t)chain[0]], &last = vars_[(size_t)chain[chain_n - 1]];
+    for (size_t hi = 0; hi < sc.n_haps; ++hi) {
+      const uint16_t *h = sc.haps.data() + hi * chain_n;
+      const int mid_id = h[mid_slot];
+      const std::string &mid_allele = v.allele(mid_id);
+      SigRec rec{(uint32_t)mid_id, (uint32_t)sc.text.size(), 0, 0};
+      if (chain_n == 1 && (int)mid_allele.size() >= k_) {
+        // an allele at least k long: every k-mer inside the allele itself (var_block.hpp:130-144)
+        for (size_t p = 0; p + (size_t)k_ <= mid_allele.size(); ++p) {
+          sc.text.append(mid_allele, p, (size_t)k_);
+          ++rec.n_kmers;
         }
-        rec.text_len = (uint32_t)(sc.text.size() - rec.text_off);
-        sc.sigs.push_back(rec);
+      } else {
+        size_t len = 0;
+        int mid_pos = 0;
+        for (size_t m = 0; m < chain_n; ++m) {
+          if (m == mid_slot) mid_pos = (int)len;
+          const std::string &al = vars_[(size_t)chain[m]].allele(h[m]);
+          memcpy(hap + len, al.data(), al.size());
+          len += al.size();
+          if (m + 1 < chain_n && between[m].n) {
+            memcpy(hap + len, between[m].p, between[m].n);
+            len += between[m].n;
+          }
+        }
+        const int first_part = mid_pos + (int)mid_allele.size() / 2;
+        const int second_part = (int)len - first_part;
+        const int missing_prefix = k_ / 2 - first_part;
+        const int missing_suffix = (int)std::ceil((float)k_ / 2) - second_part;
+        // extend with reference text / cut, left then right
+        size_t from = 0;
+        if (missing_prefix >= 0) {
+          const Piece ext = ref_piece((long)first.ref_pos - missing_prefix, missing_prefix);
+          if (ext.n) sc.text.append(ext.p, ext.n);
+        } else {
+          from = std::min<size_t>(len, (size_t)(-missing_prefix));
+        }
+        if (missing_suffix >= 0) {
+          sc.text.append(hap + from, len - from);
+          const Piece ext = ref_piece((long)last.ref_pos + last.ref_size, missing_suffix);
+          if (ext.n) sc.text.append(ext.p, ext.n);
+        } else {
+          const size_t body = len - from, cut = std::min<size_t>(body, (size_t)(-missing_suffix));
+          sc.text.append(hap + from, body - cut);
+        }
+        rec.n_kmers = 1;
       }
+      rec.text_len = (uint32_t)(sc.text.size() - rec.text_off);
+      sc.sigs.push_back(rec);
     }
   }
 
