@@ -338,8 +338,12 @@ class BlockStream {
 
   // up to `max_lines` more records; the blocks they complete go to `out`.  false when nothing is left.
   bool next_batch(BlockBatch &out, size_t max_lines) {
-    out.clear();
-    if (done_) return false;
+    out.blocks.clear();  // (the records of a recycled batch stay where they are: every one in use is assigned below)
+    out.contigs.clear();
+    if (done_) {
+      out.arena.clear();
+      return false;
+    }
     // a block of whole lines (no per-line allocation; read ahead by the reader thread), decoded in parallel straight
     // into the batch's arena, behind the records of the block that was still open when the previous batch ended
     if (!reader_thread_.joinable()) start_reader(max_lines);
@@ -454,27 +458,25 @@ class BlockStream {
 class BatchPrefetcher {
  public:
   BatchPrefetcher(BlockStream &stream, size_t max_lines) : stream_(stream), max_lines_(max_lines) { launch(); }
-  // false when the VCF is exhausted; otherwise `out` holds the next batch of flushed blocks (possibly empty)
+  // false when the VCF is exhausted; otherwise `out` holds the next batch of flushed blocks (possibly empty).  What
+  // `out` held before is taken in exchange and filled next: a batch that has been through the pipeline keeps its
+  // buffers (25 MB of records), so in the steady state no batch touches fresh pages.
   bool next(BlockBatch &out) {
     if (!pending_.valid()) return false;
-    auto got = pending_.get();
-    if (!got.first) return false;
-    out = std::move(got.second);
+    if (!pending_.get()) return false;
+    std::swap(out, filling_);
     launch();
     return true;
   }
 
  private:
   void launch() {
-    pending_ = std::async(std::launch::async, [this] {
-      BlockBatch b;
-      bool ok = stream_.next_batch(b, max_lines_);
-      return std::make_pair(ok, std::move(b));
-    });
+    pending_ = std::async(std::launch::async, [this] { return stream_.next_batch(filling_, max_lines_); });
   }
   BlockStream &stream_;
   size_t max_lines_;
-  std::future<std::pair<bool, BlockBatch>> pending_;
+  BlockBatch filling_;
+  std::future<bool> pending_;
 };
 
 // signatures of a batch of blocks: tasks of ~64 consecutive variants (a block of thousands of variants is split,
@@ -533,7 +535,8 @@ class EnumeratedBatches {
       : out_(2), th_([this, &src, &refs, &o] {
           try {
             while (true) {
-              auto b = std::make_unique<Batch>();
+              std::unique_ptr<Batch> b;
+              if (!spare_.try_pop(b)) b = std::make_unique<Batch>();
               Stopwatch sw;
               if (!src.next(b->vb)) break;
               b->t_parse = sw.lap();
@@ -551,13 +554,17 @@ class EnumeratedBatches {
     if (th_.joinable()) th_.join();
   }
   bool next(std::unique_ptr<Batch> &b) { return out_.pop(b); }
+  // a batch the last stage is done with: its buffers serve a later batch (no allocation, no page faults)
+  void recycle(std::unique_ptr<Batch> &&b) {
+    if (b) spare_.try_push(std::move(b));
+  }
   void join() {
     if (th_.joinable()) th_.join();
     if (err_) std::rethrow_exception(err_);
   }
 
  private:
-  Channel<std::unique_ptr<Batch>> out_;
+  Channel<std::unique_ptr<Batch>> out_, spare_{8};
   std::exception_ptr err_;
   std::thread th_;
 };
@@ -637,6 +644,7 @@ int index_main(int argc, char **argv) {
         fprintf(stderr, "[trace] index batch: %zu blocks, %llu k-mers (%llu irregular): read+decode wait %.1f ms, enumerate %.1f ms, device %.1f ms\n",
                 b->vb.blocks.size(), (unsigned long long)sg.n_kmers(), (unsigned long long)sg.n_irregular(), b->t_parse,
                 b->t_enum, sw.lap());
+      batches.recycle(std::move(b));
     }
     batches.join();
   }
@@ -927,10 +935,10 @@ int call_main(int argc, char **argv) {
               uint64_t n = sg.var_allele_off[i + 1] - sg.var_allele_off[i];
               b->lik_off[i + 1] = b->lik_off[i] + std::max<uint64_t>(n, o.haploid ? n : n * (n + 1) / 2);
             }
-            b->lik.resize(b->lik_off[nv]);
+            b->lik.assign(b->lik_off[nv], 0.0);
           }
-          b->cov.resize(sg.n_alleles());
-          b->n_gts.resize(nv), b->status.resize(nv), b->best.resize(nv), b->gq.resize(nv);
+          b->cov.assign(sg.n_alleles(), 0);  // (a recycled batch: nothing of its previous results may show through)
+          b->n_gts.assign(nv, 0), b->status.assign(nv, 0), b->best.assign(nv, 0), b->gq.assign(nv, 0);
           mg_packed_batch in = {nv,
                                 sg.var_allele_off.data(),
                                 sg.allele_sig_off.data(),
@@ -970,7 +978,10 @@ int call_main(int argc, char **argv) {
     sw.lap();
     const mh::SignatureCsr &sg = b->sigs;
     const uint64_t nv = sg.n_variants();
-    if (nv == 0) continue;
+    if (nv == 0) {
+      batches.recycle(std::move(b));
+      continue;
+    }
     order.clear();
     for (const auto &blk : b->vb.blocks)
       for (size_t i = 0; i < blk.size(); ++i) order.push_back(&blk[i]);
@@ -986,6 +997,7 @@ int call_main(int argc, char **argv) {
     if (o.trace)
       fprintf(stderr, "[trace] call batch: %llu variants, %llu k-mers: read+decode wait %.1f ms, enumerate %.1f ms, device %.1f ms, print %.1f ms\n",
               (unsigned long long)nv, (unsigned long long)sg.n_kmers(), b->t_parse, b->t_enum, b->t_dev, sw.lap());
+    batches.recycle(std::move(b));
   }
   device.join();
   if (dev_err) std::rethrow_exception(dev_err);
