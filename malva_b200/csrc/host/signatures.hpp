@@ -437,6 +437,9 @@ class VarBlock {
     std::vector<SigRec> sigs;              // its signatures
     std::vector<Chain> left, right, forks, full;  // the chains around the current variant
     std::vector<int> reach_l, reach_r, fork_reach;
+    std::vector<uint64_t> key1, key2;      // haplotypes_scatter: the two haplotypes of a sample, one member per byte
+    std::vector<uint8_t> flag;             //   bit 0: the sample has an entry at some member, bit 1: an unphased one
+    std::vector<uint32_t> touched;         //   the samples with bit 0 set
   };
 
   // Signatures of the variants [begin, end) of the block, appended to `out`: one variant entry per block member, in
@@ -611,7 +614,7 @@ class VarBlock {
   // row per sample that deviates from the default at some member, plus one all-reference row standing for every
   // other sample (whatever its phasing flags: with no heterozygous site it yields that one haplotype).
   void haplotypes(const Chain &chain, int central, bool haploid, Scratch &sc) const {
-    if (chain.size() <= 8 && haplotypes_small(chain, central, haploid, sc)) return;
+    if (chain.size() <= 8 && (haplotypes_scatter(chain, central, haploid, sc) || haplotypes_small(chain, central, haploid, sc))) return;
     const size_t n = chain.size(), W = 2 * n + 1;
     const uint32_t central_samples = (uint32_t)vars_[(size_t)central].n_samples();
     sc.cursor.assign(n, 0);
@@ -672,6 +675,89 @@ class VarBlock {
     for (size_t i = 0; i < sc.order.size(); ++i)
       memcpy(sc.haps.data() + i * n, sc.cand.data() + (size_t)sc.order[i] * n, n * sizeof(uint16_t));
     sc.n_haps = sc.order.size();
+  }
+
+  // haplotypes_small() without the merge, for chains whose members all default to PHASED reference genotypes (or in
+  // haploid mode, where phasing is not looked at): a sample without an entry at a member then simply carries allele 0
+  // there, so the members' sparse lists can be scattered into per-sample keys one list after the other -- work
+  // proportional to the entries, not to samples x members.  Same result as the merge; false (nothing written) when
+  // the chain does not qualify or something does not fit.
+  bool haplotypes_scatter(const Chain &chain, int central, bool haploid, Scratch &sc) const {
+    const size_t n = chain.size();
+    const uint32_t central_samples = (uint32_t)vars_[(size_t)central].n_samples();
+    if (!haploid)
+      for (size_t m = 0; m < n; ++m)
+        if (!vars_[(size_t)chain[m]].default_phased) return false;
+    if (sc.flag.size() < central_samples) {
+      sc.key1.resize(central_samples, 0);
+      sc.key2.resize(central_samples, 0);
+      sc.flag.resize(central_samples, 0);
+    }
+    sc.touched.clear();
+    bool fits = true;
+    for (size_t m = 0; m < n && fits; ++m)
+      for (const GtEntry &g : vars_[(size_t)chain[m]].gts) {
+        if (g.sample >= central_samples) break;  // (the reference walks the samples of the central variant)
+        if ((g.h1 | g.h2) > 255) {
+          fits = false;
+          break;
+        }
+        uint8_t &f = sc.flag[g.sample];
+        if (!f) sc.touched.push_back(g.sample);
+        f |= g.phased ? 1 : 3;
+        sc.key1[g.sample] |= (uint64_t)g.h1 << (8 * m);
+        sc.key2[g.sample] |= (uint64_t)(haploid ? g.h1 : g.h2) << (8 * m);
+      }
+    // the distinct keys: while there are few of them (the rule: 3-4 haplotypes among ~20 candidates) a candidate is
+    // compared with the ones kept so far; beyond that everything is kept and made distinct by sort + unique at the end
+    constexpr size_t MAX_KEYS = 512, FEW = 12;
+    uint64_t keys[MAX_KEYS];
+    size_t n_keys = 0;
+    bool distinct = true;  // no two of keys[0, n_keys) are equal
+    auto add_key = [&](uint64_t key) {  // false: no room
+      if (distinct) {
+        for (size_t i = 0; i < n_keys; ++i)
+          if (keys[i] == key) return true;
+        if (n_keys >= FEW) distinct = false;
+      }
+      if (n_keys >= MAX_KEYS) return false;
+      keys[n_keys++] = key;
+      return true;
+    };
+    for (uint32_t smp : sc.touched) {  // (every touched slot is cleared again, whatever happens)
+      const uint64_t k1 = sc.key1[smp], k2 = sc.key2[smp];
+      const bool ph = (sc.flag[smp] & 2) == 0;
+      sc.key1[smp] = sc.key2[smp] = 0;
+      sc.flag[smp] = 0;
+      if (!fits) continue;
+      if (haploid) {
+        fits = add_key(k1);
+      } else if (ph) {
+        fits = add_key(k1) && add_key(k2);
+      } else {  // unphased: every way of picking one of the two alleles at each heterozygous site
+        uint64_t diff = k1 ^ k2, het_mask[8];
+        size_t n_het = 0;
+        for (size_t m = 0; m < n; ++m)
+          if ((diff >> (8 * m)) & 0xFF) het_mask[n_het++] = 0xFFull << (8 * m);
+        for (uint64_t mask = 0; mask < (1ull << n_het) && fits; ++mask) {
+          uint64_t key = k1;
+          for (size_t b = 0; b < n_het; ++b)
+            if ((mask >> b) & 1) key = (key & ~het_mask[b]) | (k2 & het_mask[b]);
+          fits = add_key(key);
+        }
+      }
+    }
+    if (!fits) return false;
+    if (sc.touched.size() < central_samples && !add_key(0)) return false;  // samples at their default everywhere
+    if (!distinct) {
+      std::sort(keys, keys + n_keys);
+      n_keys = (size_t)(std::unique(keys, keys + n_keys) - keys);
+    }
+    sc.haps.resize(n_keys * n);
+    for (size_t i = 0; i < n_keys; ++i)
+      for (size_t m = 0; m < n; ++m) sc.haps[i * n + m] = (uint16_t)((keys[i] >> (8 * m)) & 0xFF);
+    sc.n_haps = n_keys;
+    return true;
   }
 
   // The same set of haplotypes for the common case -- a chain of at most 8 members whose allele ids all fit a byte:
