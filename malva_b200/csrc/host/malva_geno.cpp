@@ -25,6 +25,7 @@
 //   malva-geno kmc-dump <kmc_output_prefix>                 lists a database as text (no GPU involved)
 //   malva-geno signatures [--index-blocks] [flags] <reference.fa> <variants.vcf>     (no GPU involved; CPU tests)
 //   malva-geno format-selftest                              the output stage's number formatting against libc (CPU tests)
+//   malva-geno container-selftest                           InlineVec / Chain against std::vector (CPU tests)
 #include <getopt.h>
 #include <sys/resource.h>
 #include <unistd.h>
@@ -813,6 +814,73 @@ int format_selftest_main() {
   return bad ? 1 : 0;
 }
 
+// CPU-only check of the two small containers of signatures.hpp against std::vector under a random series of the
+// operations the host code uses (`malva-geno container-selftest`, run by tests/test_host_cpu.py): growth past the
+// inline capacity and back, copies and moves in both states, self-assignment, strings short and long.
+int container_selftest_main() {
+  uint32_t r = 2026;
+  auto rnd = [&](uint32_t n) {
+    r = r * 1664525u + 1013904223u;
+    return (r >> 8) % n;
+  };
+  uint64_t checks = 0, bad = 0;
+  auto word = [&]() { return std::string((size_t)rnd(40), (char)('A' + rnd(26))); };  // some beyond the SSO size
+  {
+    using V = mh::InlineVec<std::string, 2>;
+    std::vector<V> a(6);
+    std::vector<std::vector<std::string>> b(6);
+    auto same = [&](size_t i) {
+      ++checks;
+      bool ok = a[i].size() == b[i].size() && a[i].empty() == b[i].empty();
+      for (size_t j = 0; ok && j < b[i].size(); ++j) ok = a[i][j] == b[i][j];
+      size_t n = 0;
+      for (const std::string &x : a[i]) ok = ok && n < b[i].size() && x == b[i][n++];
+      if (!ok || n != b[i].size()) ++bad;
+    };
+    for (int step = 0; step < 400000; ++step) {
+      const size_t i = rnd(6), j = rnd(6);
+      switch (rnd(10)) {
+        case 0: case 1: case 2: { std::string w = word(); a[i].push_back(w); b[i].push_back(w); break; }
+        case 3: { std::string w = word(); a[i].emplace_back(w.c_str()); b[i].emplace_back(w.c_str()); break; }
+        case 4: a[i].clear(); b[i].clear(); break;
+        case 5: { size_t n = rnd(7); a[i].resize(n); b[i].resize(n); break; }
+        case 6: { size_t n = rnd(7); std::string w = word(); a[i].assign(n, w); b[i].assign(n, w); break; }
+        case 7: a[i] = a[j]; b[i] = b[j]; break;
+        case 8: if (i != j) { a[i] = std::move(a[j]); b[i] = std::move(b[j]); a[j].clear(); b[j].clear(); } break;
+        default: { V c(a[j]); V d(std::move(c)); a[i] = d; b[i] = b[j]; if (!a[i].empty()) { a[i].back() += "x"; b[i].back() += "x"; } break; }
+      }
+      same(i);
+      same(j);
+    }
+  }
+  {
+    std::vector<mh::Chain> a(5);
+    std::vector<std::vector<int>> b(5);
+    auto same = [&](size_t i) {
+      ++checks;
+      bool ok = a[i].size() == b[i].size() && a[i].empty() == b[i].empty() && (b[i].empty() || a[i].back() == b[i].back());
+      for (size_t j = 0; ok && j < b[i].size(); ++j) ok = a[i][j] == b[i][j] && a[i].data()[j] == b[i][j];
+      if (!ok) ++bad;
+    };
+    for (int step = 0; step < 400000; ++step) {
+      const size_t i = rnd(5), j = rnd(5);
+      switch (rnd(8)) {
+        case 0: case 1: case 2: { int v = (int)rnd(1000); a[i].push_back(v); b[i].push_back(v); break; }
+        case 3: if (!b[i].empty()) { a[i].pop_back(); b[i].pop_back(); } break;
+        case 4: if (rnd(4) == 0) { a[i].clear(); b[i].clear(); } break;
+        case 5: a[i] = a[j]; b[i] = b[j]; break;
+        case 6: if (i != j && b[i].size() + b[j].size() < 300) { a[i].append(a[j].data(), a[j].size()); b[i].insert(b[i].end(), b[j].begin(), b[j].end()); } break;
+        default: if (i != j) { mh::Chain c(std::move(a[j])); a[j].clear(); a[i] = mh::Chain(); a[i].append_reversed(c); a[j] = std::move(c);
+                               b[i].assign(b[j].rbegin(), b[j].rend()); } break;
+      }
+      same(i);
+      same(j);
+    }
+  }
+  printf("container-selftest: %llu checks, %llu differ\n", (unsigned long long)checks, (unsigned long long)bad);
+  return bad ? 1 : 0;
+}
+
 int call_main(int argc, char **argv) {
   Options o;
   if (!parse_arguments(argc, argv, o, 3)) return EXIT_FAILURE;
@@ -1264,6 +1332,7 @@ int main(int argc, char **argv) {
     if (strcmp(argv[1], "count") == 0) return count_main(argc - 1, argv + 1);
     if (strcmp(argv[1], "kmc-dump") == 0) return kmc_dump_main(argc - 1, argv + 1);
     if (strcmp(argv[1], "format-selftest") == 0) return format_selftest_main();
+    if (strcmp(argv[1], "container-selftest") == 0) return container_selftest_main();
   } catch (const GpuError &e) {
     std::cerr << "malva-geno: GPU error: " << e.what() << " (there is no CPU fallback)" << std::endl;
     return 2;

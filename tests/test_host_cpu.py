@@ -483,3 +483,10 @@ def test_format_short_cuts_equal_the_library_calls(cli):
     "%g" over 4.7e6 values (whole numbers, fractions, -0, inf, nan, denormals, random bit patterns)"""
     r = subprocess.run([cli, "format-selftest"], capture_output=True, text=True)
     assert r.returncode == 0 and " 0 differ" in r.stdout, r.stdout + r.stderr
+
+
+def test_small_containers_equal_std_vector(cli):
+    """InlineVec (a record's short lists) and Chain (signatures.hpp) against std::vector over 800,000 random
+    operations: growth past the inline capacity, copies and moves in both states, strings beyond the SSO size"""
+    r = subprocess.run([cli, "container-selftest"], capture_output=True, text=True)
+    assert r.returncode == 0 and " 0 differ" in r.stdout, r.stdout + r.stderr
