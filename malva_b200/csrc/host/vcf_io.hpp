@@ -434,6 +434,7 @@ class VcfHeader {
   std::vector<HeaderLine> lines;
   std::vector<std::string> samples;  // as in the file
   std::vector<int> keep;             // kept samples, header order
+  std::vector<int32_t> kept_of_col;  // sample column -> its index in `keep`, -1 if dropped (filled by set_samples)
 
   static bool parse(const std::string &text, HeaderLine &h) {
     if (text.size() < 3 || text[0] != '#' || text[1] != '#') return false;
@@ -478,6 +479,7 @@ class VcfHeader {
     keep.clear();
     if (spec == "-") {
       for (size_t i = 0; i < samples.size(); ++i) keep.push_back((int)i);
+      index_kept();
       return 0;
     }
     std::vector<std::string> names;
@@ -505,7 +507,12 @@ class VcfHeader {
     }
     for (size_t j = 0; j < want.size(); ++j)
       if (want[j]) keep.push_back((int)j);
+    index_kept();
     return ret;
+  }
+  void index_kept() {
+    kept_of_col.assign(samples.size(), -1);
+    for (size_t i = 0; i < keep.size(); ++i) kept_of_col[(size_t)keep[i]] = (int32_t)i;
   }
   // print_cleaned_header (main.cpp:190-219): GT/GQ (+COVS/GTS) appended if new, all samples replaced by DONOR
   std::string cleaned(bool verbose) const {
@@ -674,25 +681,27 @@ inline int info_floats(const Field &info, const std::string &key, float *out, in
   return -1;
 }
 
-// ---- extract_genotypes for the layout panels come in: FORMAT is "GT" alone, every sample kept, every column the same
-// width -- "a|b" / "a/b" with one-symbol alleles (3 bytes + tab) or one symbol alone (haploid panels, 1 byte + tab).
+// ---- extract_genotypes for the layout panels come in: FORMAT is "GT" alone and every column has the same width --
+// "a|b" / "a/b" with one-symbol alleles (3 bytes + tab) or one symbol alone (haploid panels, 1 byte + tab).
 // Columns then sit at a fixed stride, the run of the mill ("0|0", "0/0", "0") is recognised 16 bytes at a time, and only
-// the columns that differ are decoded; the result is the sparse genotype list parse_record() would build (same
-// decisions, variant.hpp:158-211, including the one-allele rows whose second read lands on the NEXT sample's first
-// entry).  Returns false -- nothing written -- for any other layout: the caller then takes the general path.
+// the columns that differ are decoded -- those of the kept samples (-s), that is: `kept_of_col` maps a column to its
+// place among the `n_keep` kept ones.  The result is the sparse genotype list parse_record() would build (same
+// decisions, variant.hpp:158-211, including the one-allele rows whose second read lands on the NEXT kept sample's
+// first entry).  Returns false -- nothing written -- for any other layout: the caller then takes the general path.
 inline int gt_symbol(char c) {  // allele index of a one-symbol GT entry; '.' (missing) counts as the reference allele
   if (c >= '0' && c <= '9') return c - '0';
   return c == '.' ? 0 : -1;
 }
-inline bool fast_gt_columns(const char *s, const char *end, size_t ns, Variant &v) {
-  if (ns == 0 || !s) return false;
+inline bool fast_gt_columns(const char *s, const char *end, size_t n_cols, const int32_t *kept_of_col, const int *keep,
+                            size_t n_keep, Variant &v) {
+  if (n_cols == 0 || n_keep == 0 || !s) return false;
   const size_t len = (size_t)(end - s);
-  static thread_local std::vector<uint32_t> exc_tl;  // samples whose column is not the run-of-the-mill one
+  static thread_local std::vector<uint32_t> exc_tl;  // columns that are not the run-of-the-mill one
   std::vector<uint32_t> &exc = exc_tl;
   exc.clear();
   v.gts.clear();
   size_t ref_phased = 0, ref_unphased = 0;
-  if (len == 4 * ns - 1) {  // ---- "a|b" columns ----
+  if (len == 4 * n_cols - 1) {  // ---- "a|b" columns ----
     if (s[1] != '|' && s[1] != '/') return false;
     const char sep = s[1];
     const int guess = sep == '|';  // phasing of the reference-reference columns, to be confirmed by the counts
@@ -700,7 +709,7 @@ inline bool fast_gt_columns(const char *s, const char *end, size_t ns, Variant &
     uint32_t def;
     memcpy(&def, def4, 4);
     size_t i = 0;
-    const size_t whole = ns - 1;  // (the last column has no tab behind it)
+    const size_t whole = n_cols - 1;  // (the last column has no tab behind it)
 #if defined(__SSE2__)
     const __m128i d16 = _mm_set1_epi32((int)def);
     for (; i + 4 <= whole; i += 4) {
@@ -716,29 +725,33 @@ inline bool fast_gt_columns(const char *s, const char *end, size_t ns, Variant &
       memcpy(&w, s + 4 * i, 4);
       if (w != def) exc.push_back((uint32_t)i);
     }
-    exc.push_back((uint32_t)(ns - 1));
+    exc.push_back((uint32_t)(n_cols - 1));
+    size_t kept_exc = 0;
     for (uint32_t e : exc) {
       const char *q = s + 4 * (size_t)e;
       const int a1 = gt_symbol(q[0]), a2 = gt_symbol(q[2]);
-      if (a1 < 0 || a2 < 0 || (q[1] != '|' && q[1] != '/') || (e + 1 < ns && q[3] != '\t')) return false;
+      if (a1 < 0 || a2 < 0 || (q[1] != '|' && q[1] != '/') || (e + 1 < n_cols && q[3] != '\t')) return false;
+      const int32_t ki = kept_of_col[e];
+      if (ki < 0) continue;  // (a dropped sample: its column only had to be well-formed)
+      ++kept_exc;
       const uint16_t h1 = v.text_id_of(a1), h2 = v.text_id_of(a2);
       const uint8_t ph = q[1] == '|';
       if ((h1 | h2) == 0) {
         (ph ? ref_phased : ref_unphased)++;
         if (ph == guess) continue;
       }
-      v.gts.push_back(GtEntry{e, h1, h2, ph});
+      v.gts.push_back(GtEntry{(uint32_t)ki, h1, h2, ph});
     }
-    (guess ? ref_phased : ref_unphased) += ns - exc.size();
+    (guess ? ref_phased : ref_unphased) += n_keep - kept_exc;
     if ((ref_phased >= ref_unphased ? 1 : 0) != guess) return false;  // (mixed files: the general path sorts it out)
     v.default_phased = (uint8_t)guess;
-  } else if (len == 2 * ns - 1) {  // ---- one-symbol columns: sample i reads {own symbol, NEXT sample's symbol}, unphased;
-    //                                  the last one {own, own}, phased (see parse_record) ----
+  } else if (len == 2 * n_cols - 1) {  // ---- one-symbol columns: kept sample i reads {own symbol, the NEXT kept
+    //                                      sample's symbol}, unphased; the last one {own, own}, phased (parse_record) ----
     const char def2[2] = {'0', '\t'};
     uint16_t def;
     memcpy(&def, def2, 2);
     size_t i = 0;
-    const size_t whole = ns - 1;
+    const size_t whole = n_cols - 1;
 #if defined(__SSE2__)
     const __m128i d16 = _mm_set1_epi16((short)def);
     for (; i + 8 <= whole; i += 8) {
@@ -754,37 +767,43 @@ inline bool fast_gt_columns(const char *s, const char *end, size_t ns, Variant &
       memcpy(&w, s + 2 * i, 2);
       if (w != def) exc.push_back((uint32_t)i);
     }
-    if (exc.empty() || exc.back() != (uint32_t)(ns - 1)) exc.push_back((uint32_t)(ns - 1));
-    // a column that differs makes its own sample and the one before it differ
+    exc.push_back((uint32_t)(n_cols - 1));
+    // a kept column that differs makes its own sample and the kept one before it differ; the last kept sample is
+    // always looked at
     size_t n_touched = 0;
-    uint32_t last_done = 0xFFFFFFFFu;
+    int64_t last_done = -1;
+    auto visit = [&](int64_t t) {  // kept index t, ascending over the calls
+      if (t < 0 || t <= last_done) return true;
+      last_done = t;
+      ++n_touched;
+      const int a1 = gt_symbol(s[2 * (size_t)keep[t]]);
+      const bool last = (size_t)t + 1 == n_keep;
+      const int a2 = last ? a1 : gt_symbol(s[2 * (size_t)keep[t + 1]]);
+      if (a1 < 0 || a2 < 0) return false;
+      const uint16_t h1 = v.text_id_of(a1), h2 = v.text_id_of(a2);
+      const uint8_t ph = last ? 1 : 0;
+      if ((h1 | h2) == 0) {
+        (ph ? ref_phased : ref_unphased)++;
+        if (!ph) return true;
+      }
+      v.gts.push_back(GtEntry{(uint32_t)t, h1, h2, ph});
+      return true;
+    };
     for (uint32_t e : exc) {
       const char *q = s + 2 * (size_t)e;
-      if (gt_symbol(q[0]) < 0 || (e + 1 < ns && q[1] != '\t')) return false;
-      for (uint32_t t = e == 0 ? 0 : e - 1; t <= e; ++t) {
-        if (last_done != 0xFFFFFFFFu && t <= last_done) continue;
-        last_done = t;
-        ++n_touched;
-        const int a1 = gt_symbol(s[2 * (size_t)t]);
-        const bool last = t + 1 == ns;
-        const int a2 = last ? a1 : gt_symbol(s[2 * (size_t)t + 2]);
-        if (a1 < 0 || a2 < 0) return false;
-        const uint16_t h1 = v.text_id_of(a1), h2 = v.text_id_of(a2);
-        const uint8_t ph = last ? 1 : 0;
-        if ((h1 | h2) == 0) {
-          (ph ? ref_phased : ref_unphased)++;
-          if (!ph) continue;
-        }
-        v.gts.push_back(GtEntry{t, h1, h2, ph});
-      }
+      if (gt_symbol(q[0]) < 0 || (e + 1 < n_cols && q[1] != '\t')) return false;
+      const int32_t ki = kept_of_col[e];
+      if (ki < 0) continue;
+      if (!visit((int64_t)ki - 1) || !visit((int64_t)ki)) return false;
     }
-    ref_unphased += ns - n_touched;
+    if (!visit((int64_t)n_keep - 1)) return false;
+    ref_unphased += n_keep - n_touched;
     if (ref_phased >= ref_unphased) return false;  // (a panel of one or two samples: the general path)
     v.default_phased = 0;
   } else {
     return false;
   }
-  v.n_samples_ = (uint32_t)ns;
+  v.n_samples_ = (uint32_t)n_keep;
   return true;
 }
 }  // namespace detail
@@ -871,8 +890,8 @@ inline Variant parse_record(const char *line_begin, const char *line_end, const 
   // raw codes per kept sample, htslib style: ((allele + 1) << 1) | phased; `first`/`second`/ploidy per sample
   const size_t ns = header.keep.size();
   if (count_rows()) sample_rows().fetch_add(1, std::memory_order_relaxed);
-  if (gt_field == 0 && c[8].size() == 2 && ns == header.samples.size() && !general_decode_only() &&
-      detail::fast_gt_columns(samples_begin, end, ns, v)) {
+  if (gt_field == 0 && c[8].size() == 2 && header.kept_of_col.size() == header.samples.size() && !general_decode_only() &&
+      detail::fast_gt_columns(samples_begin, end, header.samples.size(), header.kept_of_col.data(), header.keep.data(), ns, v)) {
     if (count_rows()) fast_gt_rows().fetch_add(1, std::memory_order_relaxed);
     return v;
   }

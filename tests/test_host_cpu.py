@@ -463,6 +463,19 @@ def test_fixed_stride_gt_columns_equal_general_decode(cli, ref_lib, tmp_path, ha
         slow2 = _signatures_text(cli, fa, vcf, [], general=True)
         assert fast2.returncode == 0 and slow2.returncode == 0 and fast2.stdout == slow2.stdout
         assert n_samples < 3 or fast2.stdout != fast.stdout
+    # kept-sample subsets (-s): the short cut decodes the kept columns only
+    subsets = {"half": [i for i in range(n_samples) if rng.random() < 0.5], "first": [0], "last": [n_samples - 1],
+               "but_last": list(range(n_samples - 1)), "but_first": list(range(1, n_samples))}
+    for name, cols in subsets.items():
+        if not cols:
+            continue
+        lst = tmp_path / f"{name}.txt"
+        lst.write_text("".join(f"S{i}\n" for i in cols))
+        for fl in ([flags] if not haploid else [flags, []]):
+            a = _signatures_text(cli, fa, vcf, fl + ["-s", str(lst)], general=False)
+            b = _signatures_text(cli, fa, vcf, fl + ["-s", str(lst)], general=True)
+            assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+            assert a.stdout == b.stdout, (name, fl)
     tr = subprocess.run([cli, "signatures", "--trace"] + flags + [fa, vcf], capture_output=True, text=True, check=True).stderr
     took, rows = map(int, re.search(r"fixed-stride GT decode: (\d+) of (\d+) rows", tr).groups())
     assert 0.8 * len(recs) <= rows <= len(recs) and took < rows
