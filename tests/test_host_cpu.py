@@ -36,7 +36,7 @@ def cli_signatures(cli, fa, vcf, flags, index_mode):
     return blocks, used
 
 
-def expected_signatures(ref_lib, fa, vcf, k, haploid, freq_key, uniform, index_mode, strip_chr=False):
+def expected_signatures(ref_lib, fa, vcf, k, haploid, freq_key, uniform, index_mode, strip_chr=False, sample_cols=None):
     refs, name = {}, None
     for l in open(fa):
         l = l.rstrip("\n")
@@ -48,7 +48,7 @@ def expected_signatures(ref_lib, fa, vcf, k, haploid, freq_key, uniform, index_m
         else:
             refs[name].append(l.upper())
     refs = {n: "".join(v) for n, v in refs.items()}
-    _, recs = vcf_blocks.read_vcf(vcf, freq_key, uniform)
+    _, recs = vcf_blocks.read_vcf(vcf, freq_key, uniform, sample_cols)
     blocks, used = {}, []
     if recs:
         used.append(recs[0].chrom)
@@ -84,6 +84,12 @@ def test_signatures_synthetic(cli, ref_lib, case, tmp_path):
             a = _signatures_text(cli, fa, vcf, extra + ["-u", "-s", lst], general=False)
             b = _signatures_text(cli, fa, vcf, extra + ["-u", "-s", lst], general=True)
             assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout and a.stdout.count("\n") > 100
+        # ... and against VB::extract_kmers fed with the kept columns (header order, whatever the order of the list)
+        for index_mode in (True, False):
+            got, used = cli_signatures(cli, fa, vcf, ["-u", "-s", lst], index_mode)
+            exp, exp_used = expected_signatures(ref_lib, fa, vcf, case.k, case.haploid, case.freq_key, True, index_mode,
+                                                strip_chr=case.chr_prefix, sample_cols=sorted(case.sample_subset))
+            assert got == exp and used == exp_used
         return
     sig_flags = [f for f in case.flags]
     # only the flags the enumeration depends on
@@ -483,6 +489,10 @@ def test_fixed_stride_gt_columns_equal_general_decode(cli, ref_lib, tmp_path, ha
             b = _signatures_text(cli, fa, vcf, fl + ["-s", str(lst)], general=True)
             assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
             assert a.stdout == b.stdout, (name, fl)
+        if name in ("half", "but_first"):   # and what the reference's own enumeration gives for the kept columns
+            got, used = cli_signatures(cli, fa, vcf, flags + ["-s", str(lst)], False)
+            exp, exp_used = expected_signatures(ref_lib, fa, vcf, 35, haploid, "AF", False, False, sample_cols=cols)
+            assert got == exp and used == exp_used, name
     tr = subprocess.run([cli, "signatures", "--trace"] + flags + [fa, vcf], capture_output=True, text=True, check=True).stderr
     took, rows = map(int, re.search(r"fixed-stride GT decode: (\d+) of (\d+) rows", tr).groups())
     assert 0.8 * len(recs) <= rows <= len(recs) and took < rows

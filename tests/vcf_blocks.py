@@ -34,7 +34,8 @@ class Rec:
         return min([len(self.ref)] + [len(a) for a in self.alts])
 
 
-def read_vcf(path: str, freq_key: str = "AF", uniform: bool = False):
+def read_vcf(path: str, freq_key: str = "AF", uniform: bool = False, sample_cols=None):
+    """sample_cols: indices of the sample columns to keep, ascending (bcf_hdr_set_samples keeps header order)"""
     op = gzip.open if path.endswith(".gz") else open
     header, recs = [], []
     with op(path, "rt") as fh:
@@ -66,7 +67,8 @@ def read_vcf(path: str, freq_key: str = "AF", uniform: bool = False):
             if has_alts and present and len(c) > 9:
                 fmt = c[8].split(":")
                 gi = fmt.index("GT")
-                gts = [s.split(":")[gi] for s in c[9:] if s != ""]
+                cols = c[9:] if sample_cols is None else [c[9 + j] for j in sample_cols]
+                gts = [s.split(":")[gi] for s in cols if s != ""]
             recs.append(Rec(c[0], int(c[1]) - 1, c[2], c[3].upper(), alts, c[5], freqs, bool(present), has_alts, gts))
     return header, recs
 
