@@ -525,3 +525,24 @@ def test_small_containers_equal_std_vector(cli):
     operations: growth past the inline capacity, copies and moves in both states, strings beyond the SSO size"""
     r = subprocess.run([cli, "container-selftest"], capture_output=True, text=True)
     assert r.returncode == 0 and " 0 differ" in r.stdout, r.stdout + r.stderr
+
+
+def test_sars_cov2_panel_against_the_reference_enumeration(cli, ref_lib, tmp_path):
+    """BASELINE config 1's real VCF -- 15,154 records in ONE var_block (every other base of the genome has a variant:
+    chains of ~19 members) -- with 400 of its 27,934 haploid samples (the reference's own enumeration needs ~12 s for
+    these; 5 minutes for all): malva-geno signatures == VB::extract_kmers, block by block, allele by allele"""
+    import gzip
+    import random
+
+    src = os.path.join(os.path.dirname(GOLD), "sars")
+    fa, vcf = os.path.join(src, "reference_sarsCov2.fasta"), os.path.join(src, "sars_cov2.vcf.gz")
+    with gzip.open(vcf, "rt") as fh:
+        names = next(l for l in fh if l.startswith("#CHROM")).rstrip("\n").split("\t")[9:]
+    assert len(names) == 27934
+    cols = sorted(random.Random(11).sample(range(len(names)), 400))
+    lst = tmp_path / "kept.txt"
+    lst.write_text("".join(names[i] + "\n" for i in cols))
+    got, used = cli_signatures(cli, fa, vcf, ["-1", "-s", str(lst)], False)
+    exp, exp_used = expected_signatures(ref_lib, fa, vcf, 35, True, "AF", False, False, sample_cols=cols)
+    assert got == exp and used == exp_used
+    assert sum(len(v) for b in exp.values() for v in b.values()) > 30_000
