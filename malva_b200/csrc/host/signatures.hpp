@@ -12,15 +12,19 @@
 //   signature construction          var_block.hpp:95-219
 // What differs is only how the work is organised:
 //   * genotypes are kept SPARSE: per variant the samples whose genotype is not the default (reference allele on
-//     every haplotype, the variant's majority phasing flag); the haplotypes of a chain come from a merge of the
-//     chain members' sparse lists -- work proportional to the carriers, not to the panel size (27,934 samples in the
-//     SARS-CoV-2 example, a handful of carriers per record) -- plus one all-reference row for everybody else;
+//     every haplotype, the variant's majority phasing flag); the haplotypes of a chain come from the chain members'
+//     sparse lists -- scattered into per-sample keys / rows when every member defaults to phased genotypes (or in
+//     haploid mode), merged sample by sample otherwise: work proportional to the carriers, not to the panel size
+//     (27,934 samples in the SARS-CoV-2 example, a handful of carriers per record) -- plus one all-reference row for
+//     everybody else;
 //   * haplotypes are tuples of small allele ids; an allele id is the index of the first allele of the variant with
 //     the same TEXT, which is exactly the identity the reference's unordered_set<vector<string_view>> and
 //     Variant::get_allele_index (variant.hpp:228-240) use;
 //   * identical genotype patterns are collapsed before unphased patterns are expanded into their 2^n haplotypes;
 //   * duplicate signatures of an allele are dropped: the coverage of an allele is a max over its signatures
-//     (main.cpp:176-177) and filter/table inserts are idempotent, so results cannot change.
+//     (main.cpp:176-177) and filter/table inserts are idempotent, so results cannot change;
+//   * in a block sorted by position the walk that collects a variant's neighbours stops where nothing can be within
+//     reach any more (the reference walks to the end of the block, to no effect).
 // The order of the signatures of an allele is unspecified in the reference too (unordered_set iteration).
 #pragma once
 #include <algorithm>
