@@ -13,7 +13,8 @@
 //   * VCF lines are decoded and signatures enumerated in parallel (per variant, inside a block as well as across
 //     blocks), in batches; a batch goes to the device in one call (mg_add_signatures_packed / mg_genotype_packed:
 //     2-bit k-mer words) instead of one k-mer string at a time; the stages of consecutive batches overlap:
-//     read + decode | enumerate | device | format + write each run on their own thread;
+//     read (+ inflate, line cutting) | decode + group | enumerate | device | format + write each run on their own
+//     thread, and a batch the last stage is done with goes back to the first (its buffers keep their pages);
 //   * the KMC database is not decoded on the host: raw suffix records stream through pinned buffers into
 //     mg_scan_kmc_records;
 //   * the index file holds sparse lists (index_file.hpp).
