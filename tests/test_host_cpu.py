@@ -546,3 +546,20 @@ def test_sars_cov2_panel_against_the_reference_enumeration(cli, ref_lib, tmp_pat
     exp, exp_used = expected_signatures(ref_lib, fa, vcf, 35, True, "AF", False, False, sample_cols=cols)
     assert got == exp and used == exp_used
     assert sum(len(v) for b in exp.values() for v in b.values()) > 30_000
+
+
+def test_error_in_a_later_batch_ends_the_pipeline(cli, tmp_path):
+    """a malformed record in the second batch (the reader thread is a block ahead, the first batch is already being
+    enumerated): the program reports it and exits, no stage is left waiting for another"""
+    import synth_fast
+
+    fa, vcf, _, n = synth_fast.build(str(tmp_path), 4_000_000)
+    lines = open(vcf).read().split("\n")
+    assert len("\n".join(lines)) > 14_000_000        # more than one 12 MB batch of text
+    lines.insert(len(lines) - 2000, "garbage line without tabs")
+    bad = str(tmp_path / "bad.vcf")
+    open(bad, "w").write("\n".join(lines))
+    r = subprocess.run([cli, "signatures", "--threads", "4", fa, bad], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "malformed VCF record: garbage line" in r.stderr
+    good = subprocess.run([cli, "signatures", "--threads", "4", fa, vcf], capture_output=True, text=True, timeout=60)
+    assert good.returncode == 0 and good.stdout.count("\n") > n
