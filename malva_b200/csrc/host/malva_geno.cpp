@@ -427,7 +427,7 @@ class BlockStream {
   // The file is read (and inflated, and cut into lines) by a thread of its own, one block of text ahead of the
   // decode: reading a block is serial work of the same order as decoding it on all threads.
   struct TextBlock {
-    std::vector<char> store;
+    mh::TextBuf store;
     std::vector<mh::BlockLineReader::View> lines;
     bool more = false;
     double read_ms = 0;
@@ -1206,7 +1206,7 @@ struct ReadFeeder {
     for (const char *p = b; p < e; ++p) *d++ = (char)(*p & 0xDF);  // a-z -> A-Z; nothing else can become A, C, G or T
   }
   mh::BlockLineReader in_;
-  std::vector<char> store_;
+  mh::TextBuf store_;
   std::vector<mh::BlockLineReader::View> lines_;
   size_t li_ = 0;
   int format_ = 0, phase_ = 0;

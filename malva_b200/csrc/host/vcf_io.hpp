@@ -32,6 +32,25 @@
 
 namespace mh {
 
+// A byte buffer whose resize() does not clear what it exposes (the readers overwrite it at once: clearing 12 MB per
+// block first is a pass over memory for nothing).
+template <class T>
+struct NoInitAllocator : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = NoInitAllocator<U>;
+  };
+  template <class U>
+  void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+    ::new (static_cast<void *>(p)) U;
+  }
+  template <class U, class... A>
+  void construct(U *p, A &&...a) {
+    ::new (static_cast<void *>(p)) U(std::forward<A>(a)...);
+  }
+};
+using TextBuf = std::vector<char, NoInitAllocator<char>>;
+
 class LineReader {
  public:
   explicit LineReader(const std::string &path) : fp_(gzopen(path.c_str(), "r")) {
@@ -283,7 +302,7 @@ class BlockLineReader {
   }
   // whole lines, ~target bytes of them (at most max_lines; empty ones dropped unless keep_empty), read straight into
   // `store` (which keeps the views alive) -- one copy from the file, none per line; false when nothing is left
-  bool next_block(std::vector<char> &store, std::vector<View> &lines, size_t max_lines, size_t target,
+  bool next_block(TextBuf &store, std::vector<View> &lines, size_t max_lines, size_t target,
                   bool keep_empty = false) {
     lines.clear();
     // what next() left in its own buffer (header parsing) goes first
@@ -335,7 +354,7 @@ class BlockLineReader {
   }
   gzFile fp_ = nullptr;
   std::unique_ptr<BgzfSource> bgzf_;
-  std::vector<char> buf_;
+  TextBuf buf_;
   size_t pos_ = 0;
   bool eof_ = false;
 };
@@ -373,7 +392,7 @@ inline bool upper_copy(char *dst, const char *src, size_t n) {
 inline std::map<std::string, std::string> read_fasta(const std::string &path, bool strip_chr) {
   std::map<std::string, std::string> refs;
   BlockLineReader in(path);
-  std::vector<char> store;
+  TextBuf store;
   std::vector<BlockLineReader::View> lines;
   std::string *cur = nullptr;
   bool in_qual = false;
@@ -563,7 +582,7 @@ class VcfReader {
   }
 
   // the next data lines (views into `store`); false at the end of the file
-  bool next_lines(std::vector<char> &store, std::vector<BlockLineReader::View> &lines, size_t max_lines, size_t target) {
+  bool next_lines(TextBuf &store, std::vector<BlockLineReader::View> &lines, size_t max_lines, size_t target) {
     bool more = in_.next_block(store, lines, max_lines, target);
     if (has_pending_) {
       has_pending_ = false;
