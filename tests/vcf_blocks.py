@@ -112,8 +112,12 @@ def ref_extract(ref_lib, block: List[Rec], reference: str, k: int, haploid: bool
         lines.append("\t".join([str(v.pos0), v.ref, ",".join(v.alts), "1" if v.is_present else "0", " ".join(gts)]))
     text = ("\n".join(lines) + "\n").encode()
     cap = 1 << 22
-    buf = C.create_string_buffer(cap)
-    n = ref_lib.ref_extract_kmers(text, reference.encode(), k, int(haploid), buf, cap)
+    while True:          # (a dense block of a thousand variants prints tens of MB of signatures)
+        buf = C.create_string_buffer(cap)
+        n = ref_lib.ref_extract_kmers(text, reference.encode(), k, int(haploid), buf, cap)
+        if n >= 0 or cap >= (1 << 30):
+            break
+        cap *= 4
     assert n >= 0, "ref_extract_kmers output buffer too small"
     nested = [[[] for _ in range(len(v.alts) + 1)] for v in block]
     for l in buf.value.decode().split("\n"):
